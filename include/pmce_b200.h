@@ -1,0 +1,139 @@
+/*
+ * pmce_b200.h — C ABI of libpmce_b200.so: the B200 (sm_100a) implementation of the PMCE per-clip
+ * forward hot path.  Plain C: raw DEVICE pointers (fp32, row-major, contiguous, laid out exactly as the
+ * reference's torch tensors), int sizes, a caller-owned workspace and a cudaStream_t passed as void*.
+ *
+ * Contract:
+ *   - every function returns 0 on success, non-zero on error; pmce_last_error() gives the message
+ *     (thread-local).  Nothing throws, nothing calls exit().
+ *   - the library allocates nothing persistent and owns no buffers: weights blob, workspace, inputs and
+ *     outputs all belong to the caller (in the product: the PyTorch caching allocator).
+ *   - all work is enqueued on `stream`, asynchronous w.r.t. the host, no device synchronisation, no
+ *     allocation => CUDA-graph capturable; re-entrant across streams/devices.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef PMCE_B200_H
+#define PMCE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMCE_ABI_VERSION 1
+
+/* Model hyper-parameters. Mirrors the constructor arguments / cfg keys the reference reads:
+ * models.PMCE.get_model(num_joint, embed_dim, depth) lib/models/PMCE.py:23-26; cfg.DATASET.seqlen,
+ * cfg.MODEL.joint_dim/vertx_dim lib/core/config.py:48,61-62. */
+typedef struct pmce_dims {
+    int32_t num_joint;   /* J: 17 (h36m) or 19 (coco+pelvis+neck)                         */
+    int32_t embed_dim;   /* C: lifter width (256 default, 512 supported); multiple of 128 */
+    int32_t depth;       /* lifter depth (3)                                             */
+    int32_t seqlen;      /* T: frames per clip (16; 64 for the long-clip config)          */
+    int32_t num_vert_ds; /* 431 down-sampled vertices                                     */
+    int32_t num_vert;    /* 6890 SMPL vertices                                            */
+    int32_t feat_dim;    /* 2048 image-feature width                                      */
+    int32_t gru_hidden;  /* 1024                                                          */
+    int32_t coevo_dim;   /* 64 (joint_dim == vertx_dim)                                   */
+    int32_t lifter_heads;/* 8                                                             */
+} pmce_dims_t;
+
+/* Where one state_dict tensor lives inside the packed weight blob (units: floats). The tensor, viewed
+ * as [rows, cols], is copied to blob[offset + r*ld + c]. */
+typedef struct pmce_slot {
+    uint64_t offset;
+    int64_t rows, cols, ld;
+} pmce_slot_t;
+
+const char* pmce_last_error(void);
+int pmce_abi_version(void);
+
+/* ---- weights: replaces nn.Module.load_state_dict for the hot path (lib/core/base.py:67) ---------- */
+/* Size in bytes of the packed fp32 weight blob for `dims`. */
+size_t pmce_weights_bytes(const pmce_dims_t* dims);
+/* Look up a reference state_dict key (e.g. "pose_lifter.SpatialBlocks.0.attn.qkv.weight").
+ * returns 0 and fills *slot; 1 if the tensor is part of the schema but never reaches an output
+ * (the joint branch of coevoblock1/2, lib/models/CoevoDecoder.py:235-236) and is not stored;
+ * <0 if the name is not in the schema. */
+int pmce_weight_slot(const pmce_dims_t* dims, const char* name, pmce_slot_t* slot);
+/* Derived tensors computed on device once all slots are filled (currently a no-op placeholder for
+ * split-precision copies). */
+int pmce_pack_weights(const pmce_dims_t* dims, void* weights, void* stream);
+
+/* Workspace bytes needed by any forward entry point for batch size B. */
+size_t pmce_workspace_bytes(const pmce_dims_t* dims, int B);
+
+/* ---- a1: PMCE.forward, lib/models/PMCE.py:15-20 --------------------------------------------------
+ * pose2d [B,T,J,2], img_feat [B,T,2048], vj_relation [431] int32 (nearest joint per vertex,
+ * lib/models/CoevoDecoder.py:208,232) -> cam_mesh [B,6890,3], cam_pose [B,J,3], pose3d [B,J,3]. */
+int pmce_forward(const pmce_dims_t* dims, const void* weights, const float* pose2d, const float* img_feat,
+                 const int32_t* vj_relation, int B, float* cam_mesh, float* cam_pose, float* pose3d,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same, HOST buffers in and out (pinned or pageable): H2D of the inputs, forward, D2H of the three
+ * outputs, then a stream synchronise. d_io must hold pmce_io_bytes(dims,B) device bytes. This is the
+ * shape of the call lib/core/base.py:218-238 makes (`.cuda()` ... `.cpu()`). */
+size_t pmce_io_bytes(const pmce_dims_t* dims, int B);
+int pmce_forward_host(const pmce_dims_t* dims, const void* weights, const float* h_pose2d, const float* h_img_feat,
+                      const int32_t* d_vj_relation, int B, float* h_cam_mesh, float* h_cam_pose, float* h_pose3d,
+                      void* d_io, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a2/a3: GraphormerNet.forward, lib/models/PoseEstimation.py:76-115 -> pose3d [B,J,3] ---------- */
+int pmce_lifter_forward(const pmce_dims_t* dims, const void* weights, const float* pose2d, const float* img_feat,
+                        int B, float* pose3d, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a4: y[T//2] of nn.GRU(2048,1024,bidirectional,2 layers), lib/models/CoevoDecoder.py:216-221,228-229
+ * img_feat [B,T,2048] -> g [B,2048]. Layer 1 only runs the steps y[T//2] depends on. */
+int pmce_gru_mid(const pmce_dims_t* dims, const void* weights, const float* img_feat, int B, float* g,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a5: all live AdaLayerNorm gamma/beta projections at once, lib/models/CoevoDecoder.py:16-29
+ * g [B,2048] -> gb [B, pmce_adaln_slots(), 2, 64] (gamma then beta per slot). */
+int pmce_adaln_slots(void);
+int pmce_adaln_gammabeta(const pmce_dims_t* dims, const void* weights, const float* g, int B, float* gb,
+                         void* stream);
+
+/* ---- a8 (with a6 CrossAttentionBlock :64-87 and a7 Block :89-105 inside): CoevoBlock.forward,
+ * lib/models/CoevoDecoder.py:175-191.  block in {1,2,3}; joints [B,J,3], verts_in [B,431,3], gb from
+ * pmce_adaln_gammabeta -> verts_out [B,431,3]; joints_out [B,J,3] is written only when non-NULL (the
+ * reference discards it for blocks 1 and 2, :235-236; weights for it exist only for block 3). */
+int pmce_coevo_block(const pmce_dims_t* dims, const void* weights, int block, const float* joints,
+                     const float* verts_in, const float* gb, int B, float* joints_out, float* verts_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a9 tail: upsample_conv + linear_cur residual, lib/models/CoevoDecoder.py:238-244
+ * verts3 [B,431,3], g [B,2048] -> cam_mesh [B,6890,3]. */
+int pmce_mesh_epilogue(const pmce_dims_t* dims, const void* weights, const float* verts3, const float* g, int B,
+                       float* cam_mesh, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a9: Pose2Mesh.forward, lib/models/CoevoDecoder.py:226-246 (joints already in metres) ---------
+ * verts0_out (optional, [B,431,3]) receives the bit-exact gather joints[:, vj_relation, :3] (:232). */
+int pmce_decoder_forward(const pmce_dims_t* dims, const void* weights, const float* joints, const float* img_feat,
+                         const int32_t* vj_relation, int B, float* cam_pose, float* cam_mesh, float* verts0_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a11: J_regressor matvec, lib/core/base.py:225 (`torch.matmul(J_regressor[None], pred_mesh)`) --
+ * CSR form of the [R,6890] regressor (<= 11 nnz/row in the shipped arrays): out[b,r,:] =
+ * scale * sum_i vals[i] * mesh[b, cols[i], :]. */
+int pmce_jregress(const int32_t* row_ptr, const int32_t* cols, const float* vals, int R, const float* mesh,
+                  int num_vert, int B, float scale, float* out, void* stream);
+
+/* ---- a12: SMPL_Layer.forward, smplpytorch/smplpytorch/pytorch/smpl_layer.py:65-158 ----------------
+ * blend  [20670, KB] fp32, KB = smpl_blend_ld() >= 217: row (v*3+c) = [shapedirs[v,c,0:10] | posedirs[v,c,0:207] | 0]
+ * v_template [20670]; j_template [24,3] = Jreg @ v_template; j_shapedirs [24,3,10] = Jreg @ shapedirs;
+ * skin_weights [6890,24]; parents [24] int32; pose [B,72]; betas [B,10]; trans [B,3] or NULL
+ * -> verts [B,6890,3], joints [B,24,3]. workspace: smpl_workspace_bytes(B). */
+int smpl_blend_ld(void);
+size_t smpl_workspace_bytes(int B);
+int smpl_lbs_forward(const float* blend, const float* v_template, const float* j_template, const float* j_shapedirs,
+                     const float* skin_weights, const int32_t* parents, const float* pose, const float* betas,
+                     const float* trans, int B, float* verts, float* joints, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMCE_B200_H */

@@ -1,0 +1,108 @@
+"""Import the UNMODIFIED reference (`/root/reference`) on a CPU-only host.  TEST INFRASTRUCTURE.
+
+Only usable in the build container (the GPU box has no `/root/reference`): it is what
+`oracle/gen_golden.py` uses to produce `tests/golden/*.npz`, and what
+`tests/test_oracle_vs_reference.py` uses (skipped when the reference is absent) to pin the CPU
+restatement in `oracle/pmce_oracle.py`.
+
+No reference source is copied. A scratch "view" directory of *symlinks* to the read-only tree is
+built so that the reference's import-time `mkdir experiment/...` (lib/core/config.py:20-38, paths
+derived from `os.path.abspath(__file__)`, which does not resolve symlinks) lands in the scratch
+dir, and `data/base_data` (a dangling symlink in the reference) is replaced by seeded synthetic
+assets from `pmce_b200.synth`. Missing third-party modules (`timm`, `easydict`, `matplotlib`) come
+from `oracle/shims/`; hard-coded `.cuda()` calls (CoevoDecoder.py:200,207; backbones/mesh.py:62)
+are neutralised on CPU-only hosts.
+"""
+import os
+import sys
+import tempfile
+
+import torch
+
+REFERENCE_ROOT = os.environ.get("PMCE_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
+_state = {}
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "lib", "models"))
+
+
+def setup(asset_seed=7):
+    """Build the view dir, chdir into it, patch `.cuda()` and put the reference on sys.path."""
+    if _state:
+        return _state
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    if _REPO not in sys.path:
+        sys.path.insert(0, _REPO)
+    from pmce_b200 import synth
+
+    view = tempfile.mkdtemp(prefix="pmce_ref_view_")
+    # lib/ and lib/core/ must be real directories: config.py walks `<its dir>/../../` physically.
+    os.makedirs(os.path.join(view, "lib", "core"))
+    for name in os.listdir(os.path.join(REFERENCE_ROOT, "lib")):
+        if name != "core":
+            os.symlink(os.path.join(REFERENCE_ROOT, "lib", name), os.path.join(view, "lib", name))
+    for name in os.listdir(os.path.join(REFERENCE_ROOT, "lib", "core")):
+        os.symlink(os.path.join(REFERENCE_ROOT, "lib", "core", name), os.path.join(view, "lib", "core", name))
+    os.symlink(os.path.join(REFERENCE_ROOT, "smplpytorch"), os.path.join(view, "smplpytorch"))
+    os.makedirs(os.path.join(view, "data"))
+    os.makedirs(os.path.join(view, "experiment"))
+    for name in os.listdir(os.path.join(REFERENCE_ROOT, "data")):
+        if name == "base_data":
+            continue
+        os.symlink(os.path.join(REFERENCE_ROOT, "data", name), os.path.join(view, "data", name))
+    assets = synth.write_mesh_assets(view, seed=asset_seed)
+
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+
+    sys.path.insert(0, os.path.join(_HERE, "shims"))
+    sys.path.insert(0, os.path.join(view, "smplpytorch"))
+    sys.path.insert(0, os.path.join(view, "data"))
+    sys.path.insert(0, os.path.join(view, "lib"))
+    os.chdir(view)
+
+    import io
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        from core.config import cfg  # noqa: creates experiment dirs inside the view
+    from models.backbones import mesh as ref_mesh
+    if not torch.cuda.is_available():
+        defaults = list(ref_mesh.Mesh.__init__.__defaults__)
+        defaults[-1] = torch.device("cpu")
+        ref_mesh.Mesh.__init__.__defaults__ = tuple(defaults)
+    import models  # noqa: reference lib/models/__init__.py
+
+    _state.update(view=view, cfg=cfg, models=models, assets=assets)
+    return _state
+
+
+def build_pmce(num_joint=17, embed_dim=256, depth=3, seqlen=16):
+    """`models.PMCE.get_model` of the reference (lib/models/PMCE.py:23-26), eval mode."""
+    st = setup()
+    st["cfg"].DATASET.seqlen = seqlen
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = st["models"].PMCE.get_model(num_joint, embed_dim, depth)
+    return model.eval()
+
+
+def build_smpl_layer(buffers):
+    """Reference `SMPL_Layer` with `__init__` bypassed (it needs licensed pkl files + chumpy,
+    smpl_layer.py:30-37); `forward` (smpl_layer.py:65-158) then runs verbatim."""
+    setup()
+    from smplpytorch.pytorch.smpl_layer import SMPL_Layer
+    layer = SMPL_Layer.__new__(SMPL_Layer)
+    torch.nn.Module.__init__(layer)
+    layer.center_idx = None
+    layer.gender = "neutral"
+    for k in ("th_betas", "th_shapedirs", "th_posedirs", "th_v_template", "th_J_regressor", "th_weights"):
+        layer.register_buffer(k, buffers[k].clone())
+    layer.kintree_parents = list(buffers["kintree_parents"])
+    layer.num_joints = len(layer.kintree_parents)
+    return layer.eval()

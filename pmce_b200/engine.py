@@ -1,0 +1,288 @@
+"""Host-side driver of libpmce_b200: packed weights, workspace, launches, CUDA-graph replay.
+
+PyTorch is used for device memory (caching allocator), streams and graphs only; all arithmetic on
+the hot path happens inside the C-ABI library (`include/pmce_b200.h`). Nothing here falls back to
+PyTorch ops or to the CPU: non-CUDA inputs raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PmceDims, PmceSlot, PmceError, check
+
+N_VERT, N_VERT_DS, F_IMG, H_GRU, D_COEVO = 6890, 431, 2048, 1024, 64
+
+
+def make_dims(num_joint=17, embed_dim=256, depth=3, seqlen=16):
+    return PmceDims(num_joint=num_joint, embed_dim=embed_dim, depth=depth, seqlen=seqlen, num_vert_ds=N_VERT_DS,
+                    num_vert=N_VERT, feat_dim=F_IMG, gru_hidden=H_GRU, coevo_dim=D_COEVO, lifter_heads=8)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda_f32(t, name, shape=None):
+    if not isinstance(t, torch.Tensor):
+        raise PmceError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise PmceError(f"{name}: must be a CUDA tensor — pmce_b200 has no CPU path (got device {t.device})")
+    if t.dtype != torch.float32:
+        raise PmceError(f"{name}: must be float32 (got {t.dtype})")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise PmceError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+class Engine:
+    """One model instance's packed weights + scratch on one device."""
+
+    def __init__(self, dims, use_graph=None):
+        self.lib = _lib.load()
+        self.dims = dims
+        self._dp = C.byref(self.dims)
+        nbytes = self.lib.pmce_weights_bytes(self._dp)
+        if nbytes == 0:
+            check(1, "pmce_weights_bytes")
+        self.weight_bytes = nbytes
+        self.weights = None
+        self.vj = None
+        self._ws = None
+        self._graphs = {}
+        if use_graph is None:
+            use_graph = os.environ.get("PMCE_B200_GRAPH", "1") != "0"
+        self.use_graph = use_graph
+        self.launch_count = 0
+
+    # ---- weights -------------------------------------------------------------------------------------
+    def pack(self, named_tensors, device, vj_relation=None):
+        """Copy reference-schema tensors (`state_dict` names) into the packed device blob."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise PmceError("weights must be packed onto a CUDA device")
+        blob = torch.zeros(self.weight_bytes // 4, dtype=torch.float32, device=device)
+        slot = PmceSlot()
+        for name, t in named_tensors:
+            rc = self.lib.pmce_weight_slot(self._dp, name.encode(), C.byref(slot))
+            if rc == 1:
+                continue  # never reaches an output (joint branch of coevoblock1/2)
+            if rc != 0:
+                check(rc, f"pmce_weight_slot({name})")
+            src = t.detach().to(device=device, dtype=torch.float32).reshape(slot.rows, slot.cols)
+            dst = blob[slot.offset: slot.offset + slot.rows * slot.ld].view(slot.rows, slot.ld)[:, :slot.cols]
+            dst.copy_(src)
+        with torch.cuda.device(device):
+            check(self.lib.pmce_pack_weights(self._dp, _ptr(blob), _stream()), "pmce_pack_weights")
+        self.weights = blob
+        if vj_relation is not None:
+            self.vj = torch.as_tensor(np.asarray(vj_relation).astype(np.int32), device=device)
+        self._graphs.clear()
+        return self
+
+    def _workspace(self, B, device):
+        need = self.lib.pmce_workspace_bytes(self._dp, B)
+        if need == 0:
+            check(1, "pmce_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+            self._graphs.clear()
+        return self._ws
+
+    def _ready(self, need_vj=False):
+        if self.weights is None:
+            raise PmceError("weights have not been packed (call Engine.pack / load_state_dict first)")
+        if need_vj and self.vj is None:
+            raise PmceError("vj_relation has not been set")
+
+    # ---- whole forward (a1) --------------------------------------------------------------------------
+    def _forward_eager(self, pose2d, img_feat, mesh, cam_pose, pose3d):
+        B = pose2d.shape[0]
+        ws = self._workspace(B, pose2d.device)
+        check(self.lib.pmce_forward(self._dp, _ptr(self.weights), _ptr(pose2d), _ptr(img_feat), _ptr(self.vj), B,
+                                    _ptr(mesh), _ptr(cam_pose), _ptr(pose3d), _ptr(ws), ws.numel(), _stream()),
+              "pmce_forward")
+
+    def forward(self, pose2d, img_feat):
+        """PMCE.forward: ([B,T,J,2], [B,T,2048]) -> (cam_mesh [B,6890,3], cam_pose [B,J,3], pose3d [B,J,3])."""
+        self._ready(need_vj=True)
+        d = self.dims
+        B = pose2d.shape[0] if isinstance(pose2d, torch.Tensor) and pose2d.dim() == 4 else -1
+        pose2d = _require_cuda_f32(pose2d, "pose2d", (B, d.seqlen, d.num_joint, 2))
+        img_feat = _require_cuda_f32(img_feat, "img_feat", (B, d.seqlen, d.feat_dim))
+        dev = pose2d.device
+        if dev != self.weights.device:
+            raise PmceError(f"inputs on {dev} but weights on {self.weights.device}")
+        with torch.cuda.device(dev):
+            if not self.use_graph or torch.cuda.is_current_stream_capturing():
+                mesh = torch.empty(B, d.num_vert, 3, device=dev)
+                cam_pose = torch.empty(B, d.num_joint, 3, device=dev)
+                pose3d = torch.empty(B, d.num_joint, 3, device=dev)
+                self._forward_eager(pose2d, img_feat, mesh, cam_pose, pose3d)
+                return mesh, cam_pose, pose3d
+            g = self._graphs.get(B)
+            if g is None:
+                g = self._capture(B, dev)
+            g["p2d"].copy_(pose2d)
+            g["feat"].copy_(img_feat)
+            g["graph"].replay()
+            return g["mesh"].clone(), g["cam_pose"].clone(), g["pose3d"].clone()
+
+    def _capture(self, B, dev):
+        d = self.dims
+        st = dict(p2d=torch.zeros(B, d.seqlen, d.num_joint, 2, device=dev),
+                  feat=torch.zeros(B, d.seqlen, d.feat_dim, device=dev),
+                  mesh=torch.empty(B, d.num_vert, 3, device=dev),
+                  cam_pose=torch.empty(B, d.num_joint, 3, device=dev),
+                  pose3d=torch.empty(B, d.num_joint, 3, device=dev))
+        self._workspace(B, dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):      # warm-up outside capture (func attributes, lazy module load)
+            self._forward_eager(st["p2d"], st["feat"], st["mesh"], st["cam_pose"], st["pose3d"])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._forward_eager(st["p2d"], st["feat"], st["mesh"], st["cam_pose"], st["pose3d"])
+        st["graph"] = graph
+        self._graphs[B] = st
+        return st
+
+    def forward_host(self, pose2d_cpu, img_feat_cpu, out=None):
+        """The C-ABI host-buffer call (`pmce_forward_host`): pinned/pageable CPU tensors in, CPU tensors out."""
+        self._ready(need_vj=True)
+        d = self.dims
+        B = pose2d_cpu.shape[0]
+        dev = self.weights.device
+        for t, n in ((pose2d_cpu, "pose2d"), (img_feat_cpu, "img_feat")):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise PmceError(f"{n}: forward_host expects contiguous float32 CPU tensors")
+        if out is None:
+            out = (torch.empty(B, d.num_vert, 3).pin_memory(), torch.empty(B, d.num_joint, 3).pin_memory(),
+                   torch.empty(B, d.num_joint, 3).pin_memory())
+        with torch.cuda.device(dev):
+            ws = self._workspace(B, dev)
+            io_bytes = self.lib.pmce_io_bytes(self._dp, B)
+            if getattr(self, "_io", None) is None or self._io.numel() < io_bytes:
+                self._io = torch.empty(io_bytes, dtype=torch.uint8, device=dev)
+            check(self.lib.pmce_forward_host(self._dp, _ptr(self.weights), _ptr(pose2d_cpu), _ptr(img_feat_cpu),
+                                             _ptr(self.vj), B, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(self._io),
+                                             _ptr(ws), ws.numel(), _stream()), "pmce_forward_host")
+        return out
+
+    # ---- sub-paths (each is a C-ABI entry point; used by the module API and by the parity tests) --------
+    def lifter(self, pose2d, img_feat):
+        self._ready()
+        d = self.dims
+        B = pose2d.shape[0]
+        pose2d = _require_cuda_f32(pose2d, "pose2d", (B, d.seqlen, d.num_joint, 2))
+        img_feat = _require_cuda_f32(img_feat, "img_feat", (B, d.seqlen, d.feat_dim))
+        with torch.cuda.device(pose2d.device):
+            ws = self._workspace(B, pose2d.device)
+            out = torch.empty(B, d.num_joint, 3, device=pose2d.device)
+            check(self.lib.pmce_lifter_forward(self._dp, _ptr(self.weights), _ptr(pose2d), _ptr(img_feat), B, _ptr(out),
+                                               _ptr(ws), ws.numel(), _stream()), "pmce_lifter_forward")
+        return out
+
+    def gru_mid(self, img_feat):
+        self._ready()
+        d = self.dims
+        B = img_feat.shape[0]
+        img_feat = _require_cuda_f32(img_feat, "img_feat", (B, d.seqlen, d.feat_dim))
+        with torch.cuda.device(img_feat.device):
+            ws = self._workspace(B, img_feat.device)
+            g = torch.empty(B, d.feat_dim, device=img_feat.device)
+            check(self.lib.pmce_gru_mid(self._dp, _ptr(self.weights), _ptr(img_feat), B, _ptr(g), _ptr(ws), ws.numel(),
+                                        _stream()), "pmce_gru_mid")
+        return g
+
+    def adaln_gammabeta(self, g):
+        self._ready()
+        B = g.shape[0]
+        g = _require_cuda_f32(g, "g", (B, self.dims.feat_dim))
+        with torch.cuda.device(g.device):
+            gb = torch.empty(B, self.lib.pmce_adaln_slots(), 2, self.dims.coevo_dim, device=g.device)
+            check(self.lib.pmce_adaln_gammabeta(self._dp, _ptr(self.weights), _ptr(g), B, _ptr(gb), _stream()),
+                  "pmce_adaln_gammabeta")
+        return gb
+
+    def coevo_block(self, block, joints, verts, gb, want_joints=False):
+        self._ready()
+        d = self.dims
+        B = joints.shape[0]
+        joints = _require_cuda_f32(joints, "joints", (B, d.num_joint, 3))
+        verts = _require_cuda_f32(verts, "verts", (B, d.num_vert_ds, 3))
+        gb = _require_cuda_f32(gb, "gb")
+        with torch.cuda.device(joints.device):
+            ws = self._workspace(B, joints.device)
+            jout = torch.empty_like(joints) if want_joints else None
+            vout = torch.empty_like(verts)
+            check(self.lib.pmce_coevo_block(self._dp, _ptr(self.weights), block, _ptr(joints), _ptr(verts), _ptr(gb), B,
+                                            _ptr(jout), _ptr(vout), _ptr(ws), ws.numel(), _stream()), "pmce_coevo_block")
+        return jout, vout
+
+    def mesh_epilogue(self, verts3, g):
+        self._ready()
+        d = self.dims
+        B = verts3.shape[0]
+        verts3 = _require_cuda_f32(verts3, "verts3", (B, d.num_vert_ds, 3))
+        g = _require_cuda_f32(g, "g", (B, d.feat_dim))
+        with torch.cuda.device(g.device):
+            ws = self._workspace(B, g.device)
+            mesh = torch.empty(B, d.num_vert, 3, device=g.device)
+            check(self.lib.pmce_mesh_epilogue(self._dp, _ptr(self.weights), _ptr(verts3), _ptr(g), B, _ptr(mesh), _ptr(ws),
+                                              ws.numel(), _stream()), "pmce_mesh_epilogue")
+        return mesh
+
+    def decoder(self, joints, img_feat, want_verts0=False):
+        """Pose2Mesh.forward: (joints [B,J,3] metres, img_feat [B,T,2048]) -> (cam_pose, cam_mesh[, verts0])."""
+        self._ready(need_vj=True)
+        d = self.dims
+        B = joints.shape[0]
+        joints = _require_cuda_f32(joints, "joints", (B, d.num_joint, 3))
+        img_feat = _require_cuda_f32(img_feat, "img_feat", (B, d.seqlen, d.feat_dim))
+        with torch.cuda.device(joints.device):
+            ws = self._workspace(B, joints.device)
+            cam_pose = torch.empty(B, d.num_joint, 3, device=joints.device)
+            mesh = torch.empty(B, d.num_vert, 3, device=joints.device)
+            v0 = torch.empty(B, d.num_vert_ds, 3, device=joints.device) if want_verts0 else None
+            check(self.lib.pmce_decoder_forward(self._dp, _ptr(self.weights), _ptr(joints), _ptr(img_feat), _ptr(self.vj), B,
+                                                _ptr(cam_pose), _ptr(mesh), _ptr(v0), _ptr(ws), ws.numel(), _stream()),
+                  "pmce_decoder_forward")
+        return (cam_pose, mesh, v0) if want_verts0 else (cam_pose, mesh)
+
+
+class JRegressor:
+    """Sparse joint regressor (`torch.matmul(J_regressor[None], pred_mesh)`, reference lib/core/base.py:225).
+
+    The shipped regressors have 105-107 non-zeros out of 17x6890; stored as CSR on the device.
+    """
+
+    def __init__(self, J_dense, device):
+        self.lib = _lib.load()
+        J = np.asarray(J_dense, dtype=np.float32)
+        self.R, self.V = J.shape
+        rows, cols = np.nonzero(J)
+        order = np.lexsort((cols, rows))
+        rows, cols = rows[order], cols[order]
+        row_ptr = np.zeros(self.R + 1, dtype=np.int32)
+        np.add.at(row_ptr, rows + 1, 1)
+        self.row_ptr = torch.as_tensor(np.cumsum(row_ptr).astype(np.int32), device=device)
+        self.cols = torch.as_tensor(cols.astype(np.int32), device=device)
+        self.vals = torch.as_tensor(J[rows, cols], device=device)
+
+    def __call__(self, mesh, scale=1.0):
+        B = mesh.shape[0]
+        mesh = _require_cuda_f32(mesh, "mesh", (B, self.V, 3))
+        with torch.cuda.device(mesh.device):
+            out = torch.empty(B, self.R, 3, device=mesh.device)
+            check(self.lib.pmce_jregress(_ptr(self.row_ptr), _ptr(self.cols), _ptr(self.vals), self.R, _ptr(mesh), self.V, B,
+                                         float(scale), _ptr(out), _stream()), "pmce_jregress")
+        return out

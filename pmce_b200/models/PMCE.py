@@ -1,0 +1,35 @@
+"""Top-level module: pose lifter -> /1000 -> co-evolution decoder.
+
+Drop-in for reference lib/models/PMCE.py (`PMCE` :7-20, `get_model` :23-26). One `pmce_forward` call
+(include/pmce_b200.h) covers the whole of `PMCE.forward`, replayed from a CUDA graph per batch size.
+"""
+import torch
+import torch.nn as nn
+
+from ..config import cfg
+from . import CoevoDecoder, PoseEstimation
+from ._base import EngineModule, make_dims
+
+
+class PMCE(EngineModule):
+    def __init__(self, num_joint, embed_dim, depth):
+        super().__init__()
+        self.num_joint = num_joint
+        self.pose_lifter = PoseEstimation.get_model(num_joint, embed_dim, depth, pretrained=cfg.MODEL.posenet_pretrained)
+        self.pose_mesh_coevo = CoevoDecoder.get_model(num_joint, embed_dim)
+
+    def _engine_dims(self):
+        pl = self.pose_lifter
+        return make_dims(self.num_joint, pl.embed_dim, pl.depth, pl.num_frames)
+
+    def _engine_vj(self):
+        return self.pose_mesh_coevo.vj_relation
+
+    @torch.no_grad()
+    def forward(self, pose2d, img_feat):
+        """pose2d [B,T,J,2], img_feat [B,T,2048] -> (cam_mesh [B,6890,3], cam_pose [B,J,3], pose3d [B,J,3])."""
+        return self.engine().forward(pose2d, img_feat)
+
+
+def get_model(num_joint, embed_dim, depth):
+    return PMCE(num_joint, embed_dim, depth)

@@ -1,0 +1,220 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same seeded inputs, against the
+golden fixtures the unmodified reference produced, and through size-independent properties at full batch sizes.
+
+Tolerances: the gate (BASELINE.json north_star) is 1e-3 abs fp32 on cam_mesh / cam_pose (metres) and bit-exact
+for the regressor-index gather; the asserts below are 10x tighter than the gate."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, dense_regressor
+from pmce_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GATE = 1e-3          # north_star gate, metres
+TOL = 1e-4           # what we assert
+PMCE_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "pmce_*.npz")))
+
+
+def _case(path):
+    g = np.load(path)
+    J, C, depth, T, B = [int(v) for v in g["config"]]
+    sd = synth.make_state_dict(int(g["weight_seed"]), init_vertices=g["init_vertices"],
+                               lifter_out_scale=float(g["lifter_out_scale"]), num_joint=J, embed_dim=C, depth=depth, seqlen=T)
+    p2d, feat = synth.make_inputs(B, T, J, seed=int(g["input_seed"]))
+    return g, sd, p2d, feat, (J, C, depth, T, B)
+
+
+def _model(sd, J, C, depth, T, graph=True):
+    from pmce_b200 import models
+    from pmce_b200.config import cfg
+    cfg.DATASET.seqlen = T
+    m = models.PMCE.get_model(J, C, depth)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    m.engine().use_graph = graph
+    return m
+
+
+@pytest.fixture(scope="module")
+def base(assets_root, lib):
+    """J=17 C=256 T=16 model + oracle intermediates on the golden inputs (B=2)."""
+    from oracle import pmce_oracle as po
+    g, sd, p2d, feat, (J, C, depth, T, B) = _case(os.path.join(GOLDEN, "pmce_J17_C256_T16_B2.npz"))
+    with torch.no_grad():
+        o_mesh, o_pose, o_p3, inter = po.pmce_forward(sd, p2d, feat, g["vj_relation"], return_intermediates=True)
+    m = _model(sd, J, C, depth, T, graph=False)
+    return dict(g=g, sd=sd, p2d=p2d, feat=feat, m=m, eng=m.engine(), o_mesh=o_mesh, o_pose=o_pose, o_p3=o_p3, inter=inter)
+
+
+def _maxabs(a, b):
+    return float((a.detach().cpu() - torch.as_tensor(b)).abs().max())
+
+
+# ---- sub-paths, each through its own C-ABI entry point -------------------------------------------------------------
+
+def test_lifter_vs_oracle(base):
+    out = base["eng"].lifter(base["p2d"].cuda(), base["feat"].cuda())
+    ref = base["o_p3"]
+    assert _maxabs(out, ref) <= 1e-4 * float(ref.abs().max())     # pose3d is on a ~300 mm scale here
+
+
+def test_gru_mid_vs_oracle(base):
+    g = base["eng"].gru_mid(base["feat"].cuda())
+    assert _maxabs(g, base["inter"]["g"]) < 2e-5
+
+
+def test_adaln_gammabeta_vs_oracle(base):
+    from oracle import pmce_oracle as po
+    sd, gref = base["sd"], base["inter"]["g"]
+    gb = base["eng"].adaln_gammabeta(gref.cuda()).cpu()
+    # slot order: per block vertx_CA(q,k,v,2), vertx_SA(1,2); block 3 additionally joint_CA(q,k,v,2), joint_SA(1,2)
+    names = []
+    for k in (1, 2, 3):
+        for st in (("vertx",) if k < 3 else ("vertx", "joint")):
+            names += [f"coevoblock{k}.{st}_CA_FFN.{n}" for n in ("normq", "normk", "normv", "norm2")]
+            names += [f"coevoblock{k}.{st}_SA_FFN.{n}" for n in ("norm1", "norm2")]
+    assert len(names) == 24
+    for s, n in enumerate(names):
+        p = "pose_mesh_coevo." + n
+        gam = po._lin(sd, p + ".mlp_gamma", gref)
+        bet = po._lin(sd, p + ".mlp_beta", gref)
+        assert (gb[:, s, 0] - gam).abs().max() < 2e-5 and (gb[:, s, 1] - bet).abs().max() < 2e-5, n
+
+
+def test_coevo_blocks_vs_oracle(base):
+    from oracle import pmce_oracle as po
+    eng, sd, inter = base["eng"], base["sd"], base["inter"]
+    joints = (base["o_p3"] / 1000).contiguous()
+    gb = eng.adaln_gammabeta(inter["g"].cuda())
+    v_in = inter["verts0"]
+    for k in (1, 2, 3):
+        with torch.no_grad():
+            j_ref, v_ref = po.coevo_block(sd, f"pose_mesh_coevo.coevoblock{k}.", joints, v_in, inter["g"])
+        j_out, v_out = eng.coevo_block(k, joints.cuda(), v_in.contiguous().cuda(), gb, want_joints=(k == 3))
+        assert _maxabs(v_out, v_ref) < TOL, k
+        if k == 3:
+            assert _maxabs(j_out, j_ref) < TOL
+        v_in = v_ref
+    # the reference discards joints1/joints2; asking for them is an error, not a silent wrong answer
+    from pmce_b200._lib import PmceError
+    with pytest.raises(PmceError, match="joint-branch"):
+        eng.coevo_block(1, joints.cuda(), inter["verts0"].contiguous().cuda(), gb, want_joints=True)
+
+
+def test_mesh_epilogue_vs_oracle(base):
+    import torch.nn.functional as F
+    sd, inter = base["sd"], base["inter"]
+    p = "pose_mesh_coevo."
+    v3, g = inter["verts3"], inter["g"]
+    with torch.no_grad():
+        ref = F.conv1d(v3, sd[p + "upsample_conv.weight"], sd[p + "upsample_conv.bias"], padding=1)
+        ref = ref + torch.stack([F.linear(F.relu(g), sd[f"{p}linear_cur{i}.weight"], sd[f"{p}linear_cur{i}.bias"]) for i in (1, 2, 3)], -1)
+    out = base["eng"].mesh_epilogue(v3.contiguous().cuda(), g.cuda())
+    assert _maxabs(out, ref) < TOL
+    assert _maxabs(out, base["o_mesh"]) < TOL
+
+
+def test_decoder_and_bit_exact_gather(base):
+    joints = (base["o_p3"] / 1000).contiguous()
+    cam_pose, mesh, v0 = base["eng"].decoder(joints.cuda(), base["feat"].cuda(), want_verts0=True)
+    # gather is a pure copy: bit exact (CoevoDecoder.py:232)
+    assert torch.equal(v0.cpu(), joints[:, torch.as_tensor(base["g"]["vj_relation"]), :])
+    assert _maxabs(mesh, base["o_mesh"]) < TOL and _maxabs(cam_pose, base["o_pose"]) < TOL
+
+
+# ---- whole forward vs the reference's own outputs ----------------------------------------------------------------------
+
+@pytest.mark.parametrize("path", PMCE_FIXTURES, ids=[os.path.basename(p)[:-4] for p in PMCE_FIXTURES])
+def test_forward_vs_reference_golden(assets_root, lib, path):
+    g, sd, p2d, feat, (J, C, depth, T, B) = _case(path)
+    m = _model(sd, J, C, depth, T, graph=True)
+    for _ in range(2):   # second call replays the CUDA graph
+        mesh, cam_pose, pose3d = m(p2d.cuda(), feat.cuda())
+    e_mesh, e_pose = _maxabs(mesh, g["cam_mesh"]), _maxabs(cam_pose, g["cam_pose"])
+    e_p3 = _maxabs(pose3d, g["pose3d"]) / float(np.abs(g["pose3d"]).max())
+    mpve = float((mesh.cpu() - torch.as_tensor(g["cam_mesh"])).norm(dim=-1).mean())
+    print(f"{os.path.basename(path)}: max|d mesh|={e_mesh:.2e} max|d pose|={e_pose:.2e} rel|d pose3d|={e_p3:.2e} MPVE={mpve:.2e}")
+    assert e_mesh < TOL < GATE and e_pose < TOL and e_p3 < 1e-4 and mpve < TOL
+    # the caller's post-step (core/base.py:223-225), sparse J-regressor vs the reference's dense matmul
+    from pmce_b200.engine import JRegressor
+    jr = JRegressor(dense_regressor("h36m"), "cuda")
+    pp = jr(mesh, scale=1000.0)
+    assert _maxabs(pp, g["pred_pose_h36m"]) < 0.2     # millimetres (values ~1e3)
+    dense = torch.matmul(torch.as_tensor(dense_regressor("h36m"), dtype=torch.float32)[None], mesh.cpu() * 1000)
+    assert _maxabs(pp, dense) < 2e-3
+
+
+def test_graph_eager_and_host_calls_agree(base):
+    m = base["m"]
+    eng = m.engine()
+    p2d, feat = base["p2d"], base["feat"]
+    eng.use_graph = False
+    a = m(p2d.cuda(), feat.cuda())
+    eng.use_graph = True
+    b = m(p2d.cuda(), feat.cuda())
+    b2 = m(p2d.cuda(), feat.cuda())
+    eng.use_graph = False
+    c = eng.forward_host(p2d.pin_memory(), feat.pin_memory())
+    for x, y, z, w in zip(a, b, b2, c):
+        assert torch.equal(x, y) and torch.equal(x, z) and torch.equal(x.cpu(), w)
+
+
+def test_clips_are_independent_at_full_batch(base):
+    """Size-independent property at BASELINE batch sizes: every clip's output depends on that clip only, so a B=64
+    batch made of the golden clips (repeated, permuted) reproduces the B=2 rows exactly-ish, and ragged B works."""
+    m = base["m"]
+    p2d, feat = base["p2d"], base["feat"]
+    ref = [t.cpu() for t in m(p2d.cuda(), feat.cuda())]
+    for B in (1, 3, 64, 65):
+        idx = torch.arange(B) % 2
+        out = m(p2d[idx].contiguous().cuda(), feat[idx].contiguous().cuda())
+        for o, r in zip(out, ref):
+            assert (o.cpu() - r[idx]).abs().max() < 2e-5, B
+    big = 256
+    idx = torch.randint(0, 2, (big,), generator=torch.Generator().manual_seed(0))
+    out = m(p2d[idx].contiguous().cuda(), feat[idx].contiguous().cuda())
+    assert (out[0].cpu() - ref[0][idx]).abs().max() < 2e-5
+    assert _maxabs(out[0][:1], base["g"]["cam_mesh"][idx[:1].numpy()]) < TOL
+
+
+def test_input_validation(base):
+    from pmce_b200._lib import PmceError
+    m = base["m"]
+    with pytest.raises(PmceError, match="CUDA tensor"):
+        m(base["p2d"], base["feat"])
+    with pytest.raises(PmceError, match="shape"):
+        m(base["p2d"][:, :8].contiguous().cuda(), base["feat"].cuda())
+    with pytest.raises(PmceError, match="float32"):
+        m(base["p2d"].cuda().double(), base["feat"].cuda())
+
+
+# ---- satellites -------------------------------------------------------------------------------------------------------
+
+def test_smpl_lbs_vs_reference_golden(lib):
+    from pmce_b200.smpl_layer import SMPL_Layer
+    g = np.load(os.path.join(GOLDEN, "smpl_lbs_B4.npz"))
+    buf = synth.make_smpl_buffers(int(g["buffer_seed"]))
+    layer = SMPL_Layer.from_buffers(buf).cuda()
+    pose, betas, trans = synth.make_smpl_inputs(4, seed=int(g["input_seed"]))
+    v, j = layer(pose.cuda(), betas.cuda(), trans.cuda())
+    assert _maxabs(v, g["verts"]) < 2e-5 and _maxabs(j, g["joints"]) < 2e-5
+    v0, j0 = layer(pose.cuda())
+    assert _maxabs(v0, g["verts_default"]) < 2e-5 and _maxabs(j0, g["joints_default"]) < 2e-5
+    # batch independence at a DataLoader-sized batch
+    idx = torch.arange(257) % 4
+    vb, jb = layer(pose[idx].cuda(), betas[idx].cuda(), trans[idx].cuda())
+    assert (vb.cpu() - v.cpu()[idx]).abs().max() < 1e-6 and (jb.cpu() - j.cpu()[idx]).abs().max() < 1e-6
+
+
+def test_jregress_coco(lib):
+    from pmce_b200.engine import JRegressor
+    J = dense_regressor("coco")
+    mesh = torch.randn(5, 6890, 3, generator=torch.Generator().manual_seed(2))
+    out = JRegressor(J, "cuda")(mesh.cuda())
+    ref = torch.matmul(torch.as_tensor(J, dtype=torch.float32)[None], mesh)
+    assert _maxabs(out, ref) < 1e-5

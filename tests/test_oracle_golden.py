@@ -1,0 +1,120 @@
+"""CPU: the oracle restatement (oracle/pmce_oracle.py) against the golden fixtures produced by the
+UNMODIFIED reference (oracle/gen_golden.py). Runs anywhere (no GPU, no /root/reference)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, dense_regressor
+from oracle import pmce_oracle as po
+from pmce_b200 import synth
+
+PMCE_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "pmce_*.npz")))
+
+
+def load_case(path):
+    g = np.load(path)
+    J, C, depth, T, B = [int(v) for v in g["config"]]
+    sd = synth.make_state_dict(int(g["weight_seed"]), init_vertices=g["init_vertices"],
+                               lifter_out_scale=float(g["lifter_out_scale"]), num_joint=J, embed_dim=C, depth=depth, seqlen=T)
+    pose2d, img_feat = synth.make_inputs(B, T, J, seed=int(g["input_seed"]))
+    return g, sd, pose2d, img_feat, (J, C, depth, T, B)
+
+
+def test_fixture_set_complete():
+    assert len(PMCE_FIXTURES) == 5
+    for n in ("J_regressors_sparse.npz", "smpl_lbs_B4.npz"):
+        assert os.path.exists(os.path.join(GOLDEN, n))
+
+
+@pytest.mark.parametrize("path", PMCE_FIXTURES, ids=[os.path.basename(p)[:-4] for p in PMCE_FIXTURES])
+def test_oracle_reproduces_reference(path):
+    g, sd, pose2d, img_feat, (J, C, depth, T, B) = load_case(path)
+    # the synthetic generators are bit-reproducible: same fingerprints as when the reference was run
+    chk = np.array([float(v.double().abs().sum()) for v in sd.values()])
+    np.testing.assert_allclose(chk, g["weight_checksum"], rtol=0, atol=0)
+    np.testing.assert_allclose([float(pose2d.double().sum()), float(img_feat.double().sum())], g["input_checksum"], rtol=0, atol=0)
+    with torch.no_grad():
+        mesh, cam_pose, pose3d, inter = po.pmce_forward(sd, pose2d, img_feat, g["vj_relation"], depth=depth, return_intermediates=True)
+    assert np.abs(mesh.numpy() - g["cam_mesh"]).max() < 2e-5
+    assert np.abs(cam_pose.numpy() - g["cam_pose"]).max() < 2e-5
+    assert np.abs(pose3d.numpy() - g["pose3d"]).max() <= 1e-5 * np.abs(g["pose3d"]).max()
+    assert np.abs(inter["g"].numpy() - g["gru_mid"]).max() < 1e-5
+    for k in (1, 2, 3):
+        assert np.abs(inter[f"verts{k}"].numpy() - g[f"verts{k}"]).max() < 2e-5
+    assert np.abs(inter["joints3"].numpy() - g["joints3"]).max() < 2e-5
+    # bit-exact integer gather (CoevoDecoder.py:232)
+    assert torch.equal(inter["verts0"], (pose3d / 1000)[:, torch.as_tensor(g["vj_relation"]), :])
+    # J-regressor post-step (core/base.py:223-225)
+    pp = po.j_regress(torch.from_numpy(dense_regressor("h36m").astype(np.float32)), torch.from_numpy(g["cam_mesh"]) * 1000)
+    assert np.abs(pp.numpy() - g["pred_pose_h36m"]).max() < 1e-3   # millimetres
+
+
+def test_gru_layer1_prune_is_exact():
+    """y[T//2] only needs layer-1 fwd steps 0..T/2 and bwd steps T-1..T/2: the oracle's full GRU
+    equals torch.nn.GRU, which is what the reference calls."""
+    sd = synth.make_state_dict(0, num_joint=17, embed_dim=256, depth=3, seqlen=16)
+    _, img_feat = synth.make_inputs(2, 16, 17, seed=3)
+    gru = torch.nn.GRU(2048, 1024, bidirectional=True, num_layers=2)
+    gru.load_state_dict({k.split("gru_cur.")[1]: v for k, v in sd.items() if "gru_cur" in k})
+    with torch.no_grad():
+        y, _ = gru(img_feat.permute(1, 0, 2))
+        g = po.gru_mid(sd, img_feat)
+    assert (y[8] - g).abs().max() < 1e-5
+
+
+def test_adaln_uses_unbiased_std():
+    torch.manual_seed(0)
+    x = torch.randn(2, 5, 64)
+    g = torch.randn(2, 2048)
+    sd = {"n.mlp_gamma.weight": torch.randn(64, 2048) * 0.02, "n.mlp_gamma.bias": torch.randn(64),
+          "n.mlp_beta.weight": torch.randn(64, 2048) * 0.02, "n.mlp_beta.bias": torch.randn(64)}
+    y = po.adaln(sd, "n", x, g)
+    mu = x.mean(-1, keepdim=True)
+    sigma = ((x - mu) ** 2).sum(-1, keepdim=True).div(63).sqrt()
+    gamma = (g @ sd["n.mlp_gamma.weight"].t() + sd["n.mlp_gamma.bias"])[:, None]
+    beta = (g @ sd["n.mlp_beta.weight"].t() + sd["n.mlp_beta.bias"])[:, None]
+    assert (y - (gamma * (x - mu) / (sigma + 1e-6) + beta)).abs().max() < 1e-5
+
+
+def test_dead_joint_branch_of_blocks_1_2():
+    """Blocks 1-2's joint branch never reaches an output (Pose2Mesh.forward :235-236): randomising its weights
+    leaves the oracle's outputs bit-identical — the justification for not storing those 100 tensors."""
+    g, sd, pose2d, img_feat, (J, C, depth, T, B) = load_case(PMCE_FIXTURES[0])
+    with torch.no_grad():
+        ref = po.pmce_forward(sd, pose2d, img_feat, g["vj_relation"])
+    sd2 = dict(sd)
+    n = 0
+    for k in sd:
+        if ("coevoblock1." in k or "coevoblock2." in k) and any(t in k for t in (
+                "joint_SA_FFN", "joint_CA_FFN", "proj_joint_feat2coor", "j_Q_embed", "v2j_K_embed", "proj_v2j_dim")):
+            sd2[k] = torch.randn_like(sd[k])
+            n += 1
+    assert n == 100
+    with torch.no_grad():
+        out = po.pmce_forward(sd2, pose2d, img_feat, g["vj_relation"])
+    for a, b in zip(ref, out):
+        assert torch.equal(a, b)
+
+
+def test_smpl_oracle_vs_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "smpl_lbs_B4.npz"))
+    buf = synth.make_smpl_buffers(int(g["buffer_seed"]))
+    pose, betas, trans = synth.make_smpl_inputs(4, seed=int(g["input_seed"]))
+    with torch.no_grad():
+        v, j = po.smpl_lbs(buf, pose, betas, trans)
+        v0, j0 = po.smpl_lbs(buf, pose)
+    assert np.isfinite(g["verts"]).all() and np.abs(g["verts"]).max() > 0.1
+    assert np.abs(v.numpy() - g["verts"]).max() < 1e-5 and np.abs(j.numpy() - g["joints"]).max() < 1e-5
+    assert np.abs(v0.numpy() - g["verts_default"]).max() < 1e-5 and np.abs(j0.numpy() - g["joints_default"]).max() < 1e-5
+
+
+def test_init_geometry_restatement():
+    g = np.load(PMCE_FIXTURES[0])
+    assets = synth.make_mesh_assets(int(g["asset_seed"]))
+    iv, vj = po.init_geometry(assets["verts"], assets["D"], dense_regressor("h36m").astype(np.float32))
+    assert np.array_equal(vj, g["vj_relation"])
+    assert np.abs(iv.numpy() - g["init_vertices"]).max() < 1e-6
+    assert vj.min() >= 0 and vj.max() < 17
