@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the PMCE per-clip forward hot path on B200 (driver contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = `PMCE.forward` over one batch of B synthetic clips per GPU (T=16 frames each). Rank 0 prints ONE JSON
+line. `--impl reference` times the reference algorithm's CPU implementation (the oracle port, torch CPU, all host
+threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+# headline workload: BASELINE.json configs[1] / north_star target ("B=64, T=16 ... C=512")
+B_PER_GPU, T, J, C, DEPTH = 64, 16, 17, 512, 3
+V = 6890
+METRIC = "clips/sec (B x T=16 frames) through PMCE.forward"
+WORKLOAD = f"PMCE.forward (lifter+GRU+CoEvoDecoder+upsample) B={B_PER_GPU}/GPU T={T} J={J} V={V} C={C}"
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_model(device):
+    import numpy as np
+    import torch
+    from pmce_b200 import synth
+    from pmce_b200 import build as _b
+    _b.build()
+    root = tempfile.mkdtemp(prefix="pmce_bench_")
+    synth.prepare_data_root(root, os.path.join(REPO, "tests", "golden", "J_regressors_sparse.npz"))
+    os.environ["PMCE_DATA_ROOT"] = root
+    os.environ["PMCE_B200_STANDALONE_CFG"] = "1"
+    from pmce_b200 import models
+    from pmce_b200.config import cfg
+    cfg.DATASET.seqlen = T
+    m = models.PMCE.get_model(J, C, DEPTH)
+    sd = synth.make_state_dict(0, init_vertices=m.state_dict()["pose_mesh_coevo.init_vertices"].numpy(), lifter_out_scale=300.0,
+                               num_joint=J, embed_dim=C, depth=DEPTH, seqlen=T)
+    m.load_state_dict(sd, strict=True)
+    return m.to(device).eval(), sd
+
+
+def cpu_oracle_clips_per_s(sd, vj, budget_s=20.0, batch=B_PER_GPU, max_iters=8):
+    """Time the oracle port (torch CPU, all host threads) on the same B=64 batch; bounded to ~budget_s."""
+    import torch
+    from oracle import pmce_oracle as po
+    from pmce_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    p2d, feat = synth.make_inputs(batch, T, J, seed=1)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        po.pmce_forward(sd, p2d, feat, vj, depth=DEPTH)      # warm-up
+        warm = time.perf_counter() - t0
+        times = []
+        while len(times) < max_iters and (sum(times) + warm) < budget_s:
+            t0 = time.perf_counter()
+            po.pmce_forward(sd, p2d, feat, vj, depth=DEPTH)
+            times.append(time.perf_counter() - t0)
+    if not times:
+        times = [warm]
+    times.sort()
+    med = times[len(times) // 2]
+    return batch / med, len(times), torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm on the host CPU (oracle port; the Python reference cannot travel)."""
+    if rank != 0:
+        return
+    import numpy as np
+    from pmce_b200 import synth
+    g = np.load(os.path.join(REPO, "tests", "golden", f"pmce_J{J}_C{C}_T{T}_B2.npz"))
+    sd = synth.make_state_dict(0, init_vertices=g["init_vertices"], lifter_out_scale=300.0, num_joint=J, embed_dim=C, depth=DEPTH, seqlen=T)
+    import torch
+    from oracle import pmce_oracle as po
+    torch.set_num_threads(os.cpu_count() or 1)
+    p2d, feat = synth.make_inputs(B_PER_GPU, T, J, seed=1)
+    steps = max(1, min(args.steps, 6))
+    warm = max(1, min(args.warmup, 2))
+    with torch.no_grad():
+        for _ in range(warm):
+            po.pmce_forward(sd, p2d, feat, g["vj_relation"], depth=DEPTH)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            po.pmce_forward(sd, p2d, feat, g["vj_relation"], depth=DEPTH)
+        dt = time.perf_counter() - t0
+    val = B_PER_GPU * steps / dt
+    cores = torch.get_num_threads()
+    sample = f"{steps} steps of the same B={B_PER_GPU} batch (bounded from --steps {args.steps}); torch CPU fp32, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD + " on host CPU"},
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="pmce_b200", choices=["pmce_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pmce_b200 import synth, _lib
+    from pmce_b200 import dist as pdist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    W = max(args.warmup, 3)
+    K = args.steps
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    model, sd = build_model(dev)
+    eng = model.engine()
+    lib = _lib.load()
+    B = B_PER_GPU
+    NSETS = 4
+    sets = [tuple(t.to(dev) for t in synth.make_inputs(B, T, J, seed=100 + rank * NSETS + i)) for i in range(NSETS)]
+    host_sets = [tuple(t.pin_memory() for t in synth.make_inputs(B, T, J, seed=100 + rank * NSETS + i)) for i in range(NSETS)]
+
+    def step(i):
+        p2d, feat = sets[i % NSETS]
+        mesh, cam_pose, pose3d = model(p2d, feat)
+        if world > 1:   # the single collective of the path: all-gather of the per-rank packed outputs
+            return pdist.all_gather_blocks(pdist.pack_outputs(mesh, cam_pose, pose3d, B))
+        return mesh
+
+    def step_e2e(i):
+        hp, hf = host_sets[i % NSETS]
+        mesh, cam_pose, pose3d = model(hp.to(dev, non_blocking=True), hf.to(dev, non_blocking=True))
+        return mesh.cpu(), cam_pose.cpu(), pose3d.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # launches per forward (counted inside the library on one eager pass; graph replays execute the same kernel nodes)
+    eng.use_graph = False
+    n0 = lib.pmce_launch_count()
+    model(*sets[0])
+    launches_per_step = int(lib.pmce_launch_count() - n0)
+    eng.use_graph = True
+
+    for i in range(W):
+        step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step, K)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (ms * 1e-3)
+
+    for i in range(W):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, K)
+    e2e_value = world * B * K / (ms_e2e * 1e-3)
+    h2d = B * (T * J * 2 + T * 2048) * 4
+    d2h = B * (V * 3 + 2 * J * 3) * 4
+
+    # roofline of the dominant kernel, timed alone with CUDA events on the launch stream
+    roof = dominant_kernel_roofline(lib, dev, peaks, B)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"batch-shard x{world}" + (" + 1 all-gather" if world > 1 else ""),
+                   "weights": "seeded random init (no checkpoints are published)",
+                   "l2": "per-step working set (weights 0.46 GB + activations) exceeds the 126 MB L2; inputs rotate over 4 resident sets",
+                   "cuda_graph": True},
+        "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
+                "path": "pinned host tensors -> .cuda() -> models.PMCE.forward -> .cpu() (what lib/core/base.py:218-238 does)"},
+        "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
+        "clocks": clocks, "roofline": roof, "peaks": peaks,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            v, n, cores = cpu_oracle_clips_per_s(sd, model.pose_mesh_coevo.vj_relation)
+            out["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                                   "sample": f"median of {n} forwards of the same B={B} batch through the oracle port (torch CPU fp32)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(lib, dev, peaks, B):
+    """The kernel with the largest share of the step today: the fp32 CUDA-core GEMM of the lifter's fc1
+    (tokens x 2C x C). Timed alone; algorithmic FLOPs = 2*M*N*K."""
+    import ctypes as Ct
+    import torch
+    M, N, K = B * T * J, 2 * C, C
+    x = torch.randn(M, K, device=dev)
+    w = torch.randn(N, K, device=dev) * 0.05
+    b = torch.randn(N, device=dev)
+    o = torch.empty(M, N, device=dev)
+    st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def call():
+        rc = lib.pmce_linear(Ct.c_void_p(x.data_ptr()), Ct.c_void_p(w.data_ptr()), Ct.c_void_p(b.data_ptr()), M, N, K, 1,
+                             Ct.c_void_p(o.data_ptr()), st)
+        assert rc == 0
+    for _ in range(5):
+        call()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 50
+    e0.record()
+    for _ in range(n):
+        call()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sec = e0.elapsed_time(e1) * 1e-3 / n
+    flops = 2.0 * M * N * K
+    ach = flops / sec / 1e12
+    return {"kernel": "gemm_tn_kernel (lifter fc1 GEMM + bias + GELU, fp32 CUDA cores)", "bound": "tensor", "achieved": ach,
+            "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+            "flops_per_launch": flops, "us_per_launch": sec * 1e6, "peak_source": peaks["source"]}
+
+
+if __name__ == "__main__":
+    main()

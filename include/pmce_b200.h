@@ -121,6 +121,15 @@ int pmce_decoder_forward(const pmce_dims_t* dims, const void* weights, const flo
 int pmce_jregress(const int32_t* row_ptr, const int32_t* cols, const float* vals, int R, const float* mesh,
                   int num_vert, int B, float scale, float* out, void* stream);
 
+/* ---- nn.Linear forward as used by every projection on the path (F.linear; e.g. lib/models/CoevoDecoder.py:19-20,
+ * timm Mlp fc1/fc2): out[M,N] = act(x[M,K] weight[N,K]^T + bias[N]); act 0 = none, 1 = exact GELU. K % 4 == 0.
+ * Exposed so the dominant GEMM can be timed / profiled in isolation. */
+int pmce_linear(const float* x, const float* weight, const float* bias, int M, int N, int K, int act, float* out,
+                void* stream);
+
+/* Cumulative number of kernels this library has launched in this process (for the bench's gpu_launches). */
+unsigned long long pmce_launch_count(void);
+
 /* ---- a12: SMPL_Layer.forward, smplpytorch/smplpytorch/pytorch/smpl_layer.py:65-158 ----------------
  * blend  [20670, KB] fp32, KB = smpl_blend_ld() >= 217: row (v*3+c) = [shapedirs[v,c,0:10] | posedirs[v,c,0:207] | 0]
  * v_template [20670]; j_template [24,3] = Jreg @ v_template; j_shapedirs [24,3,10] = Jreg @ shapedirs;

@@ -17,8 +17,14 @@
             return 10;                                                                             \
         }                                                                                          \
     } while (0)
-#define CKL() CK(cudaGetLastError())
+#define CKL() do { count_launch(); CK(cudaGetLastError()); } while (0)
+#define CKG(expr) do { count_launch(); CK(expr); } while (0)
 #define RET(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+#include <atomic>
+static std::atomic<unsigned long long> g_launches{0};
+static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" unsigned long long pmce_launch_count(void) { return g_launches.load(); }
 
 namespace {
 
@@ -93,7 +99,7 @@ int linear(const float* A, int lda, const float* W, int ldw, const float* bias, 
            cudaStream_t st, int act = 0, const float* resid = nullptr, const float* rowadd = nullptr, int period = 1) {
     GemmEpi e = gemm_epi_plain(ldc);
     e.bias = bias; e.act = act; e.resid = resid; e.rowadd = rowadd; e.rowadd_period = period;
-    CK(launch_gemm_tn(A, lda, W, ldw, out, M, N, K, e, st));
+    CKG(launch_gemm_tn(A, lda, W, ldw, out, M, N, K, e, st));
     return 0;
 }
 
@@ -229,7 +235,7 @@ int gru_mid(const Layout& L, const float* Wt, const float* img_feat, int B, floa
         GemmEpi e = gemm_epi_plain(6 * H);
         e.bias = Wt + L.bih0;
         e.rmap.div = T; e.rmap.s0 = 6 * H; e.rmap.s1 = (long long)B * 6 * H;   // row (b,t) -> t*B*6H + b*6H
-        CK(launch_gemm_tn(img_feat, F, Wt + L.wih0, F, ws.gi0, B * T, 6 * H, F, e, st));
+        CKG(launch_gemm_tn(img_feat, F, Wt + L.wih0, F, ws.gi0, B * T, 6 * H, F, e, st));
     }
     for (int s = 0; s < T; ++s) {
         GruDir dd[2];
@@ -370,14 +376,14 @@ int mesh_epilogue(const Layout& L, const float* Wt, const float* verts3, const f
         e.bias = Wt + L.ups_b;
         e.rmap.div = 3; e.rmap.s0 = (long long)V * 3; e.rmap.s1 = 1;
         e.cmap.div = 1; e.cmap.s0 = 3; e.cmap.s1 = 0;
-        CK(launch_gemm_tn(ws.im2col, ldk, Wt + L.ups_w, ldk, mesh, B * 3, V, ldk, e, st));
+        CKG(launch_gemm_tn(ws.im2col, ldk, Wt + L.ups_w, ldk, mesh, B * 3, V, ldk, e, st));
     }
     {   // mesh[b,o,l] += W_cur{l+1} relu(g[b]) + b_cur{l+1}
         GemmEpi e = gemm_epi_plain(0);
         e.bias = Wt + L.lc_b; e.a_relu = 1; e.resid = mesh;
         e.rmap.div = 1; e.rmap.s0 = (long long)V * 3; e.rmap.s1 = 0;
         e.cmap.div = V; e.cmap.s0 = 1; e.cmap.s1 = 3;
-        CK(launch_gemm_tn(g, F, Wt + L.lc_w, F, mesh, B, 3 * V, F, e, st));
+        CKG(launch_gemm_tn(g, F, Wt + L.lc_w, F, mesh, B, 3 * V, F, e, st));
     }
     return 0;
 }
@@ -520,6 +526,12 @@ extern "C" int pmce_jregress(const int32_t* row_ptr, const int32_t* cols, const 
     jregress_kernel<<<cdiv((long long)B * R * 3, 128), 128, 0, (cudaStream_t)stream>>>(row_ptr, cols, vals, R, mesh, num_vert, B, scale, out);
     CKL();
     return 0;
+}
+
+extern "C" int pmce_linear(const float* x, const float* weight, const float* bias, int M, int N, int K, int act, float* out,
+                           void* stream) {
+    if (!x || !weight || !out || M < 1 || N < 1 || K < 4 || (K & 3)) { pmce_set_error("pmce_linear: bad argument (K must be a multiple of 4)"); return 2; }
+    return linear(x, K, weight, K, bias, out, N, M, N, K, (cudaStream_t)stream, act);
 }
 
 // ---- SMPL LBS --------------------------------------------------------------------------------------

@@ -264,3 +264,15 @@ def make_smpl_inputs(batch, seed=13):
     betas = (0.5 * rng.standard_normal((batch, 10))).astype(np.float32)
     trans = rng.standard_normal((batch, 3)).astype(np.float32)
     return torch.from_numpy(pose), torch.from_numpy(betas), torch.from_numpy(trans)
+
+
+def prepare_data_root(root, sparse_regressors_npz, asset_seed=7):
+    """Populate `<root>/data/{base_data,Human36M}` with the synthetic mesh assets and the H36M joint regressor
+    rebuilt (exactly) from its sparse fixture; returns `root`. Point PMCE_DATA_ROOT at it."""
+    write_mesh_assets(root, seed=asset_seed)
+    g = np.load(sparse_regressors_npz)
+    J = np.zeros(tuple(g["h36m_shape"]), dtype=np.float64)
+    J[g["h36m_rows"], g["h36m_cols"]] = g["h36m_vals"]
+    os.makedirs(os.path.join(root, "data", "Human36M"), exist_ok=True)
+    np.save(os.path.join(root, "data", "Human36M", "J_regressor_h36m_correct.npy"), J)
+    return root
