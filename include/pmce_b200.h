@@ -127,6 +127,13 @@ int pmce_jregress(const int32_t* row_ptr, const int32_t* cols, const float* vals
 int pmce_linear(const float* x, const float* weight, const float* bias, int M, int N, int K, int act, float* out,
                 void* stream);
 
+/* Same contract on the tcgen05 tensor-core path: operands are split on device into bf16 hi/lo pairs
+ * (3 bf16 MMAs per product, fp32 accumulate in TMEM, ~2^-16 relative error), tiles fed by TMA. K % 8 == 0.
+ * scratch: pmce_linear_tc_scratch_bytes(M,N,K) device bytes, 256-byte aligned. */
+size_t pmce_linear_tc_scratch_bytes(int M, int N, int K);
+int pmce_linear_tc(const float* x, const float* weight, const float* bias, int M, int N, int K, int act, float* out,
+                   void* scratch, size_t scratch_bytes, void* stream);
+
 /* Cumulative number of kernels this library has launched in this process (for the bench's gpu_launches). */
 unsigned long long pmce_launch_count(void);
 

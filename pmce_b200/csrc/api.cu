@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
+#include "gemm_tc.cuh"
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -532,6 +533,35 @@ extern "C" int pmce_linear(const float* x, const float* weight, const float* bia
                            void* stream) {
     if (!x || !weight || !out || M < 1 || N < 1 || K < 4 || (K & 3)) { pmce_set_error("pmce_linear: bad argument (K must be a multiple of 4)"); return 2; }
     return linear(x, K, weight, K, bias, out, N, M, N, K, (cudaStream_t)stream, act);
+}
+
+extern "C" size_t pmce_linear_tc_scratch_bytes(int M, int N, int K) {
+    auto al = [](size_t n) { return (n + 127) / 128 * 128; };
+    return 2 * (al((size_t)M * K) + al((size_t)N * K)) * sizeof(__nv_bfloat16);
+}
+
+extern "C" int pmce_linear_tc(const float* x, const float* weight, const float* bias, int M, int N, int K, int act, float* out,
+                              void* scratch, size_t scratch_bytes, void* stream) {
+    if (!x || !weight || !out || !scratch || M < 1 || N < 1 || K < 8 || (K & 7)) { pmce_set_error("pmce_linear_tc: bad argument (K must be a multiple of 8)"); return 2; }
+    if (scratch_bytes < pmce_linear_tc_scratch_bytes(M, N, K)) { pmce_set_error("pmce_linear_tc: scratch too small"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    auto al = [](size_t n) { return (n + 127) / 128 * 128; };
+    __nv_bfloat16* a_hi = (__nv_bfloat16*)scratch;
+    __nv_bfloat16* a_lo = a_hi + al((size_t)M * K);
+    __nv_bfloat16* w_hi = a_lo + al((size_t)M * K);
+    __nv_bfloat16* w_lo = w_hi + al((size_t)N * K);
+    split_rows_kernel<<<cdiv((long long)M * (K / 4), 256), 256, 0, st>>>(x, M, K, K, 0, a_hi, a_lo, K);
+    CKL();
+    split_rows_kernel<<<cdiv((long long)N * (K / 4), 256), 256, 0, st>>>(weight, N, K, K, 0, w_hi, w_lo, K);
+    CKL();
+    TcOperand A{a_hi, a_lo, M, K, K}, W{w_hi, w_lo, N, K, K};
+    TcEpi e;
+    memset(&e, 0, sizeof(e));
+    e.bias = bias; e.act = act; e.out_f32 = out; e.ld_out = N; e.rowadd_period = 1;
+    int rc = launch_linear_tc(A, W, e, st);
+    count_launch();
+    if (rc) { pmce_set_error("pmce_linear_tc: launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
+    return 0;
 }
 
 // ---- SMPL LBS --------------------------------------------------------------------------------------

@@ -1,0 +1,258 @@
+// tcgen05 / TMA / TMEM GEMM for sm_100a with split-bf16 ("bf16x3") operands and a fused epilogue:
+//     out[M,N] = epi( A[M,K] * W[N,K]^T ),   A = A_hi + A_lo,  W = W_hi + W_lo  (bf16 pairs, K-contiguous)
+// One CTA computes a 128 x BN tile. Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA
+// issuer (one lane), warps 2..5 = epilogue (TMEM lane group = warp_id % 4, one output row per thread).
+// smem ring of STAGES x {A_hi, A_lo, W_hi, W_lo} tiles of [rows][64 bf16] written by TMA with the 128-byte
+// swizzle the UMMA descriptors expect; full/empty mbarriers between TMA and MMA, one more MMA -> epilogue.
+#pragma once
+#include "tc_common.cuh"
+#include "common.cuh"
+
+struct TcEpi {
+    const float* bias;      // [N] or null
+    const float* resid;     // fp32 [M, ld_resid] or null
+    const float* rowadd;    // [period, N] or null (added at row % period)
+    int rowadd_period;
+    int ld_resid;
+    int act;                // 0 none, 1 exact GELU
+    float* out_f32;         // fp32 [M, ld_out] or null
+    __nv_bfloat16* out_hi;  // split output [M, ld_split] or null (both hi and lo, or neither)
+    __nv_bfloat16* out_lo;
+    int ld_out, ld_split;
+};
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;   // bf16 elements = 128 bytes = one swizzle row
+
+template <int BN>
+struct TcCfg {
+    static constexpr int A_TILE = TC_BM * 128;          // bytes per A half (hi or lo)
+    static constexpr int W_TILE = BN * 128;
+    static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(STAGES >= 2, "tile too large");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                 int M, int N, int K, TcEpi e) {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
+    const int nkb = (K + TC_BK - 1) / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA_hi); tc::tma_prefetch_desc(&tmA_lo);
+        tc::tma_prefetch_desc(&tmW_hi); tc::tma_prefetch_desc(&tmW_lo);
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+        tc::mbar_init(tmem_full_bar, 1);
+        tc::fence_barrier_init();
+        tc::fence_proxy_async();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr_smem, BN);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                tc::tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
+                tc::tma_load_2d(st + Cfg::A_TILE, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
+                tc::tma_load_2d(st + 2 * Cfg::A_TILE, &tmW_hi, &full_bar[s], kb * TC_BK, n0);
+                tc::tma_load_2d(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tmW_lo, &full_bar[s], kb * TC_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(TC_BM, BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                tc::mbar_wait(&full_bar[s], ph);
+                tc::tc_fence_after();
+                const uint32_t st = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint64_t a_hi = tc::umma_desc_sw128(st), a_lo = tc::umma_desc_sw128(st + Cfg::A_TILE);
+                const uint64_t w_hi = tc::umma_desc_sw128(st + 2 * Cfg::A_TILE), w_lo = tc::umma_desc_sw128(st + 2 * Cfg::A_TILE + Cfg::W_TILE);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                    // small cross terms first, then the leading term
+                    tc::umma_bf16(tmem_base, tc::umma_desc_advance_k(a_lo, k), tc::umma_desc_advance_k(w_hi, k), idesc, (kb | k) != 0);
+                    tc::umma_bf16(tmem_base, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_lo, k), idesc, 1);
+                    tc::umma_bf16(tmem_base, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_hi, k), idesc, 1);
+                }
+                tc::umma_commit(&empty_bar[s]);          // smem slot free once these MMAs have read it
+            }
+            tc::umma_commit(tmem_full_bar);              // accumulator complete
+        }
+    } else {
+        // ---- epilogue: 4 warps, warp q = warp % 4 owns TMEM lanes [32q, 32q+32) = tile rows ----
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        tc::mbar_wait(tmem_full_bar, 0);
+        tc::tc_fence_after();
+        const bool row_ok = row < M;
+        const float* radd = (e.rowadd && row_ok) ? e.rowadd + (size_t)(row % e.rowadd_period) * N : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tc::tmem_ld_wait();
+            const int col0 = n0 + c0;
+            if (row_ok && col0 < N) {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            const bool full = (col0 + 32 <= N);
+            if (full) {
+                if (e.bias) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) { float4 b = ld4(e.bias + col0 + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
+                }
+                if (e.act == 1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+                }
+                if (radd) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) { float4 b = ld4(radd + col0 + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
+                }
+                if (e.resid) {
+                    const float* rp = e.resid + (size_t)row * e.ld_resid + col0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) { float4 b = ld4(rp + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
+                }
+                if (e.out_f32) {
+                    float* op = e.out_f32 + (size_t)row * e.ld_out + col0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) st4(op + i, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
+                }
+                if (e.out_hi) {
+                    uint4* hp = reinterpret_cast<uint4*>(e.out_hi + (size_t)row * e.ld_split + col0);
+                    uint4* lp = reinterpret_cast<uint4*>(e.out_lo + (size_t)row * e.ld_split + col0);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 h, l;
+                        tc::split_bf16x2(f[i], f[i + 1], h.x, l.x); tc::split_bf16x2(f[i + 2], f[i + 3], h.y, l.y);
+                        tc::split_bf16x2(f[i + 4], f[i + 5], h.z, l.z); tc::split_bf16x2(f[i + 6], f[i + 7], h.w, l.w);
+                        hp[i / 8] = h; lp[i / 8] = l;
+                    }
+                }
+            } else {
+                for (int i = 0; i < 32; ++i) {
+                    const int col = col0 + i;
+                    if (col >= N) break;
+                    float x = f[i];
+                    if (e.bias) x += e.bias[col];
+                    if (e.act == 1) x = gelu_erf(x);
+                    if (radd) x += radd[col];
+                    if (e.resid) x += e.resid[(size_t)row * e.ld_resid + col];
+                    if (e.out_f32) e.out_f32[(size_t)row * e.ld_out + col] = x;
+                    if (e.out_hi) {
+                        __nv_bfloat16 h, l;
+                        tc::split_bf16(x, h, l);
+                        e.out_hi[(size_t)row * e.ld_split + col] = h;
+                        e.out_lo[(size_t)row * e.ld_split + col] = l;
+                    }
+                }
+            }
+            }
+            __syncwarp();     // tcgen05.ld is .sync.aligned: reconverge before the next chunk
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+}
+
+// fp32 [rows, cols] (ld) -> bf16 hi / lo [rows, ld_out]; optional relu on the way (linear_cur input).
+__global__ void split_rows_kernel(const float* __restrict__ x, int rows, int cols, int ld, int relu, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, int ld_out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per 4 elements
+    const int c4 = cols / 4;
+    if (idx >= (size_t)rows * c4) return;
+    const int r = (int)(idx / c4), c = (int)(idx % c4) * 4;
+    float4 v = ld4(x + (size_t)r * ld + c);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    uint2 h, l;
+    tc::split_bf16x2(v.x, v.y, h.x, l.x);
+    tc::split_bf16x2(v.z, v.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(hi + (size_t)r * ld_out + c) = h;
+    *reinterpret_cast<uint2*>(lo + (size_t)r * ld_out + c) = l;
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows][64], 128-byte swizzle, zero OOB fill.
+static inline int make_tmap_bf16(CUtensorMap* m, const void* ptr, int rows, int cols, int ld, int box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return 1;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+struct TcOperand {   // split bf16 matrix [rows, cols], row stride ld (elements)
+    const __nv_bfloat16* hi; const __nv_bfloat16* lo; int rows, cols, ld;
+};
+
+template <int BN>
+static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, const TcEpi& e, cudaStream_t st) {
+    CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+    if (make_tmap_bf16(&ta_hi, A.hi, A.rows, A.cols, A.ld, TC_BM) || make_tmap_bf16(&ta_lo, A.lo, A.rows, A.cols, A.ld, TC_BM) ||
+        make_tmap_bf16(&tw_hi, W.hi, W.rows, W.cols, W.ld, BN) || make_tmap_bf16(&tw_lo, W.lo, W.rows, W.cols, W.ld, BN))
+        return 1;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES) != cudaSuccess) return 2;
+        configured = true;
+    }
+    dim3 grid((W.rows + BN - 1) / BN, (A.rows + TC_BM - 1) / TC_BM);
+    linear_tc_kernel<BN><<<grid, 192, TcCfg<BN>::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, A.rows, W.rows, A.cols, e);
+    return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
+// Requirements: A.cols == W.cols (K), K % 8 == 0, ld % 8 == 0, 16-byte aligned bases.
+static inline int launch_linear_tc(const TcOperand& A, const TcOperand& W, const TcEpi& e, cudaStream_t st) {
+    const int N = W.rows;
+    const long long tiles_m = (A.rows + TC_BM - 1) / TC_BM;
+    if (N % 256 == 0 && tiles_m * (N / 256) >= 148) return launch_linear_tc_bn<256>(A, W, e, st);
+    if (N >= 128 && tiles_m * ((N + 127) / 128) >= 120) return launch_linear_tc_bn<128>(A, W, e, st);
+    if (N > 32) return launch_linear_tc_bn<64>(A, W, e, st);
+    return launch_linear_tc_bn<32>(A, W, e, st);
+}
