@@ -59,8 +59,9 @@ size_t pmce_weights_bytes(const pmce_dims_t* dims);
  * (the joint branch of coevoblock1/2, lib/models/CoevoDecoder.py:235-236) and is not stored;
  * <0 if the name is not in the schema. */
 int pmce_weight_slot(const pmce_dims_t* dims, const char* name, pmce_slot_t* slot);
-/* Derived tensors computed on device once all slots are filled (currently a no-op placeholder for
- * split-precision copies). */
+/* Derived tensors computed on device once all slots are filled: the blob is [fp32 | bf16 hi | bf16 lo] and this
+ * writes the split-bf16 copies (hi = bf16(w), lo = bf16(w - hi)) the tensor-core GEMMs read. Must be called
+ * after the last slot copy and before any forward entry point. */
 int pmce_pack_weights(const pmce_dims_t* dims, void* weights, void* stream);
 
 /* Workspace bytes needed by any forward entry point for batch size B. */
@@ -94,7 +95,7 @@ int pmce_gru_mid(const pmce_dims_t* dims, const void* weights, const float* img_
  * g [B,2048] -> gb [B, pmce_adaln_slots(), 2, 64] (gamma then beta per slot). */
 int pmce_adaln_slots(void);
 int pmce_adaln_gammabeta(const pmce_dims_t* dims, const void* weights, const float* g, int B, float* gb,
-                         void* stream);
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a8 (with a6 CrossAttentionBlock :64-87 and a7 Block :89-105 inside): CoevoBlock.forward,
  * lib/models/CoevoDecoder.py:175-191.  block in {1,2,3}; joints [B,J,3], verts_in [B,431,3], gb from

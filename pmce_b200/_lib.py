@@ -40,7 +40,7 @@ SIGNATURES = {
     "pmce_lifter_forward": (C.c_int, [_DP, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_gru_mid": (C.c_int, [_DP, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_adaln_slots": (C.c_int, []),
-    "pmce_adaln_gammabeta": (C.c_int, [_DP, _P, _P, C.c_int, _P, _P]),
+    "pmce_adaln_gammabeta": (C.c_int, [_DP, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_coevo_block": (C.c_int, [_DP, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "pmce_mesh_epilogue": (C.c_int, [_DP, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_decoder_forward": (C.c_int, [_DP, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),

@@ -1,8 +1,14 @@
 // libpmce_b200: C-ABI entry points and host-side orchestration of the PMCE forward hot path.
 // All device work is enqueued on the caller's stream; no allocation, no synchronisation (graph-capturable).
+//
+// Data flow: the residual streams and everything attention reads stay fp32; every tensor that is the A operand of a
+// projection is produced directly in split-bf16 form (hi/lo pair) by the kernel that computes it, and every weight
+// matrix has a split-bf16 copy (made once by pmce_pack_weights), so all projections run on the tcgen05 GEMM
+// (gemm_tc.cuh). The fp32 CUDA-core GEMM (gemm_simt.cuh) remains as the exact reference entry point (pmce_linear).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include "../../include/pmce_b200.h"
 #include "layout.h"
 #include "common.cuh"
@@ -22,7 +28,6 @@
 #define CKG(expr) do { count_launch(); CK(expr); } while (0)
 #define RET(x) do { int _r = (x); if (_r) return _r; } while (0)
 
-#include <atomic>
 static std::atomic<unsigned long long> g_launches{0};
 static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" unsigned long long pmce_launch_count(void) { return g_launches.load(); }
@@ -30,54 +35,68 @@ extern "C" unsigned long long pmce_launch_count(void) { return g_launches.load()
 namespace {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+typedef __nv_bfloat16 bf16;
 
 // ---------------------------------------------------------------------------------------------------
-// workspace carving (floats, 256-byte aligned chunks)
+// workspace carving (256-byte aligned chunks)
 // ---------------------------------------------------------------------------------------------------
 struct Carver {
-    float* base;
-    size_t cur;
-    float* take(size_t n) {
-        float* p = base ? base + cur : nullptr;
-        cur += (n + 63) / 64 * 64;
+    char* base;
+    size_t cur;   // bytes
+    void* take_bytes(size_t n) {
+        void* p = base ? base + cur : nullptr;
+        cur += (n + 255) / 256 * 256;
         return p;
+    }
+    float* f32(size_t n) { return (float*)take_bytes(n * 4); }
+    SplitOut split(size_t n) {
+        SplitOut s;
+        s.hi = (bf16*)take_bytes(n * 2);
+        s.lo = (bf16*)take_bytes(n * 2);
+        return s;
     }
 };
 
 struct Workspace {
+    SplitOut feat_s;                                   // img_feat [B*T, F] split (shared by lifter embed and GRU)
     // lifter
-    float *imgemb, *x, *xn, *qkv, *att, *hid, *r3, *joints_m;
+    float *imgemb, *x, *qkv, *r3, *joints_m;
+    SplitOut xn_s, att_s, hid_s;
     // gru
     float *gi0, *y0, *gi1f, *gi1b, *h1[2][2], *g;
+    SplitOut y0_s, g_s, gr_s;
     // decoder
-    float *gb, *verts[3], *Jf, *Vf, *xqv, *tA, *tA2, *Qv, *xkj, *tJ, *Kj, *Vj, *att_d, *qkv_d, *hid_d;
-    float *xqj, *xkv, *Kv, *Vv, *Qj, *attj, *qkvj, *hidj, *im2col;
-    size_t floats;
+    float *gb, *verts[3], *Jf, *Vf, *xqv, *Qv, *xkj, *Kj, *Vj, *qkv_d;
+    float *xqj, *xkv, *Kv, *Vv, *Qj, *qkvj;
+    SplitOut Jf_s, Vf_s, tA_s, tA2_s, tJ_s, att_ds, hid_ds, attj_s, hidj_s, im2col_s;
+    size_t bytes;
 };
 
 Workspace carve(const pmce_dims_t& d, int B, void* base) {
     Workspace w;
-    Carver c{(float*)base, 0};
+    Carver c{(char*)base, 0};
     const size_t J = d.num_joint, C = d.embed_dim, T = d.seqlen, Vd = d.num_vert_ds, H = d.gru_hidden, F = d.feat_dim, D = d.coevo_dim;
     const size_t N = (size_t)B * T * J;
-    w.imgemb = c.take((size_t)B * T * C);
-    w.x = c.take(N * C); w.xn = c.take(N * C); w.qkv = c.take(N * 3 * C); w.att = c.take(N * C); w.hid = c.take(N * 2 * C);
-    w.r3 = c.take(N * 3); w.joints_m = c.take((size_t)B * J * 3);
+    w.feat_s = c.split((size_t)B * T * F);
+    w.imgemb = c.f32((size_t)B * T * C);
+    w.x = c.f32(N * C); w.qkv = c.f32(N * 3 * C); w.r3 = c.f32(N * 3); w.joints_m = c.f32((size_t)B * J * 3);
+    w.xn_s = c.split(N * C); w.att_s = c.split(N * C); w.hid_s = c.split(N * 2 * C);
     const size_t mid = T / 2;
-    w.gi0 = c.take((size_t)T * B * 6 * H); w.y0 = c.take((size_t)T * B * 2 * H);
-    w.gi1f = c.take((mid + 1) * B * 3 * H); w.gi1b = c.take((T - mid) * B * 3 * H);
-    for (int dir = 0; dir < 2; ++dir) for (int i = 0; i < 2; ++i) w.h1[dir][i] = c.take((size_t)B * H);
-    w.g = c.take((size_t)B * F);
-    w.gb = c.take((size_t)B * PMCE_ADALN_SLOTS * 2 * D);
-    for (int i = 0; i < 3; ++i) w.verts[i] = c.take((size_t)B * Vd * 3);
+    w.gi0 = c.f32((size_t)T * B * 6 * H); w.y0 = c.f32((size_t)T * B * 2 * H);
+    w.gi1f = c.f32((mid + 1) * B * 3 * H); w.gi1b = c.f32((T - mid) * B * 3 * H);
+    for (int dir = 0; dir < 2; ++dir) for (int i = 0; i < 2; ++i) w.h1[dir][i] = c.f32((size_t)B * H);
+    w.g = c.f32((size_t)B * F);
+    w.y0_s = c.split((size_t)T * B * 2 * H); w.g_s = c.split((size_t)B * F); w.gr_s = c.split((size_t)B * F);
+    w.gb = c.f32((size_t)B * PMCE_ADALN_SLOTS * 2 * D);
+    for (int i = 0; i < 3; ++i) w.verts[i] = c.f32((size_t)B * Vd * 3);
     const size_t nv = (size_t)B * Vd, nj = (size_t)B * J;
-    w.Jf = c.take(nj * D); w.Vf = c.take(nv * D); w.xqv = c.take(nv * D); w.tA = c.take(nv * D); w.tA2 = c.take(nv * D);
-    w.Qv = c.take(nv * D); w.xkj = c.take(nj * D); w.tJ = c.take(nj * D); w.Kj = c.take(nj * D); w.Vj = c.take(nj * D);
-    w.att_d = c.take(nv * D); w.qkv_d = c.take(nv * 3 * D); w.hid_d = c.take(nv * 4 * D);
-    w.xqj = c.take(nj * D); w.xkv = c.take(nv * D); w.Kv = c.take(nv * D); w.Vv = c.take(nv * D); w.Qj = c.take(nj * D);
-    w.attj = c.take(nj * D); w.qkvj = c.take(nj * 3 * D); w.hidj = c.take(nj * 4 * D);
-    w.im2col = c.take((size_t)B * 3 * ((Vd * 3 + 3) / 4 * 4));
-    w.floats = c.cur;
+    w.Jf = c.f32(nj * D); w.Vf = c.f32(nv * D); w.xqv = c.f32(nv * D); w.Qv = c.f32(nv * D);
+    w.xkj = c.f32(nj * D); w.Kj = c.f32(nj * D); w.Vj = c.f32(nj * D); w.qkv_d = c.f32(nv * 3 * D);
+    w.xqj = c.f32(nj * D); w.xkv = c.f32(nv * D); w.Kv = c.f32(nv * D); w.Vv = c.f32(nv * D); w.Qj = c.f32(nj * D); w.qkvj = c.f32(nj * 3 * D);
+    w.Jf_s = c.split(nj * D); w.Vf_s = c.split(nv * D); w.tA_s = c.split(nv * D); w.tA2_s = c.split(nv * D); w.tJ_s = c.split(nj * D);
+    w.att_ds = c.split(nv * D); w.hid_ds = c.split(nv * 4 * D); w.attj_s = c.split(nj * D); w.hidj_s = c.split(nj * 4 * D);
+    w.im2col_s = c.split((size_t)B * 3 * ((Vd * 3 + 7) / 8 * 8));
+    w.bytes = c.cur;
     return w;
 }
 
@@ -86,50 +105,79 @@ int check_ws(const pmce_dims_t& d, int B, void* ws, size_t bytes, Workspace* out
     if (!ws) { pmce_set_error("workspace is NULL"); return 2; }
     if (((uintptr_t)ws) & 255) { pmce_set_error("workspace must be 256-byte aligned"); return 2; }
     *out = carve(d, B, ws);
-    if (out->floats * sizeof(float) > bytes) {
-        pmce_set_error("workspace too small: need %zu bytes, got %zu", out->floats * sizeof(float), bytes);
-        return 2;
-    }
+    if (out->bytes > bytes) { pmce_set_error("workspace too small: need %zu bytes, got %zu", out->bytes, bytes); return 2; }
     return 0;
+}
+
+// packed weights: fp32 region, then bf16 hi copy, then bf16 lo copy (same element offsets)
+struct Weights {
+    const float* f;
+    const bf16* hi;
+    const bf16* lo;
+};
+Weights weights_view(const Layout& L, const void* blob) {
+    Weights w;
+    w.f = (const float*)blob;
+    w.hi = (const bf16*)(w.f + L.total_floats);
+    w.lo = w.hi + L.total_floats;
+    return w;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------------
-int linear(const float* A, int lda, const float* W, int ldw, const float* bias, float* out, int ldc, int M, int N, int K,
-           cudaStream_t st, int act = 0, const float* resid = nullptr, const float* rowadd = nullptr, int period = 1) {
-    GemmEpi e = gemm_epi_plain(ldc);
-    e.bias = bias; e.act = act; e.resid = resid; e.rowadd = rowadd; e.rowadd_period = period;
-    CKG(launch_gemm_tn(A, lda, W, ldw, out, M, N, K, e, st));
+struct EpiOpt {
+    const float* bias = nullptr;
+    int act = 0;
+    const float* resid = nullptr; int ld_resid = 0;
+    const float* rowadd = nullptr; int period = 1;
+    float* out = nullptr; int ld_out = 0;
+    SplitOut outs{nullptr, nullptr}; int ld_split = 0;
+    bool mapped = false; RowMap rmap{1, 0, 0}, cmap{1, 0, 0};
+};
+
+// out = epi(A[M,K] * W[N,K]^T) on the tcgen05 path; A split [M,K] (ld lda), W at float offset w_off in the blob (ld ldw).
+int linear_tc(const SplitOut& A, int lda, int M, int K, const Weights& W, size_t w_off, int ldw, int N, const EpiOpt& o, cudaStream_t st) {
+    if ((K & 7) || (lda & 7) || (ldw & 7)) { pmce_set_error("linear_tc: K/lda/ldw must be multiples of 8 (K=%d lda=%d ldw=%d)", K, lda, ldw); return 3; }
+    TcOperand a{A.hi, A.lo, M, K, lda}, w{W.hi + w_off, W.lo + w_off, N, K, ldw};
+    TcEpi e;
+    memset(&e, 0, sizeof(e));
+    e.bias = o.bias; e.act = o.act; e.resid = o.resid; e.ld_resid = o.ld_resid; e.rowadd = o.rowadd; e.rowadd_period = o.period;
+    e.out_f32 = o.out; e.ld_out = o.ld_out; e.out_hi = o.outs.hi; e.out_lo = o.outs.lo; e.ld_split = o.ld_split;
+    e.mapped = o.mapped ? 1 : 0; e.rmap = o.rmap; e.cmap = o.cmap;
+    count_launch();
+    const int rc = launch_linear_tc(a, w, e, st);
+    if (rc) { pmce_set_error("tensor-core GEMM launch failed (%d; M=%d N=%d K=%d): %s", rc, M, N, K, cudaGetErrorString(cudaGetLastError())); return 10; }
     return 0;
 }
 
-template <int D>
-int launch_attn_d(const float* Q, AttnAddr aq, const float* K, const float* V, AttnAddr akv, float* O, AttnAddr ao, int nseq,
-                  int H, int N1, int N2, cudaStream_t st) {
-    const size_t smem = (size_t)N2 * D * 2 * sizeof(float);
-    static size_t configured = 0;   // per-process, per-instantiation
-    if (smem > 48 * 1024 && smem > configured) {
-        CK(cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = 227 * 1024;
-    }
-    if (smem > 227 * 1024) { pmce_set_error("attention K/V tile (%zu B) exceeds shared memory", smem); return 3; }
-    const int threads = N1 >= 128 ? 128 : (N1 > 64 ? 96 : (N1 > 32 ? 64 : 32));
-    dim3 grid(cdiv(N1, threads), H, nseq);
-    if (nseq > 65535) { pmce_set_error("too many attention sequences (%d) for one launch", nseq); return 3; }
-    attn_kernel<D><<<grid, threads, smem, st>>>(Q, aq, K, V, akv, O, ao, N1, N2, 1.0f / sqrtf((float)D));
+int split_rows(const float* x, int rows, int cols, int ld, bool relu, const SplitOut& o, int ld_out, cudaStream_t st) {
+    split_rows_kernel<<<cdiv((long long)rows * (cols / 4), 256), 256, 0, st>>>(x, rows, cols, ld, relu ? 1 : 0, o.hi, o.lo, ld_out);
     CKL();
     return 0;
 }
 
-int launch_attn(int D, const float* Q, AttnAddr aq, const float* K, const float* V, AttnAddr akv, float* O, AttnAddr ao,
+template <int D>
+int launch_attn_d(const float* Q, AttnAddr aq, const float* K, const float* V, AttnAddr akv, float* O, SplitOut Os, AttnAddr ao, int nseq,
+                  int H, int N1, int N2, cudaStream_t st) {
+    const size_t smem = (size_t)N2 * D * 2 * sizeof(float);
+    if (smem > 227 * 1024) { pmce_set_error("attention K/V tile (%zu B) exceeds shared memory", smem); return 3; }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int threads = N1 >= 128 ? 128 : (N1 > 64 ? 96 : (N1 > 32 ? 64 : 32));
+    if (nseq > 65535) { pmce_set_error("too many attention sequences (%d) for one launch", nseq); return 3; }
+    dim3 grid(cdiv(N1, threads), H, nseq);
+    attn_kernel<D><<<grid, threads, smem, st>>>(Q, aq, K, V, akv, O, Os, ao, N1, N2, 1.0f / sqrtf((float)D));
+    CKL();
+    return 0;
+}
+
+int launch_attn(int D, const float* Q, AttnAddr aq, const float* K, const float* V, AttnAddr akv, float* O, SplitOut Os, AttnAddr ao,
                 int nseq, int H, int N1, int N2, cudaStream_t st) {
-    // split very large sequence counts into several launches (gridDim.z limit)
     switch (D) {
-        case 8: return launch_attn_d<8>(Q, aq, K, V, akv, O, ao, nseq, H, N1, N2, st);
-        case 16: return launch_attn_d<16>(Q, aq, K, V, akv, O, ao, nseq, H, N1, N2, st);
-        case 32: return launch_attn_d<32>(Q, aq, K, V, akv, O, ao, nseq, H, N1, N2, st);
-        case 64: return launch_attn_d<64>(Q, aq, K, V, akv, O, ao, nseq, H, N1, N2, st);
+        case 8: return launch_attn_d<8>(Q, aq, K, V, akv, O, Os, ao, nseq, H, N1, N2, st);
+        case 16: return launch_attn_d<16>(Q, aq, K, V, akv, O, Os, ao, nseq, H, N1, N2, st);
+        case 32: return launch_attn_d<32>(Q, aq, K, V, akv, O, Os, ao, nseq, H, N1, N2, st);
+        case 64: return launch_attn_d<64>(Q, aq, K, V, akv, O, Os, ao, nseq, H, N1, N2, st);
     }
     pmce_set_error("unsupported head_dim %d", D);
     return 3;
@@ -141,18 +189,20 @@ AttnAddr addr_plain(int ntok, int ld) {
     return a;
 }
 
+const SplitOut NO_SPLIT{nullptr, nullptr};
+
 int ln_rows(const float* x, int nrows, int C, const LnParams* a, const float* pos, int pos_div, int pos_mod, float* out1,
-            const LnParams* b, float* out2, cudaStream_t st) {
+            const LnParams* b, const SplitOut& out2s, cudaStream_t st) {
     LnParams za{nullptr, nullptr, 0.f};
-    ln_rows_kernel<<<cdiv(nrows, 8), 256, 0, st>>>(x, nrows, C, a ? *a : za, a ? 1 : 0, pos, pos_div, pos_mod, out1,
-                                                     b ? *b : za, b ? out2 : nullptr);
+    ln_rows_kernel<<<cdiv(nrows, 8), 256, 0, st>>>(x, nrows, C, a ? *a : za, a ? 1 : 0, pos, pos_div, pos_mod, out1, b ? *b : za, nullptr,
+                                                     b ? out2s : NO_SPLIT);
     CKL();
     return 0;
 }
 
-int adaln(const float* x, int B, int ntok, const float* gb, int slot, float* y, cudaStream_t st) {
+int adaln(const float* x, int B, int ntok, const float* gb, int slot, const SplitOut& ys, cudaStream_t st) {
     const int nrows = B * ntok;
-    adaln_apply_kernel<<<cdiv(nrows, 8), 256, 0, st>>>(x, nrows, ntok, gb, PMCE_ADALN_SLOTS * 128, slot, 1e-6f, y);
+    adaln_apply_kernel<<<cdiv(nrows, 8), 256, 0, st>>>(x, nrows, ntok, gb, PMCE_ADALN_SLOTS * 128, slot, 1e-6f, nullptr, ys);
     CKL();
     return 0;
 }
@@ -160,59 +210,69 @@ int adaln(const float* x, int B, int ntok, const float* gb, int slot, float* y, 
 // ---------------------------------------------------------------------------------------------------
 // a2/a3 lifter
 // ---------------------------------------------------------------------------------------------------
-int vit_block(const pmce_dims_t& d, const float* Wt, const VitBlockW& w, const Workspace& ws, int B, bool temporal, cudaStream_t st) {
+int vit_block(const pmce_dims_t& d, const Weights& W, const VitBlockW& w, const Workspace& ws, int B, bool temporal, cudaStream_t st) {
     const int J = d.num_joint, C = d.embed_dim, T = d.seqlen, Hh = d.lifter_heads;
     const int N = B * T * J;
-    // qkv
-    RET(linear(ws.xn, C, Wt + w.qkvw, C, Wt + w.qkvb, ws.qkv, 3 * C, N, 3 * C, C, st));
+    {   // qkv = W_qkv LN1(x) + b
+        EpiOpt o; o.bias = W.f + w.qkvb; o.out = ws.qkv; o.ld_out = 3 * C;
+        RET(linear_tc(ws.xn_s, C, N, C, W, w.qkvw, C, 3 * C, o, st));
+    }
     AttnAddr a, ao;
     int nseq, L;
     if (!temporal) { a.seq.div = 1; a.seq.s0 = J; a.seq.s1 = 0; a.tok = 1; nseq = B * T; L = J; }
     else { a.seq.div = J; a.seq.s0 = (long long)T * J; a.seq.s1 = 1; a.tok = J; nseq = B * J; L = T; }
     a.ld = 3 * C;
     ao = a; ao.ld = C;
-    // gridDim.z <= 65535: chunk over sequences in multiples of J (keeps the (b,j) decomposition intact)
-    const int chunk = (65535 / J) * J;
+    const int chunk = (65535 / J) * J;   // gridDim.z limit; multiples of J keep the (b,j) decomposition intact
     for (int s0 = 0; s0 < nseq; s0 += chunk) {
         const int ns = nseq - s0 < chunk ? nseq - s0 : chunk;
-        const long long r0 = a.seq(s0);   // first row of sequence s0 (s0 % J == 0 in temporal mode)
-        RET(launch_attn(C / Hh, ws.qkv + r0 * 3 * C, a, ws.qkv + r0 * 3 * C + C, ws.qkv + r0 * 3 * C + 2 * C, a,
-                        ws.att + r0 * C, ao, ns, Hh, L, L, st));
+        const long long r0 = a.seq(s0);
+        SplitOut os{ws.att_s.hi + r0 * C, ws.att_s.lo + r0 * C};
+        RET(launch_attn(C / Hh, ws.qkv + r0 * 3 * C, a, ws.qkv + r0 * 3 * C + C, ws.qkv + r0 * 3 * C + 2 * C, a, nullptr, os, ao, ns, Hh, L, L, st));
     }
-    // proj + residual (in place on x)
-    RET(linear(ws.att, C, Wt + w.projw, C, Wt + w.projb, ws.x, C, N, C, C, st, 0, ws.x));
-    // norm2 -> xn
-    LnParams n2{Wt + w.n2w, Wt + w.n2b, 1e-6f};
-    RET(ln_rows(ws.x, N, C, &n2, nullptr, 1, 1, ws.xn, nullptr, nullptr, st));
-    RET(linear(ws.xn, C, Wt + w.fc1w, C, Wt + w.fc1b, ws.hid, 2 * C, N, 2 * C, C, st, 1));
-    RET(linear(ws.hid, 2 * C, Wt + w.fc2w, 2 * C, Wt + w.fc2b, ws.x, C, N, C, 2 * C, st, 0, ws.x));
+    {   // x += W_proj att + b
+        EpiOpt o; o.bias = W.f + w.projb; o.resid = ws.x; o.ld_resid = C; o.out = ws.x; o.ld_out = C;
+        RET(linear_tc(ws.att_s, C, N, C, W, w.projw, C, C, o, st));
+    }
+    LnParams n2{W.f + w.n2w, W.f + w.n2b, 1e-6f};
+    RET(ln_rows(ws.x, N, C, nullptr, nullptr, 1, 1, nullptr, &n2, ws.xn_s, st));
+    {   // hid = gelu(W_fc1 LN2(x) + b)
+        EpiOpt o; o.bias = W.f + w.fc1b; o.act = 1; o.outs = ws.hid_s; o.ld_split = 2 * C;
+        RET(linear_tc(ws.xn_s, C, N, C, W, w.fc1w, C, 2 * C, o, st));
+    }
+    {   // x += W_fc2 hid + b
+        EpiOpt o; o.bias = W.f + w.fc2b; o.resid = ws.x; o.ld_resid = C; o.out = ws.x; o.ld_out = C;
+        RET(linear_tc(ws.hid_s, 2 * C, N, 2 * C, W, w.fc2w, 2 * C, C, o, st));
+    }
     return 0;
 }
 
-int lifter(const Layout& L, const float* Wt, const float* pose2d, const float* img_feat, int B, float* pose3d,
-           const Workspace& ws, cudaStream_t st) {
+int lifter(const Layout& L, const Weights& W, const float* pose2d, int B, float* pose3d, const Workspace& ws, cudaStream_t st) {
     const pmce_dims_t& d = L.d;
     const int J = d.num_joint, C = d.embed_dim, T = d.seqlen, F = d.feat_dim;
     const int N = B * T * J;
-    RET(linear(img_feat, F, Wt + L.iew, F, Wt + L.ieb, ws.imgemb, C, B * T, C, F, st));
-    LnParams s0n1{Wt + L.sp[0].n1w, Wt + L.sp[0].n1b, 1e-6f};
-    lifter_embed_kernel<<<cdiv(N, 8), 256, 0, st>>>(pose2d, ws.imgemb, Wt + L.jew, Wt + L.jeb, Wt + L.spos, N, J, C, s0n1, ws.x, ws.xn);
+    {   // imgfeat_embed for every frame (feat_s prepared by the caller)
+        EpiOpt o; o.bias = W.f + L.ieb; o.out = ws.imgemb; o.ld_out = C;
+        RET(linear_tc(ws.feat_s, F, B * T, F, W, L.iew, F, C, o, st));
+    }
+    LnParams s0n1{W.f + L.sp[0].n1w, W.f + L.sp[0].n1b, 1e-6f};
+    lifter_embed_kernel<<<cdiv(N, 8), 256, 0, st>>>(pose2d, ws.imgemb, W.f + L.jew, W.f + L.jeb, W.f + L.spos, N, J, C, s0n1, ws.x, nullptr, ws.xn_s);
     CKL();
-    LnParams ns{Wt + L.nsw, Wt + L.nsb, 1e-6f}, nt{Wt + L.ntw, Wt + L.ntb, 1e-6f};
+    LnParams ns{W.f + L.nsw, W.f + L.nsb, 1e-6f}, nt{W.f + L.ntw, W.f + L.ntb, 1e-6f};
     for (int i = 0; i < d.depth; ++i) {
-        RET(vit_block(d, Wt, L.sp[i], ws, B, false, st));
-        LnParams tn1{Wt + L.tp[i].n1w, Wt + L.tp[i].n1b, 1e-6f};
-        RET(ln_rows(ws.x, N, C, &ns, i == 0 ? Wt + L.tpos : nullptr, J, T, ws.x, &tn1, ws.xn, st));
-        RET(vit_block(d, Wt, L.tp[i], ws, B, true, st));
+        RET(vit_block(d, W, L.sp[i], ws, B, false, st));
+        LnParams tn1{W.f + L.tp[i].n1w, W.f + L.tp[i].n1b, 1e-6f};
+        RET(ln_rows(ws.x, N, C, &ns, i == 0 ? W.f + L.tpos : nullptr, J, T, ws.x, &tn1, ws.xn_s, st));
+        RET(vit_block(d, W, L.tp[i], ws, B, true, st));
         if (i + 1 < d.depth) {
-            LnParams sn1{Wt + L.sp[i + 1].n1w, Wt + L.sp[i + 1].n1b, 1e-6f};
-            RET(ln_rows(ws.x, N, C, &nt, nullptr, 1, 1, ws.x, &sn1, ws.xn, st));
+            LnParams sn1{W.f + L.sp[i + 1].n1w, W.f + L.sp[i + 1].n1b, 1e-6f};
+            RET(ln_rows(ws.x, N, C, &nt, nullptr, 1, 1, ws.x, &sn1, ws.xn_s, st));
         }
     }
-    LnParams nh{Wt + L.r0w, Wt + L.r0b, 1e-5f};
-    lifter_head_kernel<<<cdiv(N, 8), 256, 0, st>>>(ws.x, N, C, nt, nh, Wt + L.r1w, Wt + L.r1b, ws.r3);
+    LnParams nh{W.f + L.r0w, W.f + L.r0b, 1e-5f};
+    lifter_head_kernel<<<cdiv(N, 8), 256, 0, st>>>(ws.x, N, C, nt, nh, W.f + L.r1w, W.f + L.r1b, ws.r3);
     CKL();
-    lifter_fuse_kernel<<<cdiv(B * J * 3, 256), 256, 0, st>>>(ws.r3, Wt + L.fusw, Wt + L.fusb, B, T, J, pose3d, ws.joints_m);
+    lifter_fuse_kernel<<<cdiv(B * J * 3, 256), 256, 0, st>>>(ws.r3, W.f + L.fusw, W.f + L.fusb, B, T, J, pose3d, ws.joints_m);
     CKL();
     return 0;
 }
@@ -227,34 +287,42 @@ int gru_step(const GruDir* dirs, int ndir, int B, int H, cudaStream_t st) {
     return 0;
 }
 
-int gru_mid(const Layout& L, const float* Wt, const float* img_feat, int B, float* g, const Workspace& ws, cudaStream_t st) {
+int gru_mid(const Layout& L, const Weights& W, int B, float* g, const Workspace& ws, cudaStream_t st) {
     const pmce_dims_t& d = L.d;
     const int T = d.seqlen, H = d.gru_hidden, F = d.feat_dim;
     const int mid = T / 2;
-    // layer-0 input projections for every frame and both directions, written time-major: gi0[t][b][6H]
-    {
-        GemmEpi e = gemm_epi_plain(6 * H);
-        e.bias = Wt + L.bih0;
-        e.rmap.div = T; e.rmap.s0 = 6 * H; e.rmap.s1 = (long long)B * 6 * H;   // row (b,t) -> t*B*6H + b*6H
-        CKG(launch_gemm_tn(img_feat, F, Wt + L.wih0, F, ws.gi0, B * T, 6 * H, F, e, st));
+    {   // layer-0 input projections, every frame, both directions, written time-major: gi0[t][b][6H]
+        EpiOpt o; o.bias = W.f + L.bih0; o.out = ws.gi0; o.mapped = true;
+        o.rmap.div = T; o.rmap.s0 = 6 * H; o.rmap.s1 = (long long)B * 6 * H;   // row (b,t) -> t*B*6H + b*6H
+        o.cmap.div = 1; o.cmap.s0 = 1; o.cmap.s1 = 0;
+        RET(linear_tc(ws.feat_s, F, B * T, F, W, L.wih0, F, 6 * H, o, st));
     }
     for (int s = 0; s < T; ++s) {
         GruDir dd[2];
         const int tf = s, tb = T - 1 - s;
         dd[0].gi = ws.gi0 + (size_t)tf * B * 6 * H; dd[0].ld_gi = 6 * H;
         dd[0].hprev = s > 0 ? ws.y0 + (size_t)(tf - 1) * B * 2 * H : nullptr; dd[0].ld_h = 2 * H;
-        dd[0].whh = Wt + L.whh0[0]; dd[0].bhh = Wt + L.bhh0[0];
-        dd[0].hout = ws.y0 + (size_t)tf * B * 2 * H; dd[0].ld_o = 2 * H; dd[0].hout2 = nullptr; dd[0].ld_o2 = 0;
+        dd[0].whh = W.f + L.whh0[0]; dd[0].bhh = W.f + L.bhh0[0];
+        dd[0].hout = ws.y0 + (size_t)tf * B * 2 * H; dd[0].ld_o = 2 * H;
+        dd[0].hs.hi = ws.y0_s.hi + (size_t)tf * B * 2 * H; dd[0].hs.lo = ws.y0_s.lo + (size_t)tf * B * 2 * H; dd[0].ld_s = 2 * H;
         dd[1].gi = ws.gi0 + (size_t)tb * B * 6 * H + 3 * H; dd[1].ld_gi = 6 * H;
         dd[1].hprev = s > 0 ? ws.y0 + (size_t)(tb + 1) * B * 2 * H + H : nullptr; dd[1].ld_h = 2 * H;
-        dd[1].whh = Wt + L.whh0[1]; dd[1].bhh = Wt + L.bhh0[1];
-        dd[1].hout = ws.y0 + (size_t)tb * B * 2 * H + H; dd[1].ld_o = 2 * H; dd[1].hout2 = nullptr; dd[1].ld_o2 = 0;
+        dd[1].whh = W.f + L.whh0[1]; dd[1].bhh = W.f + L.bhh0[1];
+        dd[1].hout = ws.y0 + (size_t)tb * B * 2 * H + H; dd[1].ld_o = 2 * H;
+        dd[1].hs.hi = ws.y0_s.hi + (size_t)tb * B * 2 * H + H; dd[1].hs.lo = ws.y0_s.lo + (size_t)tb * B * 2 * H + H; dd[1].ld_s = 2 * H;
         RET(gru_step(dd, 2, B, H, st));
     }
     // layer 1: only the steps y[T//2] depends on (fwd t = 0..mid, bwd t = T-1..mid)
     const int nf = mid + 1, nb = T - mid;
-    RET(linear(ws.y0, 2 * H, Wt + L.wih1[0], 2 * H, Wt + L.bih1[0], ws.gi1f, 3 * H, nf * B, 3 * H, 2 * H, st));
-    RET(linear(ws.y0 + (size_t)mid * B * 2 * H, 2 * H, Wt + L.wih1[1], 2 * H, Wt + L.bih1[1], ws.gi1b, 3 * H, nb * B, 3 * H, 2 * H, st));
+    {
+        EpiOpt o; o.bias = W.f + L.bih1[0]; o.out = ws.gi1f; o.ld_out = 3 * H;
+        RET(linear_tc(ws.y0_s, 2 * H, nf * B, 2 * H, W, L.wih1[0], 2 * H, 3 * H, o, st));
+    }
+    {
+        EpiOpt o; o.bias = W.f + L.bih1[1]; o.out = ws.gi1b; o.ld_out = 3 * H;
+        SplitOut a{ws.y0_s.hi + (size_t)mid * B * 2 * H, ws.y0_s.lo + (size_t)mid * B * 2 * H};
+        RET(linear_tc(a, 2 * H, nb * B, 2 * H, W, L.wih1[1], 2 * H, 3 * H, o, st));
+    }
     const int nsteps = nf > nb ? nf : nb;
     for (int s = 0; s < nsteps; ++s) {
         GruDir dd[2];
@@ -263,18 +331,18 @@ int gru_mid(const Layout& L, const float* Wt, const float* img_feat, int B, floa
             GruDir& x = dd[n++];
             x.gi = ws.gi1f + (size_t)s * B * 3 * H; x.ld_gi = 3 * H;
             x.hprev = s > 0 ? ws.h1[0][(s - 1) & 1] : nullptr; x.ld_h = H;
-            x.whh = Wt + L.whh1[0]; x.bhh = Wt + L.bhh1[0];
+            x.whh = W.f + L.whh1[0]; x.bhh = W.f + L.bhh1[0];
+            x.hs = NO_SPLIT; x.ld_s = 0;
             if (s == nf - 1) { x.hout = g; x.ld_o = 2 * H; } else { x.hout = ws.h1[0][s & 1]; x.ld_o = H; }
-            x.hout2 = nullptr; x.ld_o2 = 0;
         }
         if (s < nb) {
             GruDir& x = dd[n++];
             const int t = T - 1 - s;
             x.gi = ws.gi1b + (size_t)(t - mid) * B * 3 * H; x.ld_gi = 3 * H;
             x.hprev = s > 0 ? ws.h1[1][(s - 1) & 1] : nullptr; x.ld_h = H;
-            x.whh = Wt + L.whh1[1]; x.bhh = Wt + L.bhh1[1];
+            x.whh = W.f + L.whh1[1]; x.bhh = W.f + L.bhh1[1];
+            x.hs = NO_SPLIT; x.ld_s = 0;
             if (s == nb - 1) { x.hout = g + H; x.ld_o = 2 * H; } else { x.hout = ws.h1[1][s & 1]; x.ld_o = H; }
-            x.hout2 = nullptr; x.ld_o2 = 0;
         }
         RET(gru_step(dd, n, B, H, st));
     }
@@ -284,23 +352,31 @@ int gru_mid(const Layout& L, const float* Wt, const float* img_feat, int B, floa
 // ---------------------------------------------------------------------------------------------------
 // a5 AdaLN gamma/beta, a6-a8 co-evolution block
 // ---------------------------------------------------------------------------------------------------
-int adaln_gammabeta(const Layout& L, const float* Wt, const float* g, int B, float* gb, cudaStream_t st) {
+int adaln_gammabeta(const Layout& L, const Weights& W, const float* g, int B, float* gb, const SplitOut& g_s, cudaStream_t st) {
     const int N = PMCE_ADALN_SLOTS * 2 * L.d.coevo_dim, F = L.d.feat_dim;
-    return linear(g, F, Wt + L.adaln_w, F, Wt + L.adaln_b, gb, N, B, N, F, st);
+    RET(split_rows(g, B, F, F, false, g_s, F, st));
+    EpiOpt o; o.bias = W.f + L.adaln_b; o.out = gb; o.ld_out = N;
+    return linear_tc(g_s, F, B, F, W, L.adaln_w, F, N, o, st);
 }
 
 // residual-stream tail shared by CrossAttentionBlock and Block: x += proj(att); x += fc2(gelu(fc1(AdaLN_2(x))))
-int attn_tail(const float* Wt, size_t wp, size_t bp, int s2, size_t fc1w, size_t fc1b, size_t fc2w, size_t fc2b, float* x,
-              const float* att, float* tmp, float* hid, const float* gb, int B, int ntok, cudaStream_t st) {
+int attn_tail(const Weights& W, size_t wp, size_t bp, int s2, size_t fc1w, size_t fc1b, size_t fc2w, size_t fc2b, float* x, const SplitOut& att,
+              const SplitOut& tmp, const SplitOut& hid, const float* gb, int B, int ntok, cudaStream_t st) {
     const int M = B * ntok;
-    RET(linear(att, 64, Wt + wp, 64, Wt + bp, x, 64, M, 64, 64, st, 0, x));
+    { EpiOpt o; o.bias = W.f + bp; o.resid = x; o.ld_resid = 64; o.out = x; o.ld_out = 64; RET(linear_tc(att, 64, M, 64, W, wp, 64, 64, o, st)); }
     RET(adaln(x, B, ntok, gb, s2, tmp, st));
-    RET(linear(tmp, 64, Wt + fc1w, 64, Wt + fc1b, hid, 256, M, 256, 64, st, 1));
-    RET(linear(hid, 256, Wt + fc2w, 256, Wt + fc2b, x, 64, M, 64, 256, st, 0, x));
+    { EpiOpt o; o.bias = W.f + fc1b; o.act = 1; o.outs = hid; o.ld_split = 256; RET(linear_tc(tmp, 64, M, 64, W, fc1w, 64, 256, o, st)); }
+    { EpiOpt o; o.bias = W.f + fc2b; o.resid = x; o.ld_resid = 64; o.out = x; o.ld_out = 64; RET(linear_tc(hid, 256, M, 256, W, fc2w, 256, 64, o, st)); }
     return 0;
 }
 
-int coevo_block(const Layout& L, const float* Wt, int k, const float* joints, const float* verts_in, const float* gb, int B,
+int proj64(const SplitOut& a, int M, const Weights& W, size_t w, size_t b, float* out, cudaStream_t st, const float* rowadd = nullptr, int period = 1,
+           int N = 64) {
+    EpiOpt o; o.bias = W.f + b; o.out = out; o.ld_out = N; o.rowadd = rowadd; o.period = period;
+    return linear_tc(a, 64, M, 64, W, w, 64, N, o, st);
+}
+
+int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, const float* verts_in, const float* gb, int B,
                 float* joints_out, float* verts_out, const Workspace& ws, cudaStream_t st) {
     const pmce_dims_t& d = L.d;
     const CoevoW& w = L.blk[k];
@@ -310,55 +386,51 @@ int coevo_block(const Layout& L, const float* Wt, int k, const float* joints, co
     if (ja && !w.joint_alive) { pmce_set_error("coevoblock%d: joint-branch weights are not stored (output is discarded by the reference)", k + 1); return 4; }
 
     // coordinate -> feature (+pos), query streams (+Q embed)   (CoevoDecoder.py:177-183)
-    coevo_embed_kernel<<<cdiv((long long)nj * 16, 256), 256, 0, st>>>(joints, nj, J, Wt + w.jprojw, Wt + w.jprojb, Wt + w.jpos,
-                                                                      ja ? Wt + w.jQ : nullptr, ws.Jf, ja ? ws.xqj : nullptr);
+    coevo_embed_kernel<<<cdiv((long long)nj * 16, 256), 256, 0, st>>>(joints, nj, J, W.f + w.jprojw, W.f + w.jprojb, W.f + w.jpos,
+                                                                      ja ? W.f + w.jQ : nullptr, ws.Jf, ws.Jf_s, ja ? ws.xqj : nullptr);
     CKL();
-    coevo_embed_kernel<<<cdiv((long long)nv * 16, 256), 256, 0, st>>>(verts_in, nv, Vd, Wt + w.vprojw, Wt + w.vprojb, Wt + w.vpos,
-                                                                      Wt + w.vQ, ja ? ws.Vf : nullptr, ws.xqv);
+    coevo_embed_kernel<<<cdiv((long long)nv * 16, 256), 256, 0, st>>>(verts_in, nv, Vd, W.f + w.vprojw, W.f + w.vprojb, W.f + w.vpos, W.f + w.vQ,
+                                                                      ja ? ws.Vf : nullptr, ja ? ws.Vf_s : NO_SPLIT, ws.xqv);
     CKL();
     // keys: proj_j2v(Jf) + j2v_K ; proj_v2j(Vf) + v2j_K  — both from the PRE-update features (:183-184)
-    RET(linear(ws.Jf, 64, Wt + w.j2vw, 64, Wt + w.j2vb, ws.xkj, 64, nj, 64, 64, st, 0, nullptr, Wt + w.j2vK, J));
-    if (ja) RET(linear(ws.Vf, 64, Wt + w.v2jw, 64, Wt + w.v2jb, ws.xkv, 64, nv, 64, 64, st, 0, nullptr, Wt + w.v2jK, Vd));
+    RET(proj64(ws.Jf_s, nj, W, w.j2vw, w.j2vb, ws.xkj, st, W.f + w.j2vK, J));
+    if (ja) RET(proj64(ws.Vf_s, nv, W, w.v2jw, w.v2jb, ws.xkv, st, W.f + w.v2jK, Vd));
 
     // ---- vertex cross-attention block: q = vertices (431), k/v = joints (J); 2 heads x 32 ----
-    RET(adaln(ws.xqv, B, Vd, gb, w.vca.sq, ws.tA, st));
-    RET(linear(ws.tA, 64, Wt + w.vca.wq, 64, Wt + w.vca.bq, ws.Qv, 64, nv, 64, 64, st));
-    RET(adaln(ws.xkj, B, J, gb, w.vca.sk, ws.tJ, st));
-    RET(linear(ws.tJ, 64, Wt + w.vca.wk, 64, Wt + w.vca.bk, ws.Kj, 64, nj, 64, 64, st));
-    RET(adaln(ws.Jf, B, J, gb, w.vca.sv, ws.tJ, st));
-    RET(linear(ws.tJ, 64, Wt + w.vca.wv, 64, Wt + w.vca.bv, ws.Vj, 64, nj, 64, 64, st));
-    RET(launch_attn(32, ws.Qv, addr_plain(Vd, 64), ws.Kj, ws.Vj, addr_plain(J, 64), ws.att_d, addr_plain(Vd, 64), B, 2, Vd, J, st));
-    RET(attn_tail(Wt, w.vca.wp, w.vca.bp, w.vca.s2, w.vca.fc1w, w.vca.fc1b, w.vca.fc2w, w.vca.fc2b, ws.xqv, ws.att_d, ws.tA,
-                  ws.hid_d, gb, B, Vd, st));
+    RET(adaln(ws.xqv, B, Vd, gb, w.vca.sq, ws.tA_s, st));
+    RET(proj64(ws.tA_s, nv, W, w.vca.wq, w.vca.bq, ws.Qv, st));
+    RET(adaln(ws.xkj, B, J, gb, w.vca.sk, ws.tJ_s, st));
+    RET(proj64(ws.tJ_s, nj, W, w.vca.wk, w.vca.bk, ws.Kj, st));
+    RET(adaln(ws.Jf, B, J, gb, w.vca.sv, ws.tJ_s, st));
+    RET(proj64(ws.tJ_s, nj, W, w.vca.wv, w.vca.bv, ws.Vj, st));
+    RET(launch_attn(32, ws.Qv, addr_plain(Vd, 64), ws.Kj, ws.Vj, addr_plain(J, 64), nullptr, ws.att_ds, addr_plain(Vd, 64), B, 2, Vd, J, st));
+    RET(attn_tail(W, w.vca.wp, w.vca.bp, w.vca.s2, w.vca.fc1w, w.vca.fc1b, w.vca.fc2w, w.vca.fc2b, ws.xqv, ws.att_ds, ws.tA_s, ws.hid_ds, gb, B, Vd, st));
 
     if (ja) {
         // ---- joint cross-attention block: q = joints (J), k/v = vertices (431); 8 heads x 8 ----
-        RET(adaln(ws.xqj, B, J, gb, w.jca.sq, ws.tJ, st));
-        RET(linear(ws.tJ, 64, Wt + w.jca.wq, 64, Wt + w.jca.bq, ws.Qj, 64, nj, 64, 64, st));
-        RET(adaln(ws.xkv, B, Vd, gb, w.jca.sk, ws.tA, st));
-        RET(linear(ws.tA, 64, Wt + w.jca.wk, 64, Wt + w.jca.bk, ws.Kv, 64, nv, 64, 64, st));
-        RET(adaln(ws.Vf, B, Vd, gb, w.jca.sv, ws.tA2, st));
-        RET(linear(ws.tA2, 64, Wt + w.jca.wv, 64, Wt + w.jca.bv, ws.Vv, 64, nv, 64, 64, st));
-        RET(launch_attn(8, ws.Qj, addr_plain(J, 64), ws.Kv, ws.Vv, addr_plain(Vd, 64), ws.attj, addr_plain(J, 64), B, 8, J, Vd, st));
-        RET(attn_tail(Wt, w.jca.wp, w.jca.bp, w.jca.s2, w.jca.fc1w, w.jca.fc1b, w.jca.fc2w, w.jca.fc2b, ws.xqj, ws.attj, ws.tJ,
-                      ws.hidj, gb, B, J, st));
+        RET(adaln(ws.xqj, B, J, gb, w.jca.sq, ws.tJ_s, st));
+        RET(proj64(ws.tJ_s, nj, W, w.jca.wq, w.jca.bq, ws.Qj, st));
+        RET(adaln(ws.xkv, B, Vd, gb, w.jca.sk, ws.tA_s, st));
+        RET(proj64(ws.tA_s, nv, W, w.jca.wk, w.jca.bk, ws.Kv, st));
+        RET(adaln(ws.Vf, B, Vd, gb, w.jca.sv, ws.tA2_s, st));
+        RET(proj64(ws.tA2_s, nv, W, w.jca.wv, w.jca.bv, ws.Vv, st));
+        RET(launch_attn(8, ws.Qj, addr_plain(J, 64), ws.Kv, ws.Vv, addr_plain(Vd, 64), nullptr, ws.attj_s, addr_plain(J, 64), B, 8, J, Vd, st));
+        RET(attn_tail(W, w.jca.wp, w.jca.bp, w.jca.s2, w.jca.fc1w, w.jca.fc1b, w.jca.fc2w, w.jca.fc2b, ws.xqj, ws.attj_s, ws.tJ_s, ws.hidj_s, gb, B, J, st));
         // ---- joint self-attention block ----
-        RET(adaln(ws.xqj, B, J, gb, w.jsa.s1, ws.tJ, st));
-        RET(linear(ws.tJ, 64, Wt + w.jsa.qkvw, 64, Wt + w.jsa.qkvb, ws.qkvj, 192, nj, 192, 64, st));
-        RET(launch_attn(8, ws.qkvj, addr_plain(J, 192), ws.qkvj + 64, ws.qkvj + 128, addr_plain(J, 192), ws.attj, addr_plain(J, 64), B, 8, J, J, st));
-        RET(attn_tail(Wt, w.jsa.wp, w.jsa.bp, w.jsa.s2, w.jsa.fc1w, w.jsa.fc1b, w.jsa.fc2w, w.jsa.fc2b, ws.xqj, ws.attj, ws.tJ,
-                      ws.hidj, gb, B, J, st));
-        feat2coor_kernel<<<cdiv(nj, 8), 256, 0, st>>>(ws.xqj, nj, Wt + w.jf2cw, Wt + w.jf2cb, joints, joints_out);
+        RET(adaln(ws.xqj, B, J, gb, w.jsa.s1, ws.tJ_s, st));
+        RET(proj64(ws.tJ_s, nj, W, w.jsa.qkvw, w.jsa.qkvb, ws.qkvj, st, nullptr, 1, 192));
+        RET(launch_attn(8, ws.qkvj, addr_plain(J, 192), ws.qkvj + 64, ws.qkvj + 128, addr_plain(J, 192), nullptr, ws.attj_s, addr_plain(J, 64), B, 8, J, J, st));
+        RET(attn_tail(W, w.jsa.wp, w.jsa.bp, w.jsa.s2, w.jsa.fc1w, w.jsa.fc1b, w.jsa.fc2w, w.jsa.fc2b, ws.xqj, ws.attj_s, ws.tJ_s, ws.hidj_s, gb, B, J, st));
+        feat2coor_kernel<<<cdiv(nj, 8), 256, 0, st>>>(ws.xqj, nj, W.f + w.jf2cw, W.f + w.jf2cb, joints, joints_out);
         CKL();
     }
 
     // ---- vertex self-attention block: 431 x 431, 2 heads x 32 ----
-    RET(adaln(ws.xqv, B, Vd, gb, w.vsa.s1, ws.tA, st));
-    RET(linear(ws.tA, 64, Wt + w.vsa.qkvw, 64, Wt + w.vsa.qkvb, ws.qkv_d, 192, nv, 192, 64, st));
-    RET(launch_attn(32, ws.qkv_d, addr_plain(Vd, 192), ws.qkv_d + 64, ws.qkv_d + 128, addr_plain(Vd, 192), ws.att_d, addr_plain(Vd, 64), B, 2, Vd, Vd, st));
-    RET(attn_tail(Wt, w.vsa.wp, w.vsa.bp, w.vsa.s2, w.vsa.fc1w, w.vsa.fc1b, w.vsa.fc2w, w.vsa.fc2b, ws.xqv, ws.att_d, ws.tA,
-                  ws.hid_d, gb, B, Vd, st));
-    feat2coor_kernel<<<cdiv(nv, 8), 256, 0, st>>>(ws.xqv, nv, Wt + w.vf2cw, Wt + w.vf2cb, verts_in, verts_out);
+    RET(adaln(ws.xqv, B, Vd, gb, w.vsa.s1, ws.tA_s, st));
+    RET(proj64(ws.tA_s, nv, W, w.vsa.qkvw, w.vsa.qkvb, ws.qkv_d, st, nullptr, 1, 192));
+    RET(launch_attn(32, ws.qkv_d, addr_plain(Vd, 192), ws.qkv_d + 64, ws.qkv_d + 128, addr_plain(Vd, 192), nullptr, ws.att_ds, addr_plain(Vd, 64), B, 2, Vd, Vd, st));
+    RET(attn_tail(W, w.vsa.wp, w.vsa.bp, w.vsa.s2, w.vsa.fc1w, w.vsa.fc1b, w.vsa.fc2w, w.vsa.fc2b, ws.xqv, ws.att_ds, ws.tA_s, ws.hid_ds, gb, B, Vd, st));
+    feat2coor_kernel<<<cdiv(nv, 8), 256, 0, st>>>(ws.xqv, nv, W.f + w.vf2cw, W.f + w.vf2cb, verts_in, verts_out);
     CKL();
     return 0;
 }
@@ -366,42 +438,45 @@ int coevo_block(const Layout& L, const float* Wt, int k, const float* joints, co
 // ---------------------------------------------------------------------------------------------------
 // a9 tail: upsample_conv + linear_cur residual
 // ---------------------------------------------------------------------------------------------------
-int mesh_epilogue(const Layout& L, const float* Wt, const float* verts3, const float* g, int B, float* mesh, const Workspace& ws,
-                  cudaStream_t st) {
+int mesh_epilogue(const Layout& L, const Weights& W, const float* verts3, const float* g, int B, float* mesh, const Workspace& ws, cudaStream_t st) {
     const pmce_dims_t& d = L.d;
     const int Vd = d.num_vert_ds, V = d.num_vert, F = d.feat_dim, ldk = L.ups_ld;
-    upsample_im2col_kernel<<<cdiv((long long)B * 3 * ldk, 256), 256, 0, st>>>(verts3, B, Vd, ldk, ws.im2col);
+    upsample_im2col_kernel<<<cdiv((long long)B * 3 * ldk, 256), 256, 0, st>>>(verts3, B, Vd, ldk, nullptr, ws.im2col_s);
     CKL();
     {   // mesh[b,o,l] = b_up[o] + sum_{c,k} W_up[o,c,k] verts3[b,c,l+k-1]
-        GemmEpi e = gemm_epi_plain(0);
-        e.bias = Wt + L.ups_b;
-        e.rmap.div = 3; e.rmap.s0 = (long long)V * 3; e.rmap.s1 = 1;
-        e.cmap.div = 1; e.cmap.s0 = 3; e.cmap.s1 = 0;
-        CKG(launch_gemm_tn(ws.im2col, ldk, Wt + L.ups_w, ldk, mesh, B * 3, V, ldk, e, st));
+        EpiOpt o; o.bias = W.f + L.ups_b; o.out = mesh; o.mapped = true;
+        o.rmap.div = 3; o.rmap.s0 = (long long)V * 3; o.rmap.s1 = 1;
+        o.cmap.div = 1; o.cmap.s0 = 3; o.cmap.s1 = 0;
+        RET(linear_tc(ws.im2col_s, ldk, B * 3, ldk, W, L.ups_w, ldk, V, o, st));
     }
+    RET(split_rows(g, B, F, F, true, ws.gr_s, F, st));     // relu(y_mid)
     {   // mesh[b,o,l] += W_cur{l+1} relu(g[b]) + b_cur{l+1}
-        GemmEpi e = gemm_epi_plain(0);
-        e.bias = Wt + L.lc_b; e.a_relu = 1; e.resid = mesh;
-        e.rmap.div = 1; e.rmap.s0 = (long long)V * 3; e.rmap.s1 = 0;
-        e.cmap.div = V; e.cmap.s0 = 1; e.cmap.s1 = 3;
-        CKG(launch_gemm_tn(g, F, Wt + L.lc_w, F, mesh, B, 3 * V, F, e, st));
+        EpiOpt o; o.bias = W.f + L.lc_b; o.out = mesh; o.resid = mesh; o.mapped = true;
+        o.rmap.div = 1; o.rmap.s0 = (long long)V * 3; o.rmap.s1 = 0;
+        o.cmap.div = V; o.cmap.s0 = 1; o.cmap.s1 = 3;
+        RET(linear_tc(ws.gr_s, F, B, F, W, L.lc_w, F, 3 * V, o, st));
     }
     return 0;
 }
 
-int decoder(const Layout& L, const float* Wt, const float* joints, const float* img_feat, const int32_t* vj, int B, float* cam_pose,
-            float* cam_mesh, float* verts0_out, const Workspace& ws, cudaStream_t st) {
+int prepare_feat(const Layout& L, const float* img_feat, int B, const Workspace& ws, cudaStream_t st) {
+    const int F = L.d.feat_dim, T = L.d.seqlen;
+    return split_rows(img_feat, B * T, F, F, false, ws.feat_s, F, st);
+}
+
+int decoder(const Layout& L, const Weights& W, const float* joints, const int32_t* vj, int B, float* cam_pose, float* cam_mesh,
+            float* verts0_out, const Workspace& ws, cudaStream_t st) {
     const pmce_dims_t& d = L.d;
     const int J = d.num_joint, Vd = d.num_vert_ds;
-    RET(gru_mid(L, Wt, img_feat, B, ws.g, ws, st));
-    RET(adaln_gammabeta(L, Wt, ws.g, B, ws.gb, st));
+    RET(gru_mid(L, W, B, ws.g, ws, st));
+    RET(adaln_gammabeta(L, W, ws.g, B, ws.gb, ws.g_s, st));
     float* v0 = verts0_out ? verts0_out : ws.verts[2];
     gather_verts_kernel<<<cdiv((long long)B * Vd * 3, 256), 256, 0, st>>>(joints, vj, B, J, Vd, v0);
     CKL();
-    RET(coevo_block(L, Wt, 0, joints, v0, ws.gb, B, nullptr, ws.verts[0], ws, st));
-    RET(coevo_block(L, Wt, 1, joints, ws.verts[0], ws.gb, B, nullptr, ws.verts[1], ws, st));
-    RET(coevo_block(L, Wt, 2, joints, ws.verts[1], ws.gb, B, cam_pose, ws.verts[0], ws, st));
-    RET(mesh_epilogue(L, Wt, ws.verts[0], ws.g, B, cam_mesh, ws, st));
+    RET(coevo_block(L, W, 0, joints, v0, ws.gb, B, nullptr, ws.verts[0], ws, st));
+    RET(coevo_block(L, W, 1, joints, ws.verts[0], ws.gb, B, nullptr, ws.verts[1], ws, st));
+    RET(coevo_block(L, W, 2, joints, ws.verts[1], ws.gb, B, cam_pose, ws.verts[0], ws, st));
+    RET(mesh_epilogue(L, W, ws.verts[0], ws.g, B, cam_mesh, ws, st));
     return 0;
 }
 
@@ -414,22 +489,30 @@ int decoder(const Layout& L, const float* Wt, const float* joints, const float* 
     const Layout* Lp = pmce_get_layout(dims);          \
     if (!Lp) return 1;                                 \
     const Layout& L = *Lp;                             \
-    const float* Wt = (const float*)weights;           \
-    if (!Wt) { pmce_set_error("weights is NULL"); return 2; } \
+    if (!weights) { pmce_set_error("weights is NULL"); return 2; } \
+    const Weights W = weights_view(L, weights);        \
     cudaStream_t st = (cudaStream_t)stream;
+
+extern "C" size_t pmce_weights_bytes(const pmce_dims_t* dims) {
+    const Layout* L = pmce_get_layout(dims);
+    return L ? L->total_floats * 8 : 0;     // fp32 + bf16 hi + bf16 lo
+}
 
 extern "C" size_t pmce_workspace_bytes(const pmce_dims_t* dims, int B) {
     const Layout* Lp = pmce_get_layout(dims);
     if (!Lp || B < 1) return 0;
-    return carve(*dims, B, nullptr).floats * sizeof(float);
+    return carve(*dims, B, nullptr).bytes;
 }
 
 extern "C" int pmce_pack_weights(const pmce_dims_t* dims, void* weights, void* stream) {
-    (void)stream;
     const Layout* Lp = pmce_get_layout(dims);
     if (!Lp) return 1;
     if (!weights) { pmce_set_error("weights is NULL"); return 2; }
-    return 0;
+    const Weights W = weights_view(*Lp, weights);
+    const size_t n = Lp->total_floats;     // multiple of 64
+    SplitOut o{const_cast<bf16*>(W.hi), const_cast<bf16*>(W.lo)};
+    // split the whole fp32 region in one pass, viewed as [n/64, 64]
+    return split_rows(W.f, (int)(n / 64), 64, 64, false, o, 64, (cudaStream_t)stream);
 }
 
 extern "C" int pmce_lifter_forward(const pmce_dims_t* dims, const void* weights, const float* pose2d, const float* img_feat, int B,
@@ -437,7 +520,8 @@ extern "C" int pmce_lifter_forward(const pmce_dims_t* dims, const void* weights,
     GET_LAYOUT();
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
-    return lifter(L, Wt, pose2d, img_feat, B, pose3d, ws, st);
+    RET(prepare_feat(L, img_feat, B, ws, st));
+    return lifter(L, W, pose2d, B, pose3d, ws, st);
 }
 
 extern "C" int pmce_gru_mid(const pmce_dims_t* dims, const void* weights, const float* img_feat, int B, float* g, void* workspace,
@@ -445,13 +529,16 @@ extern "C" int pmce_gru_mid(const pmce_dims_t* dims, const void* weights, const 
     GET_LAYOUT();
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
-    return gru_mid(L, Wt, img_feat, B, g, ws, st);
+    RET(prepare_feat(L, img_feat, B, ws, st));
+    return gru_mid(L, W, B, g, ws, st);
 }
 
-extern "C" int pmce_adaln_gammabeta(const pmce_dims_t* dims, const void* weights, const float* g, int B, float* gb, void* stream) {
+extern "C" int pmce_adaln_gammabeta(const pmce_dims_t* dims, const void* weights, const float* g, int B, float* gb, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
     GET_LAYOUT();
-    if (B < 1) { pmce_set_error("batch size %d < 1", B); return 2; }
-    return adaln_gammabeta(L, Wt, g, B, gb, st);
+    Workspace ws;
+    RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
+    return adaln_gammabeta(L, W, g, B, gb, ws.g_s, st);
 }
 
 extern "C" int pmce_coevo_block(const pmce_dims_t* dims, const void* weights, int block, const float* joints, const float* verts_in,
@@ -461,7 +548,7 @@ extern "C" int pmce_coevo_block(const pmce_dims_t* dims, const void* weights, in
     if (block < 1 || block > 3) { pmce_set_error("block must be 1..3 (got %d)", block); return 2; }
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
-    return coevo_block(L, Wt, block - 1, joints, verts_in, gb, B, joints_out, verts_out, ws, st);
+    return coevo_block(L, W, block - 1, joints, verts_in, gb, B, joints_out, verts_out, ws, st);
 }
 
 extern "C" int pmce_mesh_epilogue(const pmce_dims_t* dims, const void* weights, const float* verts3, const float* g, int B,
@@ -469,7 +556,7 @@ extern "C" int pmce_mesh_epilogue(const pmce_dims_t* dims, const void* weights, 
     GET_LAYOUT();
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
-    return mesh_epilogue(L, Wt, verts3, g, B, cam_mesh, ws, st);
+    return mesh_epilogue(L, W, verts3, g, B, cam_mesh, ws, st);
 }
 
 extern "C" int pmce_decoder_forward(const pmce_dims_t* dims, const void* weights, const float* joints, const float* img_feat,
@@ -478,7 +565,8 @@ extern "C" int pmce_decoder_forward(const pmce_dims_t* dims, const void* weights
     GET_LAYOUT();
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
-    return decoder(L, Wt, joints, img_feat, vj_relation, B, cam_pose, cam_mesh, verts0_out, ws, st);
+    RET(prepare_feat(L, img_feat, B, ws, st));
+    return decoder(L, W, joints, vj_relation, B, cam_pose, cam_mesh, verts0_out, ws, st);
 }
 
 extern "C" int pmce_forward(const pmce_dims_t* dims, const void* weights, const float* pose2d, const float* img_feat,
@@ -487,30 +575,31 @@ extern "C" int pmce_forward(const pmce_dims_t* dims, const void* weights, const 
     GET_LAYOUT();
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
-    RET(lifter(L, Wt, pose2d, img_feat, B, pose3d, ws, st));
-    return decoder(L, Wt, ws.joints_m, img_feat, vj_relation, B, cam_pose, cam_mesh, nullptr, ws, st);
+    RET(prepare_feat(L, img_feat, B, ws, st));
+    RET(lifter(L, W, pose2d, B, pose3d, ws, st));
+    return decoder(L, W, ws.joints_m, vj_relation, B, cam_pose, cam_mesh, nullptr, ws, st);
 }
 
 extern "C" size_t pmce_io_bytes(const pmce_dims_t* dims, int B) {
     if (!dims || B < 1) return 0;
     const size_t J = dims->num_joint, T = dims->seqlen, F = dims->feat_dim, V = dims->num_vert;
-    auto al = [](size_t n) { return (n + 63) / 64 * 64; };
-    return (al((size_t)B * T * J * 2) + al((size_t)B * T * F) + al((size_t)B * V * 3) + 2 * al((size_t)B * J * 3)) * sizeof(float);
+    auto al = [](size_t n) { return (n * 4 + 255) / 256 * 256; };
+    return al((size_t)B * T * J * 2) + al((size_t)B * T * F) + al((size_t)B * V * 3) + 2 * al((size_t)B * J * 3);
 }
 
 extern "C" int pmce_forward_host(const pmce_dims_t* dims, const void* weights, const float* h_pose2d, const float* h_img_feat,
                                  const int32_t* d_vj_relation, int B, float* h_cam_mesh, float* h_cam_pose, float* h_pose3d,
                                  void* d_io, void* workspace, size_t workspace_bytes, void* stream) {
-    GET_LAYOUT();
-    (void)L;
+    if (!dims) { pmce_set_error("dims is NULL"); return 2; }
     if (!d_io) { pmce_set_error("d_io is NULL"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
     const size_t J = dims->num_joint, T = dims->seqlen, F = dims->feat_dim, V = dims->num_vert;
-    Carver c{(float*)d_io, 0};
-    float* d_p2d = c.take((size_t)B * T * J * 2);
-    float* d_feat = c.take((size_t)B * T * F);
-    float* d_mesh = c.take((size_t)B * V * 3);
-    float* d_pose = c.take((size_t)B * J * 3);
-    float* d_p3d = c.take((size_t)B * J * 3);
+    Carver c{(char*)d_io, 0};
+    float* d_p2d = c.f32((size_t)B * T * J * 2);
+    float* d_feat = c.f32((size_t)B * T * F);
+    float* d_mesh = c.f32((size_t)B * V * 3);
+    float* d_pose = c.f32((size_t)B * J * 3);
+    float* d_p3d = c.f32((size_t)B * J * 3);
     CK(cudaMemcpyAsync(d_p2d, h_pose2d, (size_t)B * T * J * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_feat, h_img_feat, (size_t)B * T * F * sizeof(float), cudaMemcpyHostToDevice, st));
     RET(pmce_forward(dims, weights, d_p2d, d_feat, d_vj_relation, B, d_mesh, d_pose, d_p3d, workspace, workspace_bytes, stream));
@@ -532,12 +621,15 @@ extern "C" int pmce_jregress(const int32_t* row_ptr, const int32_t* cols, const 
 extern "C" int pmce_linear(const float* x, const float* weight, const float* bias, int M, int N, int K, int act, float* out,
                            void* stream) {
     if (!x || !weight || !out || M < 1 || N < 1 || K < 4 || (K & 3)) { pmce_set_error("pmce_linear: bad argument (K must be a multiple of 4)"); return 2; }
-    return linear(x, K, weight, K, bias, out, N, M, N, K, (cudaStream_t)stream, act);
+    GemmEpi e = gemm_epi_plain(N);
+    e.bias = bias; e.act = act;
+    CKG(launch_gemm_tn(x, K, weight, K, out, M, N, K, e, (cudaStream_t)stream));
+    return 0;
 }
 
 extern "C" size_t pmce_linear_tc_scratch_bytes(int M, int N, int K) {
-    auto al = [](size_t n) { return (n + 127) / 128 * 128; };
-    return 2 * (al((size_t)M * K) + al((size_t)N * K)) * sizeof(__nv_bfloat16);
+    auto al = [](size_t n) { return (n * 2 + 255) / 256 * 256; };
+    return 2 * (al((size_t)M * K) + al((size_t)N * K));
 }
 
 extern "C" int pmce_linear_tc(const float* x, const float* weight, const float* bias, int M, int N, int K, int act, float* out,
@@ -545,33 +637,28 @@ extern "C" int pmce_linear_tc(const float* x, const float* weight, const float* 
     if (!x || !weight || !out || !scratch || M < 1 || N < 1 || K < 8 || (K & 7)) { pmce_set_error("pmce_linear_tc: bad argument (K must be a multiple of 8)"); return 2; }
     if (scratch_bytes < pmce_linear_tc_scratch_bytes(M, N, K)) { pmce_set_error("pmce_linear_tc: scratch too small"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
-    auto al = [](size_t n) { return (n + 127) / 128 * 128; };
-    __nv_bfloat16* a_hi = (__nv_bfloat16*)scratch;
-    __nv_bfloat16* a_lo = a_hi + al((size_t)M * K);
-    __nv_bfloat16* w_hi = a_lo + al((size_t)M * K);
-    __nv_bfloat16* w_lo = w_hi + al((size_t)N * K);
-    split_rows_kernel<<<cdiv((long long)M * (K / 4), 256), 256, 0, st>>>(x, M, K, K, 0, a_hi, a_lo, K);
-    CKL();
-    split_rows_kernel<<<cdiv((long long)N * (K / 4), 256), 256, 0, st>>>(weight, N, K, K, 0, w_hi, w_lo, K);
-    CKL();
-    TcOperand A{a_hi, a_lo, M, K, K}, W{w_hi, w_lo, N, K, K};
+    Carver c{(char*)scratch, 0};
+    SplitOut a = c.split((size_t)M * K), w = c.split((size_t)N * K);
+    RET(split_rows(x, M, K, K, false, a, K, st));
+    RET(split_rows(weight, N, K, K, false, w, K, st));
+    TcOperand A{a.hi, a.lo, M, K, K}, Wm{w.hi, w.lo, N, K, K};
     TcEpi e;
     memset(&e, 0, sizeof(e));
     e.bias = bias; e.act = act; e.out_f32 = out; e.ld_out = N; e.rowadd_period = 1;
-    int rc = launch_linear_tc(A, W, e, st);
     count_launch();
+    const int rc = launch_linear_tc(A, Wm, e, st);
     if (rc) { pmce_set_error("pmce_linear_tc: launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
     return 0;
 }
 
 // ---- SMPL LBS --------------------------------------------------------------------------------------
 #define SMPL_V 6890
-#define SMPL_LDK 220
+#define SMPL_LDK 224
 extern "C" int smpl_blend_ld(void) { return SMPL_LDK; }
 extern "C" size_t smpl_workspace_bytes(int B) {
     if (B < 1) return 0;
-    auto al = [](size_t n) { return (n + 63) / 64 * 64; };
-    return (al((size_t)B * SMPL_LDK) + al((size_t)B * 288) + al((size_t)B * SMPL_V * 3)) * sizeof(float);
+    auto al = [](size_t n) { return (n * 4 + 255) / 256 * 256; };
+    return al((size_t)B * SMPL_LDK) + al((size_t)B * 288) + al((size_t)B * SMPL_V * 3);
 }
 
 extern "C" int smpl_lbs_forward(const float* blend, const float* v_template, const float* j_template, const float* j_shapedirs,
@@ -584,14 +671,16 @@ extern "C" int smpl_lbs_forward(const float* blend, const float* v_template, con
     if (B < 1) { pmce_set_error("batch size %d < 1", B); return 2; }
     if (!workspace || workspace_bytes < smpl_workspace_bytes(B)) { pmce_set_error("smpl workspace too small"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
-    Carver c{(float*)workspace, 0};
-    float* coef = c.take((size_t)B * SMPL_LDK);
-    float* Amat = c.take((size_t)B * 288);
-    float* vposed = c.take((size_t)B * SMPL_V * 3);
+    Carver c{(char*)workspace, 0};
+    float* coef = c.f32((size_t)B * SMPL_LDK);
+    float* Amat = c.f32((size_t)B * 288);
+    float* vposed = c.f32((size_t)B * SMPL_V * 3);
     smpl_pose_kernel<<<B, 32, 0, st>>>(pose, betas, trans, j_template, j_shapedirs, parents, B, SMPL_LDK, coef, Amat, joints);
     CKL();
-    // v_posed[b, v*3+c] = v_template + [shapedirs | posedirs] . [betas | pose_map]   (smpl_layer.py:93-99)
-    RET(linear(coef, SMPL_LDK, blend, SMPL_LDK, v_template, vposed, SMPL_V * 3, B, SMPL_V * 3, SMPL_LDK, st));
+    // v_posed[b, v*3+c] = v_template + [shapedirs | posedirs] . [betas | pose_map]   (smpl_layer.py:93-99); exact fp32 GEMM
+    GemmEpi e = gemm_epi_plain(SMPL_V * 3);
+    e.bias = v_template;
+    CKG(launch_gemm_tn(coef, SMPL_LDK, blend, SMPL_LDK, vposed, B, SMPL_V * 3, SMPL_LDK, e, st));
     dim3 grid(cdiv(SMPL_V, 256), B);
     smpl_skin_kernel<<<grid, 256, 0, st>>>(vposed, Amat, skin_weights, trans, SMPL_V, verts);
     CKL();

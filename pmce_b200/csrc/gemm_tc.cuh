@@ -19,6 +19,9 @@ struct TcEpi {
     __nv_bfloat16* out_hi;  // split output [M, ld_split] or null (both hi and lo, or neither)
     __nv_bfloat16* out_lo;
     int ld_out, ld_split;
+    int vec_ok;             // set by the launcher: all row strides / bases allow 16-byte vector access
+    int mapped;             // out_f32 / resid are addressed as rmap(row) + cmap(col) instead of row*ld + col
+    RowMap rmap, cmap;
 };
 
 constexpr int TC_BM = 128;
@@ -120,7 +123,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             float f[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            const bool full = (col0 + 32 <= N);
+            const bool full = (col0 + 32 <= N) && e.vec_ok;
             if (full) {
                 if (e.bias) {
 #pragma unroll
@@ -163,8 +166,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if (e.bias) x += e.bias[col];
                     if (e.act == 1) x = gelu_erf(x);
                     if (radd) x += radd[col];
-                    if (e.resid) x += e.resid[(size_t)row * e.ld_resid + col];
-                    if (e.out_f32) e.out_f32[(size_t)row * e.ld_out + col] = x;
+                    if (e.mapped) {
+                        const long long off = e.rmap(row) + e.cmap(col);
+                        if (e.resid) x += e.resid[off];
+                        if (e.out_f32) e.out_f32[off] = x;
+                    } else {
+                        if (e.resid) x += e.resid[(size_t)row * e.ld_resid + col];
+                        if (e.out_f32) e.out_f32[(size_t)row * e.ld_out + col] = x;
+                    }
                     if (e.out_hi) {
                         __nv_bfloat16 h, l;
                         tc::split_bf16(x, h, l);
@@ -243,7 +252,11 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
         configured = true;
     }
     dim3 grid((W.rows + BN - 1) / BN, (A.rows + TC_BM - 1) / TC_BM);
-    linear_tc_kernel<BN><<<grid, 192, TcCfg<BN>::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, A.rows, W.rows, A.cols, e);
+    TcEpi ee = e;
+    auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    ee.vec_ok = !e.mapped && (W.rows % 4 == 0 || !e.rowadd) && a16(e.bias) && a16(e.rowadd) && (!e.resid || (a16(e.resid) && e.ld_resid % 4 == 0)) &&
+                (!e.out_f32 || (a16(e.out_f32) && e.ld_out % 4 == 0)) && (!e.out_hi || (a16(e.out_hi) && a16(e.out_lo) && e.ld_split % 8 == 0));
+    linear_tc_kernel<BN><<<grid, 192, TcCfg<BN>::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, A.rows, W.rows, A.cols, ee);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 

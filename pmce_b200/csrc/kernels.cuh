@@ -1,6 +1,25 @@
 // Row-wise / attention / recurrence kernels of the PMCE hot path (fp32, CUDA cores, warp-shuffle reductions).
 #pragma once
 #include "common.cuh"
+#include "tc_common.cuh"
+
+// Split-bf16 activation pair: tensors that feed a tensor-core GEMM are written as hi/lo bf16.
+struct SplitOut {
+    __nv_bfloat16* hi; __nv_bfloat16* lo;
+};
+__device__ __forceinline__ void store_split4(const SplitOut& o, size_t idx, float4 v) {
+    uint2 h, l;
+    tc::split_bf16x2(v.x, v.y, h.x, l.x);
+    tc::split_bf16x2(v.z, v.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(o.hi + idx) = h;
+    *reinterpret_cast<uint2*>(o.lo + idx) = l;
+}
+__device__ __forceinline__ void store_split2(const SplitOut& o, size_t idx, float a, float b) {
+    uint32_t h, l;
+    tc::split_bf16x2(a, b, h, l);
+    *reinterpret_cast<uint32_t*>(o.hi + idx) = h;
+    *reinterpret_cast<uint32_t*>(o.lo + idx) = l;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // LayerNorm over C features, one warp per row, C % 128 == 0, C <= 1024.
@@ -42,7 +61,7 @@ __device__ __forceinline__ void ln_inreg(float4 (&v)[MAXV], int nv, int C, const
 
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, int nrows, int C, LnParams a, int has_a, const float* __restrict__ pos,
-               int pos_div, int pos_mod, float* __restrict__ out1, LnParams bparm, float* __restrict__ out2) {
+               int pos_div, int pos_mod, float* __restrict__ out1, LnParams bparm, float* __restrict__ out2, SplitOut out2s) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= nrows) return;
@@ -69,12 +88,15 @@ ln_rows_kernel(const float* __restrict__ x, int nrows, int C, LnParams a, int ha
         for (int i = 0; i < MAXV; ++i)
             if (i < nv) st4(o + (i * 32 + lane) * 4, v[i]);
     }
-    if (out2) {
+    if (out2 || out2s.hi) {
         ln_inreg<MAXV>(v, nv, C, bparm.w, bparm.b, bparm.eps, lane);
-        float* o = out2 + (size_t)row * C;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i)
-            if (i < nv) st4(o + (i * 32 + lane) * 4, v[i]);
+            if (i < nv) {
+                const size_t idx = (size_t)row * C + (i * 32 + lane) * 4;
+                if (out2) st4(out2 + idx, v[i]);
+                if (out2s.hi) store_split4(out2s, idx, v[i]);
+            }
     }
 }
 
@@ -86,7 +108,7 @@ ln_rows_kernel(const float* __restrict__ x, int nrows, int C, LnParams a, int ha
 __global__ void __launch_bounds__(256)
 lifter_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ imgemb, const float* __restrict__ wje,
                     const float* __restrict__ bje, const float* __restrict__ spos, int ntok, int J, int C, LnParams n1,
-                    float* __restrict__ x0, float* __restrict__ xn) {
+                    float* __restrict__ x0, float* __restrict__ xn, SplitOut xns) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= ntok) return;
@@ -115,7 +137,11 @@ lifter_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ 
     ln_inreg<MAXV>(v, nv, C, n1.w, n1.b, n1.eps, lane);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
-        if (i < nv) st4(xn + (size_t)row * C + (i * 32 + lane) * 4, v[i]);
+        if (i < nv) {
+            const size_t idx = (size_t)row * C + (i * 32 + lane) * 4;
+            if (xn) st4(xn + idx, v[i]);
+            if (xns.hi) store_split4(xns, idx, v[i]);
+        }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -184,7 +210,7 @@ struct AttnAddr {
 template <int D>
 __global__ void __launch_bounds__(128)
 attn_kernel(const float* __restrict__ Q, AttnAddr aq, const float* __restrict__ K, const float* __restrict__ V, AttnAddr akv,
-            float* __restrict__ O, AttnAddr ao, int N1, int N2, float scale) {
+            float* __restrict__ O, SplitOut Os, AttnAddr ao, int N1, int N2, float scale) {
     extern __shared__ __align__(16) float smem[];
     float* Ks = smem;                       // [N2][D]
     float* Vs = smem + (size_t)N2 * D;      // [N2][D]
@@ -236,9 +262,13 @@ attn_kernel(const float* __restrict__ Q, AttnAddr aq, const float* __restrict__ 
         }
     }
     const float inv = 1.0f / l;
-    float* op = O + (size_t)(ao.seq(s) + (long long)qi * ao.tok) * ao.ld + h * D;
+    const size_t obase = (size_t)(ao.seq(s) + (long long)qi * ao.tok) * ao.ld + h * D;
 #pragma unroll
-    for (int c = 0; c < D; c += 4) st4(op + c, make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv));
+    for (int c = 0; c < D; c += 4) {
+        const float4 r = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+        if (O) st4(O + obase + c, r);
+        if (Os.hi) store_split4(Os, obase + c, r);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -247,7 +277,7 @@ attn_kernel(const float* __restrict__ Q, AttnAddr aq, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 adaln_apply_kernel(const float* __restrict__ x, int nrows, int rows_per_batch, const float* __restrict__ gb, int gb_ld,
-                   int slot, float eps, float* __restrict__ y) {
+                   int slot, float eps, float* __restrict__ y, SplitOut ys) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= nrows) return;
@@ -263,7 +293,8 @@ adaln_apply_kernel(const float* __restrict__ x, int nrows, int rows_per_batch, c
     float2 r;
     r.x = ga.x * dx * inv + be.x;
     r.y = ga.y * dy * inv + be.y;
-    *reinterpret_cast<float2*>(y + (size_t)row * 64 + lane * 2) = r;
+    if (y) *reinterpret_cast<float2*>(y + (size_t)row * 64 + lane * 2) = r;
+    if (ys.hi) store_split2(ys, (size_t)row * 64 + lane * 2, r.x, r.y);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -272,7 +303,7 @@ adaln_apply_kernel(const float* __restrict__ x, int nrows, int rows_per_batch, c
 // ------------------------------------------------------------------------------------------------------
 __global__ void coevo_embed_kernel(const float* __restrict__ coords, int nrows, int ntok, const float* __restrict__ w,
                                    const float* __restrict__ bias, const float* __restrict__ pos,
-                                   const float* __restrict__ qemb, float* __restrict__ out_f, float* __restrict__ out_q) {
+                                   const float* __restrict__ qemb, float* __restrict__ out_f, SplitOut out_fs, float* __restrict__ out_q) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nrows * 16) return;
     const int row = idx >> 4, c = (idx & 15) * 4;
@@ -285,6 +316,7 @@ __global__ void coevo_embed_kernel(const float* __restrict__ coords, int nrows, 
         f[u] = ((wr[0] * p0 + wr[1] * p1) + wr[2] * p2) + bias[c + u] + pos[(size_t)i * 64 + c + u];
     }
     if (out_f) st4(out_f + (size_t)row * 64 + c, make_float4(f[0], f[1], f[2], f[3]));
+    if (out_fs.hi) store_split4(out_fs, (size_t)row * 64 + c, make_float4(f[0], f[1], f[2], f[3]));
     if (out_q) {
         float4 qe = ld4(qemb + (size_t)i * 64 + c);
         st4(out_q + (size_t)row * 64 + c, make_float4(f[0] + qe.x, f[1] + qe.y, f[2] + qe.z, f[3] + qe.w));
@@ -319,7 +351,7 @@ __global__ void gather_verts_kernel(const float* __restrict__ joints, const int3
 
 // im2col for upsample_conv (Conv1d(431->6890,k=3,pad=1) over the xyz axis, CoevoDecoder.py:214,238):
 //   A[(b,l), c*3+k] = verts[b,c,l+k-1] (0 outside [0,3)), padded to ldk columns with zeros.
-__global__ void upsample_im2col_kernel(const float* __restrict__ verts, int B, int Vd, int ldk, float* __restrict__ A) {
+__global__ void upsample_im2col_kernel(const float* __restrict__ verts, int B, int Vd, int ldk, float* __restrict__ A, SplitOut As) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = B * 3 * ldk;
     if (idx >= total) return;
@@ -330,7 +362,8 @@ __global__ void upsample_im2col_kernel(const float* __restrict__ verts, int B, i
         const int src = l + k - 1;
         if (src >= 0 && src < 3) v = verts[((size_t)b * Vd + c) * 3 + src];
     }
-    A[idx] = v;
+    if (A) A[idx] = v;
+    if (As.hi) { __nv_bfloat16 h, l; tc::split_bf16(v, h, l); As.hi[idx] = h; As.lo[idx] = l; }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -344,8 +377,8 @@ struct GruDir {
     const float* whh;    // [3H, H]
     const float* bhh;    // [3H]
     float* hout;         // [B, H] (ld_o)
-    float* hout2;        // optional second destination (ld_o2) or nullptr
-    int ld_gi, ld_h, ld_o, ld_o2;
+    SplitOut hs;         // optional split copy of h' (ld_s) for the tensor-core consumers, or {nullptr,nullptr}
+    int ld_gi, ld_h, ld_o, ld_s;
 };
 
 __global__ void __launch_bounds__(256)
@@ -401,7 +434,7 @@ gru_step_kernel(GruDir d0, GruDir d1, int B, int H) {
         const float hp = d.hprev ? d.hprev[(size_t)row * d.ld_h + j] : 0.f;
         const float hn = (1.0f - z) * n + z * hp;
         d.hout[(size_t)row * d.ld_o + j] = hn;
-        if (d.hout2) d.hout2[(size_t)row * d.ld_o2 + j] = hn;
+        if (d.hs.hi) { __nv_bfloat16 hh, ll; tc::split_bf16(hn, hh, ll); d.hs.hi[(size_t)row * d.ld_s + j] = hh; d.hs.lo[(size_t)row * d.ld_s + j] = ll; }
     }
 }
 

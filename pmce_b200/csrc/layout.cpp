@@ -160,7 +160,7 @@ Layout* build_layout(const pmce_dims_t& d) {
     }
     if (next_slot != PMCE_ADALN_SLOTS) { delete L; pmce_set_error("internal: adaln slot count %d", next_slot); return nullptr; }
 
-    L->ups_ld = (int)((Vd * 3 + 3) / 4 * 4);
+    L->ups_ld = (int)((Vd * 3 + 7) / 8 * 8);   // K padded for 16-byte TMA row strides
     L->ups_w = b.add(p + "upsample_conv.weight", V, Vd * 3, L->ups_ld);
     L->ups_b = b.add(p + "upsample_conv.bias", 1, V);
 
@@ -217,11 +217,6 @@ const Layout* pmce_get_layout(const pmce_dims_t* dims) {
     if (!L) return nullptr;
     g_layouts.emplace_back(L);
     return L;
-}
-
-extern "C" size_t pmce_weights_bytes(const pmce_dims_t* dims) {
-    const Layout* L = pmce_get_layout(dims);
-    return L ? L->total_floats * sizeof(float) : 0;
 }
 
 extern "C" int pmce_weight_slot(const pmce_dims_t* dims, const char* name, pmce_slot_t* slot) {

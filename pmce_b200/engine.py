@@ -208,9 +208,10 @@ class Engine:
         B = g.shape[0]
         g = _require_cuda_f32(g, "g", (B, self.dims.feat_dim))
         with torch.cuda.device(g.device):
+            ws = self._workspace(B, g.device)
             gb = torch.empty(B, self.lib.pmce_adaln_slots(), 2, self.dims.coevo_dim, device=g.device)
-            check(self.lib.pmce_adaln_gammabeta(self._dp, _ptr(self.weights), _ptr(g), B, _ptr(gb), _stream()),
-                  "pmce_adaln_gammabeta")
+            check(self.lib.pmce_adaln_gammabeta(self._dp, _ptr(self.weights), _ptr(g), B, _ptr(gb), _ptr(ws), ws.numel(),
+                                                _stream()), "pmce_adaln_gammabeta")
         return gb
 
     def coevo_block(self, block, joints, verts, gb, want_joints=False):

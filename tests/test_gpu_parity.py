@@ -65,7 +65,7 @@ def test_lifter_vs_oracle(base):
 
 def test_gru_mid_vs_oracle(base):
     g = base["eng"].gru_mid(base["feat"].cuda())
-    assert _maxabs(g, base["inter"]["g"]) < 2e-5
+    assert _maxabs(g, base["inter"]["g"]) < 1e-4
 
 
 def test_adaln_gammabeta_vs_oracle(base):
@@ -83,7 +83,7 @@ def test_adaln_gammabeta_vs_oracle(base):
         p = "pose_mesh_coevo." + n
         gam = po._lin(sd, p + ".mlp_gamma", gref)
         bet = po._lin(sd, p + ".mlp_beta", gref)
-        assert (gb[:, s, 0] - gam).abs().max() < 2e-5 and (gb[:, s, 1] - bet).abs().max() < 2e-5, n
+        assert (gb[:, s, 0] - gam).abs().max() < 1e-4 and (gb[:, s, 1] - bet).abs().max() < 1e-4, n
 
 
 def test_coevo_blocks_vs_oracle(base):
