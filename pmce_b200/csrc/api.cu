@@ -651,6 +651,25 @@ extern "C" int pmce_linear_tc(const float* x, const float* weight, const float* 
     return 0;
 }
 
+extern "C" int pmce_split_bf16(const float* x, int rows, int cols, void* hi, void* lo, void* stream) {
+    if (!x || !hi || !lo || rows < 1 || cols < 4 || (cols & 3)) { pmce_set_error("pmce_split_bf16: bad argument"); return 2; }
+    SplitOut o{(bf16*)hi, (bf16*)lo};
+    return split_rows(x, rows, cols, cols, false, o, cols, (cudaStream_t)stream);
+}
+
+extern "C" int pmce_linear_tc_presplit(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int M,
+                                       int N, int K, int act, float* out, void* stream) {
+    if (!x_hi || !x_lo || !w_hi || !w_lo || !out || M < 1 || N < 1 || K < 8 || (K & 7)) { pmce_set_error("pmce_linear_tc_presplit: bad argument"); return 2; }
+    TcOperand A{(const bf16*)x_hi, (const bf16*)x_lo, M, K, K}, Wm{(const bf16*)w_hi, (const bf16*)w_lo, N, K, K};
+    TcEpi e;
+    memset(&e, 0, sizeof(e));
+    e.bias = bias; e.act = act; e.out_f32 = out; e.ld_out = N; e.rowadd_period = 1;
+    count_launch();
+    const int rc = launch_linear_tc(A, Wm, e, (cudaStream_t)stream);
+    if (rc) { pmce_set_error("pmce_linear_tc_presplit: launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
+    return 0;
+}
+
 // ---- SMPL LBS --------------------------------------------------------------------------------------
 #define SMPL_V 6890
 #define SMPL_LDK 224
