@@ -15,6 +15,7 @@
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
+#include "gru_tc.cuh"
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -64,7 +65,7 @@ struct Workspace {
     SplitOut xn_s, att_s, hid_s;
     // gru
     float *gi0, *y0, *gi1f, *gi1b, *h1[2][2], *g;
-    SplitOut y0_s, g_s, gr_s;
+    SplitOut y0_s, g_s, gr_s, h1_s[2][2];
     // decoder
     float *gb, *verts[3], *Jf, *Vf, *xqv, *Qv, *xkj, *Kj, *Vj, *qkv_d;
     float *xqj, *xkv, *Kv, *Vv, *Qj, *qkvj;
@@ -87,6 +88,7 @@ Workspace carve(const pmce_dims_t& d, int B, void* base) {
     for (int dir = 0; dir < 2; ++dir) for (int i = 0; i < 2; ++i) w.h1[dir][i] = c.f32((size_t)B * H);
     w.g = c.f32((size_t)B * F);
     w.y0_s = c.split((size_t)T * B * 2 * H); w.g_s = c.split((size_t)B * F); w.gr_s = c.split((size_t)B * F);
+    for (int dir = 0; dir < 2; ++dir) for (int i = 0; i < 2; ++i) w.h1_s[dir][i] = c.split((size_t)B * H);
     w.gb = c.f32((size_t)B * PMCE_ADALN_SLOTS * 2 * D);
     for (int i = 0; i < 3; ++i) w.verts[i] = c.f32((size_t)B * Vd * 3);
     const size_t nv = (size_t)B * Vd, nj = (size_t)B * J;
@@ -280,9 +282,41 @@ int lifter(const Layout& L, const Weights& W, const float* pose2d, int B, float*
 // ---------------------------------------------------------------------------------------------------
 // a4 GRU
 // ---------------------------------------------------------------------------------------------------
-int gru_step(const GruDir* dirs, int ndir, int B, int H, cudaStream_t st) {
-    dim3 grid(H / 16, cdiv(B, 64), ndir);
-    gru_step_kernel<<<grid, 256, 0, st>>>(dirs[0], dirs[ndir > 1 ? 1 : 0], B, H);
+// One recurrent step for up to two directions. The first step of a direction (h_prev = 0) needs no GEMM and runs the
+// CUDA-core kernel; every other step runs the tcgen05 kernel (gru_tc.cuh) on the split-bf16 copy of h_prev.
+struct GruStep {
+    GruDir d;            // fp32 view (gi, hprev, bhh, hout, hs, strides); d.whh = fp32 W_hh (CUDA-core path)
+    SplitOut hprev_s;    // split copy of h_prev [B,H] (ld_hs) — null on the first step
+    int ld_hs;
+    size_t whh_off;      // float offset of W_hh [3H,H] in the weight blob
+};
+
+int gru_step(const GruStep* s, int ndir, const Weights& W, int B, int H, cudaStream_t st) {
+    if (!s[0].d.hprev) {   // first step of both directions (they always start together)
+        dim3 grid(H / 16, cdiv(B, 64), ndir);
+        gru_step_kernel<<<grid, 256, 0, st>>>(s[0].d, s[ndir > 1 ? 1 : 0].d, B, H);
+        CKL();
+        return 0;
+    }
+    GruTcMaps maps[2];
+    GruTcDir dirs[2];
+    for (int i = 0; i < 2; ++i) {
+        const GruStep& x = s[i < ndir ? i : 0];
+        if (make_tmap_bf16(&maps[i].h_hi, x.hprev_s.hi, B, H, x.ld_hs, 128) || make_tmap_bf16(&maps[i].h_lo, x.hprev_s.lo, B, H, x.ld_hs, 128) ||
+            make_tmap_bf16(&maps[i].w_hi, W.hi + x.whh_off, 3 * H, H, H, GRU_U) || make_tmap_bf16(&maps[i].w_lo, W.lo + x.whh_off, 3 * H, H, H, GRU_U)) {
+            pmce_set_error("gru_step: cuTensorMapEncodeTiled failed");
+            return 10;
+        }
+        dirs[i].gi = x.d.gi; dirs[i].hprev = x.d.hprev; dirs[i].bhh = x.d.bhh; dirs[i].hout = x.d.hout; dirs[i].hs = x.d.hs;
+        dirs[i].ld_gi = x.d.ld_gi; dirs[i].ld_h = x.d.ld_h; dirs[i].ld_o = x.d.ld_o; dirs[i].ld_s = x.d.ld_s;
+    }
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(gru_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRU_SMEM));
+        configured = true;
+    }
+    dim3 grid(H / GRU_U, ndir, cdiv(B, 128));
+    gru_step_tc_kernel<<<grid, 192, GRU_SMEM, st>>>(maps[0], maps[1], dirs[0], dirs[1], B, H);
     CKL();
     return 0;
 }
@@ -298,19 +332,21 @@ int gru_mid(const Layout& L, const Weights& W, int B, float* g, const Workspace&
         RET(linear_tc(ws.feat_s, F, B * T, F, W, L.wih0, F, 6 * H, o, st));
     }
     for (int s = 0; s < T; ++s) {
-        GruDir dd[2];
-        const int tf = s, tb = T - 1 - s;
-        dd[0].gi = ws.gi0 + (size_t)tf * B * 6 * H; dd[0].ld_gi = 6 * H;
-        dd[0].hprev = s > 0 ? ws.y0 + (size_t)(tf - 1) * B * 2 * H : nullptr; dd[0].ld_h = 2 * H;
-        dd[0].whh = W.f + L.whh0[0]; dd[0].bhh = W.f + L.bhh0[0];
-        dd[0].hout = ws.y0 + (size_t)tf * B * 2 * H; dd[0].ld_o = 2 * H;
-        dd[0].hs.hi = ws.y0_s.hi + (size_t)tf * B * 2 * H; dd[0].hs.lo = ws.y0_s.lo + (size_t)tf * B * 2 * H; dd[0].ld_s = 2 * H;
-        dd[1].gi = ws.gi0 + (size_t)tb * B * 6 * H + 3 * H; dd[1].ld_gi = 6 * H;
-        dd[1].hprev = s > 0 ? ws.y0 + (size_t)(tb + 1) * B * 2 * H + H : nullptr; dd[1].ld_h = 2 * H;
-        dd[1].whh = W.f + L.whh0[1]; dd[1].bhh = W.f + L.bhh0[1];
-        dd[1].hout = ws.y0 + (size_t)tb * B * 2 * H + H; dd[1].ld_o = 2 * H;
-        dd[1].hs.hi = ws.y0_s.hi + (size_t)tb * B * 2 * H + H; dd[1].hs.lo = ws.y0_s.lo + (size_t)tb * B * 2 * H + H; dd[1].ld_s = 2 * H;
-        RET(gru_step(dd, 2, B, H, st));
+        GruStep dd[2];
+        for (int dir = 0; dir < 2; ++dir) {
+            const int t = dir == 0 ? s : T - 1 - s;            // frame this step produces
+            const int tp = dir == 0 ? t - 1 : t + 1;           // frame h_prev belongs to
+            const size_t off = (size_t)t * B * 2 * H + dir * H, offp = (size_t)tp * B * 2 * H + dir * H;
+            GruStep& x = dd[dir];
+            x.d.gi = ws.gi0 + (size_t)t * B * 6 * H + dir * 3 * H; x.d.ld_gi = 6 * H;
+            x.d.hprev = s > 0 ? ws.y0 + offp : nullptr; x.d.ld_h = 2 * H;
+            x.d.whh = W.f + L.whh0[dir]; x.d.bhh = W.f + L.bhh0[dir];
+            x.d.hout = ws.y0 + off; x.d.ld_o = 2 * H;
+            x.d.hs.hi = ws.y0_s.hi + off; x.d.hs.lo = ws.y0_s.lo + off; x.d.ld_s = 2 * H;
+            x.hprev_s.hi = s > 0 ? ws.y0_s.hi + offp : nullptr; x.hprev_s.lo = s > 0 ? ws.y0_s.lo + offp : nullptr; x.ld_hs = 2 * H;
+            x.whh_off = L.whh0[dir];
+        }
+        RET(gru_step(dd, 2, W, B, H, st));
     }
     // layer 1: only the steps y[T//2] depends on (fwd t = 0..mid, bwd t = T-1..mid)
     const int nf = mid + 1, nb = T - mid;
@@ -325,26 +361,22 @@ int gru_mid(const Layout& L, const Weights& W, int B, float* g, const Workspace&
     }
     const int nsteps = nf > nb ? nf : nb;
     for (int s = 0; s < nsteps; ++s) {
-        GruDir dd[2];
+        GruStep dd[2];
         int n = 0;
-        if (s < nf) {
-            GruDir& x = dd[n++];
-            x.gi = ws.gi1f + (size_t)s * B * 3 * H; x.ld_gi = 3 * H;
-            x.hprev = s > 0 ? ws.h1[0][(s - 1) & 1] : nullptr; x.ld_h = H;
-            x.whh = W.f + L.whh1[0]; x.bhh = W.f + L.bhh1[0];
-            x.hs = NO_SPLIT; x.ld_s = 0;
-            if (s == nf - 1) { x.hout = g; x.ld_o = 2 * H; } else { x.hout = ws.h1[0][s & 1]; x.ld_o = H; }
+        for (int dir = 0; dir < 2; ++dir) {
+            const int nd = dir == 0 ? nf : nb;
+            if (s >= nd) continue;
+            GruStep& x = dd[n++];
+            x.d.gi = dir == 0 ? ws.gi1f + (size_t)s * B * 3 * H : ws.gi1b + (size_t)(T - 1 - s - mid) * B * 3 * H;
+            x.d.ld_gi = 3 * H;
+            x.d.hprev = s > 0 ? ws.h1[dir][(s - 1) & 1] : nullptr; x.d.ld_h = H;
+            x.d.whh = W.f + L.whh1[dir]; x.d.bhh = W.f + L.bhh1[dir];
+            x.hprev_s = s > 0 ? ws.h1_s[dir][(s - 1) & 1] : NO_SPLIT; x.ld_hs = H;
+            x.whh_off = L.whh1[dir];
+            if (s == nd - 1) { x.d.hout = g + dir * H; x.d.ld_o = 2 * H; x.d.hs = NO_SPLIT; x.d.ld_s = 0; }
+            else { x.d.hout = ws.h1[dir][s & 1]; x.d.ld_o = H; x.d.hs = ws.h1_s[dir][s & 1]; x.d.ld_s = H; }
         }
-        if (s < nb) {
-            GruDir& x = dd[n++];
-            const int t = T - 1 - s;
-            x.gi = ws.gi1b + (size_t)(t - mid) * B * 3 * H; x.ld_gi = 3 * H;
-            x.hprev = s > 0 ? ws.h1[1][(s - 1) & 1] : nullptr; x.ld_h = H;
-            x.whh = W.f + L.whh1[1]; x.bhh = W.f + L.bhh1[1];
-            x.hs = NO_SPLIT; x.ld_s = 0;
-            if (s == nb - 1) { x.hout = g + H; x.ld_o = 2 * H; } else { x.hout = ws.h1[1][s & 1]; x.ld_o = H; }
-        }
-        RET(gru_step(dd, n, B, H, st));
+        RET(gru_step(dd, n, W, B, H, st));
     }
     return 0;
 }
@@ -464,12 +496,16 @@ int prepare_feat(const Layout& L, const float* img_feat, int B, const Workspace&
     return split_rows(img_feat, B * T, F, F, false, ws.feat_s, F, st);
 }
 
-int decoder(const Layout& L, const Weights& W, const float* joints, const int32_t* vj, int B, float* cam_pose, float* cam_mesh,
-            float* verts0_out, const Workspace& ws, cudaStream_t st) {
+// image-feature stream of the two-stream encoder: GRU -> y[T//2] -> all AdaLN gamma/beta (independent of the pose stream)
+int decoder_front(const Layout& L, const Weights& W, int B, const Workspace& ws, cudaStream_t st) {
+    RET(gru_mid(L, W, B, ws.g, ws, st));
+    return adaln_gammabeta(L, W, ws.g, B, ws.gb, ws.g_s, st);
+}
+
+int decoder_back(const Layout& L, const Weights& W, const float* joints, const int32_t* vj, int B, float* cam_pose, float* cam_mesh,
+                 float* verts0_out, const Workspace& ws, cudaStream_t st) {
     const pmce_dims_t& d = L.d;
     const int J = d.num_joint, Vd = d.num_vert_ds;
-    RET(gru_mid(L, W, B, ws.g, ws, st));
-    RET(adaln_gammabeta(L, W, ws.g, B, ws.gb, ws.g_s, st));
     float* v0 = verts0_out ? verts0_out : ws.verts[2];
     gather_verts_kernel<<<cdiv((long long)B * Vd * 3, 256), 256, 0, st>>>(joints, vj, B, J, Vd, v0);
     CKL();
@@ -478,6 +514,27 @@ int decoder(const Layout& L, const Weights& W, const float* joints, const int32_
     RET(coevo_block(L, W, 2, joints, ws.verts[1], ws.gb, B, cam_pose, ws.verts[0], ws, st));
     RET(mesh_epilogue(L, W, ws.verts[0], ws.g, B, cam_mesh, ws, st));
     return 0;
+}
+
+// Side stream + fork/join events so the two encoder streams (pose lifter / GRU image-feature aggregation) run
+// concurrently inside one pmce_forward call. One set per device, created on first use (before any graph capture: the
+// host driver always runs an eager warm-up first); the only process-lifetime state the library keeps besides the
+// layout cache.
+struct Aux {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+Aux* get_aux() {
+    static Aux aux[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    Aux& a = aux[dev];
+    if (!a.side) {
+        if (cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &a;
 }
 
 }  // namespace
@@ -566,7 +623,8 @@ extern "C" int pmce_decoder_forward(const pmce_dims_t* dims, const void* weights
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
     RET(prepare_feat(L, img_feat, B, ws, st));
-    return decoder(L, W, joints, vj_relation, B, cam_pose, cam_mesh, verts0_out, ws, st);
+    RET(decoder_front(L, W, B, ws, st));
+    return decoder_back(L, W, joints, vj_relation, B, cam_pose, cam_mesh, verts0_out, ws, st);
 }
 
 extern "C" int pmce_forward(const pmce_dims_t* dims, const void* weights, const float* pose2d, const float* img_feat,
@@ -576,8 +634,16 @@ extern "C" int pmce_forward(const pmce_dims_t* dims, const void* weights, const 
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
     RET(prepare_feat(L, img_feat, B, ws, st));
+    // fork: image-feature stream (GRU + AdaLN gamma/beta) on the side stream, pose stream (lifter) on the caller's stream
+    Aux* aux = get_aux();
+    if (!aux) { pmce_set_error("could not create the side stream/events: %s", cudaGetErrorString(cudaGetLastError())); return 10; }
+    CK(cudaEventRecord(aux->fork, st));
+    CK(cudaStreamWaitEvent(aux->side, aux->fork, 0));
+    RET(decoder_front(L, W, B, ws, aux->side));
+    CK(cudaEventRecord(aux->join, aux->side));
     RET(lifter(L, W, pose2d, B, pose3d, ws, st));
-    return decoder(L, W, ws.joints_m, vj_relation, B, cam_pose, cam_mesh, nullptr, ws, st);
+    CK(cudaStreamWaitEvent(st, aux->join, 0));
+    return decoder_back(L, W, ws.joints_m, vj_relation, B, cam_pose, cam_mesh, nullptr, ws, st);
 }
 
 extern "C" size_t pmce_io_bytes(const pmce_dims_t* dims, int B) {

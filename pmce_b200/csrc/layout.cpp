@@ -198,7 +198,7 @@ bool dims_ok(const pmce_dims_t& d) {
     if (d.depth < 1 || d.depth > PMCE_MAX_DEPTH) { pmce_set_error("depth %d out of range", d.depth); return false; }
     if (d.seqlen < 1 || d.seqlen > 256) { pmce_set_error("seqlen %d out of range [1,256]", d.seqlen); return false; }
     if (d.coevo_dim != 64) { pmce_set_error("coevo_dim must be 64 (got %d)", d.coevo_dim); return false; }
-    if (d.gru_hidden % 16 || d.gru_hidden < 16) { pmce_set_error("gru_hidden must be a multiple of 16"); return false; }
+    if (d.gru_hidden % 64 || d.gru_hidden < 64) { pmce_set_error("gru_hidden must be a multiple of 64"); return false; }
     if (d.feat_dim != 2 * d.gru_hidden) { pmce_set_error("feat_dim must equal 2*gru_hidden (AdaLN/linear_cur consume y[T//2])"); return false; }
     if (d.feat_dim % 4) { pmce_set_error("feat_dim must be a multiple of 4"); return false; }
     if (d.num_vert_ds < 1 || d.num_vert < 1) { pmce_set_error("bad vertex counts"); return false; }
