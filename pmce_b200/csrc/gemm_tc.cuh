@@ -1,9 +1,11 @@
 // tcgen05 / TMA / TMEM GEMM for sm_100a with split-bf16 ("bf16x3") operands and a fused epilogue:
 //     out[M,N] = epi( A[M,K] * W[N,K]^T ),   A = A_hi + A_lo,  W = W_hi + W_lo  (bf16 pairs, K-contiguous)
-// One CTA computes a 128 x BN tile. Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA
-// issuer (one lane), warps 2..5 = epilogue (TMEM lane group = warp_id % 4, one output row per thread).
-// smem ring of STAGES x {A_hi, A_lo, W_hi, W_lo} tiles of [rows][64 bf16] written by TMA with the 128-byte
-// swizzle the UMMA descriptors expect; full/empty mbarriers between TMA and MMA, one more MMA -> epilogue.
+// Persistent: one CTA per SM loops over 128 x BN output tiles (n fastest, so concurrently running CTAs share the A
+// tile through L2). Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
+// warps 2..9 = epilogue (TMEM lane group = warp % 4, column half = (warp-2)/4; one output row per thread).
+// Three pipelines: smem ring of STAGES x {A_hi, A_lo, W_hi, W_lo} tiles ([rows][64 bf16], written by TMA with the
+// 128-byte swizzle the UMMA descriptors expect) with full/empty mbarriers; TWO TMEM accumulators with
+// tmem_full/tmem_empty mbarriers so the epilogue of tile i overlaps the MMAs of tile i+1; the tile loop itself.
 #pragma once
 #include "tc_common.cuh"
 #include "common.cuh"
@@ -25,7 +27,9 @@ struct TcEpi {
 };
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;   // bf16 elements = 128 bytes = one swizzle row
+constexpr int TC_BK = 64;            // bf16 elements = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 320;      // TMA warp + MMA warp + 8 epilogue warps
+constexpr int TC_EPI_WARPS = 8;
 
 template <int BN>
 struct TcCfg {
@@ -34,11 +38,77 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : (200 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators
     static_assert(STAGES >= 2, "tile too large");
+    static_assert(TMEM_COLS <= 512, "TMEM");
 };
 
+// Epilogue for `NC` x 32 consecutive accumulator columns of one row (registers -> global), shared by the GEMM kernels.
+__device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& e, float (&f)[32], int row, int col0, int N, const float* radd) {
+    const bool full = (col0 + 32 <= N) && e.vec_ok;
+    if (full) {
+        if (e.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) { float4 b = ld4(e.bias + col0 + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
+        }
+        if (e.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+        }
+        if (radd) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) { float4 b = ld4(radd + col0 + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
+        }
+        if (e.resid) {
+            const float* rp = e.resid + (size_t)row * e.ld_resid + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) { float4 b = ld4(rp + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
+        }
+        if (e.out_f32) {
+            float* op = e.out_f32 + (size_t)row * e.ld_out + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) st4(op + i, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
+        }
+        if (e.out_hi) {
+            uint4* hp = reinterpret_cast<uint4*>(e.out_hi + (size_t)row * e.ld_split + col0);
+            uint4* lp = reinterpret_cast<uint4*>(e.out_lo + (size_t)row * e.ld_split + col0);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                uint4 h, l;
+                tc::split_bf16x2(f[i], f[i + 1], h.x, l.x); tc::split_bf16x2(f[i + 2], f[i + 3], h.y, l.y);
+                tc::split_bf16x2(f[i + 4], f[i + 5], h.z, l.z); tc::split_bf16x2(f[i + 6], f[i + 7], h.w, l.w);
+                hp[i / 8] = h; lp[i / 8] = l;
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < 32; ++i) {
+            const int col = col0 + i;
+            if (col >= N) break;
+            float x = f[i];
+            if (e.bias) x += e.bias[col];
+            if (e.act == 1) x = gelu_erf(x);
+            if (radd) x += radd[col];
+            if (e.mapped) {
+                const long long off = e.rmap(row) + e.cmap(col);
+                if (e.resid) x += e.resid[off];
+                if (e.out_f32) e.out_f32[off] = x;
+            } else {
+                if (e.resid) x += e.resid[(size_t)row * e.ld_resid + col];
+                if (e.out_f32) e.out_f32[(size_t)row * e.ld_out + col] = x;
+            }
+            if (e.out_hi) {
+                __nv_bfloat16 h, l;
+                tc::split_bf16(x, h, l);
+                e.out_hi[(size_t)row * e.ld_split + col] = h;
+                e.out_lo[(size_t)row * e.ld_split + col] = l;
+            }
+        }
+    }
+}
+
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                  int M, int N, int K, TcEpi e) {
@@ -48,22 +118,24 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
     const int nkb = (K + TC_BK - 1) / TC_BK;
+    const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + TC_BM - 1) / TC_BM;
+    const int num_tiles = tiles_n * tiles_m;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA_hi); tc::tma_prefetch_desc(&tmA_lo);
         tc::tma_prefetch_desc(&tmW_hi); tc::tma_prefetch_desc(&tmW_lo);
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-        tc::mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], TC_EPI_WARPS); }
         tc::fence_barrier_init();
         tc::fence_proxy_async();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_ptr_smem, BN);
+    if (warp == 1) tc::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -71,124 +143,88 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                tc::mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-                tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                tc::tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
-                tc::tma_load_2d(st + Cfg::A_TILE, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
-                tc::tma_load_2d(st + 2 * Cfg::A_TILE, &tmW_hi, &full_bar[s], kb * TC_BK, n0);
-                tc::tma_load_2d(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tmW_lo, &full_bar[s], kb * TC_BK, n0);
+            uint32_t it = 0;                                    // global k-block counter across tiles
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                    tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                    tc::tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
+                    tc::tma_load_2d(st + Cfg::A_TILE, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
+                    tc::tma_load_2d(st + 2 * Cfg::A_TILE, &tmW_hi, &full_bar[s], kb * TC_BK, n0);
+                    tc::tma_load_2d(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tmW_lo, &full_bar[s], kb * TC_BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(TC_BM, BN);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                tc::mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t acc = tcount & 1;
+                tc::mbar_wait(&tmem_empty_bar[acc], ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
                 tc::tc_fence_after();
-                const uint32_t st = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint64_t a_hi = tc::umma_desc_sw128(st), a_lo = tc::umma_desc_sw128(st + Cfg::A_TILE);
-                const uint64_t w_hi = tc::umma_desc_sw128(st + 2 * Cfg::A_TILE), w_lo = tc::umma_desc_sw128(st + 2 * Cfg::A_TILE + Cfg::W_TILE);
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    tc::mbar_wait(&full_bar[s], ph);
+                    tc::tc_fence_after();
+                    const uint32_t st = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const uint64_t a_hi = tc::umma_desc_sw128(st), a_lo = tc::umma_desc_sw128(st + Cfg::A_TILE);
+                    const uint64_t w_hi = tc::umma_desc_sw128(st + 2 * Cfg::A_TILE), w_lo = tc::umma_desc_sw128(st + 2 * Cfg::A_TILE + Cfg::W_TILE);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
-                    // small cross terms first, then the leading term
-                    tc::umma_bf16(tmem_base, tc::umma_desc_advance_k(a_lo, k), tc::umma_desc_advance_k(w_hi, k), idesc, (kb | k) != 0);
-                    tc::umma_bf16(tmem_base, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_lo, k), idesc, 1);
-                    tc::umma_bf16(tmem_base, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_hi, k), idesc, 1);
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        // small cross terms first, then the leading term
+                        tc::umma_bf16(tmem_d, tc::umma_desc_advance_k(a_lo, k), tc::umma_desc_advance_k(w_hi, k), idesc, (kb | k) != 0);
+                        tc::umma_bf16(tmem_d, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_lo, k), idesc, 1);
+                        tc::umma_bf16(tmem_d, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_hi, k), idesc, 1);
+                    }
+                    tc::umma_commit(&empty_bar[s]);          // smem slot free once these MMAs have read it
                 }
-                tc::umma_commit(&empty_bar[s]);          // smem slot free once these MMAs have read it
+                tc::umma_commit(&tmem_full_bar[acc]);        // accumulator complete
             }
-            tc::umma_commit(tmem_full_bar);              // accumulator complete
         }
     } else {
-        // ---- epilogue: 4 warps, warp q = warp % 4 owns TMEM lanes [32q, 32q+32) = tile rows ----
+        // ---- epilogue: 8 warps; lane group q = warp % 4 (TMEM lanes [32q,32q+32) = tile rows), column half = (warp-2)/4 ----
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
-        tc::mbar_wait(tmem_full_bar, 0);
-        tc::tc_fence_after();
-        const bool row_ok = row < M;
-        const float* radd = (e.rowadd && row_ok) ? e.rowadd + (size_t)(row % e.rowadd_period) * N : nullptr;
+        const int half = (warp - 2) >> 2;
+        constexpr int CHUNKS = BN / 32;                       // 32-column chunks per tile
+        constexpr int C_BEGIN_STRIDE = (CHUNKS + 1) / 2;      // chunks [0, C) for half 0, [C, CHUNKS) for half 1
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+            const uint32_t acc = tcount & 1;
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < M;
+            const float* radd = (e.rowadd && row_ok) ? e.rowadd + (size_t)(row % e.rowadd_period) * N : nullptr;
+            tc::mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1);
+            tc::tc_fence_after();
+            const int cb = half == 0 ? 0 : C_BEGIN_STRIDE, ce = half == 0 ? C_BEGIN_STRIDE : CHUNKS;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tc::tmem_ld_wait();
-            const int col0 = n0 + c0;
-            if (row_ok && col0 < N) {
-            float f[32];
+            for (int c = cb; c < ce; ++c) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                tc::tmem_ld_wait();
+                const int col0 = n0 + c * 32;
+                if (row_ok && col0 < N) {
+                    float f[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            const bool full = (col0 + 32 <= N) && e.vec_ok;
-            if (full) {
-                if (e.bias) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) { float4 b = ld4(e.bias + col0 + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    tc_epilogue_chunk(e, f, row, col0, N, radd);
                 }
-                if (e.act == 1) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
-                }
-                if (radd) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) { float4 b = ld4(radd + col0 + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
-                }
-                if (e.resid) {
-                    const float* rp = e.resid + (size_t)row * e.ld_resid + col0;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) { float4 b = ld4(rp + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
-                }
-                if (e.out_f32) {
-                    float* op = e.out_f32 + (size_t)row * e.ld_out + col0;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) st4(op + i, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
-                }
-                if (e.out_hi) {
-                    uint4* hp = reinterpret_cast<uint4*>(e.out_hi + (size_t)row * e.ld_split + col0);
-                    uint4* lp = reinterpret_cast<uint4*>(e.out_lo + (size_t)row * e.ld_split + col0);
-#pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
-                        uint4 h, l;
-                        tc::split_bf16x2(f[i], f[i + 1], h.x, l.x); tc::split_bf16x2(f[i + 2], f[i + 3], h.y, l.y);
-                        tc::split_bf16x2(f[i + 4], f[i + 5], h.z, l.z); tc::split_bf16x2(f[i + 6], f[i + 7], h.w, l.w);
-                        hp[i / 8] = h; lp[i / 8] = l;
-                    }
-                }
-            } else {
-                for (int i = 0; i < 32; ++i) {
-                    const int col = col0 + i;
-                    if (col >= N) break;
-                    float x = f[i];
-                    if (e.bias) x += e.bias[col];
-                    if (e.act == 1) x = gelu_erf(x);
-                    if (radd) x += radd[col];
-                    if (e.mapped) {
-                        const long long off = e.rmap(row) + e.cmap(col);
-                        if (e.resid) x += e.resid[off];
-                        if (e.out_f32) e.out_f32[off] = x;
-                    } else {
-                        if (e.resid) x += e.resid[(size_t)row * e.ld_resid + col];
-                        if (e.out_f32) e.out_f32[(size_t)row * e.ld_out + col] = x;
-                    }
-                    if (e.out_hi) {
-                        __nv_bfloat16 h, l;
-                        tc::split_bf16(x, h, l);
-                        e.out_hi[(size_t)row * e.ld_split + col] = h;
-                        e.out_lo[(size_t)row * e.ld_split + col] = l;
-                    }
-                }
+                __syncwarp();     // tcgen05.ld is .sync.aligned: reconverge before the next chunk
             }
-            }
-            __syncwarp();     // tcgen05.ld is .sync.aligned: reconverge before the next chunk
+            tc::tc_fence_before();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);      // this warp is done reading the accumulator
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+    if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // fp32 [rows, cols] (ld) -> bf16 hi / lo [rows, ld_out]; optional relu on the way (linear_cur input).
@@ -240,6 +276,16 @@ struct TcOperand {   // split bf16 matrix [rows, cols], row stride ld (elements)
     const __nv_bfloat16* hi; const __nv_bfloat16* lo; int rows, cols, ld;
 };
 
+static inline int tc_num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <int BN>
 static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, const TcEpi& e, cudaStream_t st) {
     CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
@@ -251,21 +297,26 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
         if (cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES) != cudaSuccess) return 2;
         configured = true;
     }
-    dim3 grid((W.rows + BN - 1) / BN, (A.rows + TC_BM - 1) / TC_BM);
+    const long long tiles = (long long)((W.rows + BN - 1) / BN) * ((A.rows + TC_BM - 1) / TC_BM);
+    const int grid = (int)(tiles < tc_num_sms() ? tiles : tc_num_sms());
     TcEpi ee = e;
     auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     ee.vec_ok = !e.mapped && (W.rows % 4 == 0 || !e.rowadd) && a16(e.bias) && a16(e.rowadd) && (!e.resid || (a16(e.resid) && e.ld_resid % 4 == 0)) &&
                 (!e.out_f32 || (a16(e.out_f32) && e.ld_out % 4 == 0)) && (!e.out_hi || (a16(e.out_hi) && a16(e.out_lo) && e.ld_split % 8 == 0));
-    linear_tc_kernel<BN><<<grid, 192, TcCfg<BN>::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, A.rows, W.rows, A.cols, ee);
+    linear_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, A.rows, W.rows, A.cols, ee);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
+// Tile width: the widest BN that still yields at least one wave of tiles; skinny problems take the narrowest tile so the
+// weight stream is spread over as many SMs as possible.
 // Requirements: A.cols == W.cols (K), K % 8 == 0, ld % 8 == 0, 16-byte aligned bases.
 static inline int launch_linear_tc(const TcOperand& A, const TcOperand& W, const TcEpi& e, cudaStream_t st) {
     const int N = W.rows;
     const long long tiles_m = (A.rows + TC_BM - 1) / TC_BM;
-    if (N % 256 == 0 && tiles_m * (N / 256) >= 148) return launch_linear_tc_bn<256>(A, W, e, st);
-    if (N >= 128 && tiles_m * ((N + 127) / 128) >= 120) return launch_linear_tc_bn<128>(A, W, e, st);
-    if (N > 32) return launch_linear_tc_bn<64>(A, W, e, st);
+    const int sms = tc_num_sms();
+    if (N >= 256 && tiles_m * ((N + 255) / 256) >= sms) return launch_linear_tc_bn<256>(A, W, e, st);
+    if (N >= 128 && tiles_m * ((N + 127) / 128) >= sms) return launch_linear_tc_bn<128>(A, W, e, st);
+    if (N >= 64 && tiles_m * ((N + 63) / 64) >= sms) return launch_linear_tc_bn<64>(A, W, e, st);
+    if (N > 32 && tiles_m * ((N + 63) / 64) * 2 > sms) return launch_linear_tc_bn<64>(A, W, e, st);
     return launch_linear_tc_bn<32>(A, W, e, st);
 }
