@@ -314,6 +314,12 @@ static inline int launch_linear_tc(const TcOperand& A, const TcOperand& W, const
     const int N = W.rows;
     const long long tiles_m = (A.rows + TC_BM - 1) / TC_BM;
     const int sms = tc_num_sms();
+    static int forced = -1;   // PMCE_TC_BN=<32|64|128|256>: tile-sweep knob for profiling (tools/gemm_sweep.py)
+    if (forced < 0) { const char* s = getenv("PMCE_TC_BN"); forced = s ? atoi(s) : 0; }
+    if (forced == 256) return launch_linear_tc_bn<256>(A, W, e, st);
+    if (forced == 128) return launch_linear_tc_bn<128>(A, W, e, st);
+    if (forced == 64) return launch_linear_tc_bn<64>(A, W, e, st);
+    if (forced == 32) return launch_linear_tc_bn<32>(A, W, e, st);
     if (N >= 256 && tiles_m * ((N + 255) / 256) >= sms) return launch_linear_tc_bn<256>(A, W, e, st);
     if (N >= 128 && tiles_m * ((N + 127) / 128) >= sms) return launch_linear_tc_bn<128>(A, W, e, st);
     if (N >= 64 && tiles_m * ((N + 63) / 64) >= sms) return launch_linear_tc_bn<64>(A, W, e, st);

@@ -238,7 +238,43 @@ attn_kernel(const float* __restrict__ Q, AttnAddr aq, const float* __restrict__ 
         o[c] = o[c + 1] = o[c + 2] = o[c + 3] = 0.f;
     }
     float m = -INFINITY, l = 0.f;
-    for (int k = 0; k < N2; ++k) {
+    int k = 0;
+    // keys in blocks of 4: one running-max update / accumulator rescale per block instead of per key
+    for (; k + 4 <= N2; k += 4) {
+        float sc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* kr = Ks + (k + j) * D;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; c += 4) {
+                float4 kk = ld4(kr + c);
+                s0 = fmaf(q[c], kk.x, s0); s1 = fmaf(q[c + 1], kk.y, s1);
+                s0 = fmaf(q[c + 2], kk.z, s0); s1 = fmaf(q[c + 3], kk.w, s1);
+            }
+            sc[j] = s0 + s1;
+        }
+        const float mn = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
+        const float alpha = expf(m - mn);
+        m = mn;
+        float p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = expf(sc[j] - mn);
+        l = l * alpha + ((p[0] + p[1]) + (p[2] + p[3]));
+#pragma unroll
+        for (int c = 0; c < D; ++c) o[c] *= alpha;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* vr = Vs + (k + j) * D;
+#pragma unroll
+            for (int c = 0; c < D; c += 4) {
+                float4 vv = ld4(vr + c);
+                o[c] = fmaf(p[j], vv.x, o[c]); o[c + 1] = fmaf(p[j], vv.y, o[c + 1]);
+                o[c + 2] = fmaf(p[j], vv.z, o[c + 2]); o[c + 3] = fmaf(p[j], vv.w, o[c + 3]);
+            }
+        }
+    }
+    for (; k < N2; ++k) {
         const float* kr = Ks + k * D;
         float sc0 = 0.f, sc1 = 0.f;
 #pragma unroll
