@@ -21,7 +21,6 @@ struct TcEpi {
     __nv_bfloat16* out_hi;  // split output [M, ld_split] or null (both hi and lo, or neither)
     __nv_bfloat16* out_lo;
     int ld_out, ld_split;
-    int vec_ok;             // set by the launcher: all row strides / bases allow 16-byte vector access
     int mapped;             // out_f32 / resid are addressed as rmap(row) + cmap(col) instead of row*ld + col
     RowMap rmap, cmap;
 };
@@ -37,60 +36,37 @@ struct TcCfg {
     static constexpr int W_TILE = BN * 128;
     static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : (200 * 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int STG_BYTES = TC_EPI_WARPS * 32 * 32 * 4;     // per-warp epilogue transpose tiles
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators
     static_assert(STAGES >= 2, "tile too large");
     static_assert(TMEM_COLS <= 512, "TMEM");
 };
 
-// Epilogue for `NC` x 32 consecutive accumulator columns of one row (registers -> global), shared by the GEMM kernels.
-__device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& e, float (&f)[32], int row, int col0, int N, const float* radd) {
-    const bool full = (col0 + 32 <= N) && e.vec_ok;
-    if (full) {
-        if (e.bias) {
+// Epilogue of one 32-row x 32-column accumulator chunk, warp-collective. The TMEM load gives each thread one ROW
+// (32 consecutive columns); writing that straight to global memory touches 32 different 128-byte lines per instruction
+// (measured: ~20 us per 128x256 tile, the GEMM's bottleneck). So the chunk is transposed through a 4 KB XOR-swizzled
+// shared-memory tile: afterwards lane = column, and every global access (bias, row-embedding, residual read, fp32 and
+// split-bf16 stores) is one fully coalesced row segment.
+__device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& e, const uint32_t (&v)[32], uint32_t* stg, int lane, int row0, int col0,
+                                                  int M, int N) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) { float4 b = ld4(e.bias + col0 + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
-        }
-        if (e.act == 1) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
-        }
-        if (radd) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) { float4 b = ld4(radd + col0 + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
-        }
-        if (e.resid) {
-            const float* rp = e.resid + (size_t)row * e.ld_resid + col0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) { float4 b = ld4(rp + i); f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w; }
-        }
-        if (e.out_f32) {
-            float* op = e.out_f32 + (size_t)row * e.ld_out + col0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) st4(op + i, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
-        }
-        if (e.out_hi) {
-            uint4* hp = reinterpret_cast<uint4*>(e.out_hi + (size_t)row * e.ld_split + col0);
-            uint4* lp = reinterpret_cast<uint4*>(e.out_lo + (size_t)row * e.ld_split + col0);
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                uint4 h, l;
-                tc::split_bf16x2(f[i], f[i + 1], h.x, l.x); tc::split_bf16x2(f[i + 2], f[i + 3], h.y, l.y);
-                tc::split_bf16x2(f[i + 4], f[i + 5], h.z, l.z); tc::split_bf16x2(f[i + 6], f[i + 7], h.w, l.w);
-                hp[i / 8] = h; lp[i / 8] = l;
-            }
-        }
-    } else {
-#pragma unroll 1
-        for (int i = 0; i < 32; ++i) {
-            const int col = col0 + i;
-            if (col >= N) break;
-            float x = f[i];
-            if (e.bias) x += e.bias[col];
-            if (e.act == 1) x = gelu_erf(x);
-            if (radd) x += radd[col];
+    for (int i = 0; i < 32; ++i) stg[lane * 32 + (i ^ lane)] = v[i];
+    __syncwarp();
+    const int col = col0 + lane;
+    const bool col_ok = col < N;
+    const float b = (e.bias && col_ok) ? e.bias[col] : 0.f;
+    const long long coff = e.mapped ? e.cmap(col) : (long long)col;
+    const int nrows = M - row0 < 32 ? M - row0 : 32;
+#pragma unroll 4
+    for (int rr = 0; rr < nrows; ++rr) {
+        float x = __uint_as_float(stg[rr * 32 + (lane ^ rr)]) + b;
+        if (e.act == 1) x = gelu_erf(x);
+        if (col_ok) {
+            const int row = row0 + rr;
+            if (e.rowadd) x += e.rowadd[(size_t)(row % e.rowadd_period) * N + col];
             if (e.mapped) {
-                const long long off = e.rmap(row) + e.cmap(col);
+                const long long off = e.rmap(row) + coff;
                 if (e.resid) x += e.resid[off];
                 if (e.out_f32) e.out_f32[off] = x;
             } else {
@@ -105,6 +81,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& e, float (&f)[32]
             }
         }
     }
+    __syncwarp();   // staging tile is reused by the next chunk
 }
 
 template <int BN>
@@ -116,7 +93,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint32_t* stg_all = reinterpret_cast<uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
@@ -198,9 +176,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
             const uint32_t acc = tcount & 1;
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < M;
-            const float* radd = (e.rowadd && row_ok) ? e.rowadd + (size_t)(row % e.rowadd_period) * N : nullptr;
+            const int row0 = m0 + q * 32;
+            uint32_t* stg = stg_all + (warp - 2) * 1024;
             tc::mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1);
             tc::tc_fence_after();
             const int cb = half == 0 ? 0 : C_BEGIN_STRIDE, ce = half == 0 ? C_BEGIN_STRIDE : CHUNKS;
@@ -210,13 +187,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 tc::tmem_ld_32x32(tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
                 tc::tmem_ld_wait();
                 const int col0 = n0 + c * 32;
-                if (row_ok && col0 < N) {
-                    float f[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    tc_epilogue_chunk(e, f, row, col0, N, radd);
-                }
-                __syncwarp();     // tcgen05.ld is .sync.aligned: reconverge before the next chunk
+                if (row0 < M && col0 < N) tc_epilogue_chunk(e, v, stg, lane, row0, col0, M, N);   // warp-uniform condition
             }
             tc::tc_fence_before();
             if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);      // this warp is done reading the accumulator
@@ -299,11 +270,7 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
     }
     const long long tiles = (long long)((W.rows + BN - 1) / BN) * ((A.rows + TC_BM - 1) / TC_BM);
     const int grid = (int)(tiles < tc_num_sms() ? tiles : tc_num_sms());
-    TcEpi ee = e;
-    auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    ee.vec_ok = !e.mapped && (W.rows % 4 == 0 || !e.rowadd) && a16(e.bias) && a16(e.rowadd) && (!e.resid || (a16(e.resid) && e.ld_resid % 4 == 0)) &&
-                (!e.out_f32 || (a16(e.out_f32) && e.ld_out % 4 == 0)) && (!e.out_hi || (a16(e.out_hi) && a16(e.out_lo) && e.ld_split % 8 == 0));
-    linear_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, A.rows, W.rows, A.cols, ee);
+    linear_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, A.rows, W.rows, A.cols, e);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
