@@ -325,10 +325,8 @@ int gru_mid(const Layout& L, const Weights& W, int B, float* g, const Workspace&
     const pmce_dims_t& d = L.d;
     const int T = d.seqlen, H = d.gru_hidden, F = d.feat_dim;
     const int mid = T / 2;
-    {   // layer-0 input projections, every frame, both directions, written time-major: gi0[t][b][6H]
-        EpiOpt o; o.bias = W.f + L.bih0; o.out = ws.gi0; o.mapped = true;
-        o.rmap.div = T; o.rmap.s0 = 6 * H; o.rmap.s1 = (long long)B * 6 * H;   // row (b,t) -> t*B*6H + b*6H
-        o.cmap.div = 1; o.cmap.s0 = 1; o.cmap.s1 = 0;
+    {   // layer-0 input projections, every frame, both directions: gi0[b][t][6H] (the step kernels stride over b with T*6H)
+        EpiOpt o; o.bias = W.f + L.bih0; o.out = ws.gi0; o.ld_out = 6 * H;
         RET(linear_tc(ws.feat_s, F, B * T, F, W, L.wih0, F, 6 * H, o, st));
     }
     for (int s = 0; s < T; ++s) {
@@ -338,7 +336,7 @@ int gru_mid(const Layout& L, const Weights& W, int B, float* g, const Workspace&
             const int tp = dir == 0 ? t - 1 : t + 1;           // frame h_prev belongs to
             const size_t off = (size_t)t * B * 2 * H + dir * H, offp = (size_t)tp * B * 2 * H + dir * H;
             GruStep& x = dd[dir];
-            x.d.gi = ws.gi0 + (size_t)t * B * 6 * H + dir * 3 * H; x.d.ld_gi = 6 * H;
+            x.d.gi = ws.gi0 + (size_t)t * 6 * H + dir * 3 * H; x.d.ld_gi = T * 6 * H;
             x.d.hprev = s > 0 ? ws.y0 + offp : nullptr; x.d.ld_h = 2 * H;
             x.d.whh = W.f + L.whh0[dir]; x.d.bhh = W.f + L.bhh0[dir];
             x.d.hout = ws.y0 + off; x.d.ld_o = 2 * H;
