@@ -308,7 +308,7 @@ def dominant_kernel_roofline(lib, dev, peaks, B):
     x = torch.randn(M, K, device=dev)
     w = torch.randn(N, K, device=dev) * 0.05
     b = torch.randn(N, device=dev)
-    o = torch.empty(M, N, device=dev)
+    oh = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(2)]
     xs = [torch.empty(M, K, dtype=torch.bfloat16, device=dev) for _ in range(2)]
     wsp = [torch.empty(N, K, dtype=torch.bfloat16, device=dev) for _ in range(2)]
     st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -317,7 +317,8 @@ def dominant_kernel_roofline(lib, dev, peaks, B):
     assert lib.pmce_split_bf16(P(w), N, K, P(wsp[0]), P(wsp[1]), st) == 0
 
     def call():
-        rc = lib.pmce_linear_tc_presplit(P(xs[0]), P(xs[1]), P(wsp[0]), P(wsp[1]), P(b), M, N, K, 1, P(o), st)
+        Z = Ct.c_void_p(0)   # exactly the forward's fc1 call: bias + GELU fused, split-bf16 output by TMA store
+        rc = lib.pmce_linear_tc_presplit(P(xs[0]), P(xs[1]), P(wsp[0]), P(wsp[1]), P(b), M, N, K, 1, Z, P(oh[0]), P(oh[1]), Z, st)
         assert rc == 0, lib.pmce_last_error()
     for _ in range(5):
         call()

@@ -135,10 +135,13 @@ size_t pmce_linear_tc_scratch_bytes(int M, int N, int K);
 int pmce_linear_tc(const float* x, const float* weight, const float* bias, int M, int N, int K, int act, float* out,
                    void* scratch, size_t scratch_bytes, void* stream);
 /* The two halves of pmce_linear_tc, so the GEMM kernel can be timed alone: split fp32 [rows,cols] (cols % 4 == 0)
- * into bf16 hi/lo (uint16 storage), and the GEMM on already split operands (x_hi/x_lo [M,K], w_hi/w_lo [N,K]). */
+ * into bf16 hi/lo (uint16 storage), and the GEMM on already split operands (x_hi/x_lo [M,K], w_hi/w_lo [N,K]) with the
+ * epilogue variants the forward uses: fp32 out (+ residual), or GELU + split-bf16 out. */
 int pmce_split_bf16(const float* x, int rows, int cols, void* hi, void* lo, void* stream);
 int pmce_linear_tc_presplit(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
-                            int M, int N, int K, int act, float* out, void* stream);
+                            int M, int N, int K, int act, float* out /* fp32 [M,N] or NULL */,
+                            void* out_hi, void* out_lo /* split bf16 [M,N] or NULL */, const float* resid /* [M,N] or NULL */,
+                            void* stream);
 
 /* Cumulative number of kernels this library has launched in this process (for the bench's gpu_launches). */
 unsigned long long pmce_launch_count(void);

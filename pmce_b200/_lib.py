@@ -49,7 +49,7 @@ SIGNATURES = {
     "pmce_linear_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "pmce_linear_tc": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_split_bf16": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
-    "pmce_linear_tc_presplit": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "pmce_linear_tc_presplit": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "pmce_launch_count": (C.c_ulonglong, []),
     "smpl_blend_ld": (C.c_int, []),
     "smpl_workspace_bytes": (C.c_size_t, [C.c_int]),

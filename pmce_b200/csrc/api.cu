@@ -722,12 +722,15 @@ extern "C" int pmce_split_bf16(const float* x, int rows, int cols, void* hi, voi
 }
 
 extern "C" int pmce_linear_tc_presplit(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int M,
-                                       int N, int K, int act, float* out, void* stream) {
-    if (!x_hi || !x_lo || !w_hi || !w_lo || !out || M < 1 || N < 1 || K < 8 || (K & 7)) { pmce_set_error("pmce_linear_tc_presplit: bad argument"); return 2; }
+                                       int N, int K, int act, float* out, void* out_hi, void* out_lo, const float* resid, void* stream) {
+    if (!x_hi || !x_lo || !w_hi || !w_lo || (!out && !out_hi) || (out_hi && !out_lo) || M < 1 || N < 1 || K < 8 || (K & 7)) {
+        pmce_set_error("pmce_linear_tc_presplit: bad argument"); return 2;
+    }
     TcOperand A{(const bf16*)x_hi, (const bf16*)x_lo, M, K, K}, Wm{(const bf16*)w_hi, (const bf16*)w_lo, N, K, K};
     TcEpi e;
     memset(&e, 0, sizeof(e));
     e.bias = bias; e.act = act; e.out_f32 = out; e.ld_out = N; e.rowadd_period = 1;
+    e.out_hi = (bf16*)out_hi; e.out_lo = (bf16*)out_lo; e.ld_split = N; e.resid = resid; e.ld_resid = N;
     count_launch();
     const int rc = launch_linear_tc(A, Wm, e, (cudaStream_t)stream);
     if (rc) { pmce_set_error("pmce_linear_tc_presplit: launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }

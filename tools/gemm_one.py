@@ -21,7 +21,12 @@ xs = [torch.empty(M, K, dtype=torch.bfloat16, device=dev) for _ in range(2)]
 ws = [torch.empty(N, K, dtype=torch.bfloat16, device=dev) for _ in range(2)]
 assert lib.pmce_split_bf16(P(x), M, K, P(xs[0]), P(xs[1]), st) == 0
 assert lib.pmce_split_bf16(P(w), N, K, P(ws[0]), P(ws[1]), st) == 0
+oh = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+Z = C.c_void_p(0)
 for _ in range(4):
-    assert lib.pmce_linear_tc_presplit(P(xs[0]), P(xs[1]), P(ws[0]), P(ws[1]), P(b), M, N, K, act, P(o), st) == 0
+    if act == 1:
+        assert lib.pmce_linear_tc_presplit(P(xs[0]), P(xs[1]), P(ws[0]), P(ws[1]), P(b), M, N, K, 1, Z, P(oh[0]), P(oh[1]), Z, st) == 0
+    else:
+        assert lib.pmce_linear_tc_presplit(P(xs[0]), P(xs[1]), P(ws[0]), P(ws[1]), P(b), M, N, K, 0, P(o), Z, Z, P(o) if act == 2 else Z, st) == 0
 torch.cuda.synchronize()
 print("ok")

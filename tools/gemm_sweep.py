@@ -9,8 +9,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pmce_b200 import _lib  # noqa: E402
 
-SHAPES = [(17408, 1024, 512, 1), (17408, 512, 1024, 0), (17408, 1536, 512, 0), (17408, 512, 512, 0),
-          (17408, 512, 256, 1), (17408, 256, 512, 0), (17408, 768, 256, 0),
+SHAPES = [(17408, 1024, 512, 1), (17408, 512, 1024, 2), (17408, 1536, 512, 0), (17408, 512, 512, 2),
+          (17408, 512, 256, 1), (17408, 256, 512, 2), (17408, 768, 256, 0),
           (1024, 6144, 2048, 0), (27584, 256, 64, 1), (27584, 64, 256, 0), (27584, 64, 64, 0), (27584, 192, 64, 0),
           (64, 3072, 2048, 0), (64, 20670, 2048, 0), (192, 6890, 1296, 0)]
 
@@ -30,7 +30,14 @@ def main():
         ws = [torch.empty(N, K, dtype=torch.bfloat16, device=dev) for _ in range(2)]
         assert lib.pmce_split_bf16(P(x), M, K, P(xs[0]), P(xs[1]), st) == 0
         assert lib.pmce_split_bf16(P(w), N, K, P(ws[0]), P(ws[1]), st) == 0
-        call = lambda: lib.pmce_linear_tc_presplit(P(xs[0]), P(xs[1]), P(ws[0]), P(ws[1]), P(b), M, N, K, act, P(o), st)
+        oh = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        Z = C.c_void_p(0)
+        if act == 1:      # fc1-style: GELU + split-bf16 output
+            call = lambda: lib.pmce_linear_tc_presplit(P(xs[0]), P(xs[1]), P(ws[0]), P(ws[1]), P(b), M, N, K, 1, Z, P(oh[0]), P(oh[1]), Z, st)
+        elif act == 2:    # proj/fc2-style: fp32 out with in-place residual
+            call = lambda: lib.pmce_linear_tc_presplit(P(xs[0]), P(xs[1]), P(ws[0]), P(ws[1]), P(b), M, N, K, 0, P(o), Z, Z, P(o), st)
+        else:
+            call = lambda: lib.pmce_linear_tc_presplit(P(xs[0]), P(xs[1]), P(ws[0]), P(ws[1]), P(b), M, N, K, 0, P(o), Z, Z, Z, st)
         for _ in range(3):
             assert call() == 0, lib.pmce_last_error()
         torch.cuda.synchronize()
