@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
 #include "gru_tc.cuh"
+#include "attn_tc.cuh"
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -225,12 +226,18 @@ int vit_block(const pmce_dims_t& d, const Weights& W, const VitBlockW& w, const 
     else { a.seq.div = J; a.seq.s0 = (long long)T * J; a.seq.s1 = 1; a.tok = J; nseq = B * J; L = T; }
     a.ld = 3 * C;
     ao = a; ao.ld = C;
+    if (C / Hh == 64 && L <= 128) {      // head_dim 64: packed block-diagonal attention on tcgen05 (attn_tc.cuh)
+        count_launch();
+        const int rc = launch_attn_tile_tc(ws.qkv, ws.qkv + C, ws.qkv + 2 * C, a, ws.att_s, ao, nseq, Hh, L, st);
+        if (rc) { pmce_set_error("attn_tile_tc launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
+    } else {
     const int chunk = (65535 / J) * J;   // gridDim.z limit; multiples of J keep the (b,j) decomposition intact
     for (int s0 = 0; s0 < nseq; s0 += chunk) {
         const int ns = nseq - s0 < chunk ? nseq - s0 : chunk;
         const long long r0 = a.seq(s0);
         SplitOut os{ws.att_s.hi + r0 * C, ws.att_s.lo + r0 * C};
         RET(launch_attn(C / Hh, ws.qkv + r0 * 3 * C, a, ws.qkv + r0 * 3 * C + C, ws.qkv + r0 * 3 * C + 2 * C, a, nullptr, os, ao, ns, Hh, L, L, st));
+    }
     }
     {   // x += W_proj att + b
         EpiOpt o; o.bias = W.f + w.projb; o.resid = ws.x; o.ld_resid = C; o.out = ws.x; o.ld_out = C;
