@@ -5,7 +5,7 @@
 //   O = P V            : tcgen05 128 x 64 x 128; V is consumed in place as an MN-major B operand (no transpose),
 //                        accumulator in TMEM columns [128,192); rows are scaled by 1/rowsum in the epilogue.
 // Warp-specialised, persistent over (tile, head) work items, double-buffered in shared memory:
-//   warps 4-7 (loaders): thread r loads q/k/v row r of the NEXT work item straight from the fp32 qkv activations (any
+//   warps 4-11 (loaders): thread (r, half) loads half of q/k/v row r of the NEXT work item straight from the fp32 qkv activations (any
 //       row addressing: the temporal pass strides over frames), splits to bf16 hi/lo and writes the 128-byte-swizzled
 //       K-major tiles UMMA expects; arrives on full[buf].
 //   warps 0-3 (math): thread r owns tile row r (= TMEM lane r) for softmax and the epilogue; thread 0 issues the MMAs.
@@ -35,14 +35,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_bmn(int M, int N) { r
 __device__ __forceinline__ void bar_sync_math() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 }  // namespace tc
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, AttnAddr a, SplitOut Os, AttnAddr ao,
                     int L, int G, int nseq, int H, float scale) {
     constexpr int D = 64;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sb = tc::smem_u32(smem);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * AT_BUF);   // [2], 128 loader arrivals each
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * AT_BUF);   // [2], 256 loader arrivals each
     uint64_t* empty_bar = full_bar + 2;                                    // [2], 1 arrival (math thread 0)
     uint64_t* bar_s = empty_bar + 2;
     uint64_t* bar_o = bar_s + 1;
@@ -50,7 +50,7 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b) { tc::mbar_init(&full_bar[b], 128); tc::mbar_init(&empty_bar[b], 1); }
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&full_bar[b], 256); tc::mbar_init(&empty_bar[b], 1); }
         tc::mbar_init(bar_s, 1);
         tc::mbar_init(bar_o, 1);
         tc::fence_barrier_init();
@@ -67,7 +67,12 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
     const int nwork = ntiles * H;
 
     if (warp >= 4) {
-        // ================= loaders =================
+        // ================= loaders: 8 warps, thread = (row, half of the 64-wide head slice) =================
+        // All 24 16-byte loads of a work item are issued before the first use: ~100 KB in flight per SM, which is what it
+        // takes to cover HBM latency at full bandwidth (a 4-warp loader with 12 loads in flight was latency-bound).
+        const int lt = tid - 128;
+        const int lr = lt & 127, hf = lt >> 7;
+        const int lg = lr / L, ltok = lr - lg * L;
         uint32_t it = 0;
         for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -75,36 +80,34 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
             const uint32_t Qh = base_s, Ql = base_s + AT_TILE, Kh = base_s + 2 * AT_TILE, Kl = base_s + 3 * AT_TILE, Vh = base_s + 4 * AT_TILE,
                            Vl = base_s + 5 * AT_TILE;
             const int tile = work / H, h = work - tile * H;
-            const int s = tile * G + g;
-            const bool valid = (g < G) && (s < nseq);
-            tc::mbar_wait(&empty_bar[buf], ((it >> 1) & 1) ^ 1);
+            const int s = tile * G + lg;
+            const bool valid = (lg < G) && (s < nseq);
+            float4 q[8], k[8], v[8];
             if (valid) {
-                const size_t base = (size_t)(a.seq(s) + (long long)tok * a.tok) * a.ld + h * D;
-#pragma unroll 2
-                for (int c = 0; c < 8; ++c) {
-                    const float4 q0 = ld4(Q + base + c * 8), q1 = ld4(Q + base + c * 8 + 4);
-                    const float4 k0 = ld4(K + base + c * 8), k1 = ld4(K + base + c * 8 + 4);
-                    const float4 v0 = ld4(V + base + c * 8), v1 = ld4(V + base + c * 8 + 4);
-                    float x[8];
-                    uint4 hh, ll;
-                    x[0] = q0.x * scale; x[1] = q0.y * scale; x[2] = q0.z * scale; x[3] = q0.w * scale;
-                    x[4] = q1.x * scale; x[5] = q1.y * scale; x[6] = q1.z * scale; x[7] = q1.w * scale;
-                    tc::split8(x, hh, ll);
-                    tc::sts16(Qh, r, c, hh); tc::sts16(Ql, r, c, ll);
-                    x[0] = k0.x; x[1] = k0.y; x[2] = k0.z; x[3] = k0.w; x[4] = k1.x; x[5] = k1.y; x[6] = k1.z; x[7] = k1.w;
-                    tc::split8(x, hh, ll);
-                    tc::sts16(Kh, r, c, hh); tc::sts16(Kl, r, c, ll);
-                    x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-                    tc::split8(x, hh, ll);
-                    tc::sts16(Vh, r, c, hh); tc::sts16(Vl, r, c, ll);
-                }
-            } else {
-                const uint4 z = make_uint4(0, 0, 0, 0);
+                const size_t base = (size_t)(a.seq(s) + (long long)ltok * a.tok) * a.ld + h * D + hf * 32;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    tc::sts16(Qh, r, c, z); tc::sts16(Ql, r, c, z); tc::sts16(Kh, r, c, z);
-                    tc::sts16(Kl, r, c, z); tc::sts16(Vh, r, c, z); tc::sts16(Vl, r, c, z);
-                }
+                for (int i = 0; i < 8; ++i) { q[i] = ld4(Q + base + i * 4); k[i] = ld4(K + base + i * 4); v[i] = ld4(V + base + i * 4); }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) q[i] = k[i] = v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            tc::mbar_wait(&empty_bar[buf], ((it >> 1) & 1) ^ 1);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float x[8];
+                uint4 hh, ll;
+                x[0] = q[2 * c].x * scale; x[1] = q[2 * c].y * scale; x[2] = q[2 * c].z * scale; x[3] = q[2 * c].w * scale;
+                x[4] = q[2 * c + 1].x * scale; x[5] = q[2 * c + 1].y * scale; x[6] = q[2 * c + 1].z * scale; x[7] = q[2 * c + 1].w * scale;
+                tc::split8(x, hh, ll);
+                tc::sts16(Qh, lr, hf * 4 + c, hh); tc::sts16(Ql, lr, hf * 4 + c, ll);
+                x[0] = k[2 * c].x; x[1] = k[2 * c].y; x[2] = k[2 * c].z; x[3] = k[2 * c].w;
+                x[4] = k[2 * c + 1].x; x[5] = k[2 * c + 1].y; x[6] = k[2 * c + 1].z; x[7] = k[2 * c + 1].w;
+                tc::split8(x, hh, ll);
+                tc::sts16(Kh, lr, hf * 4 + c, hh); tc::sts16(Kl, lr, hf * 4 + c, ll);
+                x[0] = v[2 * c].x; x[1] = v[2 * c].y; x[2] = v[2 * c].z; x[3] = v[2 * c].w;
+                x[4] = v[2 * c + 1].x; x[5] = v[2 * c + 1].y; x[6] = v[2 * c + 1].z; x[7] = v[2 * c + 1].w;
+                tc::split8(x, hh, ll);
+                tc::sts16(Vh, lr, hf * 4 + c, hh); tc::sts16(Vl, lr, hf * 4 + c, ll);
             }
             tc::fence_proxy_async();
             tc::mbar_arrive(&full_bar[buf]);
@@ -253,6 +256,6 @@ static inline int launch_attn_tile_tc(const float* Q, const float* K, const floa
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int grid = (int)(work < sms ? work : sms);
-    attn_tile_tc_kernel<<<grid, 256, AT_SMEM, st>>>(Q, K, V, a, Os, ao, L, G, nseq, H, 1.0f / sqrtf(64.0f));
+    attn_tile_tc_kernel<<<grid, 384, AT_SMEM, st>>>(Q, K, V, a, Os, ao, L, G, nseq, H, 1.0f / sqrtf(64.0f));
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
