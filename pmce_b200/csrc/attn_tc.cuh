@@ -159,11 +159,14 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
                 uint32_t v[32];
                 tc::tmem_ld_32x32(tS + lane_sel + c * 32, v);
                 tc::tmem_ld_wait();
+                if (c * 32 < ce && c * 32 + 32 > cs) {                        // this row's sequence touches the chunk (divergent, cheap)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int col = c * 32 + i;
-                    if (col >= cs && col < ce) m = fmaxf(m, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = c * 32 + i;
+                        if (col >= cs && col < ce) m = fmaxf(m, __uint_as_float(v[i]));
+                    }
                 }
+                __syncwarp();
             }
             float lsum = 0.f;
 #pragma unroll 1
@@ -178,20 +181,28 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
                 uint32_t v[32];
                 tc::tmem_ld_32x32(tS + lane_sel + c * 32, v);
                 tc::tmem_ld_wait();
+                if (c * 32 < ce && c * 32 + 32 > cs) {                        // this row's sequence touches the chunk
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float p[8];
+                    for (int j = 0; j < 4; ++j) {
+                        float p[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int col = c * 32 + j * 8 + i;
-                        p[i] = (col >= cs && col < ce) ? expf(__uint_as_float(v[j * 8 + i]) - m) : 0.f;
-                        lsum += p[i];
+                        for (int i = 0; i < 8; ++i) {
+                            const int col = c * 32 + j * 8 + i;
+                            // exp2-based fast exponential: |rel err| ~ 2^-21, two orders below the bf16x3 product error
+                            p[i] = (col >= cs && col < ce) ? __expf(__uint_as_float(v[j * 8 + i]) - m) : 0.f;
+                            lsum += p[i];
+                        }
+                        uint4 hh, ll;
+                        tc::split8(p, hh, ll);
+                        tc::sts16(Ph + t * AT_TILE, r, (c & 1) * 4 + j, hh);
+                        tc::sts16(Pl + t * AT_TILE, r, (c & 1) * 4 + j, ll);
                     }
-                    uint4 hh, ll;
-                    tc::split8(p, hh, ll);
-                    tc::sts16(Ph + t * AT_TILE, r, (c & 1) * 4 + j, hh);
-                    tc::sts16(Pl + t * AT_TILE, r, (c & 1) * 4 + j, ll);
+                } else {
+                    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { tc::sts16(Ph + t * AT_TILE, r, (c & 1) * 4 + j, z); tc::sts16(Pl + t * AT_TILE, r, (c & 1) * 4 + j, z); }
                 }
+                __syncwarp();
             }
             tc::fence_proxy_async();
             tc::tc_fence_before();
