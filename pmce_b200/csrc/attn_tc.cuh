@@ -19,7 +19,7 @@
 
 constexpr int AT_TILE = 128 * 128;                 // bytes: [128 rows][64 bf16]
 constexpr int AT_BUF = 6 * AT_TILE;                // Qh Ql Kh Kl Vh Vl   (P hi aliases Qh|Ql, P lo aliases Kh|Kl)
-constexpr int AT_SMEM = 2 * AT_BUF + 2 * AT_TILE /* O staging hi, lo */ + 1024 + 128;
+constexpr int AT_SMEM = 2 * AT_BUF + 1024 + 128;
 
 namespace tc {
 __device__ __forceinline__ void sts16(uint32_t tile, int row, int chunk, uint4 v) {   // 16-byte chunk, SW128 pattern
@@ -42,8 +42,7 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sb = tc::smem_u32(smem);
-    const uint32_t Oh = sb + 2 * AT_BUF, Ol = Oh + AT_TILE;                // output staging tiles (math warps only)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * AT_BUF + 2 * AT_TILE);   // [2], 256 loader arrivals each
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * AT_BUF);   // [2], 256 loader arrivals each
     uint64_t* empty_bar = full_bar + 2;                                    // [2], 1 arrival (math thread 0)
     uint64_t* bar_s = empty_bar + 2;
     uint64_t* bar_o = bar_s + 1;
@@ -227,47 +226,22 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
             tc::mbar_wait(bar_o, it & 1);
             tc::tc_fence_after();
 
-            // ---- epilogue: O row / rowsum -> split bf16 -> swizzled staging tiles -> coalesced global stores ----
-            // (a row-per-thread store touches 32 different 128-byte lines per instruction; staging lets 8 consecutive threads
-            //  write one full line of one row, whatever the row addressing is)
+            // ---- epilogue: O row / rowsum -> split bf16 -> global ----
+            uint32_t v0[32];
             const float inv = 1.0f / lsum;
+            const size_t ob = valid ? (size_t)(ao.seq(s) + (long long)tok * ao.tok) * ao.ld + h * D : 0;
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
-                uint32_t v0[32];
                 tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v0);
                 tc::tmem_ld_wait();
+                if (valid) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float x[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v0[j * 8 + i]) * inv;
-                    uint4 hh, ll;
-                    tc::split8(x, hh, ll);
-                    tc::sts16(Oh, r, hf * 4 + j, hh);
-                    tc::sts16(Ol, r, hf * 4 + j, ll);
+                    for (int i = 0; i < 32; i += 4)
+                        store_split4(Os, ob + hf * 32 + i, make_float4(__uint_as_float(v0[i]) * inv, __uint_as_float(v0[i + 1]) * inv,
+                                                                       __uint_as_float(v0[i + 2]) * inv, __uint_as_float(v0[i + 3]) * inv));
                 }
+                __syncwarp();
             }
-            tc::tc_fence_before();
-            tc::bar_sync_math();
-            {
-                const int chunk = tid & 7;
-#pragma unroll 1
-                for (int i = 0; i < 8; ++i) {
-                    const int row = (tid >> 3) + 16 * i;
-                    const int rg = row / L, rtok = row - rg * L;
-                    const int rs = tile * G + rg;
-                    if (rg < G && rs < nseq) {
-                        const size_t off = (size_t)(ao.seq(rs) + (long long)rtok * ao.tok) * ao.ld + h * D + chunk * 8;
-                        uint4 hh, ll;
-                        const uint32_t sa = row * 128 + ((chunk ^ (row & 7)) << 4);
-                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(hh.x), "=r"(hh.y), "=r"(hh.z), "=r"(hh.w) : "r"(Oh + sa));
-                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(ll.x), "=r"(ll.y), "=r"(ll.z), "=r"(ll.w) : "r"(Ol + sa));
-                        *reinterpret_cast<uint4*>(Os.hi + off) = hh;
-                        *reinterpret_cast<uint4*>(Os.lo + off) = ll;
-                    }
-                }
-            }
-            (void)valid; (void)s;
         }
     }
     tc::tc_fence_before();
