@@ -15,6 +15,7 @@
 // The block-diagonal trick spends 128/L x more MMA flops than the attention needs, which is free here: the CUDA-core
 // kernel it replaces ran with 17 of 32 lanes active and ~3 warps per scheduler.
 #pragma once
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "common.cuh"
 #include "kernels.cuh"
@@ -40,7 +41,7 @@ __device__ __forceinline__ void bar_sync_group(int id) { asm volatile("bar.sync 
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, AttnAddr a, SplitOut Os, AttnAddr ao,
-                    int L, int G, int nseq, int H, float scale) {
+                    int L, int G, int nseq, int H, float scale, int dbg) {
     constexpr int D = 64;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -81,7 +82,7 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
             const uint32_t base_s = sb + grp * AT_BUF;
             const int tile = work / H, h = work - tile * H;
             const int s = tile * G + lg;
-            const bool valid = (lg < G) && (s < nseq);
+            const bool valid = (lg < G) && (s < nseq) && dbg != 1;
             const size_t base = valid ? (size_t)(a.seq(s) + (long long)ltok * a.tok) * a.ld + h * D + hf * 32 : 0;
             float4 x0[8];
             // q first (in flight while we wait for the buffer), then k, v
@@ -150,6 +151,11 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
             const bool valid = (g < G) && (s < nseq);
 
             tc::mbar_wait(&full_bar[grp], j & 1);
+            if (dbg == 2) {                                                 // profiling knob: loader-only timing
+                tc::bar_sync_group(1 + grp);
+                if (issuer) tc::mbar_arrive(&empty_bar[grp]);
+                continue;
+            }
             tc::tc_fence_before();
             tc::bar_sync_group(1 + grp);                                   // the group has finished reading TMEM of its previous item
             if (issuer) {
@@ -285,6 +291,8 @@ static inline int launch_attn_tile_tc(const float* Q, const float* K, const floa
     }
     const long long want = (work + 1) / 2;                 // two items in flight per CTA
     const int grid = (int)(want < sms ? (want < 1 ? 1 : want) : sms);
-    attn_tile_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(Q, K, V, a, Os, ao, L, G, nseq, H, 1.0f / sqrtf(64.0f));
+    static int dbg = -1;   // PMCE_ATTN_DEBUG=1: loaders skip global loads; =2: math groups skip all work (profiling only, wrong results)
+    if (dbg < 0) { const char* e = getenv("PMCE_ATTN_DEBUG"); dbg = e ? atoi(e) : 0; }
+    attn_tile_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(Q, K, V, a, Os, ao, L, G, nseq, H, 1.0f / sqrtf(64.0f), dbg);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
