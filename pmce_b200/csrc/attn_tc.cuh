@@ -82,7 +82,7 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
             const uint32_t base_s = sb + grp * AT_BUF;
             const int tile = work / H, h = work - tile * H;
             const int s = tile * G + lg;
-            const bool valid = (lg < G) && (s < nseq) && dbg != 1;
+            const bool valid = (lg < G) && (s < nseq) && !(dbg & 1);
             const size_t base = valid ? (size_t)(a.seq(s) + (long long)ltok * a.tok) * a.ld + h * D + hf * 32 : 0;
             float4 x0[8];
             // q first (in flight while we wait for the buffer), then k, v
@@ -178,6 +178,7 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
             float m = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
+                if (dbg & 4) break;
                 if (c * 32 >= win_hi || c * 32 + 32 <= win_lo) continue;      // warp-uniform
                 uint32_t v[32];
                 tc::tmem_ld_32x32(tS + lane_sel + c * 32, v);
@@ -194,6 +195,7 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
             float lsum = 0.f;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
+                if (dbg & 4) { lsum = 1.f; break; }
                 const int t = c >> 1;                                         // P tile (keys 0-63 / 64-127)
                 if (c * 32 >= win_hi || c * 32 + 32 <= win_lo) {              // warp-uniform: nothing of this warp's rows lives here
                     const uint4 z = make_uint4(0, 0, 0, 0);
@@ -257,7 +259,7 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
                 uint32_t v0[32];
                 tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v0);
                 tc::tmem_ld_wait();
-                if (valid) {
+                if (valid && !(dbg & 8)) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
                         store_split4(Os, ob + hf * 32 + i, make_float4(__uint_as_float(v0[i]) * inv, __uint_as_float(v0[i + 1]) * inv,
