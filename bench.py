@@ -185,7 +185,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="pmce_b200", choices=["pmce_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -334,7 +334,9 @@ def dominant_kernel_roofline(lib, dev, peaks, B):
     flops = 2.0 * M * N * K
     ach = flops / sec / 1e12
     return {"kernel": "linear_tc_kernel (tcgen05/TMA/TMEM split-bf16 GEMM; lifter fc1 + bias + GELU)", "bound": "tensor", "achieved": ach,
-            "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+            "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1j_linear_tc_fc1_ncu_raw.csv)
+            "traffic": 56.7e6, "traffic_unit": "B", "frac_of_split_ceiling": 3.0 * ach / peaks["bf16_tflops"],
             "flops_per_launch": flops, "mma_flops_per_launch": 3 * flops, "us_per_launch": sec * 1e6, "shape_MNK": [M, N, K],
             "peak_source": peaks["source"], "note": "3 bf16 MMAs per product (bf16x3): frac ceiling is 1/3"}
 
