@@ -17,6 +17,7 @@
 #include "gemm_tc.cuh"
 #include "gru_tc.cuh"
 #include "attn_tc.cuh"
+#include "attn_flash_tc.cuh"
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -193,6 +194,15 @@ AttnAddr addr_plain(int ntok, int ld) {
 }
 
 const SplitOut NO_SPLIT{nullptr, nullptr};
+
+// head_dim-32 attention on tcgen05 (attn_flash_tc.cuh): the decoder's vertex self- and cross-attention
+int flash_attn32(const float* Q, AttnAddr aq, const float* K, const float* V, AttnAddr akv, const SplitOut& Os, AttnAddr ao, int nseq, int H, int N1,
+                 int N2, cudaStream_t st) {
+    count_launch();
+    const int rc = launch_attn_flash_tc(Q, aq, K, V, akv, Os, ao, nseq, H, N1, N2, st);
+    if (rc) { pmce_set_error("attn_flash_tc launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
+    return 0;
+}
 
 int ln_rows(const float* x, int nrows, int C, const LnParams* a, const float* pos, int pos_div, int pos_mod, float* out1,
             const LnParams* b, const SplitOut& out2s, cudaStream_t st) {
@@ -440,7 +450,7 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
     RET(proj64(ws.tJ_s, nj, W, w.vca.wk, w.vca.bk, ws.Kj, st));
     RET(adaln(ws.Jf, B, J, gb, w.vca.sv, ws.tJ_s, st));
     RET(proj64(ws.tJ_s, nj, W, w.vca.wv, w.vca.bv, ws.Vj, st));
-    RET(launch_attn(32, ws.Qv, addr_plain(Vd, 64), ws.Kj, ws.Vj, addr_plain(J, 64), nullptr, ws.att_ds, addr_plain(Vd, 64), B, 2, Vd, J, st));
+    RET(flash_attn32(ws.Qv, addr_plain(Vd, 64), ws.Kj, ws.Vj, addr_plain(J, 64), ws.att_ds, addr_plain(Vd, 64), B, 2, Vd, J, st));
     RET(attn_tail(W, w.vca.wp, w.vca.bp, w.vca.s2, w.vca.fc1w, w.vca.fc1b, w.vca.fc2w, w.vca.fc2b, ws.xqv, ws.att_ds, ws.tA_s, ws.hid_ds, gb, B, Vd, st));
 
     if (ja) {
@@ -465,7 +475,7 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
     // ---- vertex self-attention block: 431 x 431, 2 heads x 32 ----
     RET(adaln(ws.xqv, B, Vd, gb, w.vsa.s1, ws.tA_s, st));
     RET(proj64(ws.tA_s, nv, W, w.vsa.qkvw, w.vsa.qkvb, ws.qkv_d, st, nullptr, 1, 192));
-    RET(launch_attn(32, ws.qkv_d, addr_plain(Vd, 192), ws.qkv_d + 64, ws.qkv_d + 128, addr_plain(Vd, 192), nullptr, ws.att_ds, addr_plain(Vd, 64), B, 2, Vd, Vd, st));
+    RET(flash_attn32(ws.qkv_d, addr_plain(Vd, 192), ws.qkv_d + 64, ws.qkv_d + 128, addr_plain(Vd, 192), ws.att_ds, addr_plain(Vd, 64), B, 2, Vd, Vd, st));
     RET(attn_tail(W, w.vsa.wp, w.vsa.bp, w.vsa.s2, w.vsa.fc1w, w.vsa.fc1b, w.vsa.fc2w, w.vsa.fc2b, ws.xqv, ws.att_ds, ws.tA_s, ws.hid_ds, gb, B, Vd, st));
     feat2coor_kernel<<<cdiv(nv, 8), 256, 0, st>>>(ws.xqv, nv, W.f + w.vf2cw, W.f + w.vf2cb, verts_in, verts_out);
     CKL();
