@@ -71,7 +71,8 @@ struct Workspace {
     // decoder
     float *gb, *verts[3], *Jf, *Vf, *xqv, *Qv, *xkj, *Kj, *Vj, *qkv_d;
     float *xqj, *xkv, *Kv, *Vv, *Qj, *qkvj;
-    SplitOut Jf_s, Vf_s, tA_s, tA2_s, tJ_s, att_ds, hid_ds, attj_s, hidj_s, im2col_s;
+    SplitOut Jf_s, Vf_s, tA_s, tA2_s, tB_s, tJ_s, tJ2_s, att_ds, hid_ds, attj_s, hidj_s, im2col_s;
+    float* lc_mesh;
     size_t bytes;
 };
 
@@ -100,6 +101,8 @@ Workspace carve(const pmce_dims_t& d, int B, void* base) {
     w.Jf_s = c.split(nj * D); w.Vf_s = c.split(nv * D); w.tA_s = c.split(nv * D); w.tA2_s = c.split(nv * D); w.tJ_s = c.split(nj * D);
     w.att_ds = c.split(nv * D); w.hid_ds = c.split(nv * 4 * D); w.attj_s = c.split(nj * D); w.hidj_s = c.split(nj * 4 * D);
     w.im2col_s = c.split((size_t)B * 3 * ((Vd * 3 + 7) / 8 * 8));
+    w.tB_s = c.split(nv * D); w.tJ2_s = c.split(nj * D);
+    w.lc_mesh = c.f32((size_t)B * d.num_vert * 3);
     w.bytes = c.cur;
     return w;
 }
@@ -396,6 +399,29 @@ int gru_mid(const Layout& L, const Weights& W, int B, float* g, const Workspace&
     return 0;
 }
 
+// Side stream + fork/join events so the two encoder streams (pose lifter / GRU image-feature aggregation) run
+// concurrently inside one pmce_forward call. One set per device, created on first use (before any graph capture: the
+// host driver always runs an eager warm-up first); the only process-lifetime state the library keeps besides the
+// layout cache.
+struct Aux {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr;
+};
+Aux* get_aux() {
+    static Aux aux[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    Aux& a = aux[dev];
+    if (!a.side) {
+        if (cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&a.fork2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&a.join2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &a;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // a5 AdaLN gamma/beta, a6-a8 co-evolution block
 // ---------------------------------------------------------------------------------------------------
@@ -424,7 +450,7 @@ int proj64(const SplitOut& a, int M, const Weights& W, size_t w, size_t b, float
 }
 
 int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, const float* verts_in, const float* gb, int B,
-                float* joints_out, float* verts_out, const Workspace& ws, cudaStream_t st) {
+                float* joints_out, float* verts_out, const Workspace& ws, cudaStream_t st, Aux* aux = nullptr) {
     const pmce_dims_t& d = L.d;
     const CoevoW& w = L.blk[k];
     const int J = d.num_joint, Vd = d.num_vert_ds;
@@ -443,6 +469,34 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
     RET(proj64(ws.Jf_s, nj, W, w.j2vw, w.j2vb, ws.xkj, st, W.f + w.j2vK, J));
     if (ja) RET(proj64(ws.Vf_s, nv, W, w.v2jw, w.v2jb, ws.xkv, st, W.f + w.v2jK, Vd));
 
+    if (ja) {
+        // the joint branch only reads pre-update features: it runs on the side stream next to the vertex branch
+        cudaStream_t sj = st;
+        if (aux) {
+            CK(cudaEventRecord(aux->fork2, sj));
+            CK(cudaStreamWaitEvent(aux->side, aux->fork2, 0));
+            sj = aux->side;
+        }
+        // ---- joint cross-attention block: q = joints (J), k/v = vertices (431); 8 heads x 8 ----
+        RET(adaln(ws.xqj, B, J, gb, w.jca.sq, ws.tJ2_s, sj));
+        RET(proj64(ws.tJ2_s, nj, W, w.jca.wq, w.jca.bq, ws.Qj, sj));
+        RET(adaln(ws.xkv, B, Vd, gb, w.jca.sk, ws.tB_s, sj));
+        RET(proj64(ws.tB_s, nv, W, w.jca.wk, w.jca.bk, ws.Kv, sj));
+        RET(adaln(ws.Vf, B, Vd, gb, w.jca.sv, ws.tA2_s, sj));
+        RET(proj64(ws.tA2_s, nv, W, w.jca.wv, w.jca.bv, ws.Vv, sj));
+        RET(launch_attn(8, ws.Qj, addr_plain(J, 64), ws.Kv, ws.Vv, addr_plain(Vd, 64), nullptr, ws.attj_s, addr_plain(J, 64), B, 8, J, Vd, sj));
+        RET(attn_tail(W, w.jca.wp, w.jca.bp, w.jca.s2, w.jca.fc1w, w.jca.fc1b, w.jca.fc2w, w.jca.fc2b, ws.xqj, ws.attj_s, ws.tJ2_s, ws.hidj_s, gb, B, J, sj));
+        // ---- joint self-attention block ----
+        RET(adaln(ws.xqj, B, J, gb, w.jsa.s1, ws.tJ2_s, sj));
+        RET(proj64(ws.tJ2_s, nj, W, w.jsa.qkvw, w.jsa.qkvb, ws.qkvj, sj, nullptr, 1, 192));
+        RET(launch_attn(8, ws.qkvj, addr_plain(J, 192), ws.qkvj + 64, ws.qkvj + 128, addr_plain(J, 192), nullptr, ws.attj_s, addr_plain(J, 64), B, 8, J, J, sj));
+        RET(attn_tail(W, w.jsa.wp, w.jsa.bp, w.jsa.s2, w.jsa.fc1w, w.jsa.fc1b, w.jsa.fc2w, w.jsa.fc2b, ws.xqj, ws.attj_s, ws.tJ2_s, ws.hidj_s, gb, B, J, sj));
+        feat2coor_kernel<<<cdiv(nj, 8), 256, 0, sj>>>(ws.xqj, nj, W.f + w.jf2cw, W.f + w.jf2cb, joints, joints_out);
+        CKL();
+        if (aux) CK(cudaEventRecord(aux->join2, aux->side));
+    }
+
+
     // ---- vertex cross-attention block: q = vertices (431), k/v = joints (J); 2 heads x 32 ----
     RET(adaln(ws.xqv, B, Vd, gb, w.vca.sq, ws.tA_s, st));
     RET(proj64(ws.tA_s, nv, W, w.vca.wq, w.vca.bq, ws.Qv, st));
@@ -453,25 +507,6 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
     RET(flash_attn32(ws.Qv, addr_plain(Vd, 64), ws.Kj, ws.Vj, addr_plain(J, 64), ws.att_ds, addr_plain(Vd, 64), B, 2, Vd, J, st));
     RET(attn_tail(W, w.vca.wp, w.vca.bp, w.vca.s2, w.vca.fc1w, w.vca.fc1b, w.vca.fc2w, w.vca.fc2b, ws.xqv, ws.att_ds, ws.tA_s, ws.hid_ds, gb, B, Vd, st));
 
-    if (ja) {
-        // ---- joint cross-attention block: q = joints (J), k/v = vertices (431); 8 heads x 8 ----
-        RET(adaln(ws.xqj, B, J, gb, w.jca.sq, ws.tJ_s, st));
-        RET(proj64(ws.tJ_s, nj, W, w.jca.wq, w.jca.bq, ws.Qj, st));
-        RET(adaln(ws.xkv, B, Vd, gb, w.jca.sk, ws.tA_s, st));
-        RET(proj64(ws.tA_s, nv, W, w.jca.wk, w.jca.bk, ws.Kv, st));
-        RET(adaln(ws.Vf, B, Vd, gb, w.jca.sv, ws.tA2_s, st));
-        RET(proj64(ws.tA2_s, nv, W, w.jca.wv, w.jca.bv, ws.Vv, st));
-        RET(launch_attn(8, ws.Qj, addr_plain(J, 64), ws.Kv, ws.Vv, addr_plain(Vd, 64), nullptr, ws.attj_s, addr_plain(J, 64), B, 8, J, Vd, st));
-        RET(attn_tail(W, w.jca.wp, w.jca.bp, w.jca.s2, w.jca.fc1w, w.jca.fc1b, w.jca.fc2w, w.jca.fc2b, ws.xqj, ws.attj_s, ws.tJ_s, ws.hidj_s, gb, B, J, st));
-        // ---- joint self-attention block ----
-        RET(adaln(ws.xqj, B, J, gb, w.jsa.s1, ws.tJ_s, st));
-        RET(proj64(ws.tJ_s, nj, W, w.jsa.qkvw, w.jsa.qkvb, ws.qkvj, st, nullptr, 1, 192));
-        RET(launch_attn(8, ws.qkvj, addr_plain(J, 192), ws.qkvj + 64, ws.qkvj + 128, addr_plain(J, 192), nullptr, ws.attj_s, addr_plain(J, 64), B, 8, J, J, st));
-        RET(attn_tail(W, w.jsa.wp, w.jsa.bp, w.jsa.s2, w.jsa.fc1w, w.jsa.fc1b, w.jsa.fc2w, w.jsa.fc2b, ws.xqj, ws.attj_s, ws.tJ_s, ws.hidj_s, gb, B, J, st));
-        feat2coor_kernel<<<cdiv(nj, 8), 256, 0, st>>>(ws.xqj, nj, W.f + w.jf2cw, W.f + w.jf2cb, joints, joints_out);
-        CKL();
-    }
-
     // ---- vertex self-attention block: 431 x 431, 2 heads x 32 ----
     RET(adaln(ws.xqv, B, Vd, gb, w.vsa.s1, ws.tA_s, st));
     RET(proj64(ws.tA_s, nv, W, w.vsa.qkvw, w.vsa.qkvb, ws.qkv_d, st, nullptr, 1, 192));
@@ -479,31 +514,40 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
     RET(attn_tail(W, w.vsa.wp, w.vsa.bp, w.vsa.s2, w.vsa.fc1w, w.vsa.fc1b, w.vsa.fc2w, w.vsa.fc2b, ws.xqv, ws.att_ds, ws.tA_s, ws.hid_ds, gb, B, Vd, st));
     feat2coor_kernel<<<cdiv(nv, 8), 256, 0, st>>>(ws.xqv, nv, W.f + w.vf2cw, W.f + w.vf2cb, verts_in, verts_out);
     CKL();
+    if (ja && aux) CK(cudaStreamWaitEvent(st, aux->join2, 0));
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // a9 tail: upsample_conv + linear_cur residual
 // ---------------------------------------------------------------------------------------------------
-int mesh_epilogue(const Layout& L, const Weights& W, const float* verts3, const float* g, int B, float* mesh, const Workspace& ws, cudaStream_t st) {
+// linear_cur1-3(relu(y_mid)) laid out like the mesh ([B,6890,3]); depends only on the GRU output, so pmce_forward runs it
+// on the image-feature stream while the pose stream is still busy (169 MB of weights streamed once per batch)
+int mesh_residual(const Layout& L, const Weights& W, const float* g, int B, const Workspace& ws, cudaStream_t st) {
     const pmce_dims_t& d = L.d;
-    const int Vd = d.num_vert_ds, V = d.num_vert, F = d.feat_dim, ldk = L.ups_ld;
+    const int V = d.num_vert, F = d.feat_dim;
+    RET(split_rows(g, B, F, F, true, ws.gr_s, F, st));     // relu(y_mid)
+    EpiOpt o; o.bias = W.f + L.lc_b; o.out = ws.lc_mesh; o.mapped = true;
+    o.rmap.div = 1; o.rmap.s0 = (long long)V * 3; o.rmap.s1 = 0;
+    o.cmap.div = V; o.cmap.s0 = 1; o.cmap.s1 = 3;
+    return linear_tc(ws.gr_s, F, B, F, W, L.lc_w, F, 3 * V, o, st);
+}
+
+// mesh[b,o,l] = b_up[o] + sum_{c,k} W_up[o,c,k] verts3[b,c,l+k-1] + lc_mesh[b,o,l]
+int mesh_upsample(const Layout& L, const Weights& W, const float* verts3, int B, float* mesh, const Workspace& ws, cudaStream_t st) {
+    const pmce_dims_t& d = L.d;
+    const int Vd = d.num_vert_ds, V = d.num_vert, ldk = L.ups_ld;
     upsample_im2col_kernel<<<cdiv((long long)B * 3 * ldk, 256), 256, 0, st>>>(verts3, B, Vd, ldk, nullptr, ws.im2col_s);
     CKL();
-    {   // mesh[b,o,l] = b_up[o] + sum_{c,k} W_up[o,c,k] verts3[b,c,l+k-1]
-        EpiOpt o; o.bias = W.f + L.ups_b; o.out = mesh; o.mapped = true;
-        o.rmap.div = 3; o.rmap.s0 = (long long)V * 3; o.rmap.s1 = 1;
-        o.cmap.div = 1; o.cmap.s0 = 3; o.cmap.s1 = 0;
-        RET(linear_tc(ws.im2col_s, ldk, B * 3, ldk, W, L.ups_w, ldk, V, o, st));
-    }
-    RET(split_rows(g, B, F, F, true, ws.gr_s, F, st));     // relu(y_mid)
-    {   // mesh[b,o,l] += W_cur{l+1} relu(g[b]) + b_cur{l+1}
-        EpiOpt o; o.bias = W.f + L.lc_b; o.out = mesh; o.resid = mesh; o.mapped = true;
-        o.rmap.div = 1; o.rmap.s0 = (long long)V * 3; o.rmap.s1 = 0;
-        o.cmap.div = V; o.cmap.s0 = 1; o.cmap.s1 = 3;
-        RET(linear_tc(ws.gr_s, F, B, F, W, L.lc_w, F, 3 * V, o, st));
-    }
-    return 0;
+    EpiOpt o; o.bias = W.f + L.ups_b; o.out = mesh; o.resid = ws.lc_mesh; o.mapped = true;
+    o.rmap.div = 3; o.rmap.s0 = (long long)V * 3; o.rmap.s1 = 1;
+    o.cmap.div = 1; o.cmap.s0 = 3; o.cmap.s1 = 0;
+    return linear_tc(ws.im2col_s, ldk, B * 3, ldk, W, L.ups_w, ldk, V, o, st);
+}
+
+int mesh_epilogue(const Layout& L, const Weights& W, const float* verts3, const float* g, int B, float* mesh, const Workspace& ws, cudaStream_t st) {
+    RET(mesh_residual(L, W, g, B, ws, st));
+    return mesh_upsample(L, W, verts3, B, mesh, ws, st);
 }
 
 int prepare_feat(const Layout& L, const float* img_feat, int B, const Workspace& ws, cudaStream_t st) {
@@ -514,11 +558,12 @@ int prepare_feat(const Layout& L, const float* img_feat, int B, const Workspace&
 // image-feature stream of the two-stream encoder: GRU -> y[T//2] -> all AdaLN gamma/beta (independent of the pose stream)
 int decoder_front(const Layout& L, const Weights& W, int B, const Workspace& ws, cudaStream_t st) {
     RET(gru_mid(L, W, B, ws.g, ws, st));
-    return adaln_gammabeta(L, W, ws.g, B, ws.gb, ws.g_s, st);
+    RET(adaln_gammabeta(L, W, ws.g, B, ws.gb, ws.g_s, st));
+    return mesh_residual(L, W, ws.g, B, ws, st);
 }
 
 int decoder_back(const Layout& L, const Weights& W, const float* joints, const int32_t* vj, int B, float* cam_pose, float* cam_mesh,
-                 float* verts0_out, const Workspace& ws, cudaStream_t st) {
+                 float* verts0_out, const Workspace& ws, cudaStream_t st, Aux* aux = nullptr) {
     const pmce_dims_t& d = L.d;
     const int J = d.num_joint, Vd = d.num_vert_ds;
     float* v0 = verts0_out ? verts0_out : ws.verts[2];
@@ -526,30 +571,9 @@ int decoder_back(const Layout& L, const Weights& W, const float* joints, const i
     CKL();
     RET(coevo_block(L, W, 0, joints, v0, ws.gb, B, nullptr, ws.verts[0], ws, st));
     RET(coevo_block(L, W, 1, joints, ws.verts[0], ws.gb, B, nullptr, ws.verts[1], ws, st));
-    RET(coevo_block(L, W, 2, joints, ws.verts[1], ws.gb, B, cam_pose, ws.verts[0], ws, st));
-    RET(mesh_epilogue(L, W, ws.verts[0], ws.g, B, cam_mesh, ws, st));
+    RET(coevo_block(L, W, 2, joints, ws.verts[1], ws.gb, B, cam_pose, ws.verts[0], ws, st, aux));
+    RET(mesh_upsample(L, W, ws.verts[0], B, cam_mesh, ws, st));
     return 0;
-}
-
-// Side stream + fork/join events so the two encoder streams (pose lifter / GRU image-feature aggregation) run
-// concurrently inside one pmce_forward call. One set per device, created on first use (before any graph capture: the
-// host driver always runs an eager warm-up first); the only process-lifetime state the library keeps besides the
-// layout cache.
-struct Aux {
-    cudaStream_t side = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
-Aux* get_aux() {
-    static Aux aux[64];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    Aux& a = aux[dev];
-    if (!a.side) {
-        if (cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    }
-    return &a;
 }
 
 }  // namespace
@@ -658,7 +682,7 @@ extern "C" int pmce_forward(const pmce_dims_t* dims, const void* weights, const 
     CK(cudaEventRecord(aux->join, aux->side));
     RET(lifter(L, W, pose2d, B, pose3d, ws, st));
     CK(cudaStreamWaitEvent(st, aux->join, 0));
-    return decoder_back(L, W, ws.joints_m, vj_relation, B, cam_pose, cam_mesh, nullptr, ws, st);
+    return decoder_back(L, W, ws.joints_m, vj_relation, B, cam_pose, cam_mesh, nullptr, ws, st, aux);
 }
 
 extern "C" size_t pmce_io_bytes(const pmce_dims_t* dims, int B) {
