@@ -168,6 +168,18 @@ class Engine:
             out = (torch.empty(B, d.num_vert, 3).pin_memory(), torch.empty(B, d.num_joint, 3).pin_memory(),
                    torch.empty(B, d.num_joint, 3).pin_memory())
         with torch.cuda.device(dev):
+            if self.use_graph and not torch.cuda.is_current_stream_capturing():
+                # host buffers straight into / out of the captured graph's static device buffers: one H2D per input,
+                # one replay, one D2H per output, one synchronise
+                g = self._graphs.get(B) or self._capture(B, dev)
+                g["p2d"].copy_(pose2d_cpu, non_blocking=True)
+                g["feat"].copy_(img_feat_cpu, non_blocking=True)
+                g["graph"].replay()
+                out[0].copy_(g["mesh"], non_blocking=True)
+                out[1].copy_(g["cam_pose"], non_blocking=True)
+                out[2].copy_(g["pose3d"], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return out
             ws = self._workspace(B, dev)
             io_bytes = self.lib.pmce_io_bytes(self._dp, B)
             if getattr(self, "_io", None) is None or self._io.numel() < io_bytes:

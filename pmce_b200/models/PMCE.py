@@ -31,5 +31,13 @@ class PMCE(EngineModule):
         return self.engine().forward(pose2d, img_feat)
 
 
+    @torch.no_grad()
+    def forward_host(self, pose2d_cpu, img_feat_cpu, out=None):
+        """Host-buffer variant of `forward` (pinned CPU tensors in, pinned CPU tensors out): what the reference's test
+        loop does around `forward` with `.cuda()` / `.cpu()` (lib/core/base.py:218-238), as one call
+        (`pmce_forward_host` / graph replay with direct host<->device copies)."""
+        return self.engine().forward_host(pose2d_cpu, img_feat_cpu, out)
+
+
 def get_model(num_joint, embed_dim, depth):
     return PMCE(num_joint, embed_dim, depth)

@@ -159,9 +159,12 @@ def test_graph_eager_and_host_calls_agree(base):
     b = m(p2d.cuda(), feat.cuda())
     b2 = m(p2d.cuda(), feat.cuda())
     eng.use_graph = False
-    c = eng.forward_host(p2d.pin_memory(), feat.pin_memory())
-    for x, y, z, w in zip(a, b, b2, c):
-        assert torch.equal(x, y) and torch.equal(x, z) and torch.equal(x.cpu(), w)
+    c = eng.forward_host(p2d.pin_memory(), feat.pin_memory())          # C-ABI pmce_forward_host (eager launches)
+    eng.use_graph = True
+    d = [t.clone() for t in m.forward_host(p2d.pin_memory(), feat.pin_memory())]   # graph replay with direct host copies
+    eng.use_graph = False
+    for x, y, z, w, v in zip(a, b, b2, c, d):
+        assert torch.equal(x, y) and torch.equal(x, z) and torch.equal(x.cpu(), w) and torch.equal(x.cpu(), v)
 
 
 def test_clips_are_independent_at_full_batch(base):
