@@ -229,8 +229,13 @@ int adaln(const float* x, int B, int ntok, const float* gb, int slot, const Spli
 int vit_block(const pmce_dims_t& d, const Weights& W, const VitBlockW& w, const Workspace& ws, int B, bool temporal, cudaStream_t st) {
     const int J = d.num_joint, C = d.embed_dim, T = d.seqlen, Hh = d.lifter_heads;
     const int N = B * T * J;
+    const bool tc_attn = (C / Hh == 64) && (temporal ? (T <= 128 && T % 8 == 0) : (J <= 128));
+    // split-bf16 view of the qkv buffer (same bytes as the fp32 one): written by the projection when the tensor-core
+    // attention consumes it by TMA
+    SplitOut qkv_s{reinterpret_cast<bf16*>(ws.qkv), reinterpret_cast<bf16*>(ws.qkv) + (size_t)N * 3 * C};
     {   // qkv = W_qkv LN1(x) + b
-        EpiOpt o; o.bias = W.f + w.qkvb; o.out = ws.qkv; o.ld_out = 3 * C;
+        EpiOpt o; o.bias = W.f + w.qkvb;
+        if (tc_attn) { o.outs = qkv_s; o.ld_split = 3 * C; } else { o.out = ws.qkv; o.ld_out = 3 * C; }
         RET(linear_tc(ws.xn_s, C, N, C, W, w.qkvw, C, 3 * C, o, st));
     }
     AttnAddr a, ao;
@@ -239,9 +244,9 @@ int vit_block(const pmce_dims_t& d, const Weights& W, const VitBlockW& w, const 
     else { a.seq.div = J; a.seq.s0 = (long long)T * J; a.seq.s1 = 1; a.tok = J; nseq = B * J; L = T; }
     a.ld = 3 * C;
     ao = a; ao.ld = C;
-    if (C / Hh == 64 && L <= 128) {      // head_dim 64: packed block-diagonal attention on tcgen05 (attn_tc.cuh)
+    if (tc_attn) {                       // head_dim 64: packed block-diagonal attention on tcgen05 (attn_tc.cuh)
         count_launch();
-        const int rc = launch_attn_tile_tc(ws.qkv, ws.qkv + C, ws.qkv + 2 * C, a, ws.att_s, ao, nseq, Hh, L, st);
+        const int rc = launch_attn_tile_tc(qkv_s.hi, qkv_s.lo, N, C, J, T, temporal, ws.att_s, ao, nseq, Hh, st);
         if (rc) { pmce_set_error("attn_tile_tc launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
     } else {
     const int chunk = (65535 / J) * J;   // gridDim.z limit; multiples of J keep the (b,j) decomposition intact

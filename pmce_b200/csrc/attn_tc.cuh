@@ -9,9 +9,10 @@
 // alternate items and interleave on the SM's four schedulers:
 //   warps 0-3 / 4-7 (math group 0 / 1): thread r owns tile row r (= TMEM lane r) for softmax and the epilogue; the
 //       group's first thread issues its MMAs. P overwrites the group's Q/K tiles once S is complete.
-//   warps 8-15 (loaders): thread (r, half) loads half of q/k/v row r of the next item straight from the fp32 qkv
-//       activations (any row addressing: the temporal pass strides over frames), splits to bf16 hi/lo and writes the
-//       128-byte-swizzled K-major tiles UMMA expects; arrives on full[group].
+//   warp 8 (producer, one lane): the qkv projection already wrote q/k/v as split-bf16 [tokens, 3C] tensors, so the six
+//       operand tiles of an item arrive by TMA (128-byte swizzle, straight into the layout UMMA expects): one 128-row box
+//       per tensor in the spatial pass (tokens of a tile are contiguous), one T-row box per sequence in the temporal pass
+//       (3-D view [frame][joint][3C]); completion is signalled on full[group].
 // The block-diagonal trick spends 128/L x more MMA flops than the attention needs, which is free here: the CUDA-core
 // kernel it replaces ran with 17 of 32 lanes active and ~3 warps per scheduler.
 #pragma once
@@ -19,11 +20,12 @@
 #include "tc_common.cuh"
 #include "common.cuh"
 #include "kernels.cuh"
+#include "gemm_tc.cuh"
 
 constexpr int AT_TILE = 128 * 128;                 // bytes: [128 rows][64 bf16]
 constexpr int AT_BUF = 6 * AT_TILE;                // Qh Ql Kh Kl Vh Vl   (P hi aliases Qh|Ql, P lo aliases Kh|Kl)
 constexpr int AT_SMEM = 2 * AT_BUF + 1024 + 128;
-constexpr int AT_THREADS = 512;
+constexpr int AT_THREADS = 288;                   // 8 math warps + 1 producer warp
 
 namespace tc {
 __device__ __forceinline__ void sts16(uint32_t tile, int row, int chunk, uint4 v) {   // 16-byte chunk, SW128 pattern
@@ -40,13 +42,13 @@ __device__ __forceinline__ void bar_sync_group(int id) { asm volatile("bar.sync 
 }  // namespace tc
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
-attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, AttnAddr a, SplitOut Os, AttnAddr ao,
-                    int L, int G, int nseq, int H, float scale, int dbg) {
+attn_tile_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, int temporal, int C, int J, int T,
+                    SplitOut Os, AttnAddr ao, int L, int G, int nseq, int H, float scale, int dbg) {
     constexpr int D = 64;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sb = tc::smem_u32(smem);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * AT_BUF);   // [2] per group, 256 loader arrivals each
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * AT_BUF);   // [2] per group, producer arrive.expect_tx + TMA bytes
     uint64_t* empty_bar = full_bar + 2;                                    // [2] per group, 1 arrival (tcgen05.commit)
     uint64_t* bar_s = empty_bar + 2;                                       // [2] S complete
     uint64_t* bar_o = bar_s + 2;                                           // [2] O complete
@@ -55,12 +57,14 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
-            tc::mbar_init(&full_bar[b], 256); tc::mbar_init(&empty_bar[b], 1);
+            tc::mbar_init(&full_bar[b], 1); tc::mbar_init(&empty_bar[b], 1);
             tc::mbar_init(&bar_s[b], 1); tc::mbar_init(&bar_o[b], 1);
         }
         tc::fence_barrier_init();
     }
     if (warp == 0) tc::tmem_alloc(tmem_ptr_smem, 512);
+    for (int i = tid; i < 2 * AT_BUF / 16; i += AT_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);   // stale tiles stay finite
+    tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -71,60 +75,42 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
     // this CTA's items: work = blockIdx.x + n * gridDim.x, n = 0, 1, ...; item n belongs to group n & 1
 
     if (warp >= 8) {
-        // ================= loaders: 8 warps, thread = (row, half of the 64-wide head slice) =================
-        const int lt = tid - 256;
-        const int lr = lt & 127, hf = lt >> 7;
-        const int lg = lr / L, ltok = lr - lg * L;
-        uint32_t n = 0;
-        for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++n) {
-            const int grp = n & 1;
-            const uint32_t j = n >> 1;                                  // per-group item counter
-            const uint32_t base_s = sb + grp * AT_BUF;
-            const int tile = work / H, h = work - tile * H;
-            const int s = tile * G + lg;
-            const bool valid = (lg < G) && (s < nseq) && !(dbg & 1);
-            const size_t base = valid ? (size_t)(a.seq(s) + (long long)ltok * a.tok) * a.ld + h * D + hf * 32 : 0;
-            float4 x0[8];
-            // q first (in flight while we wait for the buffer), then k, v
-            if (valid) {
+        // ================= producer: one lane issues the TMA loads =================
+        if (tid == 256) {
+            tc::tma_prefetch_desc(&tm_hi);
+            tc::tma_prefetch_desc(&tm_lo);
+            uint32_t n = 0;
+            for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++n) {
+                const int grp = n & 1;
+                const uint32_t j = n >> 1;                                  // per-group item counter
+                uint8_t* base_p = smem + grp * AT_BUF;
+                const int tile = work / H, h = work - tile * H;
+                tc::mbar_wait(&empty_bar[grp], (j & 1) ^ 1);
+                if (dbg & 1) { tc::mbar_arrive(&full_bar[grp]); continue; }
+                if (!temporal) {
+                    // tokens of the tile are the 128 consecutive rows starting at tile*G*L (rows past G*L are masked, rows past the tensor are zero)
+                    tc::mbar_arrive_expect_tx(&full_bar[grp], 6 * AT_TILE);
+                    const int row0 = tile * G * L;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x0[i] = ld4(Q + base + i * 4);
-            } else {
+                    for (int x = 0; x < 3; ++x) {
+                        tc::tma_load_2d(base_p + (2 * x) * AT_TILE, &tm_hi, &full_bar[grp], x * C + h * 64, row0);
+                        tc::tma_load_2d(base_p + (2 * x + 1) * AT_TILE, &tm_lo, &full_bar[grp], x * C + h * 64, row0);
+                    }
+                } else {
+                    // sequence s = (b, j): its T frames are one [T][64] box of the 3-D view [b*T + t][j][3C], landing at rows [gl*T, gl*T+T)
+                    const int s0 = tile * G;
+                    const int ns = nseq - s0 < G ? nseq - s0 : G;
+                    tc::mbar_arrive_expect_tx(&full_bar[grp], (uint32_t)(6 * ns * T * 128));
+                    for (int gl = 0; gl < ns; ++gl) {
+                        const int sq = s0 + gl, b = sq / J, jj = sq - b * J;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            tc::mbar_wait(&empty_bar[grp], (j & 1) ^ 1);
-#pragma unroll 1
-            for (int which = 0; which < 3; ++which) {
-                float4 x1[8];
-                if (which < 2) {                                         // prefetch the next tensor's row half
-                    const float* nxt = which == 0 ? K : V;
-                    if (valid) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) x1[i] = ld4(nxt + base + i * 4);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) x1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int x = 0; x < 3; ++x) {
+                            tc::tma_load_3d(base_p + (2 * x) * AT_TILE + gl * T * 128, &tm_hi, &full_bar[grp], x * C + h * 64, jj, b * T);
+                            tc::tma_load_3d(base_p + (2 * x + 1) * AT_TILE + gl * T * 128, &tm_lo, &full_bar[grp], x * C + h * 64, jj, b * T);
+                        }
                     }
                 }
-                const float sc = which == 0 ? scale : 1.0f;
-                const uint32_t th = base_s + (2 * which) * AT_TILE, tl = th + AT_TILE;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float x[8];
-                    uint4 hh, ll;
-                    x[0] = x0[2 * c].x * sc; x[1] = x0[2 * c].y * sc; x[2] = x0[2 * c].z * sc; x[3] = x0[2 * c].w * sc;
-                    x[4] = x0[2 * c + 1].x * sc; x[5] = x0[2 * c + 1].y * sc; x[6] = x0[2 * c + 1].z * sc; x[7] = x0[2 * c + 1].w * sc;
-                    tc::split8(x, hh, ll);
-                    tc::sts16(th, lr, hf * 4 + c, hh); tc::sts16(tl, lr, hf * 4 + c, ll);
-                }
-                if (which < 2) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) x0[i] = x1[i];
-                }
             }
-            tc::fence_proxy_async();
-            tc::mbar_arrive(&full_bar[grp]);
         }
     } else {
         // ================= math: two groups of 4 warps =================
@@ -187,7 +173,7 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int col = c * 32 + i;
-                        if (col >= cs && col < ce) m = fmaxf(m, __uint_as_float(v[i]));
+                        if (col >= cs && col < ce) m = fmaxf(m, __uint_as_float(v[i]) * scale);
                     }
                 }
                 __syncwarp();
@@ -214,7 +200,7 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
                         for (int i = 0; i < 8; ++i) {
                             const int col = c * 32 + jj * 8 + i;
                             // exp2-based fast exponential: |rel err| ~ 2^-21, two orders below the bf16x3 product error
-                            p[i] = (col >= cs && col < ce) ? __expf(__uint_as_float(v[jj * 8 + i]) - m) : 0.f;
+                            p[i] = (col >= cs && col < ce) ? __expf(__uint_as_float(v[jj * 8 + i]) * scale - m) : 0.f;
                             lsum += p[i];
                         }
                         uint4 hh, ll;
@@ -274,15 +260,25 @@ attn_tile_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
     if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
-// nseq sequences of L tokens (L <= 128), H heads of 64; fp32 q/k/v addressed by `a`, split-bf16 output by `ao`.
-static inline int launch_attn_tile_tc(const float* Q, const float* K, const float* V, AttnAddr a, SplitOut Os, AttnAddr ao, int nseq, int H, int L,
-                                      cudaStream_t st) {
+// nseq sequences of L tokens (L <= 128; temporal: L % 8 == 0), H heads of 64. q|k|v are the split-bf16 [ntok, 3C] outputs of the
+// qkv projection (token rows ordered (b, t, j)); spatial: sequence = (b,t), tokens j; temporal: sequence = (b,j), tokens t.
+static inline int launch_attn_tile_tc(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, int ntok, int C, int J, int T, bool temporal, SplitOut Os,
+                                      AttnAddr ao, int nseq, int H, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(attn_tile_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return 2;
         configured = true;
     }
+    const int L = temporal ? T : J;
     const int G = 128 / L;
+    CUtensorMap th, tl;
+    if (!temporal) {
+        if (make_tmap_bf16(&th, qkv_hi, ntok, 3 * C, 3 * C, 128) || make_tmap_bf16(&tl, qkv_lo, ntok, 3 * C, 3 * C, 128)) return 1;
+    } else {
+        if (make_tmap_bf16_3d(&th, qkv_hi, 3 * C, J, ntok / J, 3LL * C, 3LL * C * J, 1, T) ||
+            make_tmap_bf16_3d(&tl, qkv_lo, 3 * C, J, ntok / J, 3LL * C, 3LL * C * J, 1, T))
+            return 1;
+    }
     const int ntiles = (nseq + G - 1) / G;
     const long long work = (long long)ntiles * H;
     int sms = 148;
@@ -293,8 +289,8 @@ static inline int launch_attn_tile_tc(const float* Q, const float* K, const floa
     }
     const long long want = (work + 1) / 2;                 // two items in flight per CTA
     const int grid = (int)(want < sms ? (want < 1 ? 1 : want) : sms);
-    static int dbg = -1;   // PMCE_ATTN_DEBUG=1: loaders skip global loads; =2: math groups skip all work (profiling only, wrong results)
+    static int dbg = -1;   // PMCE_ATTN_DEBUG: profiling knobs (wrong results): 1 no loads, 2 no math, 4 no softmax, 8 no stores
     if (dbg < 0) { const char* e = getenv("PMCE_ATTN_DEBUG"); dbg = e ? atoi(e) : 0; }
-    attn_tile_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(Q, K, V, a, Os, ao, L, G, nseq, H, 1.0f / sqrtf(64.0f), dbg);
+    attn_tile_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(th, tl, temporal ? 1 : 0, C, J, T, Os, ao, L, G, nseq, H, 1.0f / sqrtf(64.0f), dbg);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }

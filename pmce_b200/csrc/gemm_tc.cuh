@@ -16,7 +16,7 @@
 #include "tc_common.cuh"
 #include "common.cuh"
 
-enum TcMode { TC_F32 = 0, TC_F32_RESID = 1, TC_SPLIT_GELU = 2, TC_GENERIC = 3, TC_NULL = 4 };
+enum TcMode { TC_F32 = 0, TC_F32_RESID = 1, TC_SPLIT_GELU = 2, TC_GENERIC = 3, TC_NULL = 4, TC_SPLIT = 5 };
 
 struct TcEpi {
     const float* bias;      // [N] or null
@@ -112,8 +112,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA_hi); tc::tma_prefetch_desc(&tmA_lo);
         tc::tma_prefetch_desc(&tmW_hi); tc::tma_prefetch_desc(&tmW_lo);
-        if (MODE == TC_F32 || MODE == TC_F32_RESID || MODE == TC_SPLIT_GELU) tc::tma_prefetch_desc(&om.out);
-        if (MODE == TC_SPLIT_GELU) tc::tma_prefetch_desc(&om.out_lo);
+        if (MODE == TC_F32 || MODE == TC_F32_RESID || MODE == TC_SPLIT_GELU || MODE == TC_SPLIT) tc::tma_prefetch_desc(&om.out);
+        if (MODE == TC_SPLIT_GELU || MODE == TC_SPLIT) tc::tma_prefetch_desc(&om.out_lo);
         if (MODE == TC_F32_RESID) tc::tma_prefetch_desc(&om.resid);
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], TC_EPI_WARPS); }
@@ -254,13 +254,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if (e.dbg == 1) continue;
                     if (lane == 0) { tc::tma_store_2d(&om.out, stg, col0, row0); tc::tma_store_commit(); }
                     store_pending = true;
-                } else if (MODE == TC_SPLIT_GELU) {
+                } else if (MODE == TC_SPLIT_GELU || MODE == TC_SPLIT) {
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         const float4 b = ld4(e.bias + col0 + i);
-                        const float x0 = gelu_erf(__uint_as_float(v[i]) + b.x), x1 = gelu_erf(__uint_as_float(v[i + 1]) + b.y);
-                        const float x2 = gelu_erf(__uint_as_float(v[i + 2]) + b.z), x3 = gelu_erf(__uint_as_float(v[i + 3]) + b.w);
+                        float x0 = __uint_as_float(v[i]) + b.x, x1 = __uint_as_float(v[i + 1]) + b.y;
+                        float x2 = __uint_as_float(v[i + 2]) + b.z, x3 = __uint_as_float(v[i + 3]) + b.w;
+                        if (MODE == TC_SPLIT_GELU) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
                         tc::split_bf16x2(x0, x1, hi[i / 2], lo[i / 2]);
                         tc::split_bf16x2(x2, x3, hi[i / 2 + 1], lo[i / 2 + 1]);
                     }
@@ -338,6 +339,18 @@ static inline int make_tmap(CUtensorMap* m, const void* ptr, CUtensorMapDataType
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 2;
 }
+// bf16 3-D view [d2][d1][cols] with element strides (ld1, ld2) of one K-major operand tensor; box = [b2][b1][64], SW128
+static inline int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, int cols, int d1, int d2, long long ld1, long long ld2, int b1, int b2) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return 1;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld1 * 2, (cuuint64_t)ld2 * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)b1, (cuuint32_t)b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 2;
+}
 // bf16 operand tile map: box = [box_rows][64], 128-byte swizzle
 static inline int make_tmap_bf16(CUtensorMap* m, const void* ptr, int rows, int cols, int ld, int box_rows) {
     return make_tmap(m, ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, cols, ld, TC_BK, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -397,11 +410,12 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
             return launch_linear_tc_mode<BN, TC_F32_RESID>(ta, tw, om, M, N, K, e, st);
         }
     }
-    if (plain && e.out_hi && !e.out_f32 && !e.resid && e.act == 1 && a16(e.out_hi) && a16(e.out_lo) && e.ld_split % 8 == 0) {
+    if (plain && e.out_hi && !e.out_f32 && !e.resid && a16(e.out_hi) && a16(e.out_lo) && e.ld_split % 8 == 0) {
         if (make_tmap(&om.out, e.out_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, e.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) ||
             make_tmap(&om.out_lo, e.out_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, e.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))
             return 1;
-        return launch_linear_tc_mode<BN, TC_SPLIT_GELU>(ta, tw, om, M, N, K, e, st);
+        if (e.act == 1) return launch_linear_tc_mode<BN, TC_SPLIT_GELU>(ta, tw, om, M, N, K, e, st);
+        return launch_linear_tc_mode<BN, TC_SPLIT>(ta, tw, om, M, N, K, e, st);
     }
     return launch_linear_tc_mode<BN, TC_GENERIC>(ta, tw, om, M, N, K, e, st);
 }
