@@ -221,3 +221,20 @@ def test_jregress_coco(lib):
     out = JRegressor(J, "cuda")(mesh.cuda())
     ref = torch.matmul(torch.as_tensor(J, dtype=torch.float32)[None], mesh)
     assert _maxabs(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("J,C,T,B", [(19, 512, 16, 2), (17, 512, 64, 1), (17, 512, 8, 3), (17, 128, 16, 1)])
+def test_forward_vs_oracle_other_shapes(assets_root, lib, J, C, T, B):
+    """Shapes without a reference-generated fixture (the oracle itself is pinned to the reference on 5 configs): exercises
+    the tensor-core attention tilings (7 sequences of 17, 6 of 19, 2 of 64, 16 of 8 tokens per 128-row tile) and head_dim 16."""
+    from oracle import pmce_oracle as po
+    g = np.load(os.path.join(GOLDEN, "pmce_J17_C256_T16_B2.npz"))
+    sd = synth.make_state_dict(3, init_vertices=g["init_vertices"], lifter_out_scale=300.0, num_joint=J, embed_dim=C, depth=3, seqlen=T)
+    p2d, feat = synth.make_inputs(B, T, J, seed=9)
+    with torch.no_grad():
+        r_mesh, r_pose, r_p3 = po.pmce_forward(sd, p2d, feat, g["vj_relation"])
+    m = _model(sd, J, C, 3, T, graph=False)
+    mesh, cam_pose, pose3d = m(p2d.cuda(), feat.cuda())
+    e = (_maxabs(mesh, r_mesh), _maxabs(cam_pose, r_pose), _maxabs(pose3d, r_p3) / float(r_p3.abs().max()))
+    print(f"J={J} C={C} T={T} B={B}: max|d mesh|={e[0]:.2e} max|d pose|={e[1]:.2e} rel|d pose3d|={e[2]:.2e}")
+    assert e[0] < TOL and e[1] < TOL and e[2] < 1e-4
