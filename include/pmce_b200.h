@@ -105,6 +105,20 @@ int pmce_coevo_block(const pmce_dims_t* dims, const void* weights, int block, co
                      const float* verts_in, const float* gb, int B, float* joints_out, float* verts_out,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a6: CrossAttentionBlock.forward, lib/models/CoevoDecoder.py:82-87 (CrossAttention :47-62, AdaLayerNorm :16-29,
+ * timm Mlp).  `which` selects the instance of coevoblock<block>: 0 = joint_CA_FFN (:167; queries = J joints, keys/values =
+ * 431 vertices, 8 heads), 1 = vertx_CA_FFN (:169; queries = 431 vertices, keys/values = J joints, 2 heads).
+ * xq [B,N1,64], xk / xv [B,N2,64], gb from pmce_adaln_gammabeta -> out [B,N1,64] (may alias xq).  The vertex instance
+ * runs the fused kernel (one pass over the query stream: AdaLN_q, Wq, attention, Wp, residual, AdaLN_2). */
+int pmce_cross_attn_block(const pmce_dims_t* dims, const void* weights, int block, int which, const float* xq,
+                          const float* xk, const float* xv, const float* gb, int B, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* ---- a7: Block.forward, lib/models/CoevoDecoder.py:102-105 (Attention :119-131).  `which`: 0 = joint_SA_FFN (:166),
+ * 1 = vertx_SA_FFN (:168).  x [B,N,64] -> out [B,N,64] (may alias x). */
+int pmce_self_attn_block(const pmce_dims_t* dims, const void* weights, int block, int which, const float* x,
+                         const float* gb, int B, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a9 tail: upsample_conv + linear_cur residual, lib/models/CoevoDecoder.py:238-244
  * verts3 [B,431,3], g [B,2048] -> cam_mesh [B,6890,3]. */
 int pmce_mesh_epilogue(const pmce_dims_t* dims, const void* weights, const float* verts3, const float* g, int B,

@@ -42,6 +42,8 @@ SIGNATURES = {
     "pmce_adaln_slots": (C.c_int, []),
     "pmce_adaln_gammabeta": (C.c_int, [_DP, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_coevo_block": (C.c_int, [_DP, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "pmce_cross_attn_block": (C.c_int, [_DP, _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
+    "pmce_self_attn_block": (C.c_int, [_DP, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_mesh_epilogue": (C.c_int, [_DP, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_decoder_forward": (C.c_int, [_DP, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
     "pmce_jregress": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_float, _P, _P]),

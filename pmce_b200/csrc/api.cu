@@ -18,6 +18,7 @@
 #include "gru_tc.cuh"
 #include "attn_tc.cuh"
 #include "attn_flash_tc.cuh"
+#include "ca_fused.cuh"
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -454,6 +455,73 @@ int proj64(const SplitOut& a, int M, const Weights& W, size_t w, size_t b, float
     return linear_tc(a, 64, M, 64, W, w, 64, N, o, st);
 }
 
+// Scratch of one attention block over a query stream of n1 rows and a key/value stream of n2 rows (carved from the workspace)
+struct AttnScratch {
+    SplitOut tq, tk, tv;     // AdaLN outputs (split): [n1,64], [n2,64], [n2,64]   (self-attention uses tq only)
+    float *Q, *K, *V;        // projected q/k/v fp32 [n1,64], [n2,64], [n2,64]    (self-attention: Q = qkv [n1,192])
+    SplitOut att, hid;       // attention output [n1,64], MLP hidden [n1,256] (split)
+};
+
+bool ca_fused_enabled() {
+    static int on = -1;      // PMCE_CA_FUSED=0: keep the unfused launch sequence (A/B profiling, tests)
+    if (on < 0) { const char* s = getenv("PMCE_CA_FUSED"); on = (s && atoi(s) == 0) ? 0 : 1; }
+    return on == 1;
+}
+
+int mha_core(int heads, const float* Q, int ldq, const float* K, const float* V, int ldkv, const SplitOut& att, int B, int N1, int N2, cudaStream_t st) {
+    const int D = 64 / heads;
+    if (D == 32) return flash_attn32(Q, addr_plain(N1, ldq), K, V, addr_plain(N2, ldkv), att, addr_plain(N1, 64), B, heads, N1, N2, st);
+    return launch_attn(D, Q, addr_plain(N1, ldq), K, V, addr_plain(N2, ldkv), nullptr, att, addr_plain(N1, 64), B, heads, N1, N2, st);
+}
+
+// a6 CrossAttentionBlock.forward (CoevoDecoder.py:82-87): xq [B,N1,64] updated in place; xk, xv [B,N2,64]
+int cross_attn_block(const Weights& W, const CaW& w, int heads, float* xq, int N1, const float* xk, const float* xv, int N2, const float* gb, int B,
+                     const AttnScratch& s, cudaStream_t st) {
+    const int n1 = B * N1, n2 = B * N2;
+    RET(adaln(xk, B, N2, gb, w.sk, s.tk, st));
+    RET(proj64(s.tk, n2, W, w.wk, w.bk, s.K, st));
+    RET(adaln(xv, B, N2, gb, w.sv, s.tv, st));
+    RET(proj64(s.tv, n2, W, w.wv, w.bv, s.V, st));
+    if (N1 >= 128 && ca_fused_enabled() && ca_vertex_fused_supported(heads, N2)) {
+        // one pass over the query stream: AdaLN_q, Wq, attention, Wp, residual, AdaLN_2 (ca_fused.cuh)
+        CaFusedArgs a;
+        a.K = s.K; a.V = s.V; a.gb = gb; a.bq = W.f + w.bq; a.bp = W.f + w.bp;
+        a.gb_ld = PMCE_ADALN_SLOTS * 128; a.slot_q = w.sq; a.slot_2 = w.s2;
+        a.B = B; a.N1 = N1; a.N2 = N2; a.qtiles = 0; a.scale = 1.0f / sqrtf(64.0f / heads); a.eps = 1e-6f;
+        count_launch();
+        const int rc = launch_ca_vertex_fused(xq, s.tq.hi, s.tq.lo, W.hi + w.wq, W.lo + w.wq, W.hi + w.wp, W.lo + w.wp, heads, a, st);
+        if (rc) { pmce_set_error("ca_vertex_fused launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
+        { EpiOpt o; o.bias = W.f + w.fc1b; o.act = 1; o.outs = s.hid; o.ld_split = 256; RET(linear_tc(s.tq, 64, n1, 64, W, w.fc1w, 64, 256, o, st)); }
+        { EpiOpt o; o.bias = W.f + w.fc2b; o.resid = xq; o.ld_resid = 64; o.out = xq; o.ld_out = 64; RET(linear_tc(s.hid, 256, n1, 256, W, w.fc2w, 256, 64, o, st)); }
+        return 0;
+    }
+    RET(adaln(xq, B, N1, gb, w.sq, s.tq, st));
+    RET(proj64(s.tq, n1, W, w.wq, w.bq, s.Q, st));
+    RET(mha_core(heads, s.Q, 64, s.K, s.V, 64, s.att, B, N1, N2, st));
+    return attn_tail(W, w.wp, w.bp, w.s2, w.fc1w, w.fc1b, w.fc2w, w.fc2b, xq, s.att, s.tq, s.hid, gb, B, N1, st);
+}
+
+// a7 Block.forward (CoevoDecoder.py:102-105): x [B,N,64] updated in place
+int self_attn_block(const Weights& W, const SaW& w, int heads, float* x, int N, const float* gb, int B, const AttnScratch& s, cudaStream_t st) {
+    const int n = B * N;
+    RET(adaln(x, B, N, gb, w.s1, s.tq, st));
+    RET(proj64(s.tq, n, W, w.qkvw, w.qkvb, s.Q, st, nullptr, 1, 192));
+    RET(mha_core(heads, s.Q, 192, s.Q + 64, s.Q + 128, 192, s.att, B, N, N, st));
+    return attn_tail(W, w.wp, w.bp, w.s2, w.fc1w, w.fc1b, w.fc2w, w.fc2b, x, s.att, s.tq, s.hid, gb, B, N, st);
+}
+
+AttnScratch vertex_scratch(const Workspace& ws) {   // query stream = the 431 vertices
+    AttnScratch s;
+    s.tq = ws.tA_s; s.tk = ws.tJ_s; s.tv = ws.tJ_s; s.Q = ws.qkv_d; s.K = ws.Kj; s.V = ws.Vj; s.att = ws.att_ds; s.hid = ws.hid_ds;
+    return s;
+}
+AttnScratch joint_scratch(const Workspace& ws) {    // query stream = the J joints
+    AttnScratch s;
+    s.tq = ws.tJ2_s; s.tk = ws.tB_s; s.tv = ws.tA2_s; s.Q = ws.qkvj; s.K = ws.Kv; s.V = ws.Vv; s.att = ws.attj_s; s.hid = ws.hidj_s;
+    return s;
+}
+constexpr int JOINT_HEADS = 8, VERTX_HEADS = 2;      // CoevoDecoder.py:139-140
+
 int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, const float* verts_in, const float* gb, int B,
                 float* joints_out, float* verts_out, const Workspace& ws, cudaStream_t st, Aux* aux = nullptr) {
     const pmce_dims_t& d = L.d;
@@ -482,41 +550,19 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
             CK(cudaStreamWaitEvent(aux->side, aux->fork2, 0));
             sj = aux->side;
         }
-        // ---- joint cross-attention block: q = joints (J), k/v = vertices (431); 8 heads x 8 ----
-        RET(adaln(ws.xqj, B, J, gb, w.jca.sq, ws.tJ2_s, sj));
-        RET(proj64(ws.tJ2_s, nj, W, w.jca.wq, w.jca.bq, ws.Qj, sj));
-        RET(adaln(ws.xkv, B, Vd, gb, w.jca.sk, ws.tB_s, sj));
-        RET(proj64(ws.tB_s, nv, W, w.jca.wk, w.jca.bk, ws.Kv, sj));
-        RET(adaln(ws.Vf, B, Vd, gb, w.jca.sv, ws.tA2_s, sj));
-        RET(proj64(ws.tA2_s, nv, W, w.jca.wv, w.jca.bv, ws.Vv, sj));
-        RET(launch_attn(8, ws.Qj, addr_plain(J, 64), ws.Kv, ws.Vv, addr_plain(Vd, 64), nullptr, ws.attj_s, addr_plain(J, 64), B, 8, J, Vd, sj));
-        RET(attn_tail(W, w.jca.wp, w.jca.bp, w.jca.s2, w.jca.fc1w, w.jca.fc1b, w.jca.fc2w, w.jca.fc2b, ws.xqj, ws.attj_s, ws.tJ2_s, ws.hidj_s, gb, B, J, sj));
-        // ---- joint self-attention block ----
-        RET(adaln(ws.xqj, B, J, gb, w.jsa.s1, ws.tJ2_s, sj));
-        RET(proj64(ws.tJ2_s, nj, W, w.jsa.qkvw, w.jsa.qkvb, ws.qkvj, sj, nullptr, 1, 192));
-        RET(launch_attn(8, ws.qkvj, addr_plain(J, 192), ws.qkvj + 64, ws.qkvj + 128, addr_plain(J, 192), nullptr, ws.attj_s, addr_plain(J, 64), B, 8, J, J, sj));
-        RET(attn_tail(W, w.jsa.wp, w.jsa.bp, w.jsa.s2, w.jsa.fc1w, w.jsa.fc1b, w.jsa.fc2w, w.jsa.fc2b, ws.xqj, ws.attj_s, ws.tJ2_s, ws.hidj_s, gb, B, J, sj));
+        const AttnScratch s = joint_scratch(ws);
+        // joint cross-attention block: q = joints (J), k/v = vertices (431); 8 heads x 8; then joint self-attention
+        RET(cross_attn_block(W, w.jca, JOINT_HEADS, ws.xqj, J, ws.xkv, ws.Vf, Vd, gb, B, s, sj));
+        RET(self_attn_block(W, w.jsa, JOINT_HEADS, ws.xqj, J, gb, B, s, sj));
         feat2coor_kernel<<<cdiv(nj, 8), 256, 0, sj>>>(ws.xqj, nj, W.f + w.jf2cw, W.f + w.jf2cb, joints, joints_out);
         CKL();
         if (aux) CK(cudaEventRecord(aux->join2, aux->side));
     }
 
-
-    // ---- vertex cross-attention block: q = vertices (431), k/v = joints (J); 2 heads x 32 ----
-    RET(adaln(ws.xqv, B, Vd, gb, w.vca.sq, ws.tA_s, st));
-    RET(proj64(ws.tA_s, nv, W, w.vca.wq, w.vca.bq, ws.Qv, st));
-    RET(adaln(ws.xkj, B, J, gb, w.vca.sk, ws.tJ_s, st));
-    RET(proj64(ws.tJ_s, nj, W, w.vca.wk, w.vca.bk, ws.Kj, st));
-    RET(adaln(ws.Jf, B, J, gb, w.vca.sv, ws.tJ_s, st));
-    RET(proj64(ws.tJ_s, nj, W, w.vca.wv, w.vca.bv, ws.Vj, st));
-    RET(flash_attn32(ws.Qv, addr_plain(Vd, 64), ws.Kj, ws.Vj, addr_plain(J, 64), ws.att_ds, addr_plain(Vd, 64), B, 2, Vd, J, st));
-    RET(attn_tail(W, w.vca.wp, w.vca.bp, w.vca.s2, w.vca.fc1w, w.vca.fc1b, w.vca.fc2w, w.vca.fc2b, ws.xqv, ws.att_ds, ws.tA_s, ws.hid_ds, gb, B, Vd, st));
-
-    // ---- vertex self-attention block: 431 x 431, 2 heads x 32 ----
-    RET(adaln(ws.xqv, B, Vd, gb, w.vsa.s1, ws.tA_s, st));
-    RET(proj64(ws.tA_s, nv, W, w.vsa.qkvw, w.vsa.qkvb, ws.qkv_d, st, nullptr, 1, 192));
-    RET(flash_attn32(ws.qkv_d, addr_plain(Vd, 192), ws.qkv_d + 64, ws.qkv_d + 128, addr_plain(Vd, 192), ws.att_ds, addr_plain(Vd, 64), B, 2, Vd, Vd, st));
-    RET(attn_tail(W, w.vsa.wp, w.vsa.bp, w.vsa.s2, w.vsa.fc1w, w.vsa.fc1b, w.vsa.fc2w, w.vsa.fc2b, ws.xqv, ws.att_ds, ws.tA_s, ws.hid_ds, gb, B, Vd, st));
+    // vertex cross-attention block: q = vertices (431), k/v = joints (J); 2 heads x 32; then vertex self-attention 431 x 431
+    const AttnScratch s = vertex_scratch(ws);
+    RET(cross_attn_block(W, w.vca, VERTX_HEADS, ws.xqv, Vd, ws.xkj, ws.Jf, J, gb, B, s, st));
+    RET(self_attn_block(W, w.vsa, VERTX_HEADS, ws.xqv, Vd, gb, B, s, st));
     feat2coor_kernel<<<cdiv(nv, 8), 256, 0, st>>>(ws.xqv, nv, W.f + w.vf2cw, W.f + w.vf2cb, verts_in, verts_out);
     CKL();
     if (ja && aux) CK(cudaStreamWaitEvent(st, aux->join2, 0));
@@ -650,6 +696,47 @@ extern "C" int pmce_coevo_block(const pmce_dims_t* dims, const void* weights, in
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
     return coevo_block(L, W, block - 1, joints, verts_in, gb, B, joints_out, verts_out, ws, st);
+}
+
+// which: 0 = the joint stream's block (queries = J joints), 1 = the vertex stream's block (queries = 431 vertices)
+static int attn_block_args(const Layout& L, int block, int which, const char* what) {
+    if (block < 1 || block > 3) { pmce_set_error("%s: block must be 1..3 (got %d)", what, block); return 2; }
+    if (which != 0 && which != 1) { pmce_set_error("%s: which must be 0 (joint stream) or 1 (vertex stream)", what); return 2; }
+    if (which == 0 && !L.blk[block - 1].joint_alive) {
+        pmce_set_error("%s: coevoblock%d joint-branch weights are not stored (output is discarded by the reference)", what, block);
+        return 4;
+    }
+    return 0;
+}
+
+extern "C" int pmce_cross_attn_block(const pmce_dims_t* dims, const void* weights, int block, int which, const float* xq, const float* xk,
+                                     const float* xv, const float* gb, int B, float* out, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    GET_LAYOUT();
+    RET(attn_block_args(L, block, which, "pmce_cross_attn_block"));
+    if (!xq || !xk || !xv || !gb || !out) { pmce_set_error("pmce_cross_attn_block: NULL argument"); return 2; }
+    Workspace ws;
+    RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
+    const int J = dims->num_joint, Vd = dims->num_vert_ds;
+    const int N1 = which ? Vd : J, N2 = which ? J : Vd;
+    if (out != xq) CK(cudaMemcpyAsync(out, xq, (size_t)B * N1 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const CoevoW& w = L.blk[block - 1];
+    return which ? cross_attn_block(W, w.vca, VERTX_HEADS, out, N1, xk, xv, N2, gb, B, vertex_scratch(ws), st)
+                 : cross_attn_block(W, w.jca, JOINT_HEADS, out, N1, xk, xv, N2, gb, B, joint_scratch(ws), st);
+}
+
+extern "C" int pmce_self_attn_block(const pmce_dims_t* dims, const void* weights, int block, int which, const float* x, const float* gb,
+                                    int B, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    GET_LAYOUT();
+    RET(attn_block_args(L, block, which, "pmce_self_attn_block"));
+    if (!x || !gb || !out) { pmce_set_error("pmce_self_attn_block: NULL argument"); return 2; }
+    Workspace ws;
+    RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
+    const int N = which ? dims->num_vert_ds : dims->num_joint;
+    if (out != x) CK(cudaMemcpyAsync(out, x, (size_t)B * N * 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const CoevoW& w = L.blk[block - 1];
+    return which ? self_attn_block(W, w.vsa, VERTX_HEADS, out, N, gb, B, vertex_scratch(ws), st)
+                 : self_attn_block(W, w.jsa, JOINT_HEADS, out, N, gb, B, joint_scratch(ws), st);
 }
 
 extern "C" int pmce_mesh_epilogue(const pmce_dims_t* dims, const void* weights, const float* verts3, const float* g, int B,

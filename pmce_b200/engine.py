@@ -241,6 +241,37 @@ class Engine:
                                             _ptr(jout), _ptr(vout), _ptr(ws), ws.numel(), _stream()), "pmce_coevo_block")
         return jout, vout
 
+    def cross_attn_block(self, block, which, xq, xk, xv, gb):
+        """CrossAttentionBlock.forward of coevoblock<block> (which: 0 = joint_CA_FFN, 1 = vertx_CA_FFN) -> updated xq."""
+        self._ready()
+        d = self.dims
+        B = xq.shape[0]
+        n1, n2 = (d.num_vert_ds, d.num_joint) if which else (d.num_joint, d.num_vert_ds)
+        xq = _require_cuda_f32(xq, "xq", (B, n1, d.coevo_dim))
+        xk = _require_cuda_f32(xk, "xk", (B, n2, d.coevo_dim))
+        xv = _require_cuda_f32(xv, "xv", (B, n2, d.coevo_dim))
+        gb = _require_cuda_f32(gb, "gb")
+        with torch.cuda.device(xq.device):
+            ws = self._workspace(B, xq.device)
+            out = torch.empty_like(xq)
+            check(self.lib.pmce_cross_attn_block(self._dp, _ptr(self.weights), block, which, _ptr(xq), _ptr(xk), _ptr(xv), _ptr(gb), B,
+                                                 _ptr(out), _ptr(ws), ws.numel(), _stream()), "pmce_cross_attn_block")
+        return out
+
+    def self_attn_block(self, block, which, x, gb):
+        """Block.forward of coevoblock<block> (which: 0 = joint_SA_FFN, 1 = vertx_SA_FFN) -> updated x."""
+        self._ready()
+        d = self.dims
+        B = x.shape[0]
+        x = _require_cuda_f32(x, "x", (B, d.num_vert_ds if which else d.num_joint, d.coevo_dim))
+        gb = _require_cuda_f32(gb, "gb")
+        with torch.cuda.device(x.device):
+            ws = self._workspace(B, x.device)
+            out = torch.empty_like(x)
+            check(self.lib.pmce_self_attn_block(self._dp, _ptr(self.weights), block, which, _ptr(x), _ptr(gb), B, _ptr(out),
+                                                _ptr(ws), ws.numel(), _stream()), "pmce_self_attn_block")
+        return out
+
     def mesh_epilogue(self, verts3, g):
         self._ready()
         d = self.dims

@@ -106,6 +106,38 @@ def test_coevo_blocks_vs_oracle(base):
         eng.coevo_block(1, joints.cuda(), inter["verts0"].contiguous().cuda(), gb, want_joints=True)
 
 
+@pytest.mark.parametrize("B", [2, 5, 64])
+def test_attention_blocks_vs_oracle(base, B):
+    """a6 / a7 through their own entry points (pmce_cross_attn_block / pmce_self_attn_block), every live instance, on
+    N(0,1) feature streams; B=5 leaves a ragged last CTA wave and B=64 is the headline batch (257 row tiles > 2 x 148 CTAs)."""
+    from oracle import pmce_oracle as po
+    eng, sd = base["eng"], base["sd"]
+    gen = torch.Generator().manual_seed(11 + B)
+    J, Vd = 17, 431
+    g = base["inter"]["g"][torch.arange(B) % 2].contiguous()
+    gb = eng.adaln_gammabeta(g.cuda())
+    xs = {0: torch.randn(B, J, 64, generator=gen), 1: torch.randn(B, Vd, 64, generator=gen)}
+    for k in (1, 2, 3):
+        for which, name, heads in ((1, "vertx", 2), (0, "joint", 8)):
+            if which == 0 and k < 3:
+                continue
+            p = f"pose_mesh_coevo.coevoblock{k}.{name}"
+            xq, xkv = xs[which], xs[1 - which]
+            xk = xkv + 0.5 * torch.randn(xkv.shape, generator=gen)
+            with torch.no_grad():
+                ref_ca = po.cross_attention_block(sd, p + "_CA_FFN", xq, xk, xkv, g, heads)
+                ref_sa = po.self_attention_block(sd, p + "_SA_FFN", xq, g, heads)
+            out_ca = eng.cross_attn_block(k, which, xq.cuda(), xk.cuda(), xkv.cuda(), gb)
+            out_sa = eng.self_attn_block(k, which, xq.cuda(), gb)
+            e_ca, e_sa = _maxabs(out_ca, ref_ca), _maxabs(out_sa, ref_sa)
+            print(f"B={B} coevoblock{k}.{name}: CA max|d|={e_ca:.2e} (|ref| {float(ref_ca.abs().max()):.1f})  SA max|d|={e_sa:.2e}")
+            assert e_ca < 2e-4 * max(1.0, float(ref_ca.abs().max())), (k, name)
+            assert e_sa < 2e-4 * max(1.0, float(ref_sa.abs().max())), (k, name)
+    from pmce_b200._lib import PmceError
+    with pytest.raises(PmceError, match="joint-branch"):
+        eng.cross_attn_block(1, 0, xs[0].cuda(), xs[1].cuda(), xs[1].cuda(), gb)
+
+
 def test_mesh_epilogue_vs_oracle(base):
     import torch.nn.functional as F
     sd, inter = base["sd"], base["inter"]
