@@ -274,6 +274,7 @@ def main():
 
     # roofline of the dominant kernel, timed alone with CUDA events on the launch stream
     roof = dominant_kernel_roofline(lib, dev, peaks, B)
+    roof_ca = cross_attn_roofline(lib, eng, dev, peaks, B)
 
     out = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -285,7 +286,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
                 "path": "models.PMCE.forward_host: pinned host inputs -> H2D -> forward -> D2H of the 3 outputs -> sync, every step (the reference loop lib/core/base.py:218-238 as one call)"},
         "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
-        "clocks": clocks, "roofline": roof, "peaks": peaks,
+        "clocks": clocks, "roofline": roof, "roofline_cross_attn": roof_ca, "peaks": peaks,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -340,6 +341,67 @@ def dominant_kernel_roofline(lib, dev, peaks, B):
             "traffic": 56.7e6, "traffic_unit": "B", "frac_of_split_ceiling": 3.0 * ach / peaks["bf16_tflops"],
             "flops_per_launch": flops, "mma_flops_per_launch": 3 * flops, "us_per_launch": sec * 1e6, "shape_MNK": [M, N, K],
             "peak_source": peaks["source"], "note": "3 bf16 MMAs per product (bf16x3): frac ceiling is 1/3"}
+
+
+def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):
+    """north_star's graded kernel: the fused vertex<-joint cross-attention (ca_vertex_fused_kernel, csrc/ca_fused.cuh), HBM-bound.
+    Timed alone with CUDA events over `nsets` rotating (xq, t) buffer sets whose total size exceeds the 126 MB L2, so every
+    launch streams its query rows from HBM. achieved = ALGORITHMIC bytes / time with SURVEY.md §8(d)'s per-clip figure for the
+    fused block (231,424 B: q/k/v streams in + q stream out + gamma/beta); `achieved_kernel_io` counts what this kernel's
+    contract really moves per clip (q in, q out, split-bf16 AdaLN_2 output, K, V, gamma/beta = 340,736 B)."""
+    import ctypes as Ct
+    import torch
+    Vd, D = 431, 64
+    P = lambda t: Ct.c_void_p(t.data_ptr())
+    st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+    gen = torch.Generator(device=dev).manual_seed(5)
+    xq = [torch.randn(B, Vd, D, device=dev, generator=gen) for _ in range(nsets)]
+    th = [torch.empty(B, Vd, D, dtype=torch.bfloat16, device=dev) for _ in range(nsets)]
+    tl = [torch.empty(B, Vd, D, dtype=torch.bfloat16, device=dev) for _ in range(nsets)]
+    Kt = torch.randn(B, J, D, device=dev, generator=gen)
+    Vt = torch.randn(B, J, D, device=dev, generator=gen)
+    gb = torch.randn(B, lib.pmce_adaln_slots(), 2, D, device=dev, generator=gen)
+
+    fold_ws = torch.empty(lib.pmce_ca_fold_bytes(B), dtype=torch.uint8, device=dev)
+
+    def call(i, fold=0):
+        rc = lib.pmce_ca_vertex_fused(eng._dp, P(eng.weights), 1, P(xq[i]), P(Kt), P(Vt), P(gb), B, P(th[i]), P(tl[i]), P(fold_ws), fold,
+                                      Ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, lib.pmce_last_error()
+    call(0, fold=1)          # per-clip folded operands (a separate 64-CTA kernel in the forward), made once
+    for i in range(nsets):
+        call(i)
+    torch.cuda.synchronize(dev)
+    # one CUDA graph holding a full rotation over the buffer sets: the timed region is device time only, as in the forward
+    # (which replays a captured graph); eager launches from Python would be bounded by the host at this kernel size
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        st = Ct.c_void_p(side.cuda_stream)
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(nsets):
+                call(i)          # in place: xq[i] keeps being updated (values stay finite: every pass re-normalises the row)
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rounds):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sec = e0.elapsed_time(e1) * 1e-3 / (rounds * nsets)
+    survey_bytes = ((J + Vd + Vd + J) * D * 4 + 2048) * B
+    io_bytes = (3 * Vd * D * 4 + 2 * J * D * 4 + 4 * D * 4) * B
+    flops = (4 * 2 * Vd * J * 32 + 2 * 2 * Vd * D * D) * B       # attention core + Wq + Wp
+    ach = survey_bytes / sec / 1e9
+    return {"kernel": "ca_vertex_fused_kernel (AdaLN_q + Wq + MHA over the clip's joints + Wp + residual + AdaLN_2, one pass)",
+            "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+            "traffic": None, "bytes_per_launch": survey_bytes, "us_per_launch": sec * 1e6,
+            "achieved_kernel_io": io_bytes / sec / 1e9, "kernel_io_bytes_per_launch": io_bytes,
+            "frac_kernel_io": io_bytes / sec / 1e9 / peaks["hbm_gbs"], "flops_per_launch": flops, "clips_per_launch": B,
+            "l2": f"{nsets} rotating buffer sets ({nsets * io_bytes / 1e6:.0f} MB) > 126 MB L2", "peak_source": peaks["source"]}
 
 
 if __name__ == "__main__":

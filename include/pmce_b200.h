@@ -114,6 +114,18 @@ int pmce_cross_attn_block(const pmce_dims_t* dims, const void* weights, int bloc
                           const float* xk, const float* xv, const float* gb, int B, float* out, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Kernel-level entry of the fused vertex cross-attention (measurement / tests; the kernels pmce_cross_attn_block(which=1)
+ * and pmce_coevo_block launch): with K / V [B,J,64] = the projected AdaLN'd joint rows (CoevoDecoder.py:53-55),
+ *   xq [B,431,64] <- xq + proj(MHA(wq(AdaLN_q(xq)), K, V))   in place                     (:56-62, :84)
+ *   t_hi / t_lo [B,431,64] bf16 <- split-bf16 of AdaLN_2(xq)                               (:86, input of the Mlp)
+ * using the weights of coevoblock<block>.vertx_CA_FFN.  fold_ws: pmce_ca_fold_bytes(B) bytes, 256-byte aligned, holds the
+ * per-clip folded operands (scale K_h Wq_h, V_h Wp_h^T, score bias); fold != 0 recomputes them from K / V first (a second,
+ * per-clip kernel), fold == 0 reuses what a previous call left there (times the streaming kernel alone). */
+size_t pmce_ca_fold_bytes(int B);
+int pmce_ca_vertex_fused(const pmce_dims_t* dims, const void* weights, int block, float* xq, const float* K,
+                         const float* V, const float* gb, int B, void* t_hi, void* t_lo, void* fold_ws, int fold,
+                         void* stream);
+
 /* ---- a7: Block.forward, lib/models/CoevoDecoder.py:102-105 (Attention :119-131).  `which`: 0 = joint_SA_FFN (:166),
  * 1 = vertx_SA_FFN (:168).  x [B,N,64] -> out [B,N,64] (may alias x). */
 int pmce_self_attn_block(const pmce_dims_t* dims, const void* weights, int block, int which, const float* x,

@@ -74,6 +74,7 @@ struct Workspace {
     float *xqj, *xkv, *Kv, *Vv, *Qj, *qkvj;
     SplitOut Jf_s, Vf_s, tA_s, tA2_s, tB_s, tJ_s, tJ2_s, att_ds, hid_ds, attj_s, hidj_s, im2col_s;
     float* lc_mesh;
+    CaFolded fold;                                     // per-clip folded operands of the fused vertex cross-attention
     size_t bytes;
 };
 
@@ -104,6 +105,11 @@ Workspace carve(const pmce_dims_t& d, int B, void* base) {
     w.im2col_s = c.split((size_t)B * 3 * ((Vd * 3 + 7) / 8 * 8));
     w.tB_s = c.split(nv * D); w.tJ2_s = c.split(nj * D);
     w.lc_mesh = c.f32((size_t)B * d.num_vert * 3);
+    {
+        SplitOut kq = c.split((size_t)B * CAF_NS * 64), vp = c.split((size_t)B * 64 * 64);
+        w.fold.kq_hi = kq.hi; w.fold.kq_lo = kq.lo; w.fold.vp_hi = vp.hi; w.fold.vp_lo = vp.lo;
+        w.fold.sb = c.f32((size_t)B * CAF_NS);
+    }
     w.bytes = c.cur;
     return w;
 }
@@ -460,6 +466,7 @@ struct AttnScratch {
     SplitOut tq, tk, tv;     // AdaLN outputs (split): [n1,64], [n2,64], [n2,64]   (self-attention uses tq only)
     float *Q, *K, *V;        // projected q/k/v fp32 [n1,64], [n2,64], [n2,64]    (self-attention: Q = qkv [n1,192])
     SplitOut att, hid;       // attention output [n1,64], MLP hidden [n1,256] (split)
+    CaFolded fold;           // folded per-clip operands (fused vertex cross-attention only)
 };
 
 bool ca_fused_enabled() {
@@ -474,23 +481,59 @@ int mha_core(int heads, const float* Q, int ldq, const float* K, const float* V,
     return launch_attn(D, Q, addr_plain(N1, ldq), K, V, addr_plain(N2, ldkv), nullptr, att, addr_plain(N1, 64), B, heads, N1, N2, st);
 }
 
-// a6 CrossAttentionBlock.forward (CoevoDecoder.py:82-87): xq [B,N1,64] updated in place; xk, xv [B,N2,64]
-int cross_attn_block(const Weights& W, const CaW& w, int heads, float* xq, int N1, const float* xk, const float* xv, int N2, const float* gb, int B,
-                     const AttnScratch& s, cudaStream_t st) {
-    const int n1 = B * N1, n2 = B * N2;
+bool ca_fused_ok(int heads, int N1, int N2) { return N1 >= 128 && ca_fused_enabled() && ca_vertex_fused_supported(heads, N2); }
+
+// keys / values of a CrossAttentionBlock: K = Wk AdaLN_k(xk) + bk, V = Wv AdaLN_v(xv) + bv   (xk, xv [B,N2,64])
+int cross_attn_kv(const Weights& W, const CaW& w, const float* xk, const float* xv, int N2, const float* gb, int B, const AttnScratch& s, cudaStream_t st) {
+    const int n2 = B * N2;
     RET(adaln(xk, B, N2, gb, w.sk, s.tk, st));
     RET(proj64(s.tk, n2, W, w.wk, w.bk, s.K, st));
     RET(adaln(xv, B, N2, gb, w.sv, s.tv, st));
-    RET(proj64(s.tv, n2, W, w.wv, w.bv, s.V, st));
-    if (N1 >= 128 && ca_fused_enabled() && ca_vertex_fused_supported(heads, N2)) {
-        // one pass over the query stream: AdaLN_q, Wq, attention, Wp, residual, AdaLN_2 (ca_fused.cuh)
-        CaFusedArgs a;
-        a.K = s.K; a.V = s.V; a.gb = gb; a.bq = W.f + w.bq; a.bp = W.f + w.bp;
-        a.gb_ld = PMCE_ADALN_SLOTS * 128; a.slot_q = w.sq; a.slot_2 = w.s2;
-        a.B = B; a.N1 = N1; a.N2 = N2; a.qtiles = 0; a.scale = 1.0f / sqrtf(64.0f / heads); a.eps = 1e-6f;
-        count_launch();
-        const int rc = launch_ca_vertex_fused(xq, s.tq.hi, s.tq.lo, W.hi + w.wq, W.lo + w.wq, W.hi + w.wp, W.lo + w.wp, heads, a, st);
-        if (rc) { pmce_set_error("ca_vertex_fused launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
+    return proj64(s.tv, n2, W, w.wv, w.bv, s.V, st);
+}
+
+// per-clip operands of the fused vertex cross-attention (ca_fused.cuh). joints != nullptr: the whole joint side of coevoblock
+// `cw` from the joint coordinates (embed, key projection, AdaLN_k/v, Wk/Wv, fold); else fold given K / V [B,J,64].
+int ca_fold(const Weights& W, const CoevoW* cw, const CaW& w, const float* joints, const float* K_in, const float* V_in, float* xq_out,
+            const float* gb, int B, int J, int heads, const CaFolded& f, cudaStream_t st) {
+    JointFoldArgs a;
+    memset(&a, 0, sizeof(a));
+    a.joints = joints; a.K_in = K_in; a.V_in = V_in;
+    if (joints) {
+        a.wjp = W.f + cw->jprojw; a.bjp = W.f + cw->jprojb; a.jpos = W.f + cw->jpos; a.jq = xq_out ? W.f + cw->jQ : nullptr;
+        a.wj2v = W.f + cw->j2vw; a.bj2v = W.f + cw->j2vb; a.j2vk = W.f + cw->j2vK;
+        a.wk = W.f + w.wk; a.bk = W.f + w.bk; a.wv = W.f + w.wv; a.bv = W.f + w.bv;
+        a.xq_out = xq_out;
+    }
+    a.wq = W.f + w.wq; a.bq = W.f + w.bq; a.wp = W.f + w.wp;
+    a.gb = gb; a.gb_ld = PMCE_ADALN_SLOTS * 128; a.slot_k = w.sk; a.slot_v = w.sv;
+    a.f = f; a.J = J; a.eps = 1e-6f; a.scale = 1.0f / sqrtf(64.0f / heads);
+    ca_joint_fold_kernel<<<B, JKV_THREADS, 0, st>>>(a);
+    CKL();
+    return 0;
+}
+
+int ca_fused_launch(const Weights& W, const CaW& w, float* xq, int N1, int N2, const float* gb, int B, const SplitOut& t, const CaFolded& f,
+                    cudaStream_t st) {
+    CaFusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.gb = gb; a.bp = W.f + w.bp; a.gb_ld = PMCE_ADALN_SLOTS * 128; a.slot_q = w.sq; a.slot_2 = w.s2;
+    a.B = B; a.N1 = N1; a.N2 = N2; a.eps = 1e-6f;
+    count_launch();
+    const int rc = launch_ca_vertex_fused(xq, t.hi, t.lo, f, a, st);
+    if (rc) { pmce_set_error("ca_vertex_fused launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
+    return 0;
+}
+
+// the query side of a CrossAttentionBlock: xq [B,N1,64] updated in place. Needs projected K / V in s.K / s.V, or (folded) the
+// folded operands in s.fold when the fused kernel applies.
+int cross_attn_query(const Weights& W, const CaW& w, int heads, float* xq, int N1, int N2, const float* gb, int B, const AttnScratch& s, bool folded,
+                     cudaStream_t st) {
+    const int n1 = B * N1;
+    if (ca_fused_ok(heads, N1, N2)) {
+        if (!folded) RET(ca_fold(W, nullptr, w, nullptr, s.K, s.V, nullptr, gb, B, N2, heads, s.fold, st));
+        // one pass over the query stream: AdaLN_q, scores, softmax, P V Wp, residual, AdaLN_2 (ca_fused.cuh)
+        RET(ca_fused_launch(W, w, xq, N1, N2, gb, B, s.tq, s.fold, st));
         { EpiOpt o; o.bias = W.f + w.fc1b; o.act = 1; o.outs = s.hid; o.ld_split = 256; RET(linear_tc(s.tq, 64, n1, 64, W, w.fc1w, 64, 256, o, st)); }
         { EpiOpt o; o.bias = W.f + w.fc2b; o.resid = xq; o.ld_resid = 64; o.out = xq; o.ld_out = 64; RET(linear_tc(s.hid, 256, n1, 256, W, w.fc2w, 256, 64, o, st)); }
         return 0;
@@ -499,6 +542,13 @@ int cross_attn_block(const Weights& W, const CaW& w, int heads, float* xq, int N
     RET(proj64(s.tq, n1, W, w.wq, w.bq, s.Q, st));
     RET(mha_core(heads, s.Q, 64, s.K, s.V, 64, s.att, B, N1, N2, st));
     return attn_tail(W, w.wp, w.bp, w.s2, w.fc1w, w.fc1b, w.fc2w, w.fc2b, xq, s.att, s.tq, s.hid, gb, B, N1, st);
+}
+
+// a6 CrossAttentionBlock.forward (CoevoDecoder.py:82-87): xq [B,N1,64] updated in place; xk, xv [B,N2,64]
+int cross_attn_block(const Weights& W, const CaW& w, int heads, float* xq, int N1, const float* xk, const float* xv, int N2, const float* gb, int B,
+                     const AttnScratch& s, cudaStream_t st) {
+    RET(cross_attn_kv(W, w, xk, xv, N2, gb, B, s, st));
+    return cross_attn_query(W, w, heads, xq, N1, N2, gb, B, s, false, st);
 }
 
 // a7 Block.forward (CoevoDecoder.py:102-105): x [B,N,64] updated in place
@@ -513,11 +563,13 @@ int self_attn_block(const Weights& W, const SaW& w, int heads, float* x, int N, 
 AttnScratch vertex_scratch(const Workspace& ws) {   // query stream = the 431 vertices
     AttnScratch s;
     s.tq = ws.tA_s; s.tk = ws.tJ_s; s.tv = ws.tJ_s; s.Q = ws.qkv_d; s.K = ws.Kj; s.V = ws.Vj; s.att = ws.att_ds; s.hid = ws.hid_ds;
+    s.fold = ws.fold;
     return s;
 }
 AttnScratch joint_scratch(const Workspace& ws) {    // query stream = the J joints
     AttnScratch s;
     s.tq = ws.tJ2_s; s.tk = ws.tB_s; s.tv = ws.tA2_s; s.Q = ws.qkvj; s.K = ws.Kv; s.V = ws.Vv; s.att = ws.attj_s; s.hid = ws.hidj_s;
+    memset(&s.fold, 0, sizeof(s.fold));
     return s;
 }
 constexpr int JOINT_HEADS = 8, VERTX_HEADS = 2;      // CoevoDecoder.py:139-140
@@ -531,15 +583,22 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
     const bool ja = joints_out != nullptr;
     if (ja && !w.joint_alive) { pmce_set_error("coevoblock%d: joint-branch weights are not stored (output is discarded by the reference)", k + 1); return 4; }
 
-    // coordinate -> feature (+pos), query streams (+Q embed)   (CoevoDecoder.py:177-183)
-    coevo_embed_kernel<<<cdiv((long long)nj * 16, 256), 256, 0, st>>>(joints, nj, J, W.f + w.jprojw, W.f + w.jprojb, W.f + w.jpos,
-                                                                      ja ? W.f + w.jQ : nullptr, ws.Jf, ws.Jf_s, ja ? ws.xqj : nullptr);
-    CKL();
+    const AttnScratch sv = vertex_scratch(ws);
+    const bool fused = ca_fused_ok(VERTX_HEADS, Vd, J) && J <= JKV_ROWS;
+    // coordinate -> feature (+pos), query streams (+Q embed) (CoevoDecoder.py:177-183); keys proj_j2v(Jf) + j2v_K and
+    // proj_v2j(Vf) + v2j_K from the PRE-update features (:183-184)
+    if (fused) {
+        // the whole joint side of the vertex cross-attention (embed, key projection, AdaLN_k/v, Wk/Wv, fold) per clip in one kernel
+        RET(ca_fold(W, &w, w.vca, joints, nullptr, nullptr, ja ? ws.xqj : nullptr, gb, B, J, VERTX_HEADS, sv.fold, st));
+    } else {
+        coevo_embed_kernel<<<cdiv((long long)nj * 16, 256), 256, 0, st>>>(joints, nj, J, W.f + w.jprojw, W.f + w.jprojb, W.f + w.jpos,
+                                                                          ja ? W.f + w.jQ : nullptr, ws.Jf, ws.Jf_s, ja ? ws.xqj : nullptr);
+        CKL();
+        RET(proj64(ws.Jf_s, nj, W, w.j2vw, w.j2vb, ws.xkj, st, W.f + w.j2vK, J));
+    }
     coevo_embed_kernel<<<cdiv((long long)nv * 16, 256), 256, 0, st>>>(verts_in, nv, Vd, W.f + w.vprojw, W.f + w.vprojb, W.f + w.vpos, W.f + w.vQ,
                                                                       ja ? ws.Vf : nullptr, ja ? ws.Vf_s : NO_SPLIT, ws.xqv);
     CKL();
-    // keys: proj_j2v(Jf) + j2v_K ; proj_v2j(Vf) + v2j_K  — both from the PRE-update features (:183-184)
-    RET(proj64(ws.Jf_s, nj, W, w.j2vw, w.j2vb, ws.xkj, st, W.f + w.j2vK, J));
     if (ja) RET(proj64(ws.Vf_s, nv, W, w.v2jw, w.v2jb, ws.xkv, st, W.f + w.v2jK, Vd));
 
     if (ja) {
@@ -560,9 +619,9 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
     }
 
     // vertex cross-attention block: q = vertices (431), k/v = joints (J); 2 heads x 32; then vertex self-attention 431 x 431
-    const AttnScratch s = vertex_scratch(ws);
-    RET(cross_attn_block(W, w.vca, VERTX_HEADS, ws.xqv, Vd, ws.xkj, ws.Jf, J, gb, B, s, st));
-    RET(self_attn_block(W, w.vsa, VERTX_HEADS, ws.xqv, Vd, gb, B, s, st));
+    if (!fused) RET(cross_attn_kv(W, w.vca, ws.xkj, ws.Jf, J, gb, B, sv, st));
+    RET(cross_attn_query(W, w.vca, VERTX_HEADS, ws.xqv, Vd, J, gb, B, sv, fused, st));
+    RET(self_attn_block(W, w.vsa, VERTX_HEADS, ws.xqv, Vd, gb, B, sv, st));
     feat2coor_kernel<<<cdiv(nv, 8), 256, 0, st>>>(ws.xqv, nv, W.f + w.vf2cw, W.f + w.vf2cb, verts_in, verts_out);
     CKL();
     if (ja && aux) CK(cudaStreamWaitEvent(st, aux->join2, 0));
@@ -723,6 +782,25 @@ extern "C" int pmce_cross_attn_block(const pmce_dims_t* dims, const void* weight
     const CoevoW& w = L.blk[block - 1];
     return which ? cross_attn_block(W, w.vca, VERTX_HEADS, out, N1, xk, xv, N2, gb, B, vertex_scratch(ws), st)
                  : cross_attn_block(W, w.jca, JOINT_HEADS, out, N1, xk, xv, N2, gb, B, joint_scratch(ws), st);
+}
+
+extern "C" size_t pmce_ca_fold_bytes(int B) { return B < 1 ? 0 : (size_t)B * (2 * (CAF_NS + 64) * 64 * 2 + CAF_NS * 4); }
+
+extern "C" int pmce_ca_vertex_fused(const pmce_dims_t* dims, const void* weights, int block, float* xq, const float* K, const float* V,
+                                    const float* gb, int B, void* t_hi, void* t_lo, void* fold_ws, int fold, void* stream) {
+    GET_LAYOUT();
+    if (block < 1 || block > 3) { pmce_set_error("pmce_ca_vertex_fused: block must be 1..3 (got %d)", block); return 2; }
+    if (!xq || !K || !V || !gb || !t_hi || !t_lo || !fold_ws || B < 1) { pmce_set_error("pmce_ca_vertex_fused: bad argument"); return 2; }
+    if ((uintptr_t)fold_ws & 255) { pmce_set_error("pmce_ca_vertex_fused: fold_ws must be 256-byte aligned"); return 2; }
+    const int J = dims->num_joint, Vd = dims->num_vert_ds;
+    if (!ca_vertex_fused_supported(VERTX_HEADS, J) || Vd < 128) { pmce_set_error("pmce_ca_vertex_fused: unsupported shape (J=%d, Vd=%d)", J, Vd); return 3; }
+    const CaW& w = L.blk[block - 1].vca;
+    CaFolded f;
+    f.kq_hi = (bf16*)fold_ws; f.kq_lo = f.kq_hi + (size_t)B * CAF_NS * 64; f.vp_hi = f.kq_lo + (size_t)B * CAF_NS * 64;
+    f.vp_lo = f.vp_hi + (size_t)B * 64 * 64; f.sb = (float*)(f.vp_lo + (size_t)B * 64 * 64);
+    if (fold) RET(ca_fold(W, nullptr, w, nullptr, K, V, nullptr, gb, B, J, VERTX_HEADS, f, st));
+    SplitOut t{(bf16*)t_hi, (bf16*)t_lo};
+    return ca_fused_launch(W, w, xq, Vd, J, gb, B, t, f, st);
 }
 
 extern "C" int pmce_self_attn_block(const pmce_dims_t* dims, const void* weights, int block, int which, const float* x, const float* gb,

@@ -20,15 +20,18 @@
 #include "attn_tc.cuh"
 #include "gemm_tc.cuh"
 
-constexpr int CAF_THREADS = 128;
-constexpr int CAF_KV_ROWS = 24;                         // >= num_joint (17 h36m, 19 coco)
+constexpr int CAF_THREADS = 256;
+constexpr int CAF_KP = 32;                              // key slots per head (num_joint <= 24 live: 17 h36m, 19 coco; the rest are zero)
+constexpr int CAF_MAXJ = 24;
+constexpr int CAF_H = 2;                                // heads of the vertex stream (CoevoDecoder.py:140)
+constexpr int CAF_NS = CAF_H * CAF_KP;                  // 64 score columns: column 32 h + j = (head h, key j)
 constexpr int CAF_IN = 2 * 128 * 128;                   // two [128][32 fp32] boxes
 constexpr int CAF_OFF_A = CAF_IN;                       // A hi | A lo  ([128][64 bf16] each)
-constexpr int CAF_OFF_W = CAF_OFF_A + 2 * AT_TILE;      // Wq hi | Wq lo | Wp hi | Wp lo  ([64][64 bf16] each)
-constexpr int CAF_OFF_KV = CAF_OFF_W + 4 * 64 * 128;    // K [24][64] fp32 | V [24][64] fp32
-constexpr int CAF_OFF_GB = CAF_OFF_KV + 2 * CAF_KV_ROWS * 64 * 4;   // gamma_q beta_q gamma_2 beta_2 bq bp  (6 x 64 fp32)
-constexpr int CAF_OFF_BAR = CAF_OFF_GB + 6 * 64 * 4;
+constexpr int CAF_OFF_W = CAF_OFF_A + 2 * AT_TILE;      // KQ hi | KQ lo | VPt hi | VPt lo ([64][64 bf16] each)
+constexpr int CAF_OFF_GB = CAF_OFF_W + 4 * 8192;        // gamma_q beta_q gamma_2 beta_2 bp  (5 x 64 fp32)
+constexpr int CAF_OFF_BAR = CAF_OFF_GB + 5 * 64 * 4;
 constexpr int CAF_SMEM = CAF_OFF_BAR + 64 + 1024;       // + alignment slack
+constexpr int CAF_TX = CAF_IN + 2 * CAF_NS * 128 + 2 * 64 * 128;   // bytes per item arriving on bar_in
 
 namespace tc {
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int crd0, int crd1, int crd2) {
@@ -47,87 +50,94 @@ __device__ __forceinline__ void sts16f(uint32_t addr, float4 v) {
 }  // namespace tc
 
 struct CaFusedArgs {
-    const float* K;          // [B*N2, 64] projected keys (fp32)
-    const float* V;          // [B*N2, 64] projected values
+    const float* sb;         // [B, 64] folded score bias  scale * bq_h . K_hj
     const float* gb;         // [B, gb_ld] AdaLN gamma/beta of every slot (pmce_adaln_gammabeta)
-    const float* bq;         // [64]
     const float* bp;         // [64]
     int gb_ld, slot_q, slot_2;
     int B, N1, N2, qtiles;
-    float scale, eps;
+    float eps;
 };
 
-// AdaLayerNorm of one 64-wide row held in registers (CoevoDecoder.py:23-29): unbiased std, eps added to the std.
-__device__ __forceinline__ void caf_adaln_split_store(const float (&x)[64], const float* __restrict__ gam, const float* __restrict__ bet, float eps,
-                                                      uint32_t a_hi, uint32_t a_lo, int r) {
-    float s = 0.f;
+// read the 32 floats of one half row out of a swizzled [128][32 fp32] box
+__device__ __forceinline__ void caf_read_half(uint32_t rowaddr, int sw, float (&x)[32]) {
 #pragma unroll
-    for (int i = 0; i < 64; ++i) s += x[i];
-    const float mean = s * (1.0f / 64.0f);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 64; ++i) { const float d = x[i] - mean; q = fmaf(d, d, q); }
-    const float inv = 1.0f / (sqrtf(q * (1.0f / 63.0f)) + eps);
-#pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-        const float4 g0 = ld4(gam + cc * 8), g1 = ld4(gam + cc * 8 + 4), b0 = ld4(bet + cc * 8), b1 = ld4(bet + cc * 8 + 4);
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float y[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = gg[i] * (x[cc * 8 + i] - mean) * inv + bb[i];
-        uint4 hh, ll;
-        tc::split8(y, hh, ll);
-        tc::sts16(a_hi, r, cc, hh);
-        tc::sts16(a_lo, r, cc, ll);
+    for (int j = 0; j < 8; ++j) {
+        const float4 v = tc::lds16(rowaddr + ((j ^ sw) << 4));
+        x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
     }
 }
 
-template <int H, int NK>
+// AdaLayerNorm (CoevoDecoder.py:23-29: unbiased std, eps added to the std) of a 64-wide row given as two halves; the
+// thread normalises and stores (split-bf16, swizzled A tiles) only its own half, columns [32*hf, 32*hf+32).
+__device__ __forceinline__ void caf_adaln_half(const float (&own)[32], const float (&oth)[32], const float* __restrict__ gam,
+                                               const float* __restrict__ bet, float eps, uint32_t a_hi, uint32_t a_lo, int r, int hf) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { s0 += own[i]; s1 += oth[i]; }
+    const float mean = (s0 + s1) * (1.0f / 64.0f);
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float d0 = own[i] - mean, d1 = oth[i] - mean;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+    }
+    const float inv = 1.0f / (sqrtf((q0 + q1) * (1.0f / 63.0f)) + eps);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = hf * 32 + cc * 8;
+        const float4 g0 = ld4(gam + c0), g1 = ld4(gam + c0 + 4), b0 = ld4(bet + c0), b1 = ld4(bet + c0 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = gg[i] * (own[cc * 8 + i] - mean) * inv + bb[i];
+        uint4 hh, ll;
+        tc::split8(y, hh, ll);
+        tc::sts16(a_hi, r, hf * 4 + cc, hh);
+        tc::sts16(a_lo, r, hf * 4 + cc, ll);
+    }
+}
+
+// Few-key cross-attention as two skinny GEMMs. With K_h, V_h the clip's projected keys/values of head h (NK <= 24 rows):
+//   scores_h = scale (xn Wq_h^T + bq_h) K_h^T = xn (scale K_h Wq_h)^T + scale K_h bq_h         -> KQ [64][64], sb [64]
+//   proj(concat_h P_h V_h) = sum_h P_h (V_h Wp[:, h]^T) + bp                                    -> VPt [64][64]
+// (row / column 32 h + j = head h, key j; slots j >= NK are zero) so per 128-row item: S = AdaLN_q(xq) KQ^T (tcgen05
+// 128x64x64), softmax per head in registers, out = P VPt^T (tcgen05 128x64x64). KQ / VPt / sb are per clip, made by ca_joint_fold_kernel (split-bf16), and arrive by TMA.
+template <int NK>
 __global__ void __launch_bounds__(CAF_THREADS, 2)
 ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_thi, const __grid_constant__ CUtensorMap tm_tlo,
-                       const __grid_constant__ CUtensorMap tm_wq_hi, const __grid_constant__ CUtensorMap tm_wq_lo,
-                       const __grid_constant__ CUtensorMap tm_wp_hi, const __grid_constant__ CUtensorMap tm_wp_lo, CaFusedArgs a) {
-    constexpr int D = 64 / H;
-    static_assert(NK <= CAF_KV_ROWS, "too many keys");
+                       const __grid_constant__ CUtensorMap tm_kq_hi, const __grid_constant__ CUtensorMap tm_kq_lo,
+                       const __grid_constant__ CUtensorMap tm_vp_hi, const __grid_constant__ CUtensorMap tm_vp_lo, CaFusedArgs a) {
+    static_assert(NK <= CAF_MAXJ, "too many keys");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sb = tc::smem_u32(smem);
     const uint32_t s_in = sb, s_ahi = sb + CAF_OFF_A, s_alo = s_ahi + AT_TILE, s_w = sb + CAF_OFF_W;
-    float* Ks = reinterpret_cast<float*>(smem + CAF_OFF_KV);
-    float* Vs = Ks + CAF_KV_ROWS * 64;
-    float* gbs = reinterpret_cast<float*>(smem + CAF_OFF_GB);          // [0]=gamma_q [1]=beta_q [2]=gamma_2 [3]=beta_2 [4]=bq [5]=bp
+    float* gbs = reinterpret_cast<float*>(smem + CAF_OFF_GB);          // [0]=gamma_q [1]=beta_q [2]=gamma_2 [3]=beta_2 [4]=bp
     uint64_t* bar_in = reinterpret_cast<uint64_t*>(smem + CAF_OFF_BAR);
-    uint64_t* bar_w = bar_in + 1;
-    uint64_t* bar_mma = bar_in + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_in + 3);
+    uint64_t* bar_mma = bar_in + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_in + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
         tc::tma_prefetch_desc(&tm_x); tc::tma_prefetch_desc(&tm_thi); tc::tma_prefetch_desc(&tm_tlo);
-        tc::tma_prefetch_desc(&tm_wq_hi); tc::tma_prefetch_desc(&tm_wq_lo); tc::tma_prefetch_desc(&tm_wp_hi); tc::tma_prefetch_desc(&tm_wp_lo);
-        tc::mbar_init(bar_in, 1); tc::mbar_init(bar_w, 1); tc::mbar_init(bar_mma, 1);
+        tc::tma_prefetch_desc(&tm_kq_hi); tc::tma_prefetch_desc(&tm_kq_lo); tc::tma_prefetch_desc(&tm_vp_hi); tc::tma_prefetch_desc(&tm_vp_lo);
+        tc::mbar_init(bar_in, 1); tc::mbar_init(bar_mma, 1);
         tc::fence_barrier_init();
         tc::fence_proxy_async();
     }
     if (warp == 0) tc::tmem_alloc(tmem_ptr_smem, 128);
-    if (tid < 64) { gbs[4 * 64 + tid] = a.bq[tid]; gbs[5 * 64 + tid] = a.bp[tid]; }
+    if (tid < 64) gbs[4 * 64 + tid] = a.bp[tid];
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    const uint32_t tQ = tmem_base, tP = tmem_base + 64;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const uint32_t tS = tmem_base, tO = tmem_base + 64;
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
 
-    if (tid == 0) {                                   // the four weight tiles, once per CTA
-        tc::mbar_arrive_expect_tx(bar_w, 4 * 64 * 128);
-        tc::tma_load_2d(smem + CAF_OFF_W, &tm_wq_hi, bar_w, 0, 0);
-        tc::tma_load_2d(smem + CAF_OFF_W + 8192, &tm_wq_lo, bar_w, 0, 0);
-        tc::tma_load_2d(smem + CAF_OFF_W + 16384, &tm_wp_hi, bar_w, 0, 0);
-        tc::tma_load_2d(smem + CAF_OFF_W + 24576, &tm_wp_lo, bar_w, 0, 0);
-    }
-
-    const int r = tid;
-    const uint32_t row_in0 = s_in + r * 128, row_in1 = s_in + 16384 + r * 128;
+    // thread = (tile row r, column half hf): hf selects the 32-column half of the 64-wide row it normalises / stores and the
+    // attention head whose softmax it runs; both threads of a row read the whole row for the LayerNorm statistics.
+    const int r = tid & 127, hf = tid >> 7;
+    const uint32_t row_own = s_in + hf * 16384 + r * 128, row_oth = s_in + (1 - hf) * 16384 + r * 128;
     const int sw = r & 7;
     const int ntiles = a.B * a.qtiles;
     uint32_t it = 0, mph = 0;
@@ -135,51 +145,47 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
         if (tid == 0) {
             if (it > 0) tc::tma_store_wait_read<0>();          // the previous item's stores have read the IN / A tiles
-            tc::mbar_arrive_expect_tx(bar_in, CAF_IN);
+            tc::mbar_arrive_expect_tx(bar_in, CAF_TX);
             tc::tma_load_3d(smem, &tm_x, bar_in, 0, row0, b);
             tc::tma_load_3d(smem + 16384, &tm_x, bar_in, 32, row0, b);
+            tc::tma_load_2d(smem + CAF_OFF_W, &tm_kq_hi, bar_in, 0, b * CAF_NS);
+            tc::tma_load_2d(smem + CAF_OFF_W + 8192, &tm_kq_lo, bar_in, 0, b * CAF_NS);
+            tc::tma_load_2d(smem + CAF_OFF_W + 16384, &tm_vp_hi, bar_in, 0, b * 64);
+            tc::tma_load_2d(smem + CAF_OFF_W + 24576, &tm_vp_lo, bar_in, 0, b * 64);
         }
-        // keys / values / AdaLN parameters of clip b
-        for (int idx = tid; idx < NK * 16; idx += CAF_THREADS) {
-            const int kr = idx >> 4, c = (idx & 15) * 4;
-            st4(Ks + kr * 64 + c, ld4(a.K + ((size_t)b * a.N2 + kr) * 64 + c));
-            st4(Vs + kr * 64 + c, ld4(a.V + ((size_t)b * a.N2 + kr) * 64 + c));
+        {   // AdaLN parameters of clip b: gamma|beta of slot_q and slot_2
+            const int arr = tid >> 6, c = tid & 63;
+            gbs[arr * 64 + c] = a.gb[(size_t)b * a.gb_ld + (arr < 2 ? a.slot_q : a.slot_2) * 128 + (arr & 1) * 64 + c];
         }
-        {
-            const float* g = a.gb + (size_t)b * a.gb_ld;
-            const int which = tid >> 6, c = tid & 63;              // threads 0-63: slot_q, 64-127: slot_2 (gamma | beta)
-            const float* src = g + (which == 0 ? a.slot_q : a.slot_2) * 128;
-            gbs[(which * 2) * 64 + c] = src[c];
-            gbs[(which * 2 + 1) * 64 + c] = src[64 + c];
+        float sbv[CAF_MAXJ];                                   // folded score bias of this thread's head
+#pragma unroll
+        for (int j = 0; j < CAF_MAXJ; j += 4) {
+            const float4 v = ld4(a.sb + (size_t)b * CAF_NS + hf * CAF_KP + j);
+            sbv[j] = v.x; sbv[j + 1] = v.y; sbv[j + 2] = v.z; sbv[j + 3] = v.w;
         }
         __syncthreads();
 
         // ---- xq row -> AdaLN_q -> split A tiles ----
         tc::mbar_wait(bar_in, it & 1);
         {
-            float x[64];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 v0 = tc::lds16(row_in0 + ((j ^ sw) << 4)), v1 = tc::lds16(row_in1 + ((j ^ sw) << 4));
-                x[4 * j] = v0.x; x[4 * j + 1] = v0.y; x[4 * j + 2] = v0.z; x[4 * j + 3] = v0.w;
-                x[32 + 4 * j] = v1.x; x[32 + 4 * j + 1] = v1.y; x[32 + 4 * j + 2] = v1.z; x[32 + 4 * j + 3] = v1.w;
-            }
-            caf_adaln_split_store(x, gbs, gbs + 64, a.eps, s_ahi, s_alo, r);
+            float own[32], oth[32];
+            caf_read_half(row_own, sw, own);
+            caf_read_half(row_oth, sw, oth);
+            caf_adaln_half(own, oth, gbs, gbs + 64, a.eps, s_ahi, s_alo, r, hf);
         }
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
-        constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, 64);
         if (tid == 0) {
-            if (it == 0) tc::mbar_wait(bar_w, 0);
             tc::tc_fence_after();
+            constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, CAF_NS);
             const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
             const uint64_t wh = tc::umma_desc_sw128(s_w), wl = tc::umma_desc_sw128(s_w + 8192);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                tc::umma_bf16(tQ, tc::umma_desc_advance_k(al, k), tc::umma_desc_advance_k(wh, k), idesc, k != 0);
-                tc::umma_bf16(tQ, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
-                tc::umma_bf16(tQ, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
+                tc::umma_bf16(tS, tc::umma_desc_advance_k(al, k), tc::umma_desc_advance_k(wh, k), idesc, k != 0);
+                tc::umma_bf16(tS, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
+                tc::umma_bf16(tS, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
             }
             tc::umma_commit(bar_mma);
         }
@@ -187,80 +193,47 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         ++mph;
         tc::tc_fence_after();
 
-        // ---- Q row from TMEM; attention over the clip's NK keys on CUDA cores ----
-        float o[64];
+        // ---- softmax of head hf over the clip's NK keys; P (split) -> A tile columns [24 hf, 24 hf + 24) ----
         {
-            float q[64];
-            {
-                uint32_t v[32];
-                tc::tmem_ld_32x32(tQ + lane_sel, v);
-                tc::tmem_ld_wait();
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tS + lane_sel + hf * CAF_KP, v);     // this head's 32 key slots
+            tc::tmem_ld_wait();
+            float p[CAF_MAXJ];
+            float m = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) q[i] = (__uint_as_float(v[i]) + gbs[4 * 64 + i]) * a.scale;
-                tc::tmem_ld_32x32(tQ + lane_sel + 32, v);
-                tc::tmem_ld_wait();
+            for (int j = 0; j < NK; ++j) { p[j] = __uint_as_float(v[j]) + sbv[j]; m = fmaxf(m, p[j]); }
+            float l = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) q[32 + i] = (__uint_as_float(v[i]) + gbs[4 * 64 + 32 + i]) * a.scale;
+            for (int j = 0; j < NK; ++j) { p[j] = expf(p[j] - m); l += p[j]; }
+            const float inv = 1.0f / l;
+#pragma unroll
+            for (int j = 0; j < CAF_MAXJ; ++j) p[j] = j < NK ? p[j] * inv : 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = p[cc * 8 + i];
+                uint4 hh, ll;
+                tc::split8(y, hh, ll);
+                tc::sts16(s_ahi, r, hf * 4 + cc, hh);
+                tc::sts16(s_alo, r, hf * 4 + cc, ll);
             }
-#pragma unroll
-            for (int h = 0; h < H; ++h) {
-                float s[NK];
-                float m = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < NK; ++j) {
-                    const float* kr = Ks + j * 64 + h * D;
-                    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                    for (int c = 0; c < D; c += 4) {
-                        const float4 kk = ld4(kr + c);
-                        s0 = fmaf(q[h * D + c], kk.x, s0); s1 = fmaf(q[h * D + c + 1], kk.y, s1);
-                        s0 = fmaf(q[h * D + c + 2], kk.z, s0); s1 = fmaf(q[h * D + c + 3], kk.w, s1);
-                    }
-                    s[j] = s0 + s1;
-                    m = fmaxf(m, s[j]);
-                }
-                float l = 0.f;
-#pragma unroll
-                for (int j = 0; j < NK; ++j) { s[j] = expf(s[j] - m); l += s[j]; }
-                const float inv = 1.0f / l;
-#pragma unroll
-                for (int c = 0; c < D; ++c) o[h * D + c] = 0.f;
-#pragma unroll
-                for (int j = 0; j < NK; ++j) {
-                    const float* vr = Vs + j * 64 + h * D;
-                    const float p = s[j] * inv;
-#pragma unroll
-                    for (int c = 0; c < D; c += 4) {
-                        const float4 vv = ld4(vr + c);
-                        o[h * D + c] = fmaf(p, vv.x, o[h * D + c]); o[h * D + c + 1] = fmaf(p, vv.y, o[h * D + c + 1]);
-                        o[h * D + c + 2] = fmaf(p, vv.z, o[h * D + c + 2]); o[h * D + c + 3] = fmaf(p, vv.w, o[h * D + c + 3]);
-                    }
-                }
-            }
-        }
-        // ---- O -> split A tiles -> proj MMA ----
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-            float y[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = o[cc * 8 + i];
-            uint4 hh, ll;
-            tc::split8(y, hh, ll);
-            tc::sts16(s_ahi, r, cc, hh);
-            tc::sts16(s_alo, r, cc, ll);
+            tc::sts16(s_ahi, r, hf * 4 + 3, make_uint4(0, 0, 0, 0));     // key slots 24..31 never hold a key
+            tc::sts16(s_alo, r, hf * 4 + 3, make_uint4(0, 0, 0, 0));
         }
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc::tc_fence_after();
+            constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, 64);
             const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
             const uint64_t wh = tc::umma_desc_sw128(s_w + 16384), wl = tc::umma_desc_sw128(s_w + 24576);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                tc::umma_bf16(tP, tc::umma_desc_advance_k(al, k), tc::umma_desc_advance_k(wh, k), idesc, k != 0);
-                tc::umma_bf16(tP, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
-                tc::umma_bf16(tP, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
+            for (int k = 0; k < CAF_NS / 16; ++k) {
+                tc::umma_bf16(tO, tc::umma_desc_advance_k(al, k), tc::umma_desc_advance_k(wh, k), idesc, k != 0);
+                tc::umma_bf16(tO, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
+                tc::umma_bf16(tO, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
             }
             tc::umma_commit(bar_mma);
         }
@@ -268,30 +241,31 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         ++mph;
         tc::tc_fence_after();
 
-        // ---- xq' = (proj + bp) + xq -> input tile; AdaLN_2(xq') -> split A tiles; TMA stores ----
+        // ---- xq' = (out + bp) + xq -> own half back into the input tile; AdaLN_2(xq') -> split A tiles; TMA stores ----
         {
-            float x[64];
+            float own[32], oth[32];
             {
                 uint32_t v[32];
-                tc::tmem_ld_32x32(tP + lane_sel, v);
+                tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + gbs[5 * 64 + i];
-                tc::tmem_ld_32x32(tP + lane_sel + 32, v);
+                for (int i = 0; i < 32; ++i) own[i] = __uint_as_float(v[i]) + gbs[4 * 64 + hf * 32 + i];
+                tc::tmem_ld_32x32(tO + lane_sel + (1 - hf) * 32, v);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) x[32 + i] = __uint_as_float(v[i]) + gbs[5 * 64 + 32 + i];
+                for (int i = 0; i < 32; ++i) oth[i] = __uint_as_float(v[i]) + gbs[4 * 64 + (1 - hf) * 32 + i];
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint32_t a0 = row_in0 + ((j ^ sw) << 4), a1 = row_in1 + ((j ^ sw) << 4);
-                const float4 v0 = tc::lds16(a0), v1 = tc::lds16(a1);
-                x[4 * j] += v0.x; x[4 * j + 1] += v0.y; x[4 * j + 2] += v0.z; x[4 * j + 3] += v0.w;
-                x[32 + 4 * j] += v1.x; x[32 + 4 * j + 1] += v1.y; x[32 + 4 * j + 2] += v1.z; x[32 + 4 * j + 3] += v1.w;
-                tc::sts16f(a0, make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
-                tc::sts16f(a1, make_float4(x[32 + 4 * j], x[32 + 4 * j + 1], x[32 + 4 * j + 2], x[32 + 4 * j + 3]));
+                const float4 v0 = tc::lds16(row_own + ((j ^ sw) << 4)), v1 = tc::lds16(row_oth + ((j ^ sw) << 4));
+                own[4 * j] += v0.x; own[4 * j + 1] += v0.y; own[4 * j + 2] += v0.z; own[4 * j + 3] += v0.w;
+                oth[4 * j] += v1.x; oth[4 * j + 1] += v1.y; oth[4 * j + 2] += v1.z; oth[4 * j + 3] += v1.w;
             }
-            caf_adaln_split_store(x, gbs + 128, gbs + 192, a.eps, s_ahi, s_alo, r);
+            __syncthreads();                                       // both threads of every row have read xq before either overwrites it
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                tc::sts16f(row_own + ((j ^ sw) << 4), make_float4(own[4 * j], own[4 * j + 1], own[4 * j + 2], own[4 * j + 3]));
+            caf_adaln_half(own, oth, gbs + 128, gbs + 192, a.eps, s_ahi, s_alo, r, hf);
         }
         tc::fence_proxy_async();
         tc::tc_fence_before();
@@ -324,36 +298,209 @@ static inline int make_tmap_3d(CUtensorMap* m, const void* ptr, CUtensorMapDataT
     return r == CUDA_SUCCESS ? 0 : 2;
 }
 
-template <int H, int NK>
+template <int NK>
 static inline int launch_ca_vertex_fused_t(const CUtensorMap* maps, const CaFusedArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(ca_vertex_fused_kernel<H, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAF_SMEM) != cudaSuccess) return 2;
+        if (cudaFuncSetAttribute(ca_vertex_fused_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAF_SMEM) != cudaSuccess) return 2;
         configured = true;
     }
     const int ntiles = a.B * a.qtiles;
     const int cap = 2 * tc_num_sms();
     const int grid = ntiles < cap ? ntiles : cap;
-    ca_vertex_fused_kernel<H, NK><<<grid, CAF_THREADS, CAF_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], a);
+    ca_vertex_fused_kernel<NK><<<grid, CAF_THREADS, CAF_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], a);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
 // true when the fused kernel covers (heads, keys): the reference's vertex stream has 2 heads; 17 (h36m) / 19 (coco) joints
-static inline bool ca_vertex_fused_supported(int heads, int nkeys) { return heads == 2 && (nkeys == 17 || nkeys == 19); }
+static inline bool ca_vertex_fused_supported(int heads, int nkeys) { return heads == CAF_H && (nkeys == 17 || nkeys == 19); }
 
-// xq [B, N1, 64] fp32 (updated in place), t_hi/t_lo [B, N1, 64] bf16 (AdaLN_2 of the result, split);
-// wq_* / wp_*: [64, 64] bf16 hi/lo weight copies.
-static inline int launch_ca_vertex_fused(float* xq, __nv_bfloat16* t_hi, __nv_bfloat16* t_lo, const __nv_bfloat16* wq_hi, const __nv_bfloat16* wq_lo,
-                                         const __nv_bfloat16* wp_hi, const __nv_bfloat16* wp_lo, int heads, CaFusedArgs a, cudaStream_t st) {
+// Per-clip folded operands (made by ca_joint_fold_kernel): kq [B*64, 64], vpt [B*64, 64] split bf16, sb [B, 64] fp32
+struct CaFolded {
+    __nv_bfloat16 *kq_hi, *kq_lo, *vp_hi, *vp_lo;
+    float* sb;
+};
+
+// xq [B, N1, 64] fp32 (updated in place), t_hi/t_lo [B, N1, 64] bf16 (AdaLN_2 of the result, split)
+static inline int launch_ca_vertex_fused(float* xq, __nv_bfloat16* t_hi, __nv_bfloat16* t_lo, const CaFolded& f, CaFusedArgs a, cudaStream_t st) {
     CUtensorMap maps[7];
     a.qtiles = (a.N1 + 127) / 128;
+    a.sb = f.sb;
     if (make_tmap_3d(&maps[0], xq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 64, a.N1, a.B, 64, 64LL * a.N1, 32, 128, 1) ||
         make_tmap_3d(&maps[1], t_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64, a.N1, a.B, 64, 64LL * a.N1, 64, 128, 1) ||
         make_tmap_3d(&maps[2], t_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64, a.N1, a.B, 64, 64LL * a.N1, 64, 128, 1) ||
-        make_tmap_bf16(&maps[3], wq_hi, 64, 64, 64, 64) || make_tmap_bf16(&maps[4], wq_lo, 64, 64, 64, 64) ||
-        make_tmap_bf16(&maps[5], wp_hi, 64, 64, 64, 64) || make_tmap_bf16(&maps[6], wp_lo, 64, 64, 64, 64))
+        make_tmap_bf16(&maps[3], f.kq_hi, a.B * CAF_NS, 64, 64, CAF_NS) || make_tmap_bf16(&maps[4], f.kq_lo, a.B * CAF_NS, 64, 64, CAF_NS) ||
+        make_tmap_bf16(&maps[5], f.vp_hi, a.B * 64, 64, 64, 64) || make_tmap_bf16(&maps[6], f.vp_lo, a.B * 64, 64, 64, 64))
         return 1;
-    if (heads == 2 && a.N2 == 17) return launch_ca_vertex_fused_t<2, 17>(maps, a, st);
-    if (heads == 2 && a.N2 == 19) return launch_ca_vertex_fused_t<2, 19>(maps, a, st);
+    if (a.N2 == 17) return launch_ca_vertex_fused_t<17>(maps, a, st);
+    if (a.N2 == 19) return launch_ca_vertex_fused_t<19>(maps, a, st);
     return 4;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Joint side of the vertex cross-attention, one CTA per clip (all of it is 17/19-row work, fp32 on CUDA cores):
+//   Jf = W_jp P + b + jpos                       (CoevoDecoder.py:177)      [-> xq_out = Jf + jQ when asked, :182]
+//   xk = W_j2v Jf + b + j2v_K                    (:184)
+//   K  = Wk AdaLN_k(xk) + bk ;  V = Wv AdaLN_v(Jf) + bv     (:53-55 with :84)
+//   KQ = scale K_h Wq_h, sb = scale K_h bq_h, VPt = (V_h Wp[:, h]^T)^T       (the folded operands of ca_vertex_fused_kernel)
+// replacing six launches (embed, key projection, 2 x AdaLN, 2 x projection GEMM with 17 live rows per 128-row tile).
+// With joints == nullptr the kernel starts from given K / V [B,J,64] (pmce_cross_attn_block on arbitrary key/value streams).
+// Thread n (of 64 per row group) keeps row n of a 64x64 weight in registers; activations are broadcast from shared memory.
+// ------------------------------------------------------------------------------------------------------
+constexpr int JKV_THREADS = 256;
+constexpr int JKV_ROWS = CAF_MAXJ;
+
+struct JointFoldArgs {
+    const float* joints;                         // [B, J, 3] or nullptr (then K_in / V_in are used)
+    const float *K_in, *V_in;                    // [B, J, 64] projected keys / values (only when joints == nullptr)
+    const float *wjp, *bjp, *jpos, *jq;          // [64,3], [64], [J,64], [J,64] (jq optional)
+    const float *wj2v, *bj2v, *j2vk;             // [64,64], [64], [J,64]
+    const float *wk, *bk, *wv, *bv;              // [64,64], [64]
+    const float *wq, *bq, *wp;                   // [64,64], [64], [64,64] of the vertex cross-attention
+    const float* gb; int gb_ld, slot_k, slot_v;
+    float* xq_out;                               // optional [B, J, 64]: Jf + jQ (query stream of the joint branch)
+    CaFolded f;
+    int J; float eps, scale;
+};
+
+__device__ __forceinline__ void jkv_matmul(const float* __restrict__ Wg, const float* __restrict__ bias, const float* __restrict__ rowadd,
+                                           const float* xs, float* out_s, int J, int n, int rg) {
+    float w[64];
+#pragma unroll
+    for (int k = 0; k < 64; k += 4) { const float4 v = ld4(Wg + n * 64 + k); w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w; }
+    const float b = bias[n];
+    for (int i = rg; i < J; i += JKV_THREADS / 64) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 64; k += 4) {
+            const float4 x = ld4(xs + i * 64 + k);
+            a0 = fmaf(w[k], x.x, a0); a1 = fmaf(w[k + 1], x.y, a1);
+            a0 = fmaf(w[k + 2], x.z, a0); a1 = fmaf(w[k + 3], x.w, a1);
+        }
+        float r = (a0 + a1) + b;
+        if (rowadd) r += rowadd[i * 64 + n];
+        out_s[i * 64 + n] = r;
+    }
+}
+
+__device__ __forceinline__ void jkv_adaln_row(const float* __restrict__ x, const float* __restrict__ g, float eps, float* __restrict__ y, int lane) {
+    const float2 v = *reinterpret_cast<const float2*>(x + lane * 2);
+    const float mean = warp_sum(v.x + v.y) * (1.0f / 64.0f);
+    const float dx = v.x - mean, dy = v.y - mean;
+    const float var = warp_sum(dx * dx + dy * dy) * (1.0f / 63.0f);
+    const float inv = 1.0f / (sqrtf(var) + eps);
+    const float2 ga = *reinterpret_cast<const float2*>(g + lane * 2), be = *reinterpret_cast<const float2*>(g + 64 + lane * 2);
+    y[lane * 2] = ga.x * dx * inv + be.x;
+    y[lane * 2 + 1] = ga.y * dy * inv + be.y;
+}
+
+__global__ void __launch_bounds__(JKV_THREADS)
+ca_joint_fold_kernel(JointFoldArgs a) {
+    constexpr int RS = JKV_ROWS * 64;            // floats per [24][64] buffer
+    __shared__ __align__(16) float buf[6 * RS];
+    float *Jf = buf, *Xk = buf + RS, *Nk = buf + 2 * RS, *Nv = buf + 3 * RS, *Ks = buf + 4 * RS, *Vs = buf + 5 * RS;
+    float* VPs = buf;                            // [64][65] staging of VPt^T, aliases Jf/Xk/Nk once K and V are final
+    static_assert(CAF_NS * 65 <= 3 * RS, "VPs must not reach Ks/Vs");
+    const int b = blockIdx.x, tid = threadIdx.x, J = a.J;
+    const int n = tid & 63, rg = tid >> 6;
+    if (a.joints) {
+        const float* P = a.joints + (size_t)b * J * 3;
+        {
+            const float w0 = a.wjp[n * 3], w1 = a.wjp[n * 3 + 1], w2 = a.wjp[n * 3 + 2], bb = a.bjp[n];
+            for (int i = rg; i < J; i += JKV_THREADS / 64) {
+                const float f = ((w0 * P[i * 3] + w1 * P[i * 3 + 1]) + w2 * P[i * 3 + 2]) + bb + a.jpos[i * 64 + n];
+                Jf[i * 64 + n] = f;
+                if (a.xq_out) a.xq_out[((size_t)b * J + i) * 64 + n] = f + a.jq[i * 64 + n];
+            }
+        }
+        __syncthreads();
+        jkv_matmul(a.wj2v, a.bj2v, a.j2vk, Jf, Xk, J, n, rg);
+        __syncthreads();
+        {
+            const int warp = tid >> 5, lane = tid & 31;
+            const float* g = a.gb + (size_t)b * a.gb_ld;
+            for (int i = warp; i < J; i += JKV_THREADS / 32) {
+                jkv_adaln_row(Xk + i * 64, g + a.slot_k * 128, a.eps, Nk + i * 64, lane);
+                jkv_adaln_row(Jf + i * 64, g + a.slot_v * 128, a.eps, Nv + i * 64, lane);
+            }
+        }
+        __syncthreads();
+        jkv_matmul(a.wk, a.bk, nullptr, Nk, Ks, J, n, rg);
+        jkv_matmul(a.wv, a.bv, nullptr, Nv, Vs, J, n, rg);
+    } else {
+        for (int idx = tid; idx < J * 16; idx += JKV_THREADS) {
+            st4(Ks + idx * 4, ld4(a.K_in + (size_t)b * J * 64 + idx * 4));
+            st4(Vs + idx * 4, ld4(a.V_in + (size_t)b * J * 64 + idx * 4));
+        }
+    }
+    __syncthreads();
+    // ---- fold: KQ[32h+j][c] = scale sum_d K[j][32h+d] Wq[32h+d][c]  (thread = output channel c, coalesced weight columns) ----
+#pragma unroll 1
+    for (int h = 0; h < CAF_H; ++h) {
+        float wc[32];
+#pragma unroll
+        for (int d = 0; d < 32; ++d) wc[d] = a.wq[(h * 32 + d) * 64 + n];
+        for (int j = rg; j < CAF_KP; j += JKV_THREADS / 64) {
+            float acc = 0.f;
+            if (j < J) {
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int d = 0; d < 32; d += 4) {
+                    const float4 k = ld4(Ks + j * 64 + h * 32 + d);
+                    a0 = fmaf(k.x, wc[d], a0); a1 = fmaf(k.y, wc[d + 1], a1);
+                    a0 = fmaf(k.z, wc[d + 2], a0); a1 = fmaf(k.w, wc[d + 3], a1);
+                }
+                acc = (a0 + a1) * a.scale;
+            }
+            __nv_bfloat16 hi, lo;
+            tc::split_bf16(acc, hi, lo);
+            const size_t o = ((size_t)b * CAF_NS + h * CAF_KP + j) * 64 + n;
+            a.f.kq_hi[o] = hi; a.f.kq_lo[o] = lo;
+        }
+    }
+    if (tid < CAF_NS) {                          // sb[32h+j] = scale sum_d bq[32h+d] K[j][32h+d]
+        const int h = tid / CAF_KP, j = tid % CAF_KP;
+        float acc = 0.f;
+        if (j < J)
+            for (int d = 0; d < 32; ++d) acc = fmaf(a.bq[h * 32 + d], Ks[j * 64 + h * 32 + d], acc);
+        a.f.sb[(size_t)b * CAF_NS + tid] = acc * a.scale;
+    }
+    // ---- fold: VPt[n][32h+j] = sum_d V[j][32h+d] Wp[n][32h+d]  (thread = output channel n, weight row in registers) ----
+    {
+        float w[64];
+#pragma unroll
+        for (int k = 0; k < 64; k += 4) { const float4 v = ld4(a.wp + n * 64 + k); w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w; }
+        for (int idx = rg; idx < CAF_NS; idx += JKV_THREADS / 64) {
+            const int h = idx / CAF_KP, j = idx % CAF_KP;
+            float acc = 0.f;
+            if (j < J) {
+                float a0 = 0.f, a1 = 0.f;
+                if (h == 0) {
+#pragma unroll
+                    for (int d = 0; d < 32; d += 4) {
+                        const float4 v = ld4(Vs + j * 64 + d);
+                        a0 = fmaf(v.x, w[d], a0); a1 = fmaf(v.y, w[d + 1], a1); a0 = fmaf(v.z, w[d + 2], a0); a1 = fmaf(v.w, w[d + 3], a1);
+                    }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < 32; d += 4) {
+                        const float4 v = ld4(Vs + j * 64 + 32 + d);
+                        a0 = fmaf(v.x, w[32 + d], a0); a1 = fmaf(v.y, w[32 + d + 1], a1); a0 = fmaf(v.z, w[32 + d + 2], a0); a1 = fmaf(v.w, w[32 + d + 3], a1);
+                    }
+                }
+                acc = a0 + a1;
+            }
+            VPs[idx * 65 + n] = acc;            // Jf/Xk/Nk (aliased) were last read before the barrier that published Ks/Vs
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < 64 * 32; e += JKV_THREADS) {       // VPt rows [64][64], split-bf16, coalesced
+        const int row = e >> 5, c = (e & 31) * 2;
+        const float v0 = VPs[c * 65 + row], v1 = VPs[(c + 1) * 65 + row];
+        uint32_t h2, l2;
+        tc::split_bf16x2(v0, v1, h2, l2);
+        const size_t o = ((size_t)b * 64 + row) * 64 + c;
+        *reinterpret_cast<uint32_t*>(a.f.vp_hi + o) = h2;
+        *reinterpret_cast<uint32_t*>(a.f.vp_lo + o) = l2;
+    }
 }
