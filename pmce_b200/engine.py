@@ -189,6 +189,100 @@ class Engine:
                                              _ptr(ws), ws.numel(), _stream()), "pmce_forward_host")
         return out
 
+    # ---- pipelined host loop ---------------------------------------------------------------------------
+    def _pipeline(self, B, dev):
+        """Two slots of static device buffers + captured graphs + pinned host outputs, three streams (H2D / forward / D2H).
+        Both graphs replay on the one forward stream, so they share the workspace."""
+        pipe = getattr(self, "_pipe", {}).get(B)
+        if pipe is not None and pipe["ws"] is self._workspace(B, dev):
+            return pipe
+        d = self.dims
+        ws = self._workspace(B, dev)
+        slots = []
+        for _ in range(2):
+            sl = dict(p2d=torch.zeros(B, d.seqlen, d.num_joint, 2, device=dev), feat=torch.zeros(B, d.seqlen, d.feat_dim, device=dev),
+                      mesh=torch.empty(B, d.num_vert, 3, device=dev), cam_pose=torch.empty(B, d.num_joint, 3, device=dev),
+                      pose3d=torch.empty(B, d.num_joint, 3, device=dev),
+                      host=(torch.empty(B, d.num_vert, 3).pin_memory(), torch.empty(B, d.num_joint, 3).pin_memory(),
+                            torch.empty(B, d.num_joint, 3).pin_memory()),
+                      h2d=torch.cuda.Event(), fwd=torch.cuda.Event(), d2h=torch.cuda.Event(), used=False)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):      # warm-up outside capture
+                self._forward_eager(sl["p2d"], sl["feat"], sl["mesh"], sl["cam_pose"], sl["pose3d"])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._forward_eager(sl["p2d"], sl["feat"], sl["mesh"], sl["cam_pose"], sl["pose3d"])
+            sl["graph"] = graph
+            slots.append(sl)
+        pipe = dict(ws=ws, slots=slots, s_in=torch.cuda.Stream(device=dev), s_fwd=torch.cuda.Stream(device=dev),
+                    s_out=torch.cuda.Stream(device=dev))
+        if not hasattr(self, "_pipe"):
+            self._pipe = {}
+        self._pipe[B] = pipe
+        return pipe
+
+    def forward_host_iter(self, batches):
+        """Pipelined form of the reference's test loop (lib/core/base.py:218-238: `.cuda()` -> forward -> `.cpu()` per batch).
+
+        `batches` yields (pose2d [B,T,J,2], img_feat [B,T,2048]) contiguous float32 CPU tensors (pinned for asynchronous
+        copies) of one batch size; the generator yields (cam_mesh, cam_pose, pose3d) pinned CPU tensors in the same order.
+        The H2D copy of batch i+1 and the D2H copy of batch i-1 run on the copy engines while batch i is in the forward
+        (three streams, two buffer slots, one captured graph per slot). A yielded triple is overwritten two batches later:
+        consume (or copy) it before asking for the batch after next."""
+        self._ready(need_vj=True)
+        dev = self.weights.device
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream()
+            pipe, pending, i = None, [], 0
+            for hp, hf in batches:
+                for t, n in ((hp, "pose2d"), (hf, "img_feat")):
+                    if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                        raise PmceError(f"{n}: forward_host_iter expects contiguous float32 CPU tensors")
+                if pipe is None:
+                    B = hp.shape[0]
+                    pipe = self._pipeline(B, dev)
+                    for s in (pipe["s_in"], pipe["s_fwd"], pipe["s_out"]):
+                        s.wait_stream(cur)
+                elif hp.shape[0] != B:
+                    raise PmceError("forward_host_iter: every batch must have the same size (pad or run the tail through forward_host)")
+                sl = pipe["slots"][i & 1]
+                with torch.cuda.stream(pipe["s_in"]):
+                    if sl["used"]:
+                        pipe["s_in"].wait_event(sl["fwd"])       # the forward that read this slot's inputs has finished
+                    sl["p2d"].copy_(hp, non_blocking=True)
+                    sl["feat"].copy_(hf, non_blocking=True)
+                    sl["h2d"].record(pipe["s_in"])
+                with torch.cuda.stream(pipe["s_fwd"]):
+                    pipe["s_fwd"].wait_event(sl["h2d"])
+                    if sl["used"]:
+                        pipe["s_fwd"].wait_event(sl["d2h"])      # this slot's previous outputs have left the device
+                    sl["graph"].replay()
+                    sl["fwd"].record(pipe["s_fwd"])
+                with torch.cuda.stream(pipe["s_out"]):
+                    pipe["s_out"].wait_event(sl["fwd"])
+                    sl["host"][0].copy_(sl["mesh"], non_blocking=True)
+                    sl["host"][1].copy_(sl["cam_pose"], non_blocking=True)
+                    sl["host"][2].copy_(sl["pose3d"], non_blocking=True)
+                    sl["d2h"].record(pipe["s_out"])
+                sl["used"] = True
+                pending.append(sl)
+                i += 1
+                if len(pending) == 2:
+                    done = pending.pop(0)
+                    done["d2h"].synchronize()
+                    yield done["host"]
+            for done in pending:
+                done["d2h"].synchronize()
+                yield done["host"]
+            if pipe is not None:
+                for sl in pipe["slots"]:
+                    sl["used"] = False
+                for s in (pipe["s_in"], pipe["s_fwd"], pipe["s_out"]):
+                    cur.wait_stream(s)
+
     # ---- sub-paths (each is a C-ABI entry point; used by the module API and by the parity tests) --------
     def lifter(self, pose2d, img_feat):
         self._ready()

@@ -39,5 +39,12 @@ class PMCE(EngineModule):
         return self.engine().forward_host(pose2d_cpu, img_feat_cpu, out)
 
 
+    @torch.no_grad()
+    def forward_host_iter(self, batches):
+        """Pipelined `forward_host` over an iterable of (pose2d, img_feat) pinned CPU batches: copies of neighbouring batches
+        overlap the forward (Engine.forward_host_iter). Yields (cam_mesh, cam_pose, pose3d) pinned CPU tensors in order."""
+        return self.engine().forward_host_iter(batches)
+
+
 def get_model(num_joint, embed_dim, depth):
     return PMCE(num_joint, embed_dim, depth)

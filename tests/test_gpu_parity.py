@@ -199,6 +199,32 @@ def test_graph_eager_and_host_calls_agree(base):
         assert torch.equal(x, y) and torch.equal(x, z) and torch.equal(x.cpu(), w) and torch.equal(x.cpu(), v)
 
 
+def test_pipelined_host_iter_matches_forward(base):
+    """forward_host_iter (three streams, two slots) returns, batch by batch and in order, exactly what forward returns."""
+    m = base["m"]
+    eng = m.engine()
+    eng.use_graph = True
+    p2d, feat = base["p2d"], base["feat"]
+    gen = torch.Generator().manual_seed(3)
+    batches = []
+    for i in range(5):
+        idx = torch.randint(0, 2, (4,), generator=gen)
+        batches.append((p2d[idx].contiguous().pin_memory(), (feat[idx] * (1.0 + 0.1 * i)).contiguous().pin_memory()))
+    refs = [tuple(t.cpu() for t in m(a.cuda(), b.cuda())) for a, b in batches]
+    n = 0
+    for out, ref in zip(m.forward_host_iter(iter(batches)), refs):
+        for o, r in zip(out, ref):
+            assert torch.equal(o, r), n
+        n += 1
+    assert n == len(batches)
+    assert sum(1 for _ in m.forward_host_iter(iter(batches[:1]))) == 1      # a single batch drains correctly
+    assert sum(1 for _ in m.forward_host_iter(iter([]))) == 0
+    eng.use_graph = False
+    from pmce_b200._lib import PmceError
+    with pytest.raises(PmceError, match="same size"):
+        list(m.forward_host_iter(iter([batches[0], (p2d.pin_memory(), feat.pin_memory())])))
+
+
 def test_clips_are_independent_at_full_batch(base):
     """Size-independent property at BASELINE batch sizes: every clip's output depends on that clip only, so a B=64
     batch made of the golden clips (repeated, permuted) reproduces the B=2 rows exactly-ish, and ragged B works."""
