@@ -297,6 +297,9 @@ def main():
     # roofline of the dominant kernel, timed alone with CUDA events on the launch stream
     roof = dominant_kernel_roofline(lib, dev, peaks, B)
     roof_ca = cross_attn_roofline(lib, eng, dev, peaks, B)
+    big = cross_attn_roofline(lib, eng, dev, peaks, 256, nsets=4)      # BASELINE.json configs[2] batch: 3.5 items per CTA
+    roof_ca["at_B256"] = {k: big[k] for k in ("achieved", "frac", "us_per_launch", "achieved_kernel_io", "frac_kernel_io", "bytes_per_launch",
+                                              "kernel_io_bytes_per_launch", "clips_per_launch")}
 
     out = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -421,7 +424,7 @@ def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):
     io_bytes = (3 * Vd * D * 4 + 2 * J * D * 4 + 4 * D * 4) * B
     flops = (4 * 2 * Vd * J * 32 + 2 * 2 * Vd * D * D) * B       # attention core + Wq + Wp
     ach = survey_bytes / sec / 1e9
-    return {"kernel": "ca_vertex_fused_kernel (AdaLN_q + Wq + MHA over the clip's joints + Wp + residual + AdaLN_2, one pass)",
+    return {"kernel": "ca_vertex_fused_kernel (AdaLN_q + scores + softmax + P.V.Wp + residual + AdaLN_2 in one pass over the query stream)",
             "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
             "traffic": None, "bytes_per_launch": survey_bytes, "us_per_launch": sec * 1e6,
             "achieved_kernel_io": io_bytes / sec / 1e9, "kernel_io_bytes_per_launch": io_bytes,

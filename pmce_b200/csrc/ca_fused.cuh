@@ -25,12 +25,12 @@ constexpr int CAF_KP = 32;                              // key slots per head (n
 constexpr int CAF_MAXJ = 24;
 constexpr int CAF_H = 2;                                // heads of the vertex stream (CoevoDecoder.py:140)
 constexpr int CAF_NS = CAF_H * CAF_KP;                  // 64 score columns: column 32 h + j = (head h, key j)
-constexpr int CAF_IN = 2 * 128 * 128;                   // two [128][32 fp32] boxes
-constexpr int CAF_OFF_A = CAF_IN;                       // A hi | A lo  ([128][64 bf16] each)
-constexpr int CAF_OFF_W = CAF_OFF_A + 2 * AT_TILE;      // KQ hi | KQ lo | VPt hi | VPt lo ([64][64 bf16] each)
+constexpr int CAF_IN = 2 * 128 * 128;                   // two [128][32 fp32] boxes; the SAME 32 KB then hold the A tiles (hi | lo)
+constexpr int CAF_OFF_W = CAF_IN;                       // KQ hi | KQ lo | VPt hi | VPt lo ([64][64 bf16] each); later the t tiles (hi | lo)
 constexpr int CAF_OFF_GB = CAF_OFF_W + 4 * 8192;        // gamma_q beta_q gamma_2 beta_2 bp  (5 x 64 fp32)
-constexpr int CAF_OFF_BAR = CAF_OFF_GB + 5 * 64 * 4;
-constexpr int CAF_SMEM = CAF_OFF_BAR + 64 + 1024;       // + alignment slack
+constexpr int CAF_OFF_PART = CAF_OFF_GB + 5 * 64 * 4;   // per-thread partial sums of the LayerNorm statistics (256 fp32)
+constexpr int CAF_OFF_BAR = CAF_OFF_PART + 256 * 4;
+constexpr int CAF_SMEM = CAF_OFF_BAR + 64 + 1024;       // + alignment slack  (68 KB: three CTAs per SM)
 constexpr int CAF_TX = CAF_IN + 2 * CAF_NS * 128 + 2 * 64 * 128;   // bytes per item arriving on bar_in
 
 namespace tc {
@@ -67,21 +67,28 @@ __device__ __forceinline__ void caf_read_half(uint32_t rowaddr, int sw, float (&
     }
 }
 
-// AdaLayerNorm (CoevoDecoder.py:23-29: unbiased std, eps added to the std) of a 64-wide row given as two halves; the
-// thread normalises and stores (split-bf16, swizzled A tiles) only its own half, columns [32*hf, 32*hf+32).
-__device__ __forceinline__ void caf_adaln_half(const float (&own)[32], const float (&oth)[32], const float* __restrict__ gam,
-                                               const float* __restrict__ bet, float eps, uint32_t a_hi, uint32_t a_lo, int r, int hf) {
+// AdaLayerNorm (CoevoDecoder.py:23-29: unbiased std, eps added to the std) of a 64-wide row owned by TWO threads (32 columns
+// each, in different warps): two-pass statistics, the halves' partial sums meet in shared memory (`part`, one float per
+// thread; partner = tid ^ 128). Contains two __syncthreads, the first of which also orders every thread's earlier shared-
+// memory reads before the tile writes below. Writes the normalised half as split-bf16 into swizzled [128][64 bf16] tiles.
+__device__ __forceinline__ void caf_adaln_pair(const float (&own)[32], float* part, int tid, const float* __restrict__ gam,
+                                               const float* __restrict__ bet, float eps, uint32_t t_hi, uint32_t t_lo, int r, int hf) {
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { s0 += own[i]; s1 += oth[i]; }
-    const float mean = (s0 + s1) * (1.0f / 64.0f);
+    for (int i = 0; i < 32; i += 2) { s0 += own[i]; s1 += own[i + 1]; }
+    part[tid] = s0 + s1;
+    __syncthreads();
+    const float mean = ((s0 + s1) + part[tid ^ 128]) * (1.0f / 64.0f);
     float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const float d0 = own[i] - mean, d1 = oth[i] - mean;
+    for (int i = 0; i < 32; i += 2) {
+        const float d0 = own[i] - mean, d1 = own[i + 1] - mean;
         q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
     }
-    const float inv = 1.0f / (sqrtf((q0 + q1) * (1.0f / 63.0f)) + eps);
+    __syncthreads();                                   // every partner has read the sums before `part` is reused
+    part[tid] = q0 + q1;
+    __syncthreads();
+    const float inv = 1.0f / (sqrtf(((q0 + q1) + part[tid ^ 128]) * (1.0f / 63.0f)) + eps);
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = hf * 32 + cc * 8;
@@ -92,8 +99,8 @@ __device__ __forceinline__ void caf_adaln_half(const float (&own)[32], const flo
         for (int i = 0; i < 8; ++i) y[i] = gg[i] * (own[cc * 8 + i] - mean) * inv + bb[i];
         uint4 hh, ll;
         tc::split8(y, hh, ll);
-        tc::sts16(a_hi, r, hf * 4 + cc, hh);
-        tc::sts16(a_lo, r, hf * 4 + cc, ll);
+        tc::sts16(t_hi, r, hf * 4 + cc, hh);
+        tc::sts16(t_lo, r, hf * 4 + cc, ll);
     }
 }
 
@@ -101,9 +108,14 @@ __device__ __forceinline__ void caf_adaln_half(const float (&own)[32], const flo
 //   scores_h = scale (xn Wq_h^T + bq_h) K_h^T = xn (scale K_h Wq_h)^T + scale K_h bq_h         -> KQ [64][64], sb [64]
 //   proj(concat_h P_h V_h) = sum_h P_h (V_h Wp[:, h]^T) + bp                                    -> VPt [64][64]
 // (row / column 32 h + j = head h, key j; slots j >= NK are zero) so per 128-row item: S = AdaLN_q(xq) KQ^T (tcgen05
-// 128x64x64), softmax per head in registers, out = P VPt^T (tcgen05 128x64x64). KQ / VPt / sb are per clip, made by ca_joint_fold_kernel (split-bf16), and arrive by TMA.
+// 128x64x64), softmax per head in registers, out = P VPt^T (tcgen05 128x64x64). KQ / VPt / sb are per clip, made by
+// ca_joint_fold_kernel (split-bf16), and arrive by TMA.
+// Shared memory is two 32 KB regions that change roles through the item: X = {xq fp32 boxes -> A tiles (AdaLN_q(xq) split)
+// -> P split -> xq' fp32 boxes for the TMA store}, W = {KQ | VPt -> t tiles (AdaLN_2(xq') split) for the TMA store}; the
+// thread keeps its 32 xq values in registers for the residual. 68 KB and <= 80 registers: three CTAs (24 warps) per SM,
+// which is what hides the TMA / MMA / TMEM round trips of the per-item chain.
 template <int NK>
-__global__ void __launch_bounds__(CAF_THREADS, 2)
+__global__ void __launch_bounds__(CAF_THREADS, 3)
 ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_thi, const __grid_constant__ CUtensorMap tm_tlo,
                        const __grid_constant__ CUtensorMap tm_kq_hi, const __grid_constant__ CUtensorMap tm_kq_lo,
                        const __grid_constant__ CUtensorMap tm_vp_hi, const __grid_constant__ CUtensorMap tm_vp_lo, CaFusedArgs a) {
@@ -111,8 +123,9 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sb = tc::smem_u32(smem);
-    const uint32_t s_in = sb, s_ahi = sb + CAF_OFF_A, s_alo = s_ahi + AT_TILE, s_w = sb + CAF_OFF_W;
+    const uint32_t s_ahi = sb, s_alo = sb + AT_TILE, s_w = sb + CAF_OFF_W;
     float* gbs = reinterpret_cast<float*>(smem + CAF_OFF_GB);          // [0]=gamma_q [1]=beta_q [2]=gamma_2 [3]=beta_2 [4]=bp
+    float* part = reinterpret_cast<float*>(smem + CAF_OFF_PART);
     uint64_t* bar_in = reinterpret_cast<uint64_t*>(smem + CAF_OFF_BAR);
     uint64_t* bar_mma = bar_in + 1;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_in + 2);
@@ -134,17 +147,17 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     const uint32_t tS = tmem_base, tO = tmem_base + 64;
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
 
-    // thread = (tile row r, column half hf): hf selects the 32-column half of the 64-wide row it normalises / stores and the
-    // attention head whose softmax it runs; both threads of a row read the whole row for the LayerNorm statistics.
+    // thread = (tile row r, column half hf): hf selects the 32-column half of the 64-wide row it owns and the attention head
+    // whose softmax it runs
     const int r = tid & 127, hf = tid >> 7;
-    const uint32_t row_own = s_in + hf * 16384 + r * 128, row_oth = s_in + (1 - hf) * 16384 + r * 128;
+    const uint32_t row_own = sb + hf * 16384 + r * 128;                // this thread's half row inside the fp32 boxes
     const int sw = r & 7;
     const int ntiles = a.B * a.qtiles;
     uint32_t it = 0, mph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
         if (tid == 0) {
-            if (it > 0) tc::tma_store_wait_read<0>();          // the previous item's stores have read the IN / A tiles
+            if (it > 0) tc::tma_store_wait_read<0>();          // the previous item's stores have read both regions
             tc::mbar_arrive_expect_tx(bar_in, CAF_TX);
             tc::tma_load_3d(smem, &tm_x, bar_in, 0, row0, b);
             tc::tma_load_3d(smem + 16384, &tm_x, bar_in, 32, row0, b);
@@ -153,26 +166,16 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             tc::tma_load_2d(smem + CAF_OFF_W + 16384, &tm_vp_hi, bar_in, 0, b * 64);
             tc::tma_load_2d(smem + CAF_OFF_W + 24576, &tm_vp_lo, bar_in, 0, b * 64);
         }
-        {   // AdaLN parameters of clip b: gamma|beta of slot_q and slot_2
+        {   // AdaLN parameters of clip b: gamma|beta of slot_q and slot_2 (the previous item's readers are past its last barrier)
             const int arr = tid >> 6, c = tid & 63;
             gbs[arr * 64 + c] = a.gb[(size_t)b * a.gb_ld + (arr < 2 ? a.slot_q : a.slot_2) * 128 + (arr & 1) * 64 + c];
         }
-        float sbv[CAF_MAXJ];                                   // folded score bias of this thread's head
-#pragma unroll
-        for (int j = 0; j < CAF_MAXJ; j += 4) {
-            const float4 v = ld4(a.sb + (size_t)b * CAF_NS + hf * CAF_KP + j);
-            sbv[j] = v.x; sbv[j + 1] = v.y; sbv[j + 2] = v.z; sbv[j + 3] = v.w;
-        }
-        __syncthreads();
+        float x[32];                                           // this thread's half of the xq row, kept for the residual
 
-        // ---- xq row -> AdaLN_q -> split A tiles ----
+        // ---- xq half row -> registers; AdaLN_q -> split A tiles over the same bytes ----
         tc::mbar_wait(bar_in, it & 1);
-        {
-            float own[32], oth[32];
-            caf_read_half(row_own, sw, own);
-            caf_read_half(row_oth, sw, oth);
-            caf_adaln_half(own, oth, gbs, gbs + 64, a.eps, s_ahi, s_alo, r, hf);
-        }
+        caf_read_half(row_own, sw, x);
+        caf_adaln_pair(x, part, tid, gbs, gbs + 64, a.eps, s_ahi, s_alo, r, hf);   // first barrier inside also publishes gbs
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
@@ -189,19 +192,24 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             }
             tc::umma_commit(bar_mma);
         }
+        float p[CAF_MAXJ];                                     // folded score bias of this thread's head, then the probabilities
+#pragma unroll
+        for (int j = 0; j < CAF_MAXJ; j += 4) {
+            const float4 v = ld4(a.sb + (size_t)b * CAF_NS + hf * CAF_KP + j);
+            p[j] = v.x; p[j + 1] = v.y; p[j + 2] = v.z; p[j + 3] = v.w;
+        }
         tc::mbar_wait(bar_mma, mph & 1);
         ++mph;
         tc::tc_fence_after();
 
-        // ---- softmax of head hf over the clip's NK keys; P (split) -> A tile columns [24 hf, 24 hf + 24) ----
+        // ---- softmax of head hf over the clip's NK keys; P (split) -> A tile columns [32 hf, 32 hf + 32) ----
         {
             uint32_t v[32];
             tc::tmem_ld_32x32(tS + lane_sel + hf * CAF_KP, v);     // this head's 32 key slots
             tc::tmem_ld_wait();
-            float p[CAF_MAXJ];
             float m = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < NK; ++j) { p[j] = __uint_as_float(v[j]) + sbv[j]; m = fmaxf(m, p[j]); }
+            for (int j = 0; j < NK; ++j) { p[j] += __uint_as_float(v[j]); m = fmaxf(m, p[j]); }
             float l = 0.f;
 #pragma unroll
             for (int j = 0; j < NK; ++j) { p[j] = expf(p[j] - m); l += p[j]; }
@@ -241,40 +249,30 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         ++mph;
         tc::tc_fence_after();
 
-        // ---- xq' = (out + bp) + xq -> own half back into the input tile; AdaLN_2(xq') -> split A tiles; TMA stores ----
+        // ---- xq' = (out + bp) + xq -> fp32 boxes (region X, free: both MMAs are complete); AdaLN_2(xq') -> t tiles (region W) ----
         {
-            float own[32], oth[32];
-            {
-                uint32_t v[32];
-                tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v);
-                tc::tmem_ld_wait();
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v);
+            tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) own[i] = __uint_as_float(v[i]) + gbs[4 * 64 + hf * 32 + i];
-                tc::tmem_ld_32x32(tO + lane_sel + (1 - hf) * 32, v);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) oth[i] = __uint_as_float(v[i]) + gbs[4 * 64 + (1 - hf) * 32 + i];
+            for (int i = 0; i < 32; i += 4) {
+                const float4 bpv = ld4(gbs + 4 * 64 + hf * 32 + i);
+                x[i] = (__uint_as_float(v[i]) + bpv.x) + x[i]; x[i + 1] = (__uint_as_float(v[i + 1]) + bpv.y) + x[i + 1];
+                x[i + 2] = (__uint_as_float(v[i + 2]) + bpv.z) + x[i + 2]; x[i + 3] = (__uint_as_float(v[i + 3]) + bpv.w) + x[i + 3];
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 v0 = tc::lds16(row_own + ((j ^ sw) << 4)), v1 = tc::lds16(row_oth + ((j ^ sw) << 4));
-                own[4 * j] += v0.x; own[4 * j + 1] += v0.y; own[4 * j + 2] += v0.z; own[4 * j + 3] += v0.w;
-                oth[4 * j] += v1.x; oth[4 * j + 1] += v1.y; oth[4 * j + 2] += v1.z; oth[4 * j + 3] += v1.w;
-            }
-            __syncthreads();                                       // both threads of every row have read xq before either overwrites it
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                tc::sts16f(row_own + ((j ^ sw) << 4), make_float4(own[4 * j], own[4 * j + 1], own[4 * j + 2], own[4 * j + 3]));
-            caf_adaln_half(own, oth, gbs + 128, gbs + 192, a.eps, s_ahi, s_alo, r, hf);
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            tc::sts16f(row_own + ((j ^ sw) << 4), make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
+        caf_adaln_pair(x, part, tid, gbs + 128, gbs + 192, a.eps, s_w, s_w + AT_TILE, r, hf);
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc::tma_store_3d(&tm_x, smem, 0, row0, b);
             tc::tma_store_3d(&tm_x, smem + 16384, 32, row0, b);
-            tc::tma_store_3d(&tm_thi, smem + CAF_OFF_A, 0, row0, b);
-            tc::tma_store_3d(&tm_tlo, smem + CAF_OFF_A + AT_TILE, 0, row0, b);
+            tc::tma_store_3d(&tm_thi, smem + CAF_OFF_W, 0, row0, b);
+            tc::tma_store_3d(&tm_tlo, smem + CAF_OFF_W + AT_TILE, 0, row0, b);
             tc::tma_store_commit();
         }
     }
@@ -306,7 +304,7 @@ static inline int launch_ca_vertex_fused_t(const CUtensorMap* maps, const CaFuse
         configured = true;
     }
     const int ntiles = a.B * a.qtiles;
-    const int cap = 2 * tc_num_sms();
+    const int cap = 3 * tc_num_sms();
     const int grid = ntiles < cap ? ntiles : cap;
     ca_vertex_fused_kernel<NK><<<grid, CAF_THREADS, CAF_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], a);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;

@@ -6,9 +6,12 @@
 // Pipelines: smem ring of STAGES x {A_hi, A_lo, W_hi, W_lo} tiles ([rows][64 bf16], written by TMA with the 128-byte
 // swizzle the UMMA descriptors expect) with full/empty mbarriers; TWO TMEM accumulators with tmem_full/tmem_empty
 // mbarriers so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Epilogue (compile-time MODE): accumulator chunk (32 rows x 32 cols per warp) TMEM -> registers -> (+bias, GELU,
-// +residual) -> swizzled shared-memory staging tile -> TMA store; the residual chunk arrives by TMA load into the same
-// staging tile. The epilogue warps therefore issue no global loads/stores of their own: a row-per-thread direct store
+// Epilogue (compile-time MODE), SIXTEEN warps: TMEM lane group = warp % 4, column group = (warp-2)/4 takes every fourth
+// 16-column chunk: accumulator chunk (32 rows x 16 cols) TMEM -> registers -> (+bias, GELU, +residual) -> the warp's 2 KB
+// shared-memory staging tile -> TMA store; the residual chunk arrives by TMA load into the same staging tile. Per chunk a
+// warp waits for its previous store to have read the staging tile, so the time to drain an accumulator is set by how many
+// such round trips are in flight: 16 warps x 16-column chunks keep twice as many in flight as 8 x 32 did (the epilogue,
+// not the MMA stream, bounded the tile time: 52 us for the fc1 shape against 35 us of MMAs). The epilogue warps therefore issue no global loads/stores of their own: a row-per-thread direct store
 // touches 32 different 128-byte lines per instruction and cost ~20 us per 128x256 tile (3x the MMA time) when measured.
 // MODE TC_GENERIC keeps the direct path for strided ("mapped") outputs, row-embedding adds and unaligned N.
 #pragma once
@@ -34,23 +37,25 @@ struct TcEpi {
     int dbg;                // profiling only (PMCE_TC_DBG): 1 = stage but do not issue TMA stores, 2 = no staging either
 };
 
-struct TcOutMaps {          // TMA descriptors of the epilogue tensors (box = 32 rows x 32 columns)
-    CUtensorMap out;        // fp32 out (SWIZZLE_128B) or bf16 hi (SWIZZLE_64B)
-    CUtensorMap out_lo;     // bf16 lo (SWIZZLE_64B)
-    CUtensorMap resid;      // fp32 residual (SWIZZLE_128B)
+struct TcOutMaps {          // TMA descriptors of the epilogue tensors (box = 32 rows x 16 columns)
+    CUtensorMap out;        // fp32 out (SWIZZLE_64B) or bf16 hi (no swizzle, 32-byte rows)
+    CUtensorMap out_lo;     // bf16 lo
+    CUtensorMap resid;      // fp32 residual (SWIZZLE_64B)
 };
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;            // bf16 elements = 128 bytes = one swizzle row
-constexpr int TC_THREADS = 320;      // TMA warp + MMA warp + 8 epilogue warps
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
+constexpr int TC_CW = 16;            // epilogue chunk width in columns
+constexpr int TC_STG = 2048;         // staging bytes per epilogue warp: [32][16] fp32, or [32][16] bf16 hi + lo
 
 template <int BN>
 struct TcCfg {
     static constexpr int A_TILE = TC_BM * 128;          // bytes per A half (hi or lo)
     static constexpr int W_TILE = BN * 128;
     static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;
-    static constexpr int STG_BYTES = TC_EPI_WARPS * 4096;            // per-warp epilogue staging tiles (1024-B aligned)
+    static constexpr int STG_BYTES = TC_EPI_WARPS * TC_STG;          // per-warp epilogue staging tiles (1024-B aligned)
     static constexpr int STAGES = (196 * 1024) / STAGE_BYTES >= 4 ? 4 : (196 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // two accumulators
@@ -59,11 +64,11 @@ struct TcCfg {
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
-// Direct (row-per-thread) epilogue for one 32-column chunk: runtime flags, any addressing. Used by TC_GENERIC.
-__device__ __forceinline__ void tc_epilogue_generic(const TcEpi& e, const uint32_t (&v)[32], int row, int col0, int N) {
+// Direct (row-per-thread) epilogue for one 16-column chunk: runtime flags, any addressing. Used by TC_GENERIC.
+__device__ __forceinline__ void tc_epilogue_generic(const TcEpi& e, const uint32_t (&v)[TC_CW], int row, int col0, int N) {
     const float* radd = e.rowadd ? e.rowadd + (size_t)(row % e.rowadd_period) * N : nullptr;
 #pragma unroll 1
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < TC_CW; ++i) {
         const int col = col0 + i;
         if (col >= N) break;
         float x = __uint_as_float(v[i]);
@@ -175,14 +180,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
         }
     } else {
-        // ---- epilogue: 8 warps; lane group q = warp % 4 (TMEM lanes [32q,32q+32) = tile rows), column half = (warp-2)/4 ----
+        // ---- epilogue: 16 warps; lane group q = warp % 4 (TMEM lanes [32q,32q+32) = tile rows), column group cg = (warp-2)/4
+        //      takes the 16-column chunks cg, cg+4, cg+8, ... ----
         const int ew = warp - 2;
         const int q = warp & 3;
-        const int half = ew >> 2;
-        constexpr int CHUNKS = BN / 32;                       // 32-column chunks per tile
-        constexpr int CSPLIT = (CHUNKS + 1) / 2;              // chunks [0, CSPLIT) for half 0, [CSPLIT, CHUNKS) for half 1
-        const int cb = half == 0 ? 0 : CSPLIT, ce = half == 0 ? CSPLIT : CHUNKS;
-        uint8_t* stg = stg_all + ew * 4096;                   // this warp's staging tile
+        const int cg = ew >> 2;
+        constexpr int CH = BN / TC_CW;                        // 16-column chunks per tile
+        uint8_t* stg = stg_all + ew * TC_STG;                 // this warp's staging tile
         const uint32_t stg_u32 = tc::smem_u32(stg);
         uint32_t tcount = 0, rcount = 0;
         bool store_pending = false;
@@ -193,28 +197,29 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const int row = row0 + lane;
             tc::mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1);
             tc::tc_fence_after();
-            if (cb >= ce) {                                       // BN == 32: the second column half has no chunk
+            if (cg >= CH) {                                       // BN == 32: column groups 2 and 3 have no chunk
                 tc::tc_fence_before();
                 if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
                 continue;
             }
+            const int c_last = cg + 4 * ((CH - 1 - cg) / 4);
 #pragma unroll 1
-            for (int c = cb; c < ce; ++c) {
-                const int col0 = n0 + c * 32;
+            for (int c = cg; c < CH; c += 4) {
+                const int col0 = n0 + c * TC_CW;
                 const bool live = row0 < M && col0 < N;          // warp-uniform
                 if (MODE == TC_F32_RESID && live) {
                     // the staging tile is about to be overwritten by the residual load: the previous store must have read it
                     if (lane == 0) {
                         if (store_pending) tc::tma_store_wait_read<0>();
-                        tc::mbar_arrive_expect_tx(&resid_bar[ew], 4096);
+                        tc::mbar_arrive_expect_tx(&resid_bar[ew], TC_STG);
                         tc::tma_load_2d(stg, &om.resid, &resid_bar[ew], col0, row0);
                     }
                     store_pending = false;
                 }
-                uint32_t v[32];
-                tc::tmem_ld_32x32(tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                uint32_t v[TC_CW];
+                tc::tmem_ld_32x16(tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * TC_CW), v);
                 tc::tmem_ld_wait();
-                if (c == ce - 1) {                               // last read of this accumulator by this warp: release it early
+                if (c == c_last) {                               // last read of this accumulator by this warp: release it early
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
@@ -224,21 +229,23 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if (row < M) tc_epilogue_generic(e, v, row, col0, N);
                     __syncwarp();
                 } else if (MODE == TC_F32 || MODE == TC_F32_RESID) {
-                    float f[32];
+                    float f[TC_CW];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 b = ld4(e.bias + col0 + i);     // N % 32 == 0 in the TMA modes (checked by the launcher)
+                    for (int i = 0; i < TC_CW; i += 4) {
+                        const float4 b = ld4(e.bias + col0 + i);     // N % 16 == 0 in the TMA modes (checked by the launcher)
                         f[i] = __uint_as_float(v[i]) + b.x; f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
                         f[i + 2] = __uint_as_float(v[i + 2]) + b.z; f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
                     }
-                    const uint32_t rowaddr = stg_u32 + lane * 128;
+                    // [32 rows][16 fp32] tile, 64-byte rows, SWIZZLE_64B: 16-B chunk ^= (row >> 1) & 3
+                    const uint32_t rowaddr = stg_u32 + lane * 64;
+                    const int sw = (lane >> 1) & 3;
                     if (MODE == TC_F32_RESID) {
                         tc::mbar_wait(&resid_bar[ew], rcount & 1);
                         ++rcount;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                        for (int j = 0; j < 4; ++j) {
                             float4 r;
-                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(rowaddr + ((j ^ (lane & 7)) << 4)));
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(rowaddr + ((j ^ sw) << 4)));
                             f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
                         }
                     } else {
@@ -246,8 +253,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     }
                     if (e.dbg == 2) { if (f[0] == 123.456f) e.out_f32[0] = f[1]; continue; }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + ((j ^ (lane & 7)) << 4)), "f"(f[4 * j]), "f"(f[4 * j + 1]),
+                    for (int j = 0; j < 4; ++j)
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + ((j ^ sw) << 4)), "f"(f[4 * j]), "f"(f[4 * j + 1]),
                                      "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
                     tc::fence_proxy_async();
                     __syncwarp();
@@ -255,9 +262,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if (lane == 0) { tc::tma_store_2d(&om.out, stg, col0, row0); tc::tma_store_commit(); }
                     store_pending = true;
                 } else if (MODE == TC_SPLIT_GELU || MODE == TC_SPLIT) {
-                    uint32_t hi[16], lo[16];
+                    uint32_t hi[TC_CW / 2], lo[TC_CW / 2];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
+                    for (int i = 0; i < TC_CW; i += 4) {
                         const float4 b = ld4(e.bias + col0 + i);
                         float x0 = __uint_as_float(v[i]) + b.x, x1 = __uint_as_float(v[i + 1]) + b.y;
                         float x2 = __uint_as_float(v[i + 2]) + b.z, x3 = __uint_as_float(v[i + 3]) + b.w;
@@ -266,21 +273,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         tc::split_bf16x2(x2, x3, hi[i / 2 + 1], lo[i / 2 + 1]);
                     }
                     if (store_pending) { if (lane == 0) tc::tma_store_wait_read<0>(); __syncwarp(); }
-                    // two [32 rows][32 bf16] tiles (64-byte rows, SWIZZLE_64B: 16-B chunk ^= (row >> 1) & 3): hi at +0, lo at +2048
-                    const uint32_t rowaddr = stg_u32 + lane * 64;
-                    const int sw = (lane >> 1) & 3;
+                    // two dense [32 rows][16 bf16] tiles (32-byte rows, no swizzle): hi at +0, lo at +1024
+                    const uint32_t rowaddr = stg_u32 + lane * 32;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + ((j ^ sw) << 4)), "r"(hi[4 * j]), "r"(hi[4 * j + 1]),
+                    for (int j = 0; j < 2; ++j) {
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + (j << 4)), "r"(hi[4 * j]), "r"(hi[4 * j + 1]),
                                      "r"(hi[4 * j + 2]), "r"(hi[4 * j + 3]) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + 2048 + ((j ^ sw) << 4)), "r"(lo[4 * j]), "r"(lo[4 * j + 1]),
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + 1024 + (j << 4)), "r"(lo[4 * j]), "r"(lo[4 * j + 1]),
                                      "r"(lo[4 * j + 2]), "r"(lo[4 * j + 3]) : "memory");
                     }
                     tc::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
                         tc::tma_store_2d(&om.out, stg, col0, row0);
-                        tc::tma_store_2d(&om.out_lo, stg + 2048, col0, row0);
+                        tc::tma_store_2d(&om.out_lo, stg + 1024, col0, row0);
                         tc::tma_store_commit();
                     }
                     store_pending = true;
@@ -400,19 +406,19 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
     TcOutMaps om;
     memset(&om, 0, sizeof(om));
     if (null_epi) return launch_linear_tc_mode<BN, TC_NULL>(ta, tw, om, M, N, K, e, st);
-    // TMA epilogues need: plain row-major addressing, bias present, N % 32 == 0, 16-byte aligned bases and row strides
-    const bool plain = !e.mapped && !e.rowadd && e.bias && a16(e.bias) && (N % 32 == 0);
+    // TMA epilogues need: plain row-major addressing, bias present, N % 16 == 0, 16-byte aligned bases and row strides
+    const bool plain = !e.mapped && !e.rowadd && e.bias && a16(e.bias) && (N % TC_CW == 0);
     if (plain && e.out_f32 && !e.out_hi && e.act == 0 && a16(e.out_f32) && e.ld_out % 4 == 0) {
-        if (make_tmap(&om.out, e.out_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_out, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+        if (make_tmap(&om.out, e.out_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_out, TC_CW, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
         if (!e.resid) return launch_linear_tc_mode<BN, TC_F32>(ta, tw, om, M, N, K, e, st);
         if (a16(e.resid) && e.ld_resid % 4 == 0) {
-            if (make_tmap(&om.resid, e.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_resid, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+            if (make_tmap(&om.resid, e.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_resid, TC_CW, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
             return launch_linear_tc_mode<BN, TC_F32_RESID>(ta, tw, om, M, N, K, e, st);
         }
     }
     if (plain && e.out_hi && !e.out_f32 && !e.resid && a16(e.out_hi) && a16(e.out_lo) && e.ld_split % 8 == 0) {
-        if (make_tmap(&om.out, e.out_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, e.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) ||
-            make_tmap(&om.out_lo, e.out_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, e.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))
+        if (make_tmap(&om.out, e.out_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, e.ld_split, TC_CW, 32, CU_TENSOR_MAP_SWIZZLE_NONE) ||
+            make_tmap(&om.out_lo, e.out_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, e.ld_split, TC_CW, 32, CU_TENSOR_MAP_SWIZZLE_NONE))
             return 1;
         if (e.act == 1) return launch_linear_tc_mode<BN, TC_SPLIT_GELU>(ta, tw, om, M, N, K, e, st);
         return launch_linear_tc_mode<BN, TC_SPLIT>(ta, tw, om, M, N, K, e, st);
