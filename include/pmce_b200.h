@@ -148,6 +148,18 @@ int pmce_decoder_forward(const pmce_dims_t* dims, const void* weights, const flo
 int pmce_jregress(const int32_t* row_ptr, const int32_t* cols, const float* vals, int R, const float* mesh,
                   int num_vert, int B, float scale, float* out, void* stream);
 
+/* ---- (f)1, the step after the path: evaluation epilogue of the test loop, lib/core/base.py:223-227 with
+ * compute_both_err data/PW3D/dataset.py:269-282 (same code in data/Human36M/dataset.py:611-623).
+ * pred_pose[b] = J_regressor . (cam_mesh[b]*scale) (CSR regressor as in pmce_jregress); meshes and joint sets are root-aligned
+ * on joint 0; clip_err[b] = (mean over the n_eval evaluation joints, mean over the vertices) of the L2 error of clip b;
+ * mean_err = their means over the batch = the reference's (joint_mean_error, mesh_mean_error).
+ * cam_mesh, gt_mesh [B,V,3] in metres (scaled by `scale`, 1000 in the reference); gt_pose [B,R,3] and pred_pose [B,R,3] in mm;
+ * eval_joints [n_eval] int32 rows of the regressor (data/PW3D/dataset.py:35).  Replaces four D2H copies of [B,6890,3]
+ * tensors + numpy per batch by a 2-float result. */
+int pmce_eval_errors(const int32_t* row_ptr, const int32_t* cols, const float* vals, int R, const float* cam_mesh,
+                     const float* gt_mesh, const float* gt_pose, const int32_t* eval_joints, int n_eval, int num_vert,
+                     int B, float scale, float* pred_pose, float* clip_err, float* mean_err, void* stream);
+
 /* ---- nn.Linear forward as used by every projection on the path (F.linear; e.g. lib/models/CoevoDecoder.py:19-20,
  * timm Mlp fc1/fc2): out[M,N] = act(x[M,K] weight[N,K]^T + bias[N]); act 0 = none, 1 = exact GELU. K % 4 == 0.
  * Exposed so the dominant GEMM can be timed / profiled in isolation. */

@@ -129,10 +129,50 @@ def gen_smpl():
                         verts=v.numpy(), joints=j.numpy(), verts_default=v0.numpy(), joints_default=j0.numpy())
 
 
+def reference_method(rel_path, cls, name):
+    """Compile ONE method of a reference class from its source file where it lies (nothing is copied into the repo): the
+    dataset modules cannot be imported here (pycocotools, licensed SMPL files), but `compute_both_err` only needs numpy."""
+    import ast
+    src = open(os.path.join(rh.REFERENCE_ROOT, rel_path)).read()
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == name:
+                    mod = ast.Module(body=[fn], type_ignores=[])
+                    ns = {"np": np, "torch": torch}
+                    exec(compile(mod, os.path.join(rh.REFERENCE_ROOT, rel_path), "exec"), ns)
+                    return ns[name]
+    raise KeyError((rel_path, cls, name))
+
+
+def gen_eval():
+    """Golden vector of the evaluation epilogue (f)1: the reference's own PW3D.compute_both_err on seeded meshes."""
+    fn = reference_method("data/PW3D/dataset.py", "PW3D", "compute_both_err")
+
+    class Stub:
+        human36_eval_joint = (1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16)   # data/PW3D/dataset.py:35
+    B = 6
+    gen = torch.Generator().manual_seed(21)
+    cam_mesh = torch.randn(B, 6890, 3, generator=gen) * 0.3
+    gt_mesh = cam_mesh + torch.randn(B, 6890, 3, generator=gen) * 0.05
+    gt_pose = torch.randn(B, 17, 3, generator=gen) * 300
+    jreg = torch.from_numpy(np.load(os.path.join(rh.REFERENCE_ROOT, "data", "Human36M", "J_regressor_h36m_correct.npy")).astype(np.float32))
+    pred_mesh, gt_mm = cam_mesh * 1000, gt_mesh * 1000                    # lib/core/base.py:223
+    pred_pose = torch.matmul(jreg[None, :, :], pred_mesh)                 # :225
+    j_err, s_err = fn(Stub(), pred_mesh, gt_mm, pred_pose, gt_pose)       # :227
+    o_pose, oj, os_ = po.eval_step(jreg, cam_mesh, gt_mesh, gt_pose)
+    print("eval oracle-vs-reference:", float(j_err), float(oj), float(s_err), float(os_))
+    assert abs(float(oj) - float(j_err)) < 1e-4 and abs(float(os_) - float(s_err)) < 1e-4 and torch.equal(o_pose, pred_pose)
+    np.savez_compressed(os.path.join(GOLDEN, "eval_err_B6.npz"), seed=np.int64(21), B=np.int64(B), joint_mean_error=np.float64(j_err),
+                        mesh_mean_error=np.float64(s_err), pred_pose=pred_pose.numpy())
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     gen_jregressors()
     gen_smpl()
+    gen_eval()
     for cfg_ in CONFIGS:
         gen_pmce(*cfg_)
     print("golden fixtures written to", GOLDEN)

@@ -218,6 +218,31 @@ def j_regress(J_regressor, mesh):
     return torch.matmul(J_regressor[None, :, :], mesh)
 
 
+H36M_EVAL_JOINTS = (1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16)   # data/PW3D/dataset.py:35
+
+
+def compute_both_err(pred_mesh, target_mesh, pred_joint, target_joint, eval_joints=H36M_EVAL_JOINTS):
+    """The test loop's evaluation epilogue (data/PW3D/dataset.py:269-282, called from lib/core/base.py:227): root-align
+    meshes and joints on joint 0, keep the 14 evaluation joints, mean per-joint / per-vertex L2 error (numpy fp32).
+    Returns (joint_mean_error, mesh_mean_error)."""
+    pred_mesh, target_mesh = pred_mesh - pred_joint[:, :1, :], target_mesh - target_joint[:, :1, :]
+    pred_joint, target_joint = pred_joint - pred_joint[:, :1, :], target_joint - target_joint[:, :1, :]
+    pm, tm = pred_mesh.detach().cpu().numpy(), target_mesh.detach().cpu().numpy()
+    pj, tj = pred_joint.detach().cpu().numpy(), target_joint.detach().cpu().numpy()
+    pj, tj = pj[:, eval_joints, :], tj[:, eval_joints, :]
+    mesh_mean_error = np.power((np.power((pm - tm), 2)).sum(axis=2), 0.5).mean()
+    joint_mean_error = np.power((np.power((pj - tj), 2)).sum(axis=2), 0.5).mean()
+    return joint_mean_error, mesh_mean_error
+
+
+def eval_step(J_regressor, cam_mesh, gt_mesh, gt_pose3d, eval_joints=H36M_EVAL_JOINTS):
+    """lib/core/base.py:223-227: metres -> millimetres, J-regressor, compute_both_err. -> (pred_pose, j_error, s_error)."""
+    pred_mesh, gt_mesh = cam_mesh * 1000, gt_mesh * 1000
+    pred_pose = torch.matmul(J_regressor[None, :, :], pred_mesh)
+    j_error, s_error = compute_both_err(pred_mesh, gt_mesh, pred_pose, gt_pose3d, eval_joints)
+    return pred_pose, j_error, s_error
+
+
 # ----------------------------------------------------------------------------------------------
 # init-time geometry (host side in the reference too)
 # ----------------------------------------------------------------------------------------------

@@ -49,6 +49,7 @@ SIGNATURES = {
     "pmce_mesh_epilogue": (C.c_int, [_DP, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_decoder_forward": (C.c_int, [_DP, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
     "pmce_jregress": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
+    "pmce_eval_errors": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P]),
     "pmce_linear": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "pmce_linear_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "pmce_linear_tc": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),

@@ -74,7 +74,7 @@ struct Workspace {
     float *xqj, *xkv, *Kv, *Vv, *Qj, *qkvj;
     SplitOut Jf_s, Vf_s, tA_s, tA2_s, tB_s, tJ_s, tJ2_s, att_ds, hid_ds, attj_s, hidj_s, im2col_s;
     float* lc_mesh;
-    CaFolded fold;                                     // per-clip folded operands of the fused vertex cross-attention
+    CaFolded fold[3];                                  // per-clip folded operands of the fused vertex cross-attention, per block
     size_t bytes;
 };
 
@@ -105,10 +105,10 @@ Workspace carve(const pmce_dims_t& d, int B, void* base) {
     w.im2col_s = c.split((size_t)B * 3 * ((Vd * 3 + 7) / 8 * 8));
     w.tB_s = c.split(nv * D); w.tJ2_s = c.split(nj * D);
     w.lc_mesh = c.f32((size_t)B * d.num_vert * 3);
-    {
+    for (int k = 0; k < 3; ++k) {
         SplitOut kq = c.split((size_t)B * CAF_NS * 64), vp = c.split((size_t)B * 64 * 64);
-        w.fold.kq_hi = kq.hi; w.fold.kq_lo = kq.lo; w.fold.vp_hi = vp.hi; w.fold.vp_lo = vp.lo;
-        w.fold.sb = c.f32((size_t)B * CAF_NS);
+        w.fold[k].kq_hi = kq.hi; w.fold[k].kq_lo = kq.lo; w.fold[k].vp_hi = vp.hi; w.fold[k].vp_lo = vp.lo;
+        w.fold[k].sb = c.f32((size_t)B * CAF_NS);
     }
     w.bytes = c.cur;
     return w;
@@ -494,8 +494,8 @@ int cross_attn_kv(const Weights& W, const CaW& w, const float* xk, const float* 
 
 // per-clip operands of the fused vertex cross-attention (ca_fused.cuh). joints != nullptr: the whole joint side of coevoblock
 // `cw` from the joint coordinates (embed, key projection, AdaLN_k/v, Wk/Wv, fold); else fold given K / V [B,J,64].
-int ca_fold(const Weights& W, const CoevoW* cw, const CaW& w, const float* joints, const float* K_in, const float* V_in, float* xq_out,
-            const float* gb, int B, int J, int heads, const CaFolded& f, cudaStream_t st) {
+JointFoldArgs ca_fold_args(const Weights& W, const CoevoW* cw, const CaW& w, const float* joints, const float* K_in, const float* V_in, float* xq_out,
+                           const float* gb, int J, int heads, const CaFolded& f) {
     JointFoldArgs a;
     memset(&a, 0, sizeof(a));
     a.joints = joints; a.K_in = K_in; a.V_in = V_in;
@@ -508,9 +508,26 @@ int ca_fold(const Weights& W, const CoevoW* cw, const CaW& w, const float* joint
     a.wq = W.f + w.wq; a.bq = W.f + w.bq; a.wp = W.f + w.wp;
     a.gb = gb; a.gb_ld = PMCE_ADALN_SLOTS * 128; a.slot_k = w.sk; a.slot_v = w.sv;
     a.f = f; a.J = J; a.eps = 1e-6f; a.scale = 1.0f / sqrtf(64.0f / heads);
-    ca_joint_fold_kernel<<<B, JKV_THREADS, 0, st>>>(a);
+    return a;
+}
+
+int ca_fold_launch(const JointFoldArgs3& args, int nblk, int B, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(ca_joint_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JKV_SMEM));
+        configured = true;
+    }
+    ca_joint_fold_kernel<<<dim3(B, nblk), JKV_THREADS, JKV_SMEM, st>>>(args);
     CKL();
     return 0;
+}
+
+int ca_fold(const Weights& W, const CoevoW* cw, const CaW& w, const float* joints, const float* K_in, const float* V_in, float* xq_out,
+            const float* gb, int B, int J, int heads, const CaFolded& f, cudaStream_t st) {
+    JointFoldArgs3 args;
+    memset(&args, 0, sizeof(args));
+    args.blk[0] = ca_fold_args(W, cw, w, joints, K_in, V_in, xq_out, gb, J, heads, f);
+    return ca_fold_launch(args, 1, B, st);
 }
 
 int ca_fused_launch(const Weights& W, const CaW& w, float* xq, int N1, int N2, const float* gb, int B, const SplitOut& t, const CaFolded& f,
@@ -563,7 +580,7 @@ int self_attn_block(const Weights& W, const SaW& w, int heads, float* x, int N, 
 AttnScratch vertex_scratch(const Workspace& ws) {   // query stream = the 431 vertices
     AttnScratch s;
     s.tq = ws.tA_s; s.tk = ws.tJ_s; s.tv = ws.tJ_s; s.Q = ws.qkv_d; s.K = ws.Kj; s.V = ws.Vj; s.att = ws.att_ds; s.hid = ws.hid_ds;
-    s.fold = ws.fold;
+    s.fold = ws.fold[0];
     return s;
 }
 AttnScratch joint_scratch(const Workspace& ws) {    // query stream = the J joints
@@ -574,8 +591,12 @@ AttnScratch joint_scratch(const Workspace& ws) {    // query stream = the J join
 }
 constexpr int JOINT_HEADS = 8, VERTX_HEADS = 2;      // CoevoDecoder.py:139-140
 
+bool coevo_fused(const pmce_dims_t& d) { return ca_fused_ok(VERTX_HEADS, d.num_vert_ds, d.num_joint) && d.num_joint <= JKV_ROWS; }
+
+// prefolded: the folded operands of this block (ws.fold[k]) and, for block 3, the joint query stream ws.xqj were already made
+// by decoder_fold_all (the joint side of all three blocks depends only on the lifter's joints and on gb).
 int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, const float* verts_in, const float* gb, int B,
-                float* joints_out, float* verts_out, const Workspace& ws, cudaStream_t st, Aux* aux = nullptr) {
+                float* joints_out, float* verts_out, const Workspace& ws, cudaStream_t st, Aux* aux = nullptr, bool prefolded = false) {
     const pmce_dims_t& d = L.d;
     const CoevoW& w = L.blk[k];
     const int J = d.num_joint, Vd = d.num_vert_ds;
@@ -583,13 +604,14 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
     const bool ja = joints_out != nullptr;
     if (ja && !w.joint_alive) { pmce_set_error("coevoblock%d: joint-branch weights are not stored (output is discarded by the reference)", k + 1); return 4; }
 
-    const AttnScratch sv = vertex_scratch(ws);
-    const bool fused = ca_fused_ok(VERTX_HEADS, Vd, J) && J <= JKV_ROWS;
+    AttnScratch sv = vertex_scratch(ws);
+    const bool fused = coevo_fused(d);
+    if (prefolded) sv.fold = ws.fold[k];
     // coordinate -> feature (+pos), query streams (+Q embed) (CoevoDecoder.py:177-183); keys proj_j2v(Jf) + j2v_K and
     // proj_v2j(Vf) + v2j_K from the PRE-update features (:183-184)
     if (fused) {
         // the whole joint side of the vertex cross-attention (embed, key projection, AdaLN_k/v, Wk/Wv, fold) per clip in one kernel
-        RET(ca_fold(W, &w, w.vca, joints, nullptr, nullptr, ja ? ws.xqj : nullptr, gb, B, J, VERTX_HEADS, sv.fold, st));
+        if (!prefolded) RET(ca_fold(W, &w, w.vca, joints, nullptr, nullptr, ja ? ws.xqj : nullptr, gb, B, J, VERTX_HEADS, sv.fold, st));
     } else {
         coevo_embed_kernel<<<cdiv((long long)nj * 16, 256), 256, 0, st>>>(joints, nj, J, W.f + w.jprojw, W.f + w.jprojb, W.f + w.jpos,
                                                                           ja ? W.f + w.jQ : nullptr, ws.Jf, ws.Jf_s, ja ? ws.xqj : nullptr);
@@ -679,9 +701,17 @@ int decoder_back(const Layout& L, const Weights& W, const float* joints, const i
     float* v0 = verts0_out ? verts0_out : ws.verts[2];
     gather_verts_kernel<<<cdiv((long long)B * Vd * 3, 256), 256, 0, st>>>(joints, vj, B, J, Vd, v0);
     CKL();
-    RET(coevo_block(L, W, 0, joints, v0, ws.gb, B, nullptr, ws.verts[0], ws, st));
-    RET(coevo_block(L, W, 1, joints, ws.verts[0], ws.gb, B, nullptr, ws.verts[1], ws, st));
-    RET(coevo_block(L, W, 2, joints, ws.verts[1], ws.gb, B, cam_pose, ws.verts[0], ws, st, aux));
+    const bool pre = coevo_fused(d);
+    if (pre) {   // every block reads the SAME joints (CoevoDecoder.py:235-237 pass P, not P^k): one launch makes all three joint sides
+        JointFoldArgs3 args;
+        memset(&args, 0, sizeof(args));
+        for (int k = 0; k < 3; ++k)
+            args.blk[k] = ca_fold_args(W, &L.blk[k], L.blk[k].vca, joints, nullptr, nullptr, k == 2 ? ws.xqj : nullptr, ws.gb, J, VERTX_HEADS, ws.fold[k]);
+        RET(ca_fold_launch(args, 3, B, st));
+    }
+    RET(coevo_block(L, W, 0, joints, v0, ws.gb, B, nullptr, ws.verts[0], ws, st, nullptr, pre));
+    RET(coevo_block(L, W, 1, joints, ws.verts[0], ws.gb, B, nullptr, ws.verts[1], ws, st, nullptr, pre));
+    RET(coevo_block(L, W, 2, joints, ws.verts[1], ws.gb, B, cam_pose, ws.verts[0], ws, st, aux, pre));
     RET(mesh_upsample(L, W, ws.verts[0], B, cam_mesh, ws, st));
     return 0;
 }
@@ -889,6 +919,23 @@ extern "C" int pmce_jregress(const int32_t* row_ptr, const int32_t* cols, const 
                              int B, float scale, float* out, void* stream) {
     if (!row_ptr || !cols || !vals || !mesh || !out || R < 1 || B < 1) { pmce_set_error("pmce_jregress: bad argument"); return 2; }
     jregress_kernel<<<cdiv((long long)B * R * 3, 128), 128, 0, (cudaStream_t)stream>>>(row_ptr, cols, vals, R, mesh, num_vert, B, scale, out);
+    CKL();
+    return 0;
+}
+
+extern "C" int pmce_eval_errors(const int32_t* row_ptr, const int32_t* cols, const float* vals, int R, const float* cam_mesh,
+                                const float* gt_mesh, const float* gt_pose, const int32_t* eval_joints, int n_eval, int num_vert, int B,
+                                float scale, float* pred_pose, float* clip_err, float* mean_err, void* stream) {
+    if (!row_ptr || !cols || !vals || !cam_mesh || !gt_mesh || !gt_pose || !eval_joints || !pred_pose || !clip_err || !mean_err) {
+        pmce_set_error("pmce_eval_errors: NULL argument"); return 2;
+    }
+    if (R < 1 || B < 1 || num_vert < 1 || n_eval < 1 || n_eval > 256) { pmce_set_error("pmce_eval_errors: bad size (R=%d B=%d V=%d n_eval=%d)", R, B, num_vert, n_eval); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    jregress_kernel<<<cdiv((long long)B * R * 3, 128), 128, 0, st>>>(row_ptr, cols, vals, R, cam_mesh, num_vert, B, scale, pred_pose);
+    CKL();
+    eval_err_kernel<<<B, 256, 0, st>>>(cam_mesh, gt_mesh, pred_pose, gt_pose, eval_joints, n_eval, R, num_vert, scale, clip_err);
+    CKL();
+    eval_mean_kernel<<<1, 64, 0, st>>>(clip_err, B, mean_err);
     CKL();
     return 0;
 }

@@ -361,11 +361,27 @@ struct JointFoldArgs {
     int J; float eps, scale;
 };
 
-__device__ __forceinline__ void jkv_matmul(const float* __restrict__ Wg, const float* __restrict__ bias, const float* __restrict__ rowadd,
+constexpr int JKV_WLD = 68;                      // smem row stride (floats) of a staged 64x64 weight: conflict-free float4 rows
+constexpr int JKV_WMAT = 64 * JKV_WLD;           // floats per staged weight
+constexpr int JKV_SMEM = 4 * JKV_WMAT * 4;       // W_j2v (then Wq) | Wk | Wv | Wp  — 106 KB with the static buffers: two CTAs per SM
+
+// stage one [64,64] fp32 weight into shared memory with cp.async (16-byte chunks, row stride JKV_WLD)
+__device__ __forceinline__ void jkv_stage_weight(const float* __restrict__ Wg, float* Ws, int tid) {
+    for (int idx = tid; idx < 64 * 16; idx += JKV_THREADS) {
+        const int row = idx >> 4, c = (idx & 15) * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(Ws + row * JKV_WLD + c)), "l"(Wg + row * 64 + c) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// out[i][n] = W[n,:] . xs[i,:] + bias[n] (+ rowadd[i][n]) for the rows i of this thread's row group; W staged in smem
+__device__ __forceinline__ void jkv_matmul(const float* Ws, const float* __restrict__ bias, const float* __restrict__ rowadd,
                                            const float* xs, float* out_s, int J, int n, int rg) {
     float w[64];
 #pragma unroll
-    for (int k = 0; k < 64; k += 4) { const float4 v = ld4(Wg + n * 64 + k); w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w; }
+    for (int k = 0; k < 64; k += 4) { const float4 v = ld4(Ws + n * JKV_WLD + k); w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w; }
     const float b = bias[n];
     for (int i = rg; i < J; i += JKV_THREADS / 64) {
         float a0 = 0.f, a1 = 0.f;
@@ -392,15 +408,26 @@ __device__ __forceinline__ void jkv_adaln_row(const float* __restrict__ x, const
     y[lane * 2 + 1] = ga.y * dy * inv + be.y;
 }
 
+struct JointFoldArgs3 { JointFoldArgs blk[3]; };   // blockIdx.y selects the co-evolution block: their joint sides are independent
+
 __global__ void __launch_bounds__(JKV_THREADS)
-ca_joint_fold_kernel(JointFoldArgs a) {
+ca_joint_fold_kernel(const __grid_constant__ JointFoldArgs3 args) {
+    const JointFoldArgs& a = args.blk[blockIdx.y];
     constexpr int RS = JKV_ROWS * 64;            // floats per [24][64] buffer
     __shared__ __align__(16) float buf[6 * RS];
     float *Jf = buf, *Xk = buf + RS, *Nk = buf + 2 * RS, *Nv = buf + 3 * RS, *Ks = buf + 4 * RS, *Vs = buf + 5 * RS;
     float* VPs = buf;                            // [64][65] staging of VPt^T, aliases Jf/Xk/Nk once K and V are final
     static_assert(CAF_NS * 65 <= 3 * RS, "VPs must not reach Ks/Vs");
+    extern __shared__ __align__(16) float wsm[];   // the five 64x64 weights, all in flight from the first instruction
+    float *Wj2v = wsm, *Wk = wsm + JKV_WMAT, *Wv = wsm + 2 * JKV_WMAT, *Wp = wsm + 3 * JKV_WMAT, *Wq = wsm;   // Wq reuses W_j2v's slot
     const int b = blockIdx.x, tid = threadIdx.x, J = a.J;
     const int n = tid & 63, rg = tid >> 6;
+    if (a.joints) {
+        jkv_stage_weight(a.wj2v, Wj2v, tid); cp_async_commit();
+        jkv_stage_weight(a.wk, Wk, tid); jkv_stage_weight(a.wv, Wv, tid); jkv_stage_weight(a.wp, Wp, tid); cp_async_commit();
+    } else {
+        jkv_stage_weight(a.wq, Wq, tid); jkv_stage_weight(a.wp, Wp, tid); cp_async_commit();
+    }
     if (a.joints) {
         const float* P = a.joints + (size_t)b * J * 3;
         {
@@ -411,9 +438,11 @@ ca_joint_fold_kernel(JointFoldArgs a) {
                 if (a.xq_out) a.xq_out[((size_t)b * J + i) * 64 + n] = f + a.jq[i * 64 + n];
             }
         }
+        cp_async_wait<1>();
         __syncthreads();
-        jkv_matmul(a.wj2v, a.bj2v, a.j2vk, Jf, Xk, J, n, rg);
+        jkv_matmul(Wj2v, a.bj2v, a.j2vk, Jf, Xk, J, n, rg);
         __syncthreads();
+        jkv_stage_weight(a.wq, Wq, tid); cp_async_commit();      // W_j2v's slot is free: Wq lands under the LayerNorm / K / V phases
         {
             const int warp = tid >> 5, lane = tid & 31;
             const float* g = a.gb + (size_t)b * a.gb_ld;
@@ -422,22 +451,24 @@ ca_joint_fold_kernel(JointFoldArgs a) {
                 jkv_adaln_row(Jf + i * 64, g + a.slot_v * 128, a.eps, Nv + i * 64, lane);
             }
         }
+        cp_async_wait<1>();
         __syncthreads();
-        jkv_matmul(a.wk, a.bk, nullptr, Nk, Ks, J, n, rg);
-        jkv_matmul(a.wv, a.bv, nullptr, Nv, Vs, J, n, rg);
+        jkv_matmul(Wk, a.bk, nullptr, Nk, Ks, J, n, rg);
+        jkv_matmul(Wv, a.bv, nullptr, Nv, Vs, J, n, rg);
     } else {
         for (int idx = tid; idx < J * 16; idx += JKV_THREADS) {
             st4(Ks + idx * 4, ld4(a.K_in + (size_t)b * J * 64 + idx * 4));
             st4(Vs + idx * 4, ld4(a.V_in + (size_t)b * J * 64 + idx * 4));
         }
     }
+    cp_async_wait<0>();
     __syncthreads();
     // ---- fold: KQ[32h+j][c] = scale sum_d K[j][32h+d] Wq[32h+d][c]  (thread = output channel c, coalesced weight columns) ----
 #pragma unroll 1
     for (int h = 0; h < CAF_H; ++h) {
         float wc[32];
 #pragma unroll
-        for (int d = 0; d < 32; ++d) wc[d] = a.wq[(h * 32 + d) * 64 + n];
+        for (int d = 0; d < 32; ++d) wc[d] = Wq[(h * 32 + d) * JKV_WLD + n];
         for (int j = rg; j < CAF_KP; j += JKV_THREADS / 64) {
             float acc = 0.f;
             if (j < J) {
@@ -467,7 +498,7 @@ ca_joint_fold_kernel(JointFoldArgs a) {
     {
         float w[64];
 #pragma unroll
-        for (int k = 0; k < 64; k += 4) { const float4 v = ld4(a.wp + n * 64 + k); w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w; }
+        for (int k = 0; k < 64; k += 4) { const float4 v = ld4(Wp + n * JKV_WLD + k); w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w; }
         for (int idx = rg; idx < CAF_NS; idx += JKV_THREADS / 64) {
             const int h = idx / CAF_KP, j = idx % CAF_KP;
             float acc = 0.f;

@@ -489,6 +489,58 @@ __global__ void jregress_kernel(const int32_t* __restrict__ row_ptr, const int32
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Evaluation epilogue of the test loop (lib/core/base.py:223-227 + data/PW3D/dataset.py:269-282 compute_both_err), one CTA
+// per clip: root-align predicted / target mesh and joints on joint 0, mean per-vertex L2 and mean per-evaluation-joint L2.
+//   pred mesh = cam_mesh * scale, target mesh = gt_mesh * scale (metres -> mm), pred_pose (already in mm, from
+//   jregress_kernel), gt_pose in mm.   clip_err[b] = (joint mean error, mesh mean error) of clip b.
+// The reference does this with four device->host copies of [B,6890,3] tensors and numpy every batch.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eval_err_kernel(const float* __restrict__ cam_mesh, const float* __restrict__ gt_mesh, const float* __restrict__ pred_pose,
+                const float* __restrict__ gt_pose, const int32_t* __restrict__ eval_joints, int n_eval, int R, int V, float scale,
+                float* __restrict__ clip_err) {
+    __shared__ float red[2][8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* pp = pred_pose + (size_t)b * R * 3;
+    const float* gp = gt_pose + (size_t)b * R * 3;
+    const float rpx = pp[0], rpy = pp[1], rpz = pp[2], rgx = gp[0], rgy = gp[1], rgz = gp[2];
+    const float* pm = cam_mesh + (size_t)b * V * 3;
+    const float* gm = gt_mesh + (size_t)b * V * 3;
+    float macc = 0.f;
+    for (int v = tid; v < V; v += blockDim.x) {
+        const float dx = (pm[v * 3] * scale - rpx) - (gm[v * 3] * scale - rgx);
+        const float dy = (pm[v * 3 + 1] * scale - rpy) - (gm[v * 3 + 1] * scale - rgy);
+        const float dz = (pm[v * 3 + 2] * scale - rpz) - (gm[v * 3 + 2] * scale - rgz);
+        macc += sqrtf((dx * dx + dy * dy) + dz * dz);
+    }
+    float jacc = 0.f;
+    if (tid < n_eval) {
+        const int j = eval_joints[tid];
+        const float dx = (pp[j * 3] - rpx) - (gp[j * 3] - rgx), dy = (pp[j * 3 + 1] - rpy) - (gp[j * 3 + 1] - rgy),
+                    dz = (pp[j * 3 + 2] - rpz) - (gp[j * 3 + 2] - rgz);
+        jacc = sqrtf((dx * dx + dy * dy) + dz * dz);
+    }
+    macc = warp_sum(macc); jacc = warp_sum(jacc);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = jacc; red[1][tid >> 5] = macc; }
+    __syncthreads();
+    if (tid < 2) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[tid][w];
+        clip_err[(size_t)b * 2 + tid] = t / (float)(tid == 0 ? n_eval : V);
+    }
+}
+
+// mean over clips (fixed order: deterministic) -> mean_err = (joint_mean_error, mesh_mean_error)
+__global__ void __launch_bounds__(64)
+eval_mean_kernel(const float* __restrict__ clip_err, int B, float* __restrict__ mean_err) {
+    const int which = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (int b = lane; b < B; b += 32) acc += clip_err[(size_t)b * 2 + which];
+    acc = warp_sum(acc);
+    if (lane == 0) mean_err[which] = acc / (float)B;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // SMPL LBS (smpl_layer.py:65-158)
 // kernel A, one thread block (32 threads) per sample: rodrigues, joint regression from betas, FK chain,
 // rest-pose removal -> A[b,24,12] (3x4 per joint), coef[b, :] = [betas(10) | vec(R_1..23 - I)(207) | 0 pad], joints.

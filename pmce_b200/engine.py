@@ -424,3 +424,27 @@ class JRegressor:
             check(self.lib.pmce_jregress(_ptr(self.row_ptr), _ptr(self.cols), _ptr(self.vals), self.R, _ptr(mesh), self.V, B,
                                          float(scale), _ptr(out), _stream()), "pmce_jregress")
         return out
+
+    def eval_errors(self, cam_mesh, gt_mesh, gt_pose, eval_joints=(1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16), scale=1000.0):
+        """The test loop's evaluation epilogue (reference lib/core/base.py:223-227 + data/PW3D/dataset.py:269-282) on the
+        device: cam_mesh / gt_mesh [B,V,3] in metres, gt_pose [B,R,3] in mm ->
+        (pred_pose [B,R,3] mm, clip_err [B,2] = per-clip (joint, mesh) mean error, mean_err [2] = (j_error, s_error))."""
+        B = cam_mesh.shape[0]
+        cam_mesh = _require_cuda_f32(cam_mesh, "cam_mesh", (B, self.V, 3))
+        gt_mesh = _require_cuda_f32(gt_mesh, "gt_mesh", (B, self.V, 3))
+        gt_pose = _require_cuda_f32(gt_pose, "gt_pose", (B, self.R, 3))
+        dev = cam_mesh.device
+        key = tuple(int(j) for j in eval_joints)
+        if getattr(self, "_eval_key", None) != (key, dev):
+            if not key or min(key) < 0 or max(key) >= self.R:
+                raise PmceError(f"eval_joints must index the {self.R} regressor rows")
+            self._eval_idx = torch.tensor(key, dtype=torch.int32, device=dev)
+            self._eval_key = (key, dev)
+        with torch.cuda.device(dev):
+            pred_pose = torch.empty(B, self.R, 3, device=dev)
+            clip_err = torch.empty(B, 2, device=dev)
+            mean_err = torch.empty(2, device=dev)
+            check(self.lib.pmce_eval_errors(_ptr(self.row_ptr), _ptr(self.cols), _ptr(self.vals), self.R, _ptr(cam_mesh), _ptr(gt_mesh),
+                                            _ptr(gt_pose), _ptr(self._eval_idx), len(key), self.V, B, float(scale), _ptr(pred_pose),
+                                            _ptr(clip_err), _ptr(mean_err), _stream()), "pmce_eval_errors")
+        return pred_pose, clip_err, mean_err

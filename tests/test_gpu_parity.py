@@ -272,6 +272,31 @@ def test_smpl_lbs_vs_reference_golden(lib):
     assert (vb.cpu() - v.cpu()[idx]).abs().max() < 1e-6 and (jb.cpu() - j.cpu()[idx]).abs().max() < 1e-6
 
 
+def test_eval_epilogue_vs_reference_golden(lib):
+    """(f)1 pmce_eval_errors against the reference's own compute_both_err value and the oracle, incl. per-clip errors."""
+    from oracle import pmce_oracle as po
+    from pmce_b200.engine import JRegressor
+    g = np.load(os.path.join(GOLDEN, "eval_err_B6.npz"))
+    B = int(g["B"])
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    cam_mesh = torch.randn(B, 6890, 3, generator=gen) * 0.3
+    gt_mesh = cam_mesh + torch.randn(B, 6890, 3, generator=gen) * 0.05
+    gt_pose = torch.randn(B, 17, 3, generator=gen) * 300
+    jr = JRegressor(dense_regressor("h36m"), "cuda")
+    pred_pose, clip_err, mean_err = jr.eval_errors(cam_mesh.cuda(), gt_mesh.cuda(), gt_pose.cuda())
+    assert _maxabs(pred_pose, g["pred_pose"]) < 2e-3                         # mm, values ~1e3
+    assert abs(float(mean_err[0]) - float(g["joint_mean_error"])) < 1e-4 * float(g["joint_mean_error"])
+    assert abs(float(mean_err[1]) - float(g["mesh_mean_error"])) < 1e-4 * float(g["mesh_mean_error"])
+    jreg = torch.as_tensor(dense_regressor("h36m"), dtype=torch.float32)
+    for b in range(B):                                                       # per-clip values = the oracle on a batch of one
+        _, j1, s1 = po.eval_step(jreg, cam_mesh[b:b + 1], gt_mesh[b:b + 1], gt_pose[b:b + 1])
+        assert abs(float(clip_err[b, 0]) - float(j1)) < 1e-4 * float(j1) and abs(float(clip_err[b, 1]) - float(s1)) < 1e-4 * float(s1)
+    # ragged / large batch: the batch mean is the mean of the per-clip means
+    idx = torch.arange(130) % B
+    _, ce, me = jr.eval_errors(cam_mesh[idx].cuda(), gt_mesh[idx].cuda(), gt_pose[idx].cuda())
+    assert torch.allclose(ce.cpu(), clip_err.cpu()[idx], rtol=1e-6) and abs(float(me[1]) - float(ce[:, 1].mean())) < 1e-3
+
+
 def test_jregress_coco(lib):
     from pmce_b200.engine import JRegressor
     J = dense_regressor("coco")

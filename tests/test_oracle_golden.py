@@ -118,3 +118,21 @@ def test_init_geometry_restatement():
     assert np.array_equal(vj, g["vj_relation"])
     assert np.abs(iv.numpy() - g["init_vertices"]).max() < 1e-6
     assert vj.min() >= 0 and vj.max() < 17
+
+
+def test_eval_epilogue_oracle_vs_reference_golden():
+    """(f)1: the restated compute_both_err / eval step against the value the reference's own PW3D.compute_both_err produced
+    (oracle/gen_golden.py::gen_eval compiles that method from the reference tree)."""
+    import torch
+    from conftest import dense_regressor
+    from oracle import pmce_oracle as po
+    g = np.load(os.path.join(GOLDEN, "eval_err_B6.npz"))
+    B = int(g["B"])
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    cam_mesh = torch.randn(B, 6890, 3, generator=gen) * 0.3
+    gt_mesh = cam_mesh + torch.randn(B, 6890, 3, generator=gen) * 0.05
+    gt_pose = torch.randn(B, 17, 3, generator=gen) * 300
+    jreg = torch.as_tensor(dense_regressor("h36m"), dtype=torch.float32)
+    pred_pose, j_err, s_err = po.eval_step(jreg, cam_mesh, gt_mesh, gt_pose)
+    assert np.abs(pred_pose.numpy() - g["pred_pose"]).max() < 1e-3        # mm
+    assert abs(float(j_err) - float(g["joint_mean_error"])) < 1e-3 and abs(float(s_err) - float(g["mesh_mean_error"])) < 1e-3
