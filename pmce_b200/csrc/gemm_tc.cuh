@@ -50,10 +50,10 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + ep
 constexpr int TC_CW = 16;            // epilogue chunk width in columns
 constexpr int TC_STG = 2048;         // staging bytes per epilogue warp: [32][16] fp32, or [32][16] bf16 hi + lo
 
-template <int BN>
+template <int BN, int NCTA = 1>
 struct TcCfg {
     static constexpr int A_TILE = TC_BM * 128;          // bytes per A half (hi or lo)
-    static constexpr int W_TILE = BN * 128;
+    static constexpr int W_TILE = (BN / NCTA) * 128;    // per CTA: a CTA pair holds half of the tile's W rows each
     static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;
     static constexpr int STG_BYTES = TC_EPI_WARPS * TC_STG;          // per-warp epilogue staging tiles (1024-B aligned)
     static constexpr int STAGES = (196 * 1024) / STAGE_BYTES >= 4 ? 4 : (196 * 1024) / STAGE_BYTES;
@@ -62,6 +62,7 @@ struct TcCfg {
     static_assert(STAGES >= 2, "tile too large");
     static_assert(TMEM_COLS <= 512, "TMEM");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+    static_assert(NCTA == 1 || (NCTA == 2 && BN == 256), "CTA pairs run 256 x 256 tiles");
 };
 
 // Direct (row-per-thread) epilogue for one 16-column chunk: runtime flags, any addressing. Used by TC_GENERIC.
@@ -92,12 +93,15 @@ __device__ __forceinline__ void tc_epilogue_generic(const TcEpi& e, const uint32
     }
 }
 
-template <int BN, int MODE>
+// NCTA == 2: the same kernel on CTA pairs (cluster of 2, tcgen05 cta_group::2): one 256 x 256 tile per pair, each CTA loads
+// its 128 rows of A and HALF of the tile's W rows (a third less operand traffic L2->SM and smem per FLOP than two 128 x 256
+// tiles), the leader issues the MMAs for both, each CTA drains its own 128 accumulator rows.
+template <int BN, int MODE, int NCTA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                  const __grid_constant__ TcOutMaps om, int M, int N, int K, TcEpi e) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, NCTA>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -111,8 +115,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (K + TC_BK - 1) / TC_BK;
-    const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + TC_BM - 1) / TC_BM;
+    const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + NCTA * TC_BM - 1) / (NCTA * TC_BM);
     const int num_tiles = tiles_n * tiles_m;
+    const uint32_t rank = NCTA == 2 ? tc::cluster_ctarank() : 0;          // position in the CTA pair
+    const int tile0 = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;    // tiles are dealt to pairs
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA_hi); tc::tma_prefetch_desc(&tmA_lo);
@@ -121,42 +127,53 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (MODE == TC_SPLIT_GELU || MODE == TC_SPLIT) tc::tma_prefetch_desc(&om.out_lo);
         if (MODE == TC_F32_RESID) tc::tma_prefetch_desc(&om.resid);
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], TC_EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], NCTA * TC_EPI_WARPS); }
         for (int w = 0; w < TC_EPI_WARPS; ++w) tc::mbar_init(&resid_bar[w], 1);
         tc::fence_barrier_init();
         tc::fence_proxy_async();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    if (warp == 1) { if (NCTA == 2) tc::tmem_alloc_pair(tmem_ptr_smem, Cfg::TMEM_COLS); else tc::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); }
     tc::tc_fence_before();
     __syncthreads();
+    if (NCTA == 2) tc::cluster_sync_all();               // the peer's barriers are initialised before anything signals them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;                                    // global k-block counter across tiles
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+                const int m0 = (tile / tiles_n) * (NCTA * TC_BM) + (int)rank * TC_BM, n0 = (tile % tiles_n) * BN + (int)rank * (BN / NCTA);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     tc::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-                    tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                    tc::tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
-                    tc::tma_load_2d(st + Cfg::A_TILE, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
-                    tc::tma_load_2d(st + 2 * Cfg::A_TILE, &tmW_hi, &full_bar[s], kb * TC_BK, n0);
-                    tc::tma_load_2d(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tmW_lo, &full_bar[s], kb * TC_BK, n0);
+                    if (NCTA == 1) {
+                        tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                        tc::tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
+                        tc::tma_load_2d(st + Cfg::A_TILE, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
+                        tc::tma_load_2d(st + 2 * Cfg::A_TILE, &tmW_hi, &full_bar[s], kb * TC_BK, n0);
+                        tc::tma_load_2d(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tmW_lo, &full_bar[s], kb * TC_BK, n0);
+                    } else {
+                        // both CTAs' bytes are counted on the LEADER's barrier (the only MMA issuer waits there)
+                        const uint32_t fb = tc::mapa_rank(tc::smem_u32(&full_bar[s]), 0);
+                        if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+                        tc::tma_load_2d_pair(st, &tmA_hi, fb, kb * TC_BK, m0);
+                        tc::tma_load_2d_pair(st + Cfg::A_TILE, &tmA_lo, fb, kb * TC_BK, m0);
+                        tc::tma_load_2d_pair(st + 2 * Cfg::A_TILE, &tmW_hi, fb, kb * TC_BK, n0);
+                        tc::tma_load_2d_pair(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tmW_lo, fb, kb * TC_BK, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(TC_BM, BN);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(NCTA * TC_BM, BN);
             uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
                 const uint32_t acc = tcount & 1;
-                tc::mbar_wait(&tmem_empty_bar[acc], ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+                tc::mbar_wait(&tmem_empty_bar[acc], ((tcount >> 1) & 1) ^ 1);     // epilogue(s) have drained this accumulator
                 tc::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -170,13 +187,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
                         // small cross terms first, then the leading term
-                        tc::umma_bf16(tmem_d, tc::umma_desc_advance_k(a_lo, k), tc::umma_desc_advance_k(w_hi, k), idesc, (kb | k) != 0);
-                        tc::umma_bf16(tmem_d, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_lo, k), idesc, 1);
-                        tc::umma_bf16(tmem_d, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_hi, k), idesc, 1);
+                        if (NCTA == 1) {
+                            tc::umma_bf16(tmem_d, tc::umma_desc_advance_k(a_lo, k), tc::umma_desc_advance_k(w_hi, k), idesc, (kb | k) != 0);
+                            tc::umma_bf16(tmem_d, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_lo, k), idesc, 1);
+                            tc::umma_bf16(tmem_d, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_hi, k), idesc, 1);
+                        } else {
+                            tc::umma_bf16_pair(tmem_d, tc::umma_desc_advance_k(a_lo, k), tc::umma_desc_advance_k(w_hi, k), idesc, (kb | k) != 0);
+                            tc::umma_bf16_pair(tmem_d, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_lo, k), idesc, 1);
+                            tc::umma_bf16_pair(tmem_d, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_hi, k), idesc, 1);
+                        }
                     }
-                    tc::umma_commit(&empty_bar[s]);          // smem slot free once these MMAs have read it
+                    if (NCTA == 1) tc::umma_commit(&empty_bar[s]); else tc::umma_commit_pair(&empty_bar[s]);   // smem slot free once these MMAs have read it
                 }
-                tc::umma_commit(&tmem_full_bar[acc]);        // accumulator complete
+                if (NCTA == 1) tc::umma_commit(&tmem_full_bar[acc]); else tc::umma_commit_pair(&tmem_full_bar[acc]);   // accumulator complete
             }
         }
     } else {
@@ -190,8 +213,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const uint32_t stg_u32 = tc::smem_u32(stg);
         uint32_t tcount = 0, rcount = 0;
         bool store_pending = false;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-            const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+        // accumulator-drained arrivals go to the leader's barrier (its MMA thread is the only waiter)
+        const uint32_t te_bar[2] = {tc::mapa_rank(tc::smem_u32(&tmem_empty_bar[0]), 0), tc::mapa_rank(tc::smem_u32(&tmem_empty_bar[1]), 0)};
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
+            const int m0 = (tile / tiles_n) * (NCTA * TC_BM) + (int)rank * TC_BM, n0 = (tile % tiles_n) * BN;
             const uint32_t acc = tcount & 1;
             const int row0 = m0 + q * 32;
             const int row = row0 + lane;
@@ -199,7 +224,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             tc::tc_fence_after();
             if (cg >= CH) {                                       // BN == 32: column groups 2 and 3 have no chunk
                 tc::tc_fence_before();
-                if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
+                if (lane == 0) { if (NCTA == 1) tc::mbar_arrive(&tmem_empty_bar[acc]); else tc::mbar_arrive_cluster(te_bar[acc]); }
                 continue;
             }
             const int c_last = cg + 4 * ((CH - 1 - cg) / 4);
@@ -222,7 +247,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (c == c_last) {                               // last read of this accumulator by this warp: release it early
                     tc::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
+                    if (lane == 0) { if (NCTA == 1) tc::mbar_arrive(&tmem_empty_bar[acc]); else tc::mbar_arrive_cluster(te_bar[acc]); }
                 }
                 if (!live) continue;                             // warp-uniform
                 if (MODE == TC_GENERIC) {
@@ -297,7 +322,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (NCTA == 2) tc::cluster_sync_all();               // neither CTA leaves (or frees TMEM) while its peer may still touch it
+    if (warp == 1) { if (NCTA == 2) tc::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // fp32 [rows, cols] (ld) -> bf16 hi / lo [rows, ld_out]; optional relu on the way (linear_cur input).
@@ -376,25 +402,55 @@ static inline int tc_num_sms() {
     return n;
 }
 
+// 256-wide tiles run on CTA pairs (cta_group::2) when the problem is large in N and K: measured with tools/gemm_sweep.py,
+// M=17408: N=1536,K=512 69.8 -> 63.4 us, N=1024,K=512 (GELU) 55.5 -> 52.3, N=512,K=1024 48.5 -> 45.9, N=512,K=512 unchanged;
+// K=256 shapes lose 1-2 us (three 64 KB stages hold fewer k-blocks than the tile needs to hide the fill).
+// PMCE_TC_PAIR=0 disables, =2 forces pairs for every 256-wide tile (tests).
+static inline bool tc_pair_enabled(int M, int N, int K) {
+    static int mode = -1;
+    if (mode < 0) { const char* s = getenv("PMCE_TC_PAIR"); mode = s ? atoi(s) : 1; }
+    if (mode == 0 || M <= TC_BM) return false;
+    return mode >= 2 || (N >= 512 && K >= 512);
+}
+
 template <int BN, int MODE>
 static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap* tw, const TcOutMaps& om, int M, int N, int K, const TcEpi& e,
                                         cudaStream_t st) {
+    if (BN == 256 && tc_pair_enabled(M, N, K)) {
+        constexpr int BNP = BN == 256 ? 256 : 256;
+        static bool configured2 = false;
+        if (!configured2) {
+            if (cudaFuncSetAttribute(linear_tc_kernel<BNP, MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BNP, 2>::SMEM_BYTES) != cudaSuccess) return 2;
+            configured2 = true;
+        }
+        const long long tiles = (long long)((N + 255) / 256) * ((M + 2 * TC_BM - 1) / (2 * TC_BM));
+        const int pairs = (int)(tiles < tc_num_sms() / 2 ? tiles : tc_num_sms() / 2);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BNP, 2>::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 2>, ta[0], ta[1], tw[0], tw[1], om, M, N, K, e) == cudaSuccess ? 0 : 3;
+    }
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(linear_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES) != cudaSuccess) return 2;
+        if (cudaFuncSetAttribute(linear_tc_kernel<BN, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES) != cudaSuccess) return 2;
         configured = true;
     }
     const long long tiles = (long long)((N + BN - 1) / BN) * ((M + TC_BM - 1) / TC_BM);
     const int grid = (int)(tiles < tc_num_sms() ? tiles : tc_num_sms());
-    linear_tc_kernel<BN, MODE><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta[0], ta[1], tw[0], tw[1], om, M, N, K, e);
+    linear_tc_kernel<BN, MODE, 1><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta[0], ta[1], tw[0], tw[1], om, M, N, K, e);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
 template <int BN>
 static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, const TcEpi& e, cudaStream_t st) {
     CUtensorMap ta[2], tw[2];
+    const int wbox = (BN == 256 && tc_pair_enabled(A.rows, W.rows, A.cols)) ? BN / 2 : BN;    // a CTA of a pair loads half of the W rows
     if (make_tmap_bf16(&ta[0], A.hi, A.rows, A.cols, A.ld, TC_BM) || make_tmap_bf16(&ta[1], A.lo, A.rows, A.cols, A.ld, TC_BM) ||
-        make_tmap_bf16(&tw[0], W.hi, W.rows, W.cols, W.ld, BN) || make_tmap_bf16(&tw[1], W.lo, W.rows, W.cols, W.ld, BN))
+        make_tmap_bf16(&tw[0], W.hi, W.rows, W.cols, W.ld, wbox) || make_tmap_bf16(&tw[1], W.lo, W.rows, W.cols, W.ld, wbox))
         return 1;
     const int M = A.rows, N = W.rows, K = A.cols;
     auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -426,8 +482,7 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
     return launch_linear_tc_mode<BN, TC_GENERIC>(ta, tw, om, M, N, K, e, st);
 }
 
-// Tile width: the widest BN that still yields at least one wave of tiles; skinny problems take the narrowest tile so the
-// weight stream is spread over as many SMs as possible.
+// Tile width: the BN in {256,128,64,32} with the lowest estimated launch time (rounds x per-round cost).
 // Requirements: A.cols == W.cols (K), K % 8 == 0, ld % 8 == 0, 16-byte aligned bases.
 static inline int launch_linear_tc(const TcOperand& A, const TcOperand& W, const TcEpi& e, cudaStream_t st) {
     const int N = W.rows;
@@ -439,9 +494,18 @@ static inline int launch_linear_tc(const TcOperand& A, const TcOperand& W, const
     if (forced == 128) return launch_linear_tc_bn<128>(A, W, e, st);
     if (forced == 64) return launch_linear_tc_bn<64>(A, W, e, st);
     if (forced == 32) return launch_linear_tc_bn<32>(A, W, e, st);
-    if (N >= 256 && tiles_m * ((N + 255) / 256) >= sms) return launch_linear_tc_bn<256>(A, W, e, st);
-    if (N >= 128 && tiles_m * ((N + 127) / 128) >= sms) return launch_linear_tc_bn<128>(A, W, e, st);
-    if (N >= 64 && tiles_m * ((N + 63) / 64) >= sms) return launch_linear_tc_bn<64>(A, W, e, st);
-    if (N > 32 && tiles_m * ((N + 63) / 64) * 2 > sms) return launch_linear_tc_bn<64>(A, W, e, st);
+    // cost model fitted to tools/gemm_sweep.py: a launch takes ceil(tiles / SMs) rounds and a round costs a fixed part
+    // (pipeline fill, one epilogue drain) plus a part proportional to the tile width; ties go to the wider tile (fewer A re-reads)
+    int best = 32;
+    long long best_cost = -1;
+    for (int bn = 256; bn >= 32; bn >>= 1) {
+        if (bn > 32 && bn / 2 >= N) continue;                     // at least half of the tile's columns must exist
+        const long long tiles = tiles_m * ((N + bn - 1) / bn);
+        const long long cost = ((tiles + sms - 1) / sms) * (32 + bn);
+        if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
+    }
+    if (best == 256) return launch_linear_tc_bn<256>(A, W, e, st);
+    if (best == 128) return launch_linear_tc_bn<128>(A, W, e, st);
+    if (best == 64) return launch_linear_tc_bn<64>(A, W, e, st);
     return launch_linear_tc_bn<32>(A, W, e, st);
 }

@@ -49,3 +49,15 @@ def test_linear_tc_matches_fp64(lib, M, N, K, act):
     assert torch.isfinite(out_tc).all()
     assert e_f32 < 2e-6
     assert e_tc < 3e-5          # bf16x3: ~2^-16 per product, far below single-pass TF32 (~5e-4)
+
+
+def test_cta_pair_gemm_in_subprocess():
+    """The cta_group::2 (CTA pair) variant of the GEMM on every shape above, forced on with 256-wide tiles (the library reads
+    its knobs once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PMCE_TC_PAIR="2", PMCE_TC_BN="256")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", "test_linear_tc_matches_fp64"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
