@@ -196,6 +196,18 @@ int smpl_lbs_forward(const float* blend, const float* v_template, const float* j
                      const float* trans, int B, float* verts, float* joints, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* (f)4, the data path's use of the layer: get_smpl_coord (data/PW3D/dataset.py:70-88, data/Human36M/dataset.py:91-110 ...)
+ * runs SMPL_Layer.forward per sample on the CPU inside the DataLoader workers and multiplies by 1000 (metre -> millimetre).
+ * Same as smpl_lbs_forward for a whole batch, with verts and joints multiplied by out_scale on the way out.  When
+ * blend_hi / blend_lo are given (split-bf16 copies of the blend matrix from pmce_split_bf16, [20672, smpl_blend_ld()] with
+ * rows >= 20670 zero, and v_template padded to 20672 floats) the blend-shape product runs on the tensor cores (bf16x3) and
+ * `blend` may be NULL; otherwise it is the exact fp32 CUDA-core GEMM. */
+int smpl_lbs_forward_scaled(const float* blend, const void* blend_hi, const void* blend_lo, const float* v_template,
+                            const float* j_template, const float* j_shapedirs, const float* skin_weights,
+                            const int32_t* parents, const float* pose, const float* betas, const float* trans, int B,
+                            float out_scale, float* verts, float* joints, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -217,8 +217,12 @@ int flash_attn32(const float* Q, AttnAddr aq, const float* K, const float* V, At
 int ln_rows(const float* x, int nrows, int C, const LnParams* a, const float* pos, int pos_div, int pos_mod, float* out1,
             const LnParams* b, const SplitOut& out2s, cudaStream_t st) {
     LnParams za{nullptr, nullptr, 0.f};
-    ln_rows_kernel<<<cdiv(nrows, 8), 256, 0, st>>>(x, nrows, C, a ? *a : za, a ? 1 : 0, pos, pos_div, pos_mod, out1, b ? *b : za, nullptr,
-                                                     b ? out2s : NO_SPLIT);
+    const int nv = C / 128;
+    const dim3 grid(cdiv(nrows, 8));
+#define LN_LAUNCH(MV) ln_rows_kernel<MV><<<grid, 256, 0, st>>>(x, nrows, C, a ? *a : za, a ? 1 : 0, pos, pos_div, pos_mod, out1, b ? *b : za, nullptr, \
+                                                          b ? out2s : NO_SPLIT)
+    if (nv <= 1) LN_LAUNCH(1); else if (nv <= 2) LN_LAUNCH(2); else if (nv <= 4) LN_LAUNCH(4); else LN_LAUNCH(8);
+#undef LN_LAUNCH
     CKL();
     return 0;
 }
@@ -933,7 +937,9 @@ extern "C" int pmce_eval_errors(const int32_t* row_ptr, const int32_t* cols, con
     cudaStream_t st = (cudaStream_t)stream;
     jregress_kernel<<<cdiv((long long)B * R * 3, 128), 128, 0, st>>>(row_ptr, cols, vals, R, cam_mesh, num_vert, B, scale, pred_pose);
     CKL();
-    eval_err_kernel<<<B, 256, 0, st>>>(cam_mesh, gt_mesh, pred_pose, gt_pose, eval_joints, n_eval, R, num_vert, scale, clip_err);
+    if (((uintptr_t)cam_mesh | (uintptr_t)gt_mesh) & 7) { pmce_set_error("pmce_eval_errors: meshes must be 8-byte aligned"); return 2; }
+    if ((num_vert & 1) && B > 1) { pmce_set_error("pmce_eval_errors: odd vertex counts are supported for B = 1 only (8-byte loads)"); return 2; }
+    eval_err_kernel<<<B, EVAL_THREADS, 0, st>>>(cam_mesh, gt_mesh, pred_pose, gt_pose, eval_joints, n_eval, R, num_vert, scale, clip_err);
     CKL();
     eval_mean_kernel<<<1, 64, 0, st>>>(clip_err, B, mean_err);
     CKL();
@@ -999,17 +1005,19 @@ extern "C" int pmce_linear_tc_presplit(const void* x_hi, const void* x_lo, const
 #define SMPL_V 6890
 #define SMPL_LDK 224
 extern "C" int smpl_blend_ld(void) { return SMPL_LDK; }
+#define SMPL_NPAD 20672      /* 6890*3 rounded up to the GEMM epilogue's 16-column chunk */
 extern "C" size_t smpl_workspace_bytes(int B) {
     if (B < 1) return 0;
-    auto al = [](size_t n) { return (n * 4 + 255) / 256 * 256; };
-    return al((size_t)B * SMPL_LDK) + al((size_t)B * 288) + al((size_t)B * SMPL_V * 3);
+    auto al = [](size_t n) { return (n + 255) / 256 * 256; };
+    return al((size_t)B * SMPL_LDK * 4) + al((size_t)B * 288 * 4) + al((size_t)B * SMPL_NPAD * 4) + 2 * al((size_t)B * SMPL_LDK * 2);
 }
 
-extern "C" int smpl_lbs_forward(const float* blend, const float* v_template, const float* j_template, const float* j_shapedirs,
-                                const float* skin_weights, const int32_t* parents, const float* pose, const float* betas,
-                                const float* trans, int B, float* verts, float* joints, void* workspace, size_t workspace_bytes,
-                                void* stream) {
-    if (!blend || !v_template || !j_template || !j_shapedirs || !skin_weights || !parents || !pose || !betas || !verts || !joints) {
+extern "C" int smpl_lbs_forward_scaled(const float* blend, const void* blend_hi, const void* blend_lo, const float* v_template,
+                                       const float* j_template, const float* j_shapedirs, const float* skin_weights, const int32_t* parents,
+                                       const float* pose, const float* betas, const float* trans, int B, float out_scale, float* verts,
+                                       float* joints, void* workspace, size_t workspace_bytes, void* stream) {
+    if ((!blend && !blend_hi) || (blend_hi && !blend_lo) || !v_template || !j_template || !j_shapedirs || !skin_weights || !parents || !pose || !betas ||
+        !verts || !joints) {
         pmce_set_error("smpl_lbs_forward: NULL argument"); return 2;
     }
     if (B < 1) { pmce_set_error("batch size %d < 1", B); return 2; }
@@ -1018,15 +1026,35 @@ extern "C" int smpl_lbs_forward(const float* blend, const float* v_template, con
     Carver c{(char*)workspace, 0};
     float* coef = c.f32((size_t)B * SMPL_LDK);
     float* Amat = c.f32((size_t)B * 288);
-    float* vposed = c.f32((size_t)B * SMPL_V * 3);
-    smpl_pose_kernel<<<B, 32, 0, st>>>(pose, betas, trans, j_template, j_shapedirs, parents, B, SMPL_LDK, coef, Amat, joints);
+    float* vposed = c.f32((size_t)B * SMPL_NPAD);
+    SplitOut coef_s = c.split((size_t)B * SMPL_LDK);
+    smpl_pose_kernel<<<B, 32, 0, st>>>(pose, betas, trans, j_template, j_shapedirs, parents, B, SMPL_LDK, coef, Amat, joints, out_scale);
     CKL();
-    // v_posed[b, v*3+c] = v_template + [shapedirs | posedirs] . [betas | pose_map]   (smpl_layer.py:93-99); exact fp32 GEMM
-    GemmEpi e = gemm_epi_plain(SMPL_V * 3);
-    e.bias = v_template;
-    CKG(launch_gemm_tn(coef, SMPL_LDK, blend, SMPL_LDK, vposed, B, SMPL_V * 3, SMPL_LDK, e, st));
+    // v_posed[b, v*3+c] = v_template + [shapedirs | posedirs] . [betas | pose_map]   (smpl_layer.py:93-99)
+    int ld_vp;
+    if (blend_hi) {
+        // tensor cores (bf16x3, as every projection of the forward): blend_hi/lo and v_template are padded to SMPL_NPAD rows
+        RET(split_rows(coef, B, SMPL_LDK, SMPL_LDK, false, coef_s, SMPL_LDK, st));
+        Weights Wb{nullptr, (const bf16*)blend_hi, (const bf16*)blend_lo};
+        EpiOpt o; o.bias = v_template; o.out = vposed; o.ld_out = SMPL_NPAD;
+        RET(linear_tc(coef_s, SMPL_LDK, B, SMPL_LDK, Wb, 0, SMPL_LDK, SMPL_NPAD, o, st));
+        ld_vp = SMPL_NPAD;
+    } else {
+        GemmEpi e = gemm_epi_plain(SMPL_V * 3);      // exact fp32 CUDA-core GEMM
+        e.bias = v_template;
+        CKG(launch_gemm_tn(coef, SMPL_LDK, blend, SMPL_LDK, vposed, B, SMPL_V * 3, SMPL_LDK, e, st));
+        ld_vp = SMPL_V * 3;
+    }
     dim3 grid(cdiv(SMPL_V, 256), B);
-    smpl_skin_kernel<<<grid, 256, 0, st>>>(vposed, Amat, skin_weights, trans, SMPL_V, verts);
+    smpl_skin_kernel<<<grid, 256, 0, st>>>(vposed, Amat, skin_weights, trans, SMPL_V, ld_vp, verts, out_scale);
     CKL();
     return 0;
+}
+
+extern "C" int smpl_lbs_forward(const float* blend, const float* v_template, const float* j_template, const float* j_shapedirs,
+                                const float* skin_weights, const int32_t* parents, const float* pose, const float* betas,
+                                const float* trans, int B, float* verts, float* joints, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    return smpl_lbs_forward_scaled(blend, nullptr, nullptr, v_template, j_template, j_shapedirs, skin_weights, parents, pose, betas, trans, B,
+                                   1.0f, verts, joints, workspace, workspace_bytes, stream);
 }

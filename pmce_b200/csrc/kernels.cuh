@@ -59,13 +59,13 @@ __device__ __forceinline__ void ln_inreg(float4 (&v)[MAXV], int nv, int C, const
         }
 }
 
+template <int MAXV>   // C / 128 rounded up to a power of two (1, 2, 4, 8): the row lives in MAXV float4 per lane
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, int nrows, int C, LnParams a, int has_a, const float* __restrict__ pos,
                int pos_div, int pos_mod, float* __restrict__ out1, LnParams bparm, float* __restrict__ out2, SplitOut out2s) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= nrows) return;
-    constexpr int MAXV = 8;
     const int nv = C / 128;
     float4 v[MAXV];
     const float* xr = x + (size_t)row * C;
@@ -495,22 +495,36 @@ __global__ void jregress_kernel(const int32_t* __restrict__ row_ptr, const int32
 //   jregress_kernel), gt_pose in mm.   clip_err[b] = (joint mean error, mesh mean error) of clip b.
 // The reference does this with four device->host copies of [B,6890,3] tensors and numpy every batch.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int EVAL_THREADS = 512;
+__global__ void __launch_bounds__(EVAL_THREADS)
 eval_err_kernel(const float* __restrict__ cam_mesh, const float* __restrict__ gt_mesh, const float* __restrict__ pred_pose,
                 const float* __restrict__ gt_pose, const int32_t* __restrict__ eval_joints, int n_eval, int R, int V, float scale,
                 float* __restrict__ clip_err) {
-    __shared__ float red[2][8];
+    __shared__ float red[2][EVAL_THREADS / 32];
     const int b = blockIdx.x, tid = threadIdx.x;
     const float* pp = pred_pose + (size_t)b * R * 3;
     const float* gp = gt_pose + (size_t)b * R * 3;
     const float rpx = pp[0], rpy = pp[1], rpz = pp[2], rgx = gp[0], rgy = gp[1], rgz = gp[2];
-    const float* pm = cam_mesh + (size_t)b * V * 3;
-    const float* gm = gt_mesh + (size_t)b * V * 3;
+    // root-aligned difference (p*s - rp) - (g*s - rg) evaluated as in the reference, two vertices (six floats = three
+    // 8-byte loads per mesh; a clip's mesh starts 8-byte aligned when V is even) per thread and iteration
+    const float2* pm = reinterpret_cast<const float2*>(cam_mesh + (size_t)b * V * 3);
+    const float2* gm = reinterpret_cast<const float2*>(gt_mesh + (size_t)b * V * 3);
     float macc = 0.f;
-    for (int v = tid; v < V; v += blockDim.x) {
-        const float dx = (pm[v * 3] * scale - rpx) - (gm[v * 3] * scale - rgx);
-        const float dy = (pm[v * 3 + 1] * scale - rpy) - (gm[v * 3 + 1] * scale - rgy);
-        const float dz = (pm[v * 3 + 2] * scale - rpz) - (gm[v * 3 + 2] * scale - rgz);
+    const int npair = V >> 1;
+    for (int i = tid; i < npair; i += EVAL_THREADS) {
+        const float2 p0 = pm[3 * i], p1 = pm[3 * i + 1], p2 = pm[3 * i + 2];
+        const float2 g0 = gm[3 * i], g1 = gm[3 * i + 1], g2 = gm[3 * i + 2];
+        const float ax = (p0.x * scale - rpx) - (g0.x * scale - rgx), ay = (p0.y * scale - rpy) - (g0.y * scale - rgy),
+                    az = (p1.x * scale - rpz) - (g1.x * scale - rgz);
+        const float bx = (p1.y * scale - rpx) - (g1.y * scale - rgx), by = (p2.x * scale - rpy) - (g2.x * scale - rgy),
+                    bz = (p2.y * scale - rpz) - (g2.y * scale - rgz);
+        macc += sqrtf((ax * ax + ay * ay) + az * az) + sqrtf((bx * bx + by * by) + bz * bz);
+    }
+    if ((V & 1) && tid == 0) {                      // odd vertex count: the last vertex, scalar loads
+        const float* p = cam_mesh + ((size_t)b * V + V - 1) * 3;
+        const float* g = gt_mesh + ((size_t)b * V + V - 1) * 3;
+        const float dx = (p[0] * scale - rpx) - (g[0] * scale - rgx), dy = (p[1] * scale - rpy) - (g[1] * scale - rgy),
+                    dz = (p[2] * scale - rpz) - (g[2] * scale - rgz);
         macc += sqrtf((dx * dx + dy * dy) + dz * dz);
     }
     float jacc = 0.f;
@@ -525,7 +539,7 @@ eval_err_kernel(const float* __restrict__ cam_mesh, const float* __restrict__ gt
     __syncthreads();
     if (tid < 2) {
         float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += red[tid][w];
+        for (int w = 0; w < EVAL_THREADS / 32; ++w) t += red[tid][w];
         clip_err[(size_t)b * 2 + tid] = t / (float)(tid == 0 ? n_eval : V);
     }
 }
@@ -549,7 +563,7 @@ __global__ void __launch_bounds__(32)
 smpl_pose_kernel(const float* __restrict__ pose, const float* __restrict__ betas, const float* __restrict__ trans,
                  const float* __restrict__ j_template, const float* __restrict__ j_shapedirs,
                  const int32_t* __restrict__ parents, int B, int ldc, float* __restrict__ coef, float* __restrict__ Aout,
-                 float* __restrict__ joints) {
+                 float* __restrict__ joints, float out_scale) {
     const int b = blockIdx.x, lane = threadIdx.x;
     __shared__ float R[24][9];
     __shared__ float Jr[24][3];
@@ -607,9 +621,9 @@ smpl_pose_kernel(const float* __restrict__ pose, const float* __restrict__ betas
     __syncwarp();
     if (lane < 24) {
         const float tx = trans ? trans[(size_t)b * 3] : 0.f, ty = trans ? trans[(size_t)b * 3 + 1] : 0.f, tz = trans ? trans[(size_t)b * 3 + 2] : 0.f;
-        joints[((size_t)b * 24 + lane) * 3 + 0] = G[lane][3] + tx;
-        joints[((size_t)b * 24 + lane) * 3 + 1] = G[lane][7] + ty;
-        joints[((size_t)b * 24 + lane) * 3 + 2] = G[lane][11] + tz;
+        joints[((size_t)b * 24 + lane) * 3 + 0] = (G[lane][3] + tx) * out_scale;
+        joints[((size_t)b * 24 + lane) * 3 + 1] = (G[lane][7] + ty) * out_scale;
+        joints[((size_t)b * 24 + lane) * 3 + 2] = (G[lane][11] + tz) * out_scale;
         // A = G - [0 | G . (Jr,0)]  (smpl_layer.py:126-132)
         float* a = Aout + ((size_t)b * 24 + lane) * 12;
 #pragma unroll
@@ -625,7 +639,7 @@ smpl_pose_kernel(const float* __restrict__ pose, const float* __restrict__ betas
 // One thread per (sample, vertex); the sample's 24 3x4 transforms sit in shared memory.
 __global__ void __launch_bounds__(256)
 smpl_skin_kernel(const float* __restrict__ v_posed, const float* __restrict__ Amat, const float* __restrict__ weights,
-                 const float* __restrict__ trans, int V, float* __restrict__ verts) {
+                 const float* __restrict__ trans, int V, int ld_vp, float* __restrict__ verts, float out_scale) {
     __shared__ float As[24 * 12];
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < 288; i += blockDim.x) As[i] = Amat[(size_t)b * 288 + i];
@@ -645,12 +659,12 @@ smpl_skin_kernel(const float* __restrict__ v_posed, const float* __restrict__ Am
 #pragma unroll
             for (int e = 0; e < 12; ++e) T[e] = fmaf(ww[u], As[(i + u) * 12 + e], T[e]);
     }
-    const float* vp = v_posed + ((size_t)b * V + v) * 3;
+    const float* vp = v_posed + (size_t)b * ld_vp + (size_t)v * 3;
     const float x = vp[0], y = vp[1], z = vp[2];
     float ox = ((T[0] * x + T[1] * y) + T[2] * z) + T[3];
     float oy = ((T[4] * x + T[5] * y) + T[6] * z) + T[7];
     float oz = ((T[8] * x + T[9] * y) + T[10] * z) + T[11];
     if (trans) { ox += trans[(size_t)b * 3]; oy += trans[(size_t)b * 3 + 1]; oz += trans[(size_t)b * 3 + 2]; }
     float* o = verts + ((size_t)b * V + v) * 3;
-    o[0] = ox; o[1] = oy; o[2] = oz;
+    o[0] = ox * out_scale; o[1] = oy * out_scale; o[2] = oz * out_scale;
 }

@@ -81,18 +81,36 @@ class SMPL_Layer(Module):
         blend[:, :10] = self.th_shapedirs.reshape(V * 3, 10)
         blend[:, 10:217] = self.th_posedirs.reshape(V * 3, 207)
         vt = self.th_v_template.reshape(V * 3).contiguous()
+        # tensor-core copies: blend matrix and template padded to 20672 rows (the GEMM epilogue's 16-column chunk), split-bf16
+        npad = 20672
+        blend_pad = torch.zeros(npad, ld, device=dev)
+        blend_pad[:V * 3] = blend
+        vt_pad = torch.zeros(npad, device=dev)
+        vt_pad[:V * 3] = vt
+        blend_hi = torch.empty(npad, ld, dtype=torch.bfloat16, device=dev)
+        blend_lo = torch.empty(npad, ld, dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pmce_split_bf16(_ptr(blend_pad), npad, ld, _ptr(blend_hi), _ptr(blend_lo), _stream()), "pmce_split_bf16")
         Jreg = self.th_J_regressor.double()
         j_template = (Jreg @ self.th_v_template[0].double()).float().contiguous()                       # [24,3]
         j_shapedirs = torch.einsum("jv,vck->jck", Jreg, self.th_shapedirs.double()).float().contiguous()  # [24,3,10]
         parents = torch.as_tensor(np.array([max(p, 0) if i else 0 for i, p in enumerate(self.kintree_parents)],
                                            dtype=np.int32) % 24, device=dev)
         packed = dict(dev=dev, lib=lib, blend=blend, vt=vt, jt=j_template, js=j_shapedirs, parents=parents,
-                      weights=self.th_weights.contiguous(), ws=None)
+                      weights=self.th_weights.contiguous(), ws=None, blend_hi=blend_hi, blend_lo=blend_lo, vt_pad=vt_pad)
         object.__setattr__(self, "_packed", packed)
         return packed
 
     @torch.no_grad()
-    def forward(self, th_pose_axisang, th_betas=torch.zeros(1), th_trans=torch.zeros(1)):
+    def get_smpl_coord(self, pose_param, shape_param, trans_param):
+        """Batched form of the datasets' `get_smpl_coord` (reference data/PW3D/dataset.py:70-88, data/Human36M/dataset.py,
+        data/MPII3D/dataset.py ...): pose [B,72], shape [B,10], trans [B,3] CUDA tensors ->
+        (smpl_mesh_coord [B,6890,3], smpl_joint_coord [B,24,3]) in MILLIMETRES, one launch sequence for the whole batch
+        instead of one CPU SMPL_Layer call per sample inside the DataLoader workers."""
+        return self.forward(pose_param, shape_param, trans_param, _out_scale=1000.0)
+
+    @torch.no_grad()
+    def forward(self, th_pose_axisang, th_betas=torch.zeros(1), th_trans=torch.zeros(1), _out_scale=1.0):
         p = self._pack()
         lib, dev = p["lib"], p["dev"]
         B = th_pose_axisang.shape[0]
@@ -112,9 +130,12 @@ class SMPL_Layer(Module):
                 p["ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
             verts = torch.empty(B, 6890, 3, device=dev)
             joints = torch.empty(B, 24, 3, device=dev)
-            check(lib.smpl_lbs_forward(_ptr(p["blend"]), _ptr(p["vt"]), _ptr(p["jt"]), _ptr(p["js"]), _ptr(p["weights"]),
-                                       _ptr(p["parents"]), _ptr(pose), _ptr(betas), _ptr(trans), B, _ptr(verts), _ptr(joints),
-                                       _ptr(p["ws"]), p["ws"].numel(), _stream()), "smpl_lbs_forward")
+            tcp = os.environ.get("PMCE_SMPL_FP32", "0") != "1"      # PMCE_SMPL_FP32=1: exact fp32 CUDA-core blend-shape GEMM
+            check(lib.smpl_lbs_forward_scaled(_ptr(p["blend"]), _ptr(p["blend_hi"] if tcp else None), _ptr(p["blend_lo"] if tcp else None),
+                                              _ptr(p["vt_pad"] if tcp else p["vt"]), _ptr(p["jt"]), _ptr(p["js"]), _ptr(p["weights"]),
+                                              _ptr(p["parents"]), _ptr(pose), _ptr(betas), _ptr(trans), B, float(_out_scale),
+                                              _ptr(verts), _ptr(joints), _ptr(p["ws"]), p["ws"].numel(), _stream()),
+                  "smpl_lbs_forward")
         if trans is None and self.center_idx is not None:   # not used by PMCE (lib/smpl.py:50-51 passes none)
             center = joints[:, self.center_idx].unsqueeze(1).clone()
             joints -= center

@@ -266,6 +266,9 @@ def test_smpl_lbs_vs_reference_golden(lib):
     assert _maxabs(v, g["verts"]) < 2e-5 and _maxabs(j, g["joints"]) < 2e-5
     v0, j0 = layer(pose.cuda())
     assert _maxabs(v0, g["verts_default"]) < 2e-5 and _maxabs(j0, g["joints_default"]) < 2e-5
+    # (f)4 get_smpl_coord: the data path's metre -> millimetre form (data/PW3D/dataset.py:84-87), batched
+    vm, jm = layer.get_smpl_coord(pose.cuda(), betas.cuda(), trans.cuda())
+    assert _maxabs(vm, g["verts"] * 1000) < 2e-2 and _maxabs(jm, g["joints"] * 1000) < 2e-2
     # batch independence at a DataLoader-sized batch
     idx = torch.arange(257) % 4
     vb, jb = layer(pose[idx].cuda(), betas[idx].cuda(), trans[idx].cuda())
