@@ -257,7 +257,7 @@ int vit_block(const pmce_dims_t& d, const Weights& W, const VitBlockW& w, const 
     ao = a; ao.ld = C;
     if (tc_attn) {                       // head_dim 64: packed block-diagonal attention on tcgen05 (attn_tc.cuh)
         count_launch();
-        const int rc = launch_attn_tile_tc(qkv_s.hi, qkv_s.lo, N, C, J, T, temporal, ws.att_s, ao, nseq, Hh, st);
+        const int rc = launch_attn_tile_tc(qkv_s.hi, qkv_s.lo, N, C, J, T, temporal, ws.att_s, nseq, Hh, st);
         if (rc) { pmce_set_error("attn_tile_tc launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
     } else {
     const int chunk = (65535 / J) * J;   // gridDim.z limit; multiples of J keep the (b,j) decomposition intact

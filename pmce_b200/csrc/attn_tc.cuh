@@ -41,9 +41,28 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_bmn(int M, int N) { r
 __device__ __forceinline__ void bar_sync_group(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 }  // namespace tc
 
+namespace tc {
+__device__ __forceinline__ void tma_store_3d_bulk(const CUtensorMap* m, uint32_t smem_src, int crd0, int crd1, int crd2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(crd0), "r"(crd1), "r"(crd2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_bulk(const CUtensorMap* m, uint32_t smem_src, int crd0, int crd1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(crd0), "r"(crd1)
+                 : "memory");
+}
+}  // namespace tc
+
+// Output: each thread writes its O row (split-bf16) into the group's Q tiles (free once the PV MMAs are complete) in the
+// swizzled tile layout and ONE thread stores the tile by TMA - spatial pass: one [G*L rows][64] box per half (the padding rows
+// of the tile belong to the next tile and are not part of the box), temporal pass: one [T][1][64] box per sequence of the 3-D
+// view. The smem buffer is handed back to the producer only after the store has read it. (Row-per-thread global stores cost
+// 14 us of a 58 us spatial launch and 20 us of a 53 us temporal one: PMCE_ATTN_DEBUG=8.)
 __global__ void __launch_bounds__(AT_THREADS, 1)
-attn_tile_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, int temporal, int C, int J, int T,
-                    SplitOut Os, AttnAddr ao, int L, int G, int nseq, int H, float scale, int dbg) {
+attn_tile_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_ohi,
+                    const __grid_constant__ CUtensorMap tm_olo, int temporal, int C, int J, int T, int L, int G, int nseq, int H, float scale,
+                    int dbg) {
     constexpr int D = 64;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -232,28 +251,52 @@ attn_tile_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                     tc::umma_bf16(tO, ph, bvh, idesc, 1);
                 }
                 tc::umma_commit(&bar_o[grp]);
-                tc::umma_commit(&empty_bar[grp]);                           // smem buffer is free once these MMAs have read it
             }
             tc::mbar_wait(&bar_o[grp], j & 1);
             tc::tc_fence_after();
 
-            // ---- epilogue: O row / rowsum -> split bf16 -> global ----
+            // ---- epilogue: O row / rowsum -> split bf16 -> staging tiles (the group's Q tiles) -> TMA store ----
             const float inv = 1.0f / lsum;
-            const size_t ob = valid ? (size_t)(ao.seq(s) + (long long)tok * ao.tok) * ao.ld + h * D : 0;
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
                 uint32_t v0[32];
                 tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v0);
                 tc::tmem_ld_wait();
-                if (valid && !(dbg & 8)) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        store_split4(Os, ob + hf * 32 + i, make_float4(__uint_as_float(v0[i]) * inv, __uint_as_float(v0[i + 1]) * inv,
-                                                                       __uint_as_float(v0[i + 2]) * inv, __uint_as_float(v0[i + 3]) * inv));
+                for (int jj = 0; jj < 4; ++jj) {
+                    float o8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o8[i] = __uint_as_float(v0[jj * 8 + i]) * inv;
+                    uint4 hh, ll;
+                    tc::split8(o8, hh, ll);
+                    tc::sts16(Qh, r, hf * 4 + jj, hh);
+                    tc::sts16(Ql, r, hf * 4 + jj, ll);
                 }
-                __syncwarp();
+            }
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            tc::bar_sync_group(1 + grp);
+            if (issuer) {
+                if (!(dbg & 8)) {
+                    if (!temporal) {
+                        tc::tma_store_2d_bulk(&tm_ohi, Qh, h * 64, tile * G * L);
+                        tc::tma_store_2d_bulk(&tm_olo, Ql, h * 64, tile * G * L);
+                    } else {
+                        const int s0 = tile * G;
+                        const int ns = nseq - s0 < G ? nseq - s0 : G;
+                        for (int gl = 0; gl < ns; ++gl) {
+                            const int sq = s0 + gl, b = sq / J, jj = sq - b * J;
+                            tc::tma_store_3d_bulk(&tm_ohi, Qh + gl * T * 128, h * 64, jj, b * T);
+                            tc::tma_store_3d_bulk(&tm_olo, Ql + gl * T * 128, h * 64, jj, b * T);
+                        }
+                    }
+                    tc::tma_store_commit();
+                    tc::tma_store_wait_read<0>();
+                }
+                tc::mbar_arrive(&empty_bar[grp]);                           // the producer may refill the buffer
             }
         }
+        if (issuer) tc::tma_store_wait<0>();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -263,7 +306,7 @@ attn_tile_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 // nseq sequences of L tokens (L <= 128; temporal: L % 8 == 0), H heads of 64. q|k|v are the split-bf16 [ntok, 3C] outputs of the
 // qkv projection (token rows ordered (b, t, j)); spatial: sequence = (b,t), tokens j; temporal: sequence = (b,j), tokens t.
 static inline int launch_attn_tile_tc(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, int ntok, int C, int J, int T, bool temporal, SplitOut Os,
-                                      AttnAddr ao, int nseq, int H, cudaStream_t st) {
+                                      int nseq, int H, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(attn_tile_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return 2;
@@ -271,12 +314,16 @@ static inline int launch_attn_tile_tc(const __nv_bfloat16* qkv_hi, const __nv_bf
     }
     const int L = temporal ? T : J;
     const int G = 128 / L;
-    CUtensorMap th, tl;
+    CUtensorMap th, tl, toh, tol;      // Os: split-bf16 output [ntok, C], rows in the same (b, t, j) order as qkv
     if (!temporal) {
-        if (make_tmap_bf16(&th, qkv_hi, ntok, 3 * C, 3 * C, 128) || make_tmap_bf16(&tl, qkv_lo, ntok, 3 * C, 3 * C, 128)) return 1;
+        if (make_tmap_bf16(&th, qkv_hi, ntok, 3 * C, 3 * C, 128) || make_tmap_bf16(&tl, qkv_lo, ntok, 3 * C, 3 * C, 128) ||
+            make_tmap_bf16(&toh, Os.hi, ntok, C, C, G * L) || make_tmap_bf16(&tol, Os.lo, ntok, C, C, G * L))
+            return 1;
     } else {
         if (make_tmap_bf16_3d(&th, qkv_hi, 3 * C, J, ntok / J, 3LL * C, 3LL * C * J, 1, T) ||
-            make_tmap_bf16_3d(&tl, qkv_lo, 3 * C, J, ntok / J, 3LL * C, 3LL * C * J, 1, T))
+            make_tmap_bf16_3d(&tl, qkv_lo, 3 * C, J, ntok / J, 3LL * C, 3LL * C * J, 1, T) ||
+            make_tmap_bf16_3d(&toh, Os.hi, C, J, ntok / J, (long long)C, (long long)C * J, 1, T) ||
+            make_tmap_bf16_3d(&tol, Os.lo, C, J, ntok / J, (long long)C, (long long)C * J, 1, T))
             return 1;
     }
     const int ntiles = (nseq + G - 1) / G;
@@ -291,6 +338,6 @@ static inline int launch_attn_tile_tc(const __nv_bfloat16* qkv_hi, const __nv_bf
     const int grid = (int)(want < sms ? (want < 1 ? 1 : want) : sms);
     static int dbg = -1;   // PMCE_ATTN_DEBUG: profiling knobs (wrong results): 1 no loads, 2 no math, 4 no softmax, 8 no stores
     if (dbg < 0) { const char* e = getenv("PMCE_ATTN_DEBUG"); dbg = e ? atoi(e) : 0; }
-    attn_tile_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(th, tl, temporal ? 1 : 0, C, J, T, Os, ao, L, G, nseq, H, 1.0f / sqrtf(64.0f), dbg);
+    attn_tile_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(th, tl, toh, tol, temporal ? 1 : 0, C, J, T, L, G, nseq, H, 1.0f / sqrtf(64.0f), dbg);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
