@@ -363,10 +363,11 @@ def dominant_kernel_roofline(lib, dev, peaks, B):
     sec = e0.elapsed_time(e1) * 1e-3 / n
     flops = 2.0 * M * N * K
     ach = flops / sec / 1e12
-    return {"kernel": "linear_tc_kernel (tcgen05/TMA/TMEM split-bf16 GEMM; lifter fc1 + bias + GELU)", "bound": "tensor", "achieved": ach,
+    return {"kernel": "linear_tc_kernel<256, TC_SPLIT_GELU, pair> (tcgen05 cta_group::2 / TMA / TMEM split-bf16 GEMM; lifter fc1 + bias + GELU)", "bound": "tensor", "achieved": ach,
             "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1j_linear_tc_fc1_ncu_raw.csv)
-            "traffic": 56.7e6, "traffic_unit": "B", "frac_of_split_ceiling": 3.0 * ach / peaks["bf16_tflops"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1p_linear_tc_fc1_pair_ncu_raw.csv:
+            # 37.8 MB read + 21.8 MB written; the rest of the 71 MB split output is still in L2 when the kernel ends)
+            "traffic": 59.5e6, "traffic_unit": "B", "frac_of_split_ceiling": 3.0 * ach / peaks["bf16_tflops"],
             "flops_per_launch": flops, "mma_flops_per_launch": 3 * flops, "us_per_launch": sec * 1e6, "shape_MNK": [M, N, K],
             "peak_source": peaks["source"], "note": "3 bf16 MMAs per product (bf16x3): frac ceiling is 1/3"}
 
@@ -426,7 +427,8 @@ def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):
     ach = survey_bytes / sec / 1e9
     return {"kernel": "ca_vertex_fused_kernel (AdaLN_q + scores + softmax + P.V.Wp + residual + AdaLN_2 in one pass over the query stream)",
             "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-            "traffic": None, "bytes_per_launch": survey_bytes, "us_per_launch": sec * 1e6,
+            # ncu --set full at B=64 (profiles/r1p_ca_ncu_table.txt): 9.28 MB read, the 14 MB written stay in L2 past the kernel's end
+            "traffic": 9.29e6 if B == 64 else None, "traffic_unit": "B", "bytes_per_launch": survey_bytes, "us_per_launch": sec * 1e6,
             "achieved_kernel_io": io_bytes / sec / 1e9, "kernel_io_bytes_per_launch": io_bytes,
             "frac_kernel_io": io_bytes / sec / 1e9 / peaks["hbm_gbs"], "flops_per_launch": flops, "clips_per_launch": B,
             "l2": f"{nsets} rotating buffer sets ({nsets * io_bytes / 1e6:.0f} MB) > 126 MB L2", "peak_source": peaks["source"]}
