@@ -1045,8 +1045,8 @@ extern "C" int smpl_lbs_forward_scaled(const float* blend, const void* blend_hi,
         CKG(launch_gemm_tn(coef, SMPL_LDK, blend, SMPL_LDK, vposed, B, SMPL_V * 3, SMPL_LDK, e, st));
         ld_vp = SMPL_V * 3;
     }
-    dim3 grid(cdiv(SMPL_V, 256), B);
-    smpl_skin_kernel<<<grid, 256, 0, st>>>(vposed, Amat, skin_weights, trans, SMPL_V, ld_vp, verts, out_scale);
+    dim3 grid(cdiv(SMPL_V, 256), cdiv(B, SMPL_SKIN_NB));
+    smpl_skin_kernel<<<grid, 256, 0, st>>>(vposed, Amat, skin_weights, trans, SMPL_V, B, ld_vp, verts, out_scale);
     CKL();
     return 0;
 }

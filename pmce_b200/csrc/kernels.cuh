@@ -636,35 +636,43 @@ smpl_pose_kernel(const float* __restrict__ pose, const float* __restrict__ betas
 }
 
 // kernel B, skinning (smpl_layer.py:134-155): T_v = sum_i w[v,i] A_i ; verts = T_v [v_posed;1] + trans.
-// One thread per (sample, vertex); the sample's 24 3x4 transforms sit in shared memory.
+// One thread per vertex, SMPL_SKIN_NB samples per CTA: the vertex's 24 skinning weights are read ONCE into registers and
+// reused for every sample of the CTA (one sample per CTA re-read the 661 KB weight table per sample: 169 MB of L2 traffic at
+// B=256 and 50 us; the transforms of the CTA's samples sit in shared memory and are read as 16-byte broadcasts).
+constexpr int SMPL_SKIN_NB = 8;
 __global__ void __launch_bounds__(256)
 smpl_skin_kernel(const float* __restrict__ v_posed, const float* __restrict__ Amat, const float* __restrict__ weights,
-                 const float* __restrict__ trans, int V, int ld_vp, float* __restrict__ verts, float out_scale) {
-    __shared__ float As[24 * 12];
-    const int b = blockIdx.y;
-    for (int i = threadIdx.x; i < 288; i += blockDim.x) As[i] = Amat[(size_t)b * 288 + i];
+                 const float* __restrict__ trans, int V, int B, int ld_vp, float* __restrict__ verts, float out_scale) {
+    __shared__ __align__(16) float As[SMPL_SKIN_NB][24 * 12];
+    const int b0 = blockIdx.y * SMPL_SKIN_NB;
+    const int nb = B - b0 < SMPL_SKIN_NB ? B - b0 : SMPL_SKIN_NB;
+    for (int i = threadIdx.x; i < nb * 288; i += blockDim.x) As[i / 288][i % 288] = Amat[(size_t)b0 * 288 + i];
     __syncthreads();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
-    float T[12];
-#pragma unroll
-    for (int e = 0; e < 12; ++e) T[e] = 0.f;
-    const float* wv = weights + (size_t)v * 24;
+    float w[24];
 #pragma unroll
     for (int i = 0; i < 24; i += 4) {
-        const float4 w4 = ld4(wv + i);
-        const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int e = 0; e < 12; ++e) T[e] = fmaf(ww[u], As[(i + u) * 12 + e], T[e]);
+        const float4 w4 = ld4(weights + (size_t)v * 24 + i);
+        w[i] = w4.x; w[i + 1] = w4.y; w[i + 2] = w4.z; w[i + 3] = w4.w;
     }
-    const float* vp = v_posed + (size_t)b * ld_vp + (size_t)v * 3;
-    const float x = vp[0], y = vp[1], z = vp[2];
-    float ox = ((T[0] * x + T[1] * y) + T[2] * z) + T[3];
-    float oy = ((T[4] * x + T[5] * y) + T[6] * z) + T[7];
-    float oz = ((T[8] * x + T[9] * y) + T[10] * z) + T[11];
-    if (trans) { ox += trans[(size_t)b * 3]; oy += trans[(size_t)b * 3 + 1]; oz += trans[(size_t)b * 3 + 2]; }
-    float* o = verts + ((size_t)b * V + v) * 3;
-    o[0] = ox * out_scale; o[1] = oy * out_scale; o[2] = oz * out_scale;
+    for (int s = 0; s < nb; ++s) {
+        const int b = b0 + s;
+        float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
+#pragma unroll
+        for (int i = 0; i < 24; ++i) {
+            const float4 a0 = ld4(&As[s][i * 12]), a1 = ld4(&As[s][i * 12 + 4]), a2 = ld4(&As[s][i * 12 + 8]);
+            T0.x = fmaf(w[i], a0.x, T0.x); T0.y = fmaf(w[i], a0.y, T0.y); T0.z = fmaf(w[i], a0.z, T0.z); T0.w = fmaf(w[i], a0.w, T0.w);
+            T1.x = fmaf(w[i], a1.x, T1.x); T1.y = fmaf(w[i], a1.y, T1.y); T1.z = fmaf(w[i], a1.z, T1.z); T1.w = fmaf(w[i], a1.w, T1.w);
+            T2.x = fmaf(w[i], a2.x, T2.x); T2.y = fmaf(w[i], a2.y, T2.y); T2.z = fmaf(w[i], a2.z, T2.z); T2.w = fmaf(w[i], a2.w, T2.w);
+        }
+        const float* vp = v_posed + (size_t)b * ld_vp + (size_t)v * 3;
+        const float x = vp[0], y = vp[1], z = vp[2];
+        float ox = ((T0.x * x + T0.y * y) + T0.z * z) + T0.w;
+        float oy = ((T1.x * x + T1.y * y) + T1.z * z) + T1.w;
+        float oz = ((T2.x * x + T2.y * y) + T2.z * z) + T2.w;
+        if (trans) { ox += trans[(size_t)b * 3]; oy += trans[(size_t)b * 3 + 1]; oz += trans[(size_t)b * 3 + 2]; }
+        float* o = verts + ((size_t)b * V + v) * 3;
+        o[0] = ox * out_scale; o[1] = oy * out_scale; o[2] = oz * out_scale;
+    }
 }
