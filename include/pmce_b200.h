@@ -74,6 +74,18 @@ int pmce_forward(const pmce_dims_t* dims, const void* weights, const float* pose
                  const int32_t* vj_relation, int B, float* cam_mesh, float* cam_pose, float* pose3d,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- (f)3: overlapping windows of one track (lib/_img_utils.py:58-92 `view_as_windows(indexes, (seqlen,), step=stride)`; the
+ * demo runs PMCE.forward once per window with stride 1, main/run_demo.py:145).  pose2d_seq [num_frames,J,2], img_feat_seq
+ * [num_frames,2048]; window w = frames [w*stride, w*stride + T), nwin = pmce_sliding_windows(...) = (num_frames-T)/stride + 1;
+ * outputs as pmce_forward with B = nwin.  Same results as pmce_forward on the materialised windows, but everything that is a
+ * function of one frame is computed once per frame instead of once per window: imgfeat_embed, the token embedding and
+ * SpatialBlocks[0] (PoseEstimation.py:78-84), and the GRU layer-0 input projection (CoevoDecoder.py:228).
+ * workspace: pmce_workspace_bytes(dims, nwin).  1 <= stride <= T. */
+int pmce_sliding_windows(const pmce_dims_t* dims, int num_frames, int stride);
+int pmce_forward_sliding(const pmce_dims_t* dims, const void* weights, const float* pose2d_seq, const float* img_feat_seq,
+                         const int32_t* vj_relation, int num_frames, int stride, float* cam_mesh, float* cam_pose,
+                         float* pose3d, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same, HOST buffers in and out (pinned or pageable): H2D of the inputs, forward, D2H of the three
  * outputs, then a stream synchronise. d_io must hold pmce_io_bytes(dims,B) device bytes. This is the
  * shape of the call lib/core/base.py:218-238 makes (`.cuda()` ... `.cpu()`). */

@@ -35,6 +35,8 @@ SIGNATURES = {
     "pmce_pack_weights": (C.c_int, [_DP, _P, _P]),
     "pmce_workspace_bytes": (C.c_size_t, [_DP, C.c_int]),
     "pmce_forward": (C.c_int, [_DP, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
+    "pmce_sliding_windows": (C.c_int, [_DP, C.c_int, C.c_int]),
+    "pmce_forward_sliding": (C.c_int, [_DP, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
     "pmce_io_bytes": (C.c_size_t, [_DP, C.c_int]),
     "pmce_forward_host": (C.c_int, [_DP, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "pmce_lifter_forward": (C.c_int, [_DP, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),

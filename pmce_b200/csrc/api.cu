@@ -70,8 +70,8 @@ struct Workspace {
     float *gi0, *y0, *gi1f, *gi1b, *h1[2][2], *g;
     SplitOut y0_s, g_s, gr_s, h1_s[2][2];
     // decoder
-    float *gb, *verts[3], *Jf, *Vf, *xqv, *Qv, *xkj, *Kj, *Vj, *qkv_d;
-    float *xqj, *xkv, *Kv, *Vv, *Qj, *qkvj;
+    float *gb, *verts[3], *Jf, *Vf, *xqv, *xkj, *Kj, *Vj, *qkv_d;
+    float *xqj, *xkv, *Kv, *Vv, *qkvj;
     SplitOut Jf_s, Vf_s, tA_s, tA2_s, tB_s, tJ_s, tJ2_s, att_ds, hid_ds, attj_s, hidj_s, im2col_s;
     float* lc_mesh;
     CaFolded fold[3];                                  // per-clip folded operands of the fused vertex cross-attention, per block
@@ -97,9 +97,9 @@ Workspace carve(const pmce_dims_t& d, int B, void* base) {
     w.gb = c.f32((size_t)B * PMCE_ADALN_SLOTS * 2 * D);
     for (int i = 0; i < 3; ++i) w.verts[i] = c.f32((size_t)B * Vd * 3);
     const size_t nv = (size_t)B * Vd, nj = (size_t)B * J;
-    w.Jf = c.f32(nj * D); w.Vf = c.f32(nv * D); w.xqv = c.f32(nv * D); w.Qv = c.f32(nv * D);
+    w.Jf = c.f32(nj * D); w.Vf = c.f32(nv * D); w.xqv = c.f32(nv * D);
     w.xkj = c.f32(nj * D); w.Kj = c.f32(nj * D); w.Vj = c.f32(nj * D); w.qkv_d = c.f32(nv * 3 * D);
-    w.xqj = c.f32(nj * D); w.xkv = c.f32(nv * D); w.Kv = c.f32(nv * D); w.Vv = c.f32(nv * D); w.Qj = c.f32(nj * D); w.qkvj = c.f32(nj * 3 * D);
+    w.xqj = c.f32(nj * D); w.xkv = c.f32(nv * D); w.Kv = c.f32(nv * D); w.Vv = c.f32(nv * D); w.qkvj = c.f32(nj * 3 * D);
     w.Jf_s = c.split(nj * D); w.Vf_s = c.split(nv * D); w.tA_s = c.split(nv * D); w.tA2_s = c.split(nv * D); w.tJ_s = c.split(nj * D);
     w.att_ds = c.split(nv * D); w.hid_ds = c.split(nv * 4 * D); w.attj_s = c.split(nj * D); w.hidj_s = c.split(nj * 4 * D);
     w.im2col_s = c.split((size_t)B * 3 * ((Vd * 3 + 7) / 8 * 8));
@@ -215,12 +215,12 @@ int flash_attn32(const float* Q, AttnAddr aq, const float* K, const float* V, At
 }
 
 int ln_rows(const float* x, int nrows, int C, const LnParams* a, const float* pos, int pos_div, int pos_mod, float* out1,
-            const LnParams* b, const SplitOut& out2s, cudaStream_t st) {
+            const LnParams* b, const SplitOut& out2s, cudaStream_t st, int map_rows = 0, int map_stride = 0) {
     LnParams za{nullptr, nullptr, 0.f};
     const int nv = C / 128;
     const dim3 grid(cdiv(nrows, 8));
 #define LN_LAUNCH(MV) ln_rows_kernel<MV><<<grid, 256, 0, st>>>(x, nrows, C, a ? *a : za, a ? 1 : 0, pos, pos_div, pos_mod, out1, b ? *b : za, nullptr, \
-                                                          b ? out2s : NO_SPLIT)
+                                                          b ? out2s : NO_SPLIT, map_rows, map_stride)
     if (nv <= 1) LN_LAUNCH(1); else if (nv <= 2) LN_LAUNCH(2); else if (nv <= 4) LN_LAUNCH(4); else LN_LAUNCH(8);
 #undef LN_LAUNCH
     CKL();
@@ -237,9 +237,12 @@ int adaln(const float* x, int B, int ntok, const float* gb, int slot, const Spli
 // ---------------------------------------------------------------------------------------------------
 // a2/a3 lifter
 // ---------------------------------------------------------------------------------------------------
-int vit_block(const pmce_dims_t& d, const Weights& W, const VitBlockW& w, const Workspace& ws, int B, bool temporal, cudaStream_t st) {
+// F = number of frames the token buffer holds (F * J tokens): B * T for window-major batches; the per-frame spatial pass of
+// pmce_forward_sliding runs on the distinct frames of overlapping windows. The temporal pass needs window-major tokens (F % T == 0).
+int vit_block(const pmce_dims_t& d, const Weights& W, const VitBlockW& w, const Workspace& ws, int F, bool temporal, cudaStream_t st) {
     const int J = d.num_joint, C = d.embed_dim, T = d.seqlen, Hh = d.lifter_heads;
-    const int N = B * T * J;
+    const int N = F * J;
+    const int B = F / T;
     const bool tc_attn = (C / Hh == 64) && (temporal ? (T <= 128 && T % 8 == 0) : (J <= 128));
     // split-bf16 view of the qkv buffer (same bytes as the fp32 one): written by the projection when the tensor-core
     // attention consumes it by TMA
@@ -251,7 +254,7 @@ int vit_block(const pmce_dims_t& d, const Weights& W, const VitBlockW& w, const 
     }
     AttnAddr a, ao;
     int nseq, L;
-    if (!temporal) { a.seq.div = 1; a.seq.s0 = J; a.seq.s1 = 0; a.tok = 1; nseq = B * T; L = J; }
+    if (!temporal) { a.seq.div = 1; a.seq.s0 = J; a.seq.s1 = 0; a.tok = 1; nseq = F; L = J; }
     else { a.seq.div = J; a.seq.s0 = (long long)T * J; a.seq.s1 = 1; a.tok = J; nseq = B * J; L = T; }
     a.ld = 3 * C;
     ao = a; ao.ld = C;
@@ -285,23 +288,38 @@ int vit_block(const pmce_dims_t& d, const Weights& W, const VitBlockW& w, const 
     return 0;
 }
 
-int lifter(const Layout& L, const Weights& W, const float* pose2d, int B, float* pose3d, const Workspace& ws, cudaStream_t st) {
+// Windows b = 0..B-1 of T frames each over a track of nfr frames: window b covers frames [b*fstride, b*fstride + T).
+// fstride == T, nfr == B*T: the ordinary batch of materialised clips. fstride < T (pmce_forward_sliding): overlapping windows
+// of one track - everything that is a function of a single frame (imgfeat_embed, the token embedding and SpatialBlocks[0],
+// PoseEstimation.py:78-84: spatial attention only mixes the joints of one frame) is computed once per FRAME, then gathered
+// into the window-major token order by the LayerNorm that follows it.
+int lifter(const Layout& L, const Weights& W, const float* pose2d, int B, int nfr, int fstride, float* pose3d, const Workspace& ws,
+           cudaStream_t st) {
     const pmce_dims_t& d = L.d;
     const int J = d.num_joint, C = d.embed_dim, T = d.seqlen, F = d.feat_dim;
     const int N = B * T * J;
+    const bool sliding = fstride != T;
     {   // imgfeat_embed for every frame (feat_s prepared by the caller)
         EpiOpt o; o.bias = W.f + L.ieb; o.out = ws.imgemb; o.ld_out = C;
-        RET(linear_tc(ws.feat_s, F, B * T, F, W, L.iew, F, C, o, st));
+        RET(linear_tc(ws.feat_s, F, nfr, F, W, L.iew, F, C, o, st));
     }
     LnParams s0n1{W.f + L.sp[0].n1w, W.f + L.sp[0].n1b, 1e-6f};
-    lifter_embed_kernel<<<cdiv(N, 8), 256, 0, st>>>(pose2d, ws.imgemb, W.f + L.jew, W.f + L.jeb, W.f + L.spos, N, J, C, s0n1, ws.x, nullptr, ws.xn_s);
+    lifter_embed_kernel<<<cdiv(nfr * J, 8), 256, 0, st>>>(pose2d, ws.imgemb, W.f + L.jew, W.f + L.jeb, W.f + L.spos, nfr * J, J, C, s0n1, ws.x, nullptr,
+                                                         ws.xn_s);
     CKL();
     LnParams ns{W.f + L.nsw, W.f + L.nsb, 1e-6f}, nt{W.f + L.ntw, W.f + L.ntb, 1e-6f};
     for (int i = 0; i < d.depth; ++i) {
-        RET(vit_block(d, W, L.sp[i], ws, B, false, st));
+        RET(vit_block(d, W, L.sp[i], ws, i == 0 ? nfr : B * T, false, st));
         LnParams tn1{W.f + L.tp[i].n1w, W.f + L.tp[i].n1b, 1e-6f};
-        RET(ln_rows(ws.x, N, C, &ns, i == 0 ? W.f + L.tpos : nullptr, J, T, ws.x, &tn1, ws.xn_s, st));
-        RET(vit_block(d, W, L.tp[i], ws, B, true, st));
+        if (i == 0 && sliding) {
+            // frame-major tokens [nfr*J, C] -> window-major [B*T*J, C] while normalising; the copy keeps the source apart from
+            // the destination (the qkv buffer is free until the next projection)
+            CK(cudaMemcpyAsync(ws.qkv, ws.x, (size_t)nfr * J * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            RET(ln_rows(ws.qkv, N, C, &ns, W.f + L.tpos, J, T, ws.x, &tn1, ws.xn_s, st, T * J, fstride * J));
+        } else {
+            RET(ln_rows(ws.x, N, C, &ns, i == 0 ? W.f + L.tpos : nullptr, J, T, ws.x, &tn1, ws.xn_s, st));
+        }
+        RET(vit_block(d, W, L.tp[i], ws, B * T, true, st));
         if (i + 1 < d.depth) {
             LnParams sn1{W.f + L.sp[i + 1].n1w, W.f + L.sp[i + 1].n1b, 1e-6f};
             RET(ln_rows(ws.x, N, C, &nt, nullptr, 1, 1, ws.x, &sn1, ws.xn_s, st));
@@ -357,13 +375,14 @@ int gru_step(const GruStep* s, int ndir, const Weights& W, int B, int H, cudaStr
     return 0;
 }
 
-int gru_mid(const Layout& L, const Weights& W, int B, float* g, const Workspace& ws, cudaStream_t st) {
+// nfr / fstride as in lifter(): the layer-0 input projection is a per-frame product, so overlapping windows share it.
+int gru_mid(const Layout& L, const Weights& W, int B, int nfr, int fstride, float* g, const Workspace& ws, cudaStream_t st) {
     const pmce_dims_t& d = L.d;
     const int T = d.seqlen, H = d.gru_hidden, F = d.feat_dim;
     const int mid = T / 2;
-    {   // layer-0 input projections, every frame, both directions: gi0[b][t][6H] (the step kernels stride over b with T*6H)
+    {   // layer-0 input projections, every frame, both directions: gi0[frame][6H] (the step kernels stride over windows with fstride*6H)
         EpiOpt o; o.bias = W.f + L.bih0; o.out = ws.gi0; o.ld_out = 6 * H;
-        RET(linear_tc(ws.feat_s, F, B * T, F, W, L.wih0, F, 6 * H, o, st));
+        RET(linear_tc(ws.feat_s, F, nfr, F, W, L.wih0, F, 6 * H, o, st));
     }
     for (int s = 0; s < T; ++s) {
         GruStep dd[2];
@@ -372,7 +391,7 @@ int gru_mid(const Layout& L, const Weights& W, int B, float* g, const Workspace&
             const int tp = dir == 0 ? t - 1 : t + 1;           // frame h_prev belongs to
             const size_t off = (size_t)t * B * 2 * H + dir * H, offp = (size_t)tp * B * 2 * H + dir * H;
             GruStep& x = dd[dir];
-            x.d.gi = ws.gi0 + (size_t)t * 6 * H + dir * 3 * H; x.d.ld_gi = T * 6 * H;
+            x.d.gi = ws.gi0 + (size_t)t * 6 * H + dir * 3 * H; x.d.ld_gi = fstride * 6 * H;
             x.d.hprev = s > 0 ? ws.y0 + offp : nullptr; x.d.ld_h = 2 * H;
             x.d.whh = W.f + L.whh0[dir]; x.d.bhh = W.f + L.bhh0[dir];
             x.d.hout = ws.y0 + off; x.d.ld_o = 2 * H;
@@ -686,14 +705,14 @@ int mesh_epilogue(const Layout& L, const Weights& W, const float* verts3, const 
     return mesh_upsample(L, W, verts3, B, mesh, ws, st);
 }
 
-int prepare_feat(const Layout& L, const float* img_feat, int B, const Workspace& ws, cudaStream_t st) {
-    const int F = L.d.feat_dim, T = L.d.seqlen;
-    return split_rows(img_feat, B * T, F, F, false, ws.feat_s, F, st);
+int prepare_feat(const Layout& L, const float* img_feat, int nfr, const Workspace& ws, cudaStream_t st) {
+    const int F = L.d.feat_dim;
+    return split_rows(img_feat, nfr, F, F, false, ws.feat_s, F, st);
 }
 
 // image-feature stream of the two-stream encoder: GRU -> y[T//2] -> all AdaLN gamma/beta (independent of the pose stream)
-int decoder_front(const Layout& L, const Weights& W, int B, const Workspace& ws, cudaStream_t st) {
-    RET(gru_mid(L, W, B, ws.g, ws, st));
+int decoder_front(const Layout& L, const Weights& W, int B, int nfr, int fstride, const Workspace& ws, cudaStream_t st) {
+    RET(gru_mid(L, W, B, nfr, fstride, ws.g, ws, st));
     RET(adaln_gammabeta(L, W, ws.g, B, ws.gb, ws.g_s, st));
     return mesh_residual(L, W, ws.g, B, ws, st);
 }
@@ -760,8 +779,8 @@ extern "C" int pmce_lifter_forward(const pmce_dims_t* dims, const void* weights,
     GET_LAYOUT();
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
-    RET(prepare_feat(L, img_feat, B, ws, st));
-    return lifter(L, W, pose2d, B, pose3d, ws, st);
+    RET(prepare_feat(L, img_feat, B * dims->seqlen, ws, st));
+    return lifter(L, W, pose2d, B, B * dims->seqlen, dims->seqlen, pose3d, ws, st);
 }
 
 extern "C" int pmce_gru_mid(const pmce_dims_t* dims, const void* weights, const float* img_feat, int B, float* g, void* workspace,
@@ -769,8 +788,8 @@ extern "C" int pmce_gru_mid(const pmce_dims_t* dims, const void* weights, const 
     GET_LAYOUT();
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
-    RET(prepare_feat(L, img_feat, B, ws, st));
-    return gru_mid(L, W, B, g, ws, st);
+    RET(prepare_feat(L, img_feat, B * dims->seqlen, ws, st));
+    return gru_mid(L, W, B, B * dims->seqlen, dims->seqlen, g, ws, st);
 }
 
 extern "C" int pmce_adaln_gammabeta(const pmce_dims_t* dims, const void* weights, const float* g, int B, float* gb, void* workspace,
@@ -865,28 +884,54 @@ extern "C" int pmce_decoder_forward(const pmce_dims_t* dims, const void* weights
     GET_LAYOUT();
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
-    RET(prepare_feat(L, img_feat, B, ws, st));
-    RET(decoder_front(L, W, B, ws, st));
+    RET(prepare_feat(L, img_feat, B * dims->seqlen, ws, st));
+    RET(decoder_front(L, W, B, B * dims->seqlen, dims->seqlen, ws, st));
     return decoder_back(L, W, joints, vj_relation, B, cam_pose, cam_mesh, verts0_out, ws, st);
 }
 
-extern "C" int pmce_forward(const pmce_dims_t* dims, const void* weights, const float* pose2d, const float* img_feat,
-                            const int32_t* vj_relation, int B, float* cam_mesh, float* cam_pose, float* pose3d, void* workspace,
-                            size_t workspace_bytes, void* stream) {
+// whole forward over B windows of a track of nfr frames (window b = frames [b*fstride, b*fstride+T)); fstride == T: a batch of clips
+static int forward_windows(const pmce_dims_t* dims, const void* weights, const float* pose2d, const float* img_feat, const int32_t* vj_relation,
+                           int B, int nfr, int fstride, float* cam_mesh, float* cam_pose, float* pose3d, void* workspace, size_t workspace_bytes,
+                           void* stream) {
     GET_LAYOUT();
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
-    RET(prepare_feat(L, img_feat, B, ws, st));
+    RET(prepare_feat(L, img_feat, nfr, ws, st));
     // fork: image-feature stream (GRU + AdaLN gamma/beta) on the side stream, pose stream (lifter) on the caller's stream
     Aux* aux = get_aux();
     if (!aux) { pmce_set_error("could not create the side stream/events: %s", cudaGetErrorString(cudaGetLastError())); return 10; }
     CK(cudaEventRecord(aux->fork, st));
     CK(cudaStreamWaitEvent(aux->side, aux->fork, 0));
-    RET(decoder_front(L, W, B, ws, aux->side));
+    RET(decoder_front(L, W, B, nfr, fstride, ws, aux->side));
     CK(cudaEventRecord(aux->join, aux->side));
-    RET(lifter(L, W, pose2d, B, pose3d, ws, st));
+    RET(lifter(L, W, pose2d, B, nfr, fstride, pose3d, ws, st));
     CK(cudaStreamWaitEvent(st, aux->join, 0));
     return decoder_back(L, W, ws.joints_m, vj_relation, B, cam_pose, cam_mesh, nullptr, ws, st, aux);
+}
+
+extern "C" int pmce_forward(const pmce_dims_t* dims, const void* weights, const float* pose2d, const float* img_feat,
+                            const int32_t* vj_relation, int B, float* cam_mesh, float* cam_pose, float* pose3d, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    if (!dims) { pmce_set_error("dims is NULL"); return 2; }
+    return forward_windows(dims, weights, pose2d, img_feat, vj_relation, B, B * dims->seqlen, dims->seqlen, cam_mesh, cam_pose, pose3d, workspace,
+                           workspace_bytes, stream);
+}
+
+extern "C" int pmce_sliding_windows(const pmce_dims_t* dims, int num_frames, int stride) {
+    if (!dims || stride < 1 || num_frames < dims->seqlen) return 0;
+    return (num_frames - dims->seqlen) / stride + 1;
+}
+
+extern "C" int pmce_forward_sliding(const pmce_dims_t* dims, const void* weights, const float* pose2d_seq, const float* img_feat_seq,
+                                    const int32_t* vj_relation, int num_frames, int stride, float* cam_mesh, float* cam_pose, float* pose3d,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    if (!dims) { pmce_set_error("dims is NULL"); return 2; }
+    const int nwin = pmce_sliding_windows(dims, num_frames, stride);
+    if (nwin < 1) { pmce_set_error("pmce_forward_sliding: need num_frames >= seqlen (%d) and stride >= 1 (got %d frames, stride %d)", dims->seqlen, num_frames, stride); return 2; }
+    if (stride > dims->seqlen) { pmce_set_error("pmce_forward_sliding: stride %d > seqlen %d leaves gaps; use pmce_forward on the clips", stride, dims->seqlen); return 2; }
+    const int nfr = (nwin - 1) * stride + dims->seqlen;       // frames the windows actually cover
+    return forward_windows(dims, weights, pose2d_seq, img_feat_seq, vj_relation, nwin, nfr, stride, cam_mesh, cam_pose, pose3d, workspace,
+                           workspace_bytes, stream);
 }
 
 extern "C" size_t pmce_io_bytes(const pmce_dims_t* dims, int B) {

@@ -62,13 +62,17 @@ __device__ __forceinline__ void ln_inreg(float4 (&v)[MAXV], int nv, int C, const
 template <int MAXV>   // C / 128 rounded up to a power of two (1, 2, 4, 8): the row lives in MAXV float4 per lane
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, int nrows, int C, LnParams a, int has_a, const float* __restrict__ pos,
-               int pos_div, int pos_mod, float* __restrict__ out1, LnParams bparm, float* __restrict__ out2, SplitOut out2s) {
+               int pos_div, int pos_mod, float* __restrict__ out1, LnParams bparm, float* __restrict__ out2, SplitOut out2s,
+               int map_rows, int map_stride) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= nrows) return;
     const int nv = C / 128;
     float4 v[MAXV];
-    const float* xr = x + (size_t)row * C;
+    // map_rows > 0: output row r (window-major) is read from source row (r / map_rows) * map_stride + r % map_rows
+    // (frame-major tokens of overlapping windows, pmce_forward_sliding)
+    const size_t srow = map_rows > 0 ? (size_t)(row / map_rows) * map_stride + row % map_rows : (size_t)row;
+    const float* xr = x + srow * C;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
         if (i < nv) v[i] = ld4(xr + (i * 32 + lane) * 4);

@@ -189,6 +189,30 @@ class Engine:
                                              _ptr(ws), ws.numel(), _stream()), "pmce_forward_host")
         return out
 
+    def forward_sliding(self, pose2d_seq, img_feat_seq, stride=1):
+        """Overlapping windows of one track (reference lib/_img_utils.py:58-92; the demo's per-window loop, main/run_demo.py:145):
+        pose2d_seq [N,J,2], img_feat_seq [N,2048] -> the forward's three outputs for the nwin = (N-T)//stride + 1 windows
+        [w*stride, w*stride+T). Per-frame work (imgfeat_embed, token embedding, SpatialBlocks[0], GRU layer-0 input
+        projection) runs once per frame instead of once per window (`pmce_forward_sliding`)."""
+        self._ready(need_vj=True)
+        d = self.dims
+        N = pose2d_seq.shape[0] if isinstance(pose2d_seq, torch.Tensor) and pose2d_seq.dim() == 3 else -1
+        pose2d_seq = _require_cuda_f32(pose2d_seq, "pose2d_seq", (N, d.num_joint, 2))
+        img_feat_seq = _require_cuda_f32(img_feat_seq, "img_feat_seq", (N, d.feat_dim))
+        nwin = self.lib.pmce_sliding_windows(self._dp, N, int(stride))
+        if nwin < 1 or stride > d.seqlen:
+            raise PmceError(f"forward_sliding: need at least seqlen={d.seqlen} frames and 1 <= stride <= seqlen (got {N} frames, stride {stride})")
+        dev = pose2d_seq.device
+        with torch.cuda.device(dev):
+            ws = self._workspace(nwin, dev)
+            mesh = torch.empty(nwin, d.num_vert, 3, device=dev)
+            cam_pose = torch.empty(nwin, d.num_joint, 3, device=dev)
+            pose3d = torch.empty(nwin, d.num_joint, 3, device=dev)
+            check(self.lib.pmce_forward_sliding(self._dp, _ptr(self.weights), _ptr(pose2d_seq), _ptr(img_feat_seq), _ptr(self.vj), N,
+                                                int(stride), _ptr(mesh), _ptr(cam_pose), _ptr(pose3d), _ptr(ws), ws.numel(), _stream()),
+                  "pmce_forward_sliding")
+        return mesh, cam_pose, pose3d
+
     # ---- pipelined host loop ---------------------------------------------------------------------------
     def _pipeline(self, B, dev):
         """Two slots of static device buffers + captured graphs + pinned host outputs, three streams (H2D / forward / D2H).

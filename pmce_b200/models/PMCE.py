@@ -40,6 +40,13 @@ class PMCE(EngineModule):
 
 
     @torch.no_grad()
+    def forward_sliding(self, pose2d_seq, img_feat_seq, stride=1):
+        """All stride-`stride` windows of one track in one call (what the reference's demo does window by window,
+        main/run_demo.py:145 over lib/_img_utils.py:58-92 chunks): pose2d_seq [N,J,2], img_feat_seq [N,2048] ->
+        (cam_mesh [nwin,6890,3], cam_pose [nwin,J,3], pose3d [nwin,J,3]); per-frame work is shared between windows."""
+        return self.engine().forward_sliding(pose2d_seq, img_feat_seq, stride)
+
+    @torch.no_grad()
     def forward_host_iter(self, batches):
         """Pipelined `forward_host` over an iterable of (pose2d, img_feat) pinned CPU batches: copies of neighbouring batches
         overlap the forward (Engine.forward_host_iter). Yields (cam_mesh, cam_pose, pose3d) pinned CPU tensors in order."""

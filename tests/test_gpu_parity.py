@@ -243,6 +243,27 @@ def test_clips_are_independent_at_full_batch(base):
         assert _maxabs(out[0][:1], base["g"]["cam_mesh"][idx[:1].numpy()]) < TOL
 
 
+@pytest.mark.parametrize("N,stride", [(40, 1), (40, 3), (16, 1), (79, 1), (64, 16)])
+def test_sliding_windows_match_materialised_windows(base, N, stride):
+    """(f)3 pmce_forward_sliding: the windows of one track computed with per-frame sharing equal the ordinary forward on the
+    materialised (unfolded) windows."""
+    m = base["m"]
+    T, J = 16, 17
+    gen = torch.Generator().manual_seed(N * 31 + stride)
+    pose_seq = torch.randn(N, J, 2, generator=gen)
+    feat_seq = torch.randn(N, 2048, generator=gen)
+    nwin = (N - T) // stride + 1
+    idx = (torch.arange(nwin)[:, None] * stride + torch.arange(T)[None, :])          # [nwin, T] frame indices
+    ref = m(pose_seq[idx].contiguous().cuda(), feat_seq[idx].contiguous().cuda())
+    out = m.forward_sliding(pose_seq.cuda(), feat_seq.cuda(), stride=stride)
+    for o, r in zip(out, ref):
+        assert o.shape == r.shape and o.shape[0] == nwin
+        assert (o - r).abs().max() <= 1e-6 * max(1.0, float(r.abs().max())), (N, stride)
+    from pmce_b200._lib import PmceError
+    with pytest.raises(PmceError, match="forward_sliding"):
+        m.forward_sliding(pose_seq[:8].cuda(), feat_seq[:8].cuda())
+
+
 def test_input_validation(base):
     from pmce_b200._lib import PmceError
     m = base["m"]
