@@ -136,3 +136,36 @@ def test_eval_epilogue_oracle_vs_reference_golden():
     pred_pose, j_err, s_err = po.eval_step(jreg, cam_mesh, gt_mesh, gt_pose)
     assert np.abs(pred_pose.numpy() - g["pred_pose"]).max() < 1e-3        # mm
     assert abs(float(j_err) - float(g["joint_mean_error"])) < 1e-3 and abs(float(s_err) - float(g["mesh_mean_error"])) < 1e-3
+
+
+def test_folded_cross_attention_identity():
+    """The algebra ca_fused.cuh relies on, checked on the CPU against the oracle: with few keys the q- and output-projections
+    fold into per-clip operands, scores_h = xn (s K_h Wq_h)^T + s K_h bq_h and proj(concat_h P_h V_h) = sum_h P_h (V_h Wp[:,h]^T) + bp."""
+    import torch
+    from pmce_b200 import synth
+    from oracle import pmce_oracle as po
+    g = np.load(os.path.join(GOLDEN, "pmce_J17_C256_T16_B2.npz"))
+    sd = synth.make_state_dict(0, init_vertices=g["init_vertices"], lifter_out_scale=300.0, num_joint=17, embed_dim=256, depth=3, seqlen=16)
+    p = "pose_mesh_coevo.coevoblock2.vertx_CA_FFN"
+    gen = torch.Generator().manual_seed(5)
+    B, Vd, J, H, D = 3, 431, 17, 2, 32
+    xq, xk, xv = torch.randn(B, Vd, 64, generator=gen), torch.randn(B, J, 64, generator=gen), torch.randn(B, J, 64, generator=gen)
+    gfeat = torch.randn(B, 2048, generator=gen)
+    with torch.no_grad():
+        qn = po.adaln(sd, p + ".normq", xq, gfeat)
+        K = po._lin(sd, p + ".attn.wk", po.adaln(sd, p + ".normk", xk, gfeat))
+        V = po._lin(sd, p + ".attn.wv", po.adaln(sd, p + ".normv", xv, gfeat))
+        ref = xq + po._lin(sd, p + ".attn.proj", po._mhsa(po._lin(sd, p + ".attn.wq", qn), K, V, H))
+        Wq, bq = sd[p + ".attn.wq.weight"], sd[p + ".attn.wq.bias"]
+        Wp, bp = sd[p + ".attn.proj.weight"], sd[p + ".attn.proj.bias"]
+        scale = D ** -0.5
+        out = torch.zeros(B, Vd, 64)
+        for h in range(H):
+            Kh, Vh = K[:, :, h * D:(h + 1) * D], V[:, :, h * D:(h + 1) * D]
+            KQ = scale * Kh @ Wq[h * D:(h + 1) * D, :]                       # [B, J, 64]
+            sb = scale * Kh @ bq[h * D:(h + 1) * D]                          # [B, J]
+            P = torch.softmax(qn @ KQ.transpose(1, 2) + sb[:, None, :], dim=-1)
+            VP = Vh @ Wp[:, h * D:(h + 1) * D].t()                           # [B, J, 64]
+            out = out + P @ VP
+        out = xq + out + bp
+    assert float((out - ref).abs().max()) < 2e-5
