@@ -296,7 +296,7 @@ attn_tile_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 tc::mbar_arrive(&empty_bar[grp]);                           // the producer may refill the buffer
             }
         }
-        if (issuer) tc::tma_store_wait<0>();
+        if (issuer) tc::tma_store_wait_read<0>();             // smem must outlive the reads; the grid boundary orders the writes
     }
     tc::tc_fence_before();
     __syncthreads();

@@ -137,6 +137,16 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         tc::mbar_init(bar_in, 1); tc::mbar_init(bar_mma, 1);
         tc::fence_barrier_init();
         tc::fence_proxy_async();
+        if ((int)blockIdx.x < a.B * a.qtiles) {        // the first item's loads fly while TMEM is allocated and the CTA assembles
+            const int b = blockIdx.x / a.qtiles, row0 = (blockIdx.x % a.qtiles) * 128;
+            tc::mbar_arrive_expect_tx(bar_in, CAF_TX);
+            tc::tma_load_3d(smem, &tm_x, bar_in, 0, row0, b);
+            tc::tma_load_3d(smem + 16384, &tm_x, bar_in, 32, row0, b);
+            tc::tma_load_2d(smem + CAF_OFF_W, &tm_kq_hi, bar_in, 0, b * CAF_NS);
+            tc::tma_load_2d(smem + CAF_OFF_W + 8192, &tm_kq_lo, bar_in, 0, b * CAF_NS);
+            tc::tma_load_2d(smem + CAF_OFF_W + 16384, &tm_vp_hi, bar_in, 0, b * 64);
+            tc::tma_load_2d(smem + CAF_OFF_W + 24576, &tm_vp_lo, bar_in, 0, b * 64);
+        }
     }
     if (warp == 0) tc::tmem_alloc(tmem_ptr_smem, 128);
     if (tid < 64) gbs[4 * 64 + tid] = a.bp[tid];
@@ -156,8 +166,8 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     uint32_t it = 0, mph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
-        if (tid == 0) {
-            if (it > 0) tc::tma_store_wait_read<0>();          // the previous item's stores have read both regions
+        if (tid == 0 && it > 0) {                              // (the first item's loads were issued in the prologue)
+            tc::tma_store_wait_read<0>();                      // the previous item's stores have read both regions
             tc::mbar_arrive_expect_tx(bar_in, CAF_TX);
             tc::tma_load_3d(smem, &tm_x, bar_in, 0, row0, b);
             tc::tma_load_3d(smem + 16384, &tm_x, bar_in, 32, row0, b);
@@ -276,7 +286,7 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             tc::tma_store_commit();
         }
     }
-    if (tid == 0) tc::tma_store_wait<0>();
+    if (tid == 0) tc::tma_store_wait_read<0>();          // smem must outlive the reads; the grid boundary orders the writes
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base, 128);

@@ -318,7 +318,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 }
             }
         }
-        if (lane == 0) tc::tma_store_wait<0>();              // all bulk stores of this warp complete before the CTA exits
+        if (lane == 0) tc::tma_store_wait_read<0>();         // the staging tile must outlive the reads; the grid boundary orders the writes
     }
     tc::tc_fence_before();
     __syncthreads();
