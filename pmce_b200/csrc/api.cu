@@ -304,8 +304,15 @@ int lifter(const Layout& L, const Weights& W, const float* pose2d, int B, int nf
         RET(linear_tc(ws.feat_s, F, nfr, F, W, L.iew, F, C, o, st));
     }
     LnParams s0n1{W.f + L.sp[0].n1w, W.f + L.sp[0].n1b, 1e-6f};
-    lifter_embed_kernel<<<cdiv(nfr * J, 8), 256, 0, st>>>(pose2d, ws.imgemb, W.f + L.jew, W.f + L.jeb, W.f + L.spos, nfr * J, J, C, s0n1, ws.x, nullptr,
-                                                         ws.xn_s);
+    const int nvc = C / 128;
+#define ROWK_LAUNCH(KERNEL, GRID, ...)                                            \
+    do {                                                                           \
+        if (nvc <= 1) KERNEL<1><<<GRID, 256, 0, st>>>(__VA_ARGS__);                \
+        else if (nvc <= 2) KERNEL<2><<<GRID, 256, 0, st>>>(__VA_ARGS__);           \
+        else if (nvc <= 4) KERNEL<4><<<GRID, 256, 0, st>>>(__VA_ARGS__);           \
+        else KERNEL<8><<<GRID, 256, 0, st>>>(__VA_ARGS__);                         \
+    } while (0)
+    ROWK_LAUNCH(lifter_embed_kernel, cdiv(nfr * J, 8), pose2d, ws.imgemb, W.f + L.jew, W.f + L.jeb, W.f + L.spos, nfr * J, J, C, s0n1, ws.x, nullptr, ws.xn_s);
     CKL();
     LnParams ns{W.f + L.nsw, W.f + L.nsb, 1e-6f}, nt{W.f + L.ntw, W.f + L.ntb, 1e-6f};
     for (int i = 0; i < d.depth; ++i) {
@@ -326,7 +333,8 @@ int lifter(const Layout& L, const Weights& W, const float* pose2d, int B, int nf
         }
     }
     LnParams nh{W.f + L.r0w, W.f + L.r0b, 1e-5f};
-    lifter_head_kernel<<<cdiv(N, 8), 256, 0, st>>>(ws.x, N, C, nt, nh, W.f + L.r1w, W.f + L.r1b, ws.r3);
+    ROWK_LAUNCH(lifter_head_kernel, cdiv(N, 8), ws.x, N, C, nt, nh, W.f + L.r1w, W.f + L.r1b, ws.r3);
+#undef ROWK_LAUNCH
     CKL();
     lifter_fuse_kernel<<<cdiv(B * J * 3, 256), 256, 0, st>>>(ws.r3, W.f + L.fusw, W.f + L.fusb, B, T, J, pose3d, ws.joints_m);
     CKL();

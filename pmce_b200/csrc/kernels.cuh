@@ -109,6 +109,7 @@ ln_rows_kernel(const float* __restrict__ x, int nrows, int C, LnParams a, int ha
 //   x0[b,t,j,:] = W_je p2d[b,t,j,:] + b_je + imgemb[b,t,:] + spos[j,:];  xn = LN(x0)
 // imgemb already contains b_if (GEMM bias).  One warp per token.
 // ------------------------------------------------------------------------------------------------------
+template <int MAXV>   // as ln_rows_kernel: C / 128 rounded up to a power of two
 __global__ void __launch_bounds__(256)
 lifter_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ imgemb, const float* __restrict__ wje,
                     const float* __restrict__ bje, const float* __restrict__ spos, int ntok, int J, int C, LnParams n1,
@@ -116,7 +117,6 @@ lifter_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ 
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= ntok) return;
-    constexpr int MAXV = 8;
     const int nv = C / 128;
     const int j = row % J, bt = row / J;
     const float p0 = pose2d[(size_t)row * 2 + 0], p1 = pose2d[(size_t)row * 2 + 1];
@@ -152,13 +152,13 @@ lifter_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ 
 // Lifter head (PoseEstimation.py:107-113): x = norm_t(y); r = W_r LN_1e-5(x) + b_r  (one warp per token),
 // then fusion over frames + /1000 (PMCE.py:18) in lifter_fuse_kernel.
 // ------------------------------------------------------------------------------------------------------
+template <int MAXV>
 __global__ void __launch_bounds__(256)
 lifter_head_kernel(const float* __restrict__ y, int ntok, int C, LnParams nt, LnParams nh, const float* __restrict__ wr,
                    const float* __restrict__ br, float* __restrict__ r3) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= ntok) return;
-    constexpr int MAXV = 8;
     const int nv = C / 128;
     float4 v[MAXV];
 #pragma unroll
