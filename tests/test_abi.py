@@ -82,3 +82,33 @@ def test_sizes_and_error_paths(lib):
     rc = lib.pmce_forward(C.byref(d), None, None, None, None, 1, None, None, None, None, 0, None)
     assert rc != 0 and b"NULL" in lib.pmce_last_error()
     assert lib.pmce_adaln_slots() == 24 and lib.smpl_blend_ld() >= 217 and lib.smpl_workspace_bytes(2) > 0
+
+
+def test_new_entry_points_validate_before_touching_the_gpu(lib):
+    """Host-side argument checks of the round-1 additions: window arithmetic of pmce_forward_sliding ((f)3), the fold workspace
+    of the fused cross-attention, and NULL / range errors of the attention-block, evaluation and SMPL entry points."""
+    from pmce_b200 import engine
+    d = engine.make_dims()                               # T = 16
+    dp = C.byref(d)
+    assert lib.pmce_sliding_windows(dp, 16, 1) == 1 and lib.pmce_sliding_windows(dp, 79, 1) == 64
+    assert lib.pmce_sliding_windows(dp, 40, 3) == 9 and lib.pmce_sliding_windows(dp, 64, 16) == 4
+    assert lib.pmce_sliding_windows(dp, 15, 1) == 0 and lib.pmce_sliding_windows(dp, 40, 0) == 0
+    rc = lib.pmce_forward_sliding(dp, None, None, None, None, 8, 1, None, None, None, None, 0, None)
+    assert rc != 0 and b"num_frames" in lib.pmce_last_error()
+    rc = lib.pmce_forward_sliding(dp, None, None, None, None, 64, 17, None, None, None, None, 0, None)
+    assert rc != 0 and b"stride" in lib.pmce_last_error()
+    assert lib.pmce_ca_fold_bytes(0) == 0
+    assert lib.pmce_ca_fold_bytes(2) == 2 * (2 * (64 + 64) * 64 * 2 + 64 * 4)
+    blob = C.c_void_p(256)                               # non-NULL, never dereferenced: every call below fails in validation
+    rc = lib.pmce_cross_attn_block(dp, blob, 4, 1, None, None, None, None, 1, None, None, 0, None)
+    assert rc != 0 and b"block must be 1..3" in lib.pmce_last_error()
+    rc = lib.pmce_cross_attn_block(dp, blob, 1, 0, None, None, None, None, 1, None, None, 0, None)
+    assert rc != 0 and b"joint-branch" in lib.pmce_last_error()          # coevoblock1's joint branch is not stored
+    rc = lib.pmce_self_attn_block(dp, blob, 3, 2, None, None, 1, None, None, 0, None)
+    assert rc != 0 and b"which" in lib.pmce_last_error()
+    rc = lib.pmce_self_attn_block(dp, blob, 3, 1, None, None, 1, None, None, 0, None)
+    assert rc != 0 and b"NULL" in lib.pmce_last_error()
+    rc = lib.pmce_eval_errors(None, None, None, 17, None, None, None, None, 14, 6890, 1, 1000.0, None, None, None, None)
+    assert rc != 0 and b"NULL" in lib.pmce_last_error()
+    rc = lib.smpl_lbs_forward_scaled(None, None, None, None, None, None, None, None, None, None, None, 1, 1.0, None, None, None, 0, None)
+    assert rc != 0 and b"NULL" in lib.pmce_last_error()
