@@ -261,51 +261,55 @@ class Engine:
         with torch.cuda.device(dev):
             cur = torch.cuda.current_stream()
             pipe, pending, i = None, [], 0
-            for hp, hf in batches:
-                for t, n in ((hp, "pose2d"), (hf, "img_feat")):
-                    if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
-                        raise PmceError(f"{n}: forward_host_iter expects contiguous float32 CPU tensors")
-                if pipe is None:
-                    B = hp.shape[0]
-                    pipe = self._pipeline(B, dev)
-                    for s in (pipe["s_in"], pipe["s_fwd"], pipe["s_out"]):
-                        s.wait_stream(cur)
-                elif hp.shape[0] != B:
-                    raise PmceError("forward_host_iter: every batch must have the same size (pad or run the tail through forward_host)")
-                sl = pipe["slots"][i & 1]
-                with torch.cuda.stream(pipe["s_in"]):
-                    if sl["used"]:
-                        pipe["s_in"].wait_event(sl["fwd"])       # the forward that read this slot's inputs has finished
-                    sl["p2d"].copy_(hp, non_blocking=True)
-                    sl["feat"].copy_(hf, non_blocking=True)
-                    sl["h2d"].record(pipe["s_in"])
-                with torch.cuda.stream(pipe["s_fwd"]):
-                    pipe["s_fwd"].wait_event(sl["h2d"])
-                    if sl["used"]:
-                        pipe["s_fwd"].wait_event(sl["d2h"])      # this slot's previous outputs have left the device
-                    sl["graph"].replay()
-                    sl["fwd"].record(pipe["s_fwd"])
-                with torch.cuda.stream(pipe["s_out"]):
-                    pipe["s_out"].wait_event(sl["fwd"])
-                    sl["host"][0].copy_(sl["mesh"], non_blocking=True)
-                    sl["host"][1].copy_(sl["cam_pose"], non_blocking=True)
-                    sl["host"][2].copy_(sl["pose3d"], non_blocking=True)
-                    sl["d2h"].record(pipe["s_out"])
-                sl["used"] = True
-                pending.append(sl)
-                i += 1
-                if len(pending) == 2:
+            try:
+                for hp, hf in batches:
+                    for t, n in ((hp, "pose2d"), (hf, "img_feat")):
+                        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                            raise PmceError(f"{n}: forward_host_iter expects contiguous float32 CPU tensors")
+                    if pipe is None:
+                        B = hp.shape[0]
+                        pipe = self._pipeline(B, dev)
+                        for s in (pipe["s_in"], pipe["s_fwd"], pipe["s_out"]):
+                            s.wait_stream(cur)
+                    elif hp.shape[0] != B:
+                        raise PmceError("forward_host_iter: every batch must have the same size (pad or run the tail through forward_host)")
+                    sl = pipe["slots"][i & 1]
+                    with torch.cuda.stream(pipe["s_in"]):
+                        if sl["used"]:
+                            pipe["s_in"].wait_event(sl["fwd"])       # the forward that read this slot's inputs has finished
+                        sl["p2d"].copy_(hp, non_blocking=True)
+                        sl["feat"].copy_(hf, non_blocking=True)
+                        sl["h2d"].record(pipe["s_in"])
+                    with torch.cuda.stream(pipe["s_fwd"]):
+                        pipe["s_fwd"].wait_event(sl["h2d"])
+                        if sl["used"]:
+                            pipe["s_fwd"].wait_event(sl["d2h"])      # this slot's previous outputs have left the device
+                        sl["graph"].replay()
+                        sl["fwd"].record(pipe["s_fwd"])
+                    with torch.cuda.stream(pipe["s_out"]):
+                        pipe["s_out"].wait_event(sl["fwd"])
+                        sl["host"][0].copy_(sl["mesh"], non_blocking=True)
+                        sl["host"][1].copy_(sl["cam_pose"], non_blocking=True)
+                        sl["host"][2].copy_(sl["pose3d"], non_blocking=True)
+                        sl["d2h"].record(pipe["s_out"])
+                    sl["used"] = True
+                    pending.append(sl)
+                    i += 1
+                    if len(pending) == 2:
+                        done = pending.pop(0)
+                        done["d2h"].synchronize()
+                        yield done["host"]
+                while pending:
                     done = pending.pop(0)
                     done["d2h"].synchronize()
                     yield done["host"]
-            for done in pending:
-                done["d2h"].synchronize()
-                yield done["host"]
-            if pipe is not None:
-                for sl in pipe["slots"]:
-                    sl["used"] = False
-                for s in (pipe["s_in"], pipe["s_fwd"], pipe["s_out"]):
-                    cur.wait_stream(s)
+            finally:
+                # also on early exit (the consumer stopped iterating, or a batch was rejected): drain and rejoin the caller's stream
+                if pipe is not None:
+                    for s in (pipe["s_in"], pipe["s_fwd"], pipe["s_out"]):
+                        cur.wait_stream(s)
+                    for sl in pipe["slots"]:
+                        sl["used"] = False
 
     # ---- sub-paths (each is a C-ABI entry point; used by the module API and by the parity tests) --------
     def lifter(self, pose2d, img_feat):
