@@ -16,6 +16,8 @@ It is a *functional* restatement (plain tensor math over a `state_dict`, no nn.M
                               reference lib/models/CoevoDecoder.py:199-208, lib/graph_utils.py:27-46,
                               lib/models/backbones/mesh.py:81-96
   * J-regressor matvec        reference lib/core/base.py:225
+  * evaluation epilogue       reference lib/core/base.py:223-227 + data/PW3D/dataset.py:269-282 (`compute_both_err`)
+  * `SMPL_Layer.forward`      reference smplpytorch/smplpytorch/pytorch/smpl_layer.py:65-158
 The GRU follows PyTorch's documented `nn.GRU` gate equations (rows of weight_ih/hh ordered r,z,n).
 
 Pinning: the reference ships NO golden vectors or tests. This oracle is pinned
