@@ -35,6 +35,7 @@ struct TcEpi {
     int mapped;             // out_f32 / resid are addressed as rmap(row) + cmap(col) instead of row*ld + col
     RowMap rmap, cmap;
     int dbg;                // profiling only (PMCE_TC_DBG): 1 = stage but do not issue TMA stores, 2 = no staging either
+    int pair_relaxed;       // CTA pairs: release the accumulator with a relaxed cluster-scope arrive (PMCE_TC_PAIR_RELAXED=1)
 };
 
 struct TcOutMaps {          // TMA descriptors of the epilogue tensors (box = 32 rows x 16 columns)
@@ -224,7 +225,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             tc::tc_fence_after();
             if (cg >= CH) {                                       // BN == 32: column groups 2 and 3 have no chunk
                 tc::tc_fence_before();
-                if (lane == 0) { if (NCTA == 1) tc::mbar_arrive(&tmem_empty_bar[acc]); else tc::mbar_arrive_cluster(te_bar[acc]); }
+                if (lane == 0) {
+                    if (NCTA == 1) tc::mbar_arrive(&tmem_empty_bar[acc]);
+                    else if (e.pair_relaxed) tc::mbar_arrive_cluster_relaxed(te_bar[acc]);
+                    else tc::mbar_arrive_cluster(te_bar[acc]);
+                }
                 continue;
             }
             const int c_last = cg + 4 * ((CH - 1 - cg) / 4);
@@ -247,7 +252,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (c == c_last) {                               // last read of this accumulator by this warp: release it early
                     tc::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { if (NCTA == 1) tc::mbar_arrive(&tmem_empty_bar[acc]); else tc::mbar_arrive_cluster(te_bar[acc]); }
+                    if (lane == 0) {
+                        if (NCTA == 1) tc::mbar_arrive(&tmem_empty_bar[acc]);
+                        else if (e.pair_relaxed) tc::mbar_arrive_cluster_relaxed(te_bar[acc]);
+                        else tc::mbar_arrive_cluster(te_bar[acc]);
+                    }
                 }
                 if (!live) continue;                             // warp-uniform
                 if (MODE == TC_GENERIC) {
@@ -459,6 +468,9 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
     static int dbg = -1;
     if (dbg < 0) { const char* s = getenv("PMCE_TC_DBG"); dbg = s ? atoi(s) : 0; }
     const_cast<TcEpi&>(e).dbg = dbg;
+    static int relaxed = -1;   // ncu shows the release.cluster arrive (a cluster-scope fence per accumulator release) at 15 % of the pair kernel's stall samples
+    if (relaxed < 0) { const char* s = getenv("PMCE_TC_PAIR_RELAXED"); relaxed = (s && atoi(s)) ? 1 : 0; }
+    const_cast<TcEpi&>(e).pair_relaxed = relaxed;
     TcOutMaps om;
     memset(&om, 0, sizeof(om));
     if (null_epi) return launch_linear_tc_mode<BN, TC_NULL>(ta, tw, om, M, N, K, e, st);

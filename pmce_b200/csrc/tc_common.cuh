@@ -132,6 +132,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// same without release semantics: for arrivals that publish no memory (e.g. "this TMEM accumulator has been read": the
+// tcgen05 fence orders the TMEM accesses, nothing in shared/global memory is handed over)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 // TMA load into THIS CTA's smem whose completion bytes are signalled on a barrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int crd0, int crd1) {
     asm volatile(
