@@ -176,7 +176,9 @@ def run_reference(args, rank, world):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD + " on host CPU"},
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU, "weights": "seeded random init (no checkpoints are published)",
+                   "note": "reference arm: the same B=64 batch through the reference algorithm on the host CPU (rank 0 only)"},
         "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
