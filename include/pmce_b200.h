@@ -9,7 +9,10 @@
  *   - the library allocates nothing persistent and owns no buffers: weights blob, workspace, inputs and
  *     outputs all belong to the caller (in the product: the PyTorch caching allocator).
  *   - all work is enqueued on `stream`, asynchronous w.r.t. the host, no device synchronisation, no
- *     allocation => CUDA-graph capturable; re-entrant across streams/devices.
+ *     allocation => CUDA-graph capturable; re-entrant across streams/devices: concurrent calls on
+ *     different streams (each with its own workspace) are independent.  The only process-lifetime
+ *     state is the layout cache, per-(kernel, device) function attributes, and one internal side
+ *     stream + four events per (device, caller stream), created on first use under a mutex.
  *
  * Each entry point cites the reference interface it replaces (paths relative to the reference root).
  */

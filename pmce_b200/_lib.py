@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpmce_b200.so")
+# PMCE_B200_PROFILING=1 selects the -DPMCE_PROFILING build (timing knobs that corrupt results; see build.py)
+LIB_PATH = os.path.join(_HERE, "libpmce_b200_prof.so" if os.environ.get("PMCE_B200_PROFILING", "0") == "1" else "libpmce_b200.so")
 
 
 class PmceDims(C.Structure):

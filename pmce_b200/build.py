@@ -10,7 +10,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libpmce_b200.so")
+# PMCE_B200_PROFILING=1: a separate library compiled with -DPMCE_PROFILING, the only build in which the result-corrupting
+# timing knobs (PMCE_TC_NULL / PMCE_TC_DBG / PMCE_ATTN_DEBUG, tools/gemm_sweep.py) are honoured
+PROFILING = os.environ.get("PMCE_B200_PROFILING", "0") == "1"
+LIB = os.path.join(HERE, "libpmce_b200_prof.so" if PROFILING else "libpmce_b200.so")
 SOURCES = ["api.cu", "layout.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -34,7 +37,7 @@ def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into libpmce_b200.so. Returns the library path."""
     if not force and not _stale():
         return LIB
-    cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
+    cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared", *(["-DPMCE_PROFILING"] if PROFILING else []),
            "-Xptxas", "-v" if verbose else "-warn-spills", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -9,6 +9,9 @@
 #include <stdio.h>
 #include <string.h>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "../../include/pmce_b200.h"
 #include "layout.h"
 #include "common.cuh"
@@ -372,11 +375,7 @@ int gru_step(const GruStep* s, int ndir, const Weights& W, int B, int H, cudaStr
         dirs[i].gi = x.d.gi; dirs[i].hprev = x.d.hprev; dirs[i].bhh = x.d.bhh; dirs[i].hout = x.d.hout; dirs[i].hs = x.d.hs;
         dirs[i].ld_gi = x.d.ld_gi; dirs[i].ld_h = x.d.ld_h; dirs[i].ld_o = x.d.ld_o; dirs[i].ld_s = x.d.ld_s;
     }
-    static bool configured = false;
-    if (!configured) {
-        CK(cudaFuncSetAttribute(gru_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRU_SMEM));
-        configured = true;
-    }
+    if (!pmce_configure_smem<gru_step_tc_kernel>(GRU_SMEM)) { pmce_set_error("gru_step: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); return 10; }
     dim3 grid(H / GRU_U, ndir, cdiv(B, 128));
     gru_step_tc_kernel<<<grid, 192, GRU_SMEM, st>>>(maps[0], maps[1], dirs[0], dirs[1], B, H);
     CKL();
@@ -443,23 +442,28 @@ int gru_mid(const Layout& L, const Weights& W, int B, int nfr, int fstride, floa
 }
 
 // Side stream + fork/join events so the two encoder streams (pose lifter / GRU image-feature aggregation) run
-// concurrently inside one pmce_forward call. One set per device, created on first use (before any graph capture: the
-// host driver always runs an eager warm-up first); the only process-lifetime state the library keeps besides the
-// layout cache.
+// concurrently inside one pmce_forward call. One set per (device, caller stream), created on first use (before any graph
+// capture: the host driver always runs an eager warm-up first) under a mutex: calls on DIFFERENT streams of one device -
+// from one thread or several - never share a side stream or an event, so they are independent as the header promises
+// (each call also needs its own workspace: the caller owns that). Two concurrent calls on the SAME stream have no defined
+// order among themselves in CUDA either. The sets are the only process-lifetime state besides the layout cache; they are
+// never freed (a destroyed-and-recreated stream handle simply reuses its entry).
 struct Aux {
     cudaStream_t side = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr;
 };
-Aux* get_aux() {
-    static Aux aux[64];
+Aux* get_aux(cudaStream_t caller) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, Aux> table;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    Aux& a = aux[dev];
-    if (!a.side) {
-        if (cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&a.fork2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    Aux& a = table[std::make_pair(dev, caller)];           // std::map nodes are address-stable
+    if (!a.join2) {
+        if (!a.side && cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (!a.fork && cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (!a.join && cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (!a.fork2 && cudaEventCreateWithFlags(&a.fork2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&a.join2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
     return &a;
@@ -502,7 +506,7 @@ struct AttnScratch {
 
 bool ca_fused_enabled() {
     static int on = -1;      // PMCE_CA_FUSED=0: keep the unfused launch sequence (A/B profiling, tests)
-    if (on < 0) { const char* s = getenv("PMCE_CA_FUSED"); on = (s && atoi(s) == 0) ? 0 : 1; }
+    if (on < 0) on = pmce_env_int("PMCE_CA_FUSED", 1) ? 1 : 0;
     return on == 1;
 }
 
@@ -543,11 +547,7 @@ JointFoldArgs ca_fold_args(const Weights& W, const CoevoW* cw, const CaW& w, con
 }
 
 int ca_fold_launch(const JointFoldArgs3& args, int nblk, int B, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        CK(cudaFuncSetAttribute(ca_joint_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JKV_SMEM));
-        configured = true;
-    }
+    if (!pmce_configure_smem<ca_joint_fold_kernel>(JKV_SMEM)) { pmce_set_error("ca_fold: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); return 10; }
     ca_joint_fold_kernel<<<dim3(B, nblk), JKV_THREADS, JKV_SMEM, st>>>(args);
     CKL();
     return 0;
@@ -906,7 +906,7 @@ static int forward_windows(const pmce_dims_t* dims, const void* weights, const f
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
     RET(prepare_feat(L, img_feat, nfr, ws, st));
     // fork: image-feature stream (GRU + AdaLN gamma/beta) on the side stream, pose stream (lifter) on the caller's stream
-    Aux* aux = get_aux();
+    Aux* aux = get_aux(st);
     if (!aux) { pmce_set_error("could not create the side stream/events: %s", cudaGetErrorString(cudaGetLastError())); return 10; }
     CK(cudaEventRecord(aux->fork, st));
     CK(cudaStreamWaitEvent(aux->side, aux->fork, 0));

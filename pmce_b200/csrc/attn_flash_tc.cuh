@@ -247,18 +247,9 @@ attn_flash_tc_kernel(const float* __restrict__ Q, AttnAddr aq, const float* __re
 // nseq sequences, H heads of 32; queries N1 (addr aq), keys/values N2 (addr akv); split-bf16 output (addr ao).
 static inline int launch_attn_flash_tc(const float* Q, AttnAddr aq, const float* K, const float* V, AttnAddr akv, SplitOut Os, AttnAddr ao, int nseq,
                                        int H, int N1, int N2, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(attn_flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM) != cudaSuccess) return 2;
-        configured = true;
-    }
+    if (!pmce_configure_smem<attn_flash_tc_kernel>(AF_SMEM)) return 2;
     const long long work = (long long)nseq * H * ((N1 + 127) / 128);
-    int sms = 148;
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = tc_num_sms();
     const long long want = (work + 1) / 2;
     const int grid = (int)(want < sms ? (want < 1 ? 1 : want) : sms);
     attn_flash_tc_kernel<<<grid, AF_THREADS, AF_SMEM, st>>>(Q, aq, K, V, akv, Os, ao, N1, N2, nseq, H, 1.0f / sqrtf(32.0f));

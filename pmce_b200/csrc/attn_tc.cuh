@@ -307,11 +307,7 @@ attn_tile_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 // qkv projection (token rows ordered (b, t, j)); spatial: sequence = (b,t), tokens j; temporal: sequence = (b,j), tokens t.
 static inline int launch_attn_tile_tc(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, int ntok, int C, int J, int T, bool temporal, SplitOut Os,
                                       int nseq, int H, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(attn_tile_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return 2;
-        configured = true;
-    }
+    if (!pmce_configure_smem<attn_tile_tc_kernel>(AT_SMEM)) return 2;
     const int L = temporal ? T : J;
     const int G = 128 / L;
     CUtensorMap th, tl, toh, tol;      // Os: split-bf16 output [ntok, C], rows in the same (b, t, j) order as qkv
@@ -328,16 +324,11 @@ static inline int launch_attn_tile_tc(const __nv_bfloat16* qkv_hi, const __nv_bf
     }
     const int ntiles = (nseq + G - 1) / G;
     const long long work = (long long)ntiles * H;
-    int sms = 148;
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = tc_num_sms();
     const long long want = (work + 1) / 2;                 // two items in flight per CTA
     const int grid = (int)(want < sms ? (want < 1 ? 1 : want) : sms);
     static int dbg = -1;   // PMCE_ATTN_DEBUG: profiling knobs (wrong results): 1 no loads, 2 no math, 4 no softmax, 8 no stores
-    if (dbg < 0) { const char* e = getenv("PMCE_ATTN_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (dbg < 0) dbg = pmce_profiling_knob("PMCE_ATTN_DEBUG");
     attn_tile_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(th, tl, toh, tol, temporal ? 1 : 0, C, J, T, L, G, nseq, H, 1.0f / sqrtf(64.0f), dbg);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }

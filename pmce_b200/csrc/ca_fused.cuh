@@ -308,11 +308,7 @@ static inline int make_tmap_3d(CUtensorMap* m, const void* ptr, CUtensorMapDataT
 
 template <int NK>
 static inline int launch_ca_vertex_fused_t(const CUtensorMap* maps, const CaFusedArgs& a, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(ca_vertex_fused_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAF_SMEM) != cudaSuccess) return 2;
-        configured = true;
-    }
+    if (!pmce_configure_smem<ca_vertex_fused_kernel<NK>>(CAF_SMEM)) return 2;
     const int ntiles = a.B * a.qtiles;
     const int cap = 3 * tc_num_sms();
     const int grid = ntiles < cap ? ntiles : cap;

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include "tc_common.cuh"
 #include "common.cuh"
+#include "host_once.h"
 
 enum TcMode { TC_F32 = 0, TC_F32_RESID = 1, TC_SPLIT_GELU = 2, TC_GENERIC = 3, TC_NULL = 4, TC_SPLIT = 5 };
 
@@ -401,23 +402,13 @@ struct TcOperand {   // split bf16 matrix [rows, cols], row stride ld (elements)
     const __nv_bfloat16* hi; const __nv_bfloat16* lo; int rows, cols, ld;
 };
 
-static inline int tc_num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
-
 // 256-wide tiles run on CTA pairs (cta_group::2) when the problem is large in N and K: measured with tools/gemm_sweep.py,
 // M=17408: N=1536,K=512 69.8 -> 63.4 us, N=1024,K=512 (GELU) 55.5 -> 52.3, N=512,K=1024 48.5 -> 45.9, N=512,K=512 unchanged;
 // K=256 shapes lose 1-2 us (three 64 KB stages hold fewer k-blocks than the tile needs to hide the fill).
 // PMCE_TC_PAIR=0 disables, =2 forces pairs for every 256-wide tile (tests).
 static inline bool tc_pair_enabled(int M, int N, int K) {
     static int mode = -1;
-    if (mode < 0) { const char* s = getenv("PMCE_TC_PAIR"); mode = s ? atoi(s) : 1; }
+    if (mode < 0) mode = pmce_env_int("PMCE_TC_PAIR", 1);
     if (mode == 0 || M <= TC_BM) return false;
     return mode >= 2 || (N >= 512 && K >= 512);
 }
@@ -427,11 +418,7 @@ static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap
                                         cudaStream_t st) {
     if (BN == 256 && tc_pair_enabled(M, N, K)) {
         constexpr int BNP = BN == 256 ? 256 : 256;
-        static bool configured2 = false;
-        if (!configured2) {
-            if (cudaFuncSetAttribute(linear_tc_kernel<BNP, MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BNP, 2>::SMEM_BYTES) != cudaSuccess) return 2;
-            configured2 = true;
-        }
+        if (!pmce_configure_smem<linear_tc_kernel<BNP, MODE, 2>>(TcCfg<BNP, 2>::SMEM_BYTES)) return 2;
         const long long tiles = (long long)((N + 255) / 256) * ((M + 2 * TC_BM - 1) / (2 * TC_BM));
         const int pairs = (int)(tiles < tc_num_sms() / 2 ? tiles : tc_num_sms() / 2);
         cudaLaunchConfig_t cfg;
@@ -443,11 +430,7 @@ static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap
         cfg.attrs = attr; cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 2>, ta[0], ta[1], tw[0], tw[1], om, M, N, K, e) == cudaSuccess ? 0 : 3;
     }
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(linear_tc_kernel<BN, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES) != cudaSuccess) return 2;
-        configured = true;
-    }
+    if (!pmce_configure_smem<linear_tc_kernel<BN, MODE, 1>>(TcCfg<BN>::SMEM_BYTES)) return 2;
     const long long tiles = (long long)((N + BN - 1) / BN) * ((M + TC_BM - 1) / TC_BM);
     const int grid = (int)(tiles < tc_num_sms() ? tiles : tc_num_sms());
     linear_tc_kernel<BN, MODE, 1><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta[0], ta[1], tw[0], tw[1], om, M, N, K, e);
@@ -464,12 +447,12 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
     const int M = A.rows, N = W.rows, K = A.cols;
     auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     static int null_epi = -1;   // PMCE_TC_NULL=1: skip the epilogue entirely (mainloop-only timing, tools/gemm_sweep.py)
-    if (null_epi < 0) { const char* s = getenv("PMCE_TC_NULL"); null_epi = (s && atoi(s)) ? 1 : 0; }
+    if (null_epi < 0) null_epi = pmce_profiling_knob("PMCE_TC_NULL") ? 1 : 0;
     static int dbg = -1;
-    if (dbg < 0) { const char* s = getenv("PMCE_TC_DBG"); dbg = s ? atoi(s) : 0; }
+    if (dbg < 0) dbg = pmce_profiling_knob("PMCE_TC_DBG");
     const_cast<TcEpi&>(e).dbg = dbg;
     static int relaxed = -1;   // ncu shows the release.cluster arrive (a cluster-scope fence per accumulator release) at 15 % of the pair kernel's stall samples
-    if (relaxed < 0) { const char* s = getenv("PMCE_TC_PAIR_RELAXED"); relaxed = (s && atoi(s)) ? 1 : 0; }
+    if (relaxed < 0) relaxed = pmce_env_int("PMCE_TC_PAIR_RELAXED", 0) ? 1 : 0;
     const_cast<TcEpi&>(e).pair_relaxed = relaxed;
     TcOutMaps om;
     memset(&om, 0, sizeof(om));
@@ -501,7 +484,7 @@ static inline int launch_linear_tc(const TcOperand& A, const TcOperand& W, const
     const long long tiles_m = (A.rows + TC_BM - 1) / TC_BM;
     const int sms = tc_num_sms();
     static int forced = -1;   // PMCE_TC_BN=<32|64|128|256>: tile-sweep knob for profiling (tools/gemm_sweep.py)
-    if (forced < 0) { const char* s = getenv("PMCE_TC_BN"); forced = s ? atoi(s) : 0; }
+    if (forced < 0) forced = pmce_env_int("PMCE_TC_BN", 0);
     if (forced == 256) return launch_linear_tc_bn<256>(A, W, e, st);
     if (forced == 128) return launch_linear_tc_bn<128>(A, W, e, st);
     if (forced == 64) return launch_linear_tc_bn<64>(A, W, e, st);

@@ -1,0 +1,60 @@
+// Host-side helpers shared by the launchers: per-device one-time kernel configuration, per-device SM count, and the
+// environment knobs. Nothing here is cached per PROCESS that CUDA keeps per DEVICE (cudaFuncSetAttribute is per device:
+// an engine on a second GPU of the same process must configure its kernels again).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <atomic>
+
+constexpr int PMCE_MAX_DEVICES = 64;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize for `Kernel` on the CURRENT device, once per (kernel, device). Thread-safe:
+// a racing second caller at worst sets the attribute twice.
+template <auto Kernel>
+static inline bool pmce_configure_smem(int bytes) {
+    static std::atomic<unsigned long long> done{0};            // bit d = configured on device d
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (dev < 0 || dev >= PMCE_MAX_DEVICES) return cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+    const unsigned long long bit = 1ull << dev;
+    if (done.load(std::memory_order_acquire) & bit) return true;
+    if (cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+    done.fetch_or(bit, std::memory_order_release);
+    return true;
+}
+
+// SM count of the current device (cached per device)
+static inline int tc_num_sms() {
+    static std::atomic<int> n[PMCE_MAX_DEVICES];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool cacheable = dev >= 0 && dev < PMCE_MAX_DEVICES;
+    int v = cacheable ? n[dev].load(std::memory_order_relaxed) : 0;
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        if (cacheable) n[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// Tuning knob that does NOT change results (tile width, pair on/off, fused on/off): read once per process.
+static inline int pmce_env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
+// Profiling knob that makes the kernels produce WRONG results on purpose (skip loads / math / stores to time the rest).
+// Honoured only in a -DPMCE_PROFILING build (PMCE_B200_PROFILING=1 python -m pmce_b200.build -> libpmce_b200_prof.so); the
+// production library ignores it, loudly, so a leaked variable cannot silently corrupt a forward.
+static inline int pmce_profiling_knob(const char* name) {
+    const char* s = getenv(name);
+    if (!s || !atoi(s)) return 0;
+#ifdef PMCE_PROFILING
+    fprintf(stderr, "[pmce_b200] PROFILING BUILD: %s=%s is active - results are wrong by design\n", name, s);
+    return atoi(s);
+#else
+    fprintf(stderr, "[pmce_b200] %s=%s ignored: profiling knobs need the -DPMCE_PROFILING build (PMCE_B200_PROFILING=1)\n", name, s);
+    return 0;
+#endif
+}

@@ -56,6 +56,7 @@ class Engine:
         self.vj = None
         self._ws = None
         self._graphs = {}
+        self._pipe = {}
         if use_graph is None:
             use_graph = os.environ.get("PMCE_B200_GRAPH", "1") != "0"
         self.use_graph = use_graph
@@ -83,7 +84,9 @@ class Engine:
         self.weights = blob
         if vj_relation is not None:
             self.vj = torch.as_tensor(np.asarray(vj_relation).astype(np.int32), device=device)
+        # captured graphs (single-shot and pipelined) have the old blob / vj pointers baked in
         self._graphs.clear()
+        self._pipe.clear()
         return self
 
     def _workspace(self, B, device):
@@ -93,6 +96,7 @@ class Engine:
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
             self._graphs.clear()
+            self._pipe.clear()
         return self._ws
 
     def _ready(self, need_vj=False):
@@ -155,15 +159,24 @@ class Engine:
         self._graphs[B] = st
         return st
 
+    def _require_host(self, pose2d_cpu, img_feat_cpu, what):
+        """Host-buffer inputs: contiguous float32 CPU tensors of exactly (B,T,J,2) / (B,T,feat_dim) — `Tensor.copy_` into the
+        static graph buffers would silently broadcast a wrong-but-broadcastable shape."""
+        d = self.dims
+        B = pose2d_cpu.shape[0] if isinstance(pose2d_cpu, torch.Tensor) and pose2d_cpu.dim() == 4 else -1
+        for t, n, shape in ((pose2d_cpu, "pose2d", (B, d.seqlen, d.num_joint, 2)), (img_feat_cpu, "img_feat", (B, d.seqlen, d.feat_dim))):
+            if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise PmceError(f"{n}: {what} expects contiguous float32 CPU tensors")
+            if B < 1 or tuple(t.shape) != shape:
+                raise PmceError(f"{n}: {what} expected shape {shape}, got {tuple(t.shape)}")
+
     def forward_host(self, pose2d_cpu, img_feat_cpu, out=None):
         """The C-ABI host-buffer call (`pmce_forward_host`): pinned/pageable CPU tensors in, CPU tensors out."""
         self._ready(need_vj=True)
         d = self.dims
         B = pose2d_cpu.shape[0]
         dev = self.weights.device
-        for t, n in ((pose2d_cpu, "pose2d"), (img_feat_cpu, "img_feat")):
-            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
-                raise PmceError(f"{n}: forward_host expects contiguous float32 CPU tensors")
+        self._require_host(pose2d_cpu, img_feat_cpu, "forward_host")
         if out is None:
             out = (torch.empty(B, d.num_vert, 3).pin_memory(), torch.empty(B, d.num_joint, 3).pin_memory(),
                    torch.empty(B, d.num_joint, 3).pin_memory())
@@ -217,18 +230,17 @@ class Engine:
     def _pipeline(self, B, dev):
         """Two slots of static device buffers + captured graphs + pinned host outputs, three streams (H2D / forward / D2H).
         Both graphs replay on the one forward stream, so they share the workspace."""
-        pipe = getattr(self, "_pipe", {}).get(B)
-        if pipe is not None and pipe["ws"] is self._workspace(B, dev):
+        ws = self._workspace(B, dev)
+        baked = (ws.data_ptr(), self.weights.data_ptr(), self.vj.data_ptr())       # pointers the captured graphs hold
+        pipe = self._pipe.get(B)
+        if pipe is not None and pipe["baked"] == baked:
             return pipe
         d = self.dims
-        ws = self._workspace(B, dev)
         slots = []
         for _ in range(2):
             sl = dict(p2d=torch.zeros(B, d.seqlen, d.num_joint, 2, device=dev), feat=torch.zeros(B, d.seqlen, d.feat_dim, device=dev),
                       mesh=torch.empty(B, d.num_vert, 3, device=dev), cam_pose=torch.empty(B, d.num_joint, 3, device=dev),
                       pose3d=torch.empty(B, d.num_joint, 3, device=dev),
-                      host=(torch.empty(B, d.num_vert, 3).pin_memory(), torch.empty(B, d.num_joint, 3).pin_memory(),
-                            torch.empty(B, d.num_joint, 3).pin_memory()),
                       h2d=torch.cuda.Event(), fwd=torch.cuda.Event(), d2h=torch.cuda.Event(), used=False)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
@@ -241,10 +253,12 @@ class Engine:
                 self._forward_eager(sl["p2d"], sl["feat"], sl["mesh"], sl["cam_pose"], sl["pose3d"])
             sl["graph"] = graph
             slots.append(sl)
-        pipe = dict(ws=ws, slots=slots, s_in=torch.cuda.Stream(device=dev), s_fwd=torch.cuda.Stream(device=dev),
+        # THREE pinned host output sets for two device slots: result i (host set i % 3) is not written again before batch i+3
+        # is submitted, i.e. before the consumer asks for result i+2
+        hosts = [(torch.empty(B, d.num_vert, 3).pin_memory(), torch.empty(B, d.num_joint, 3).pin_memory(),
+                  torch.empty(B, d.num_joint, 3).pin_memory()) for _ in range(3)]
+        pipe = dict(ws=ws, baked=baked, slots=slots, hosts=hosts, s_in=torch.cuda.Stream(device=dev), s_fwd=torch.cuda.Stream(device=dev),
                     s_out=torch.cuda.Stream(device=dev))
-        if not hasattr(self, "_pipe"):
-            self._pipe = {}
         self._pipe[B] = pipe
         return pipe
 
@@ -254,8 +268,10 @@ class Engine:
         `batches` yields (pose2d [B,T,J,2], img_feat [B,T,2048]) contiguous float32 CPU tensors (pinned for asynchronous
         copies) of one batch size; the generator yields (cam_mesh, cam_pose, pose3d) pinned CPU tensors in the same order.
         The H2D copy of batch i+1 and the D2H copy of batch i-1 run on the copy engines while batch i is in the forward
-        (three streams, two buffer slots, one captured graph per slot). A yielded triple is overwritten two batches later:
-        consume (or copy) it before asking for the batch after next."""
+        (three streams, two device buffer slots with one captured graph each, three pinned host output sets). A yielded
+        triple stays valid while the NEXT result is requested and consumed; it is overwritten once the result after next is
+        requested, so consume (or copy) it before asking for the batch after next. `list(forward_host_iter(...))` therefore
+        aliases buffers: copy each triple as it arrives."""
         self._ready(need_vj=True)
         dev = self.weights.device
         with torch.cuda.device(dev):
@@ -263,9 +279,7 @@ class Engine:
             pipe, pending, i = None, [], 0
             try:
                 for hp, hf in batches:
-                    for t, n in ((hp, "pose2d"), (hf, "img_feat")):
-                        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
-                            raise PmceError(f"{n}: forward_host_iter expects contiguous float32 CPU tensors")
+                    self._require_host(hp, hf, "forward_host_iter")
                     if pipe is None:
                         B = hp.shape[0]
                         pipe = self._pipeline(B, dev)
@@ -274,6 +288,7 @@ class Engine:
                     elif hp.shape[0] != B:
                         raise PmceError("forward_host_iter: every batch must have the same size (pad or run the tail through forward_host)")
                     sl = pipe["slots"][i & 1]
+                    host = pipe["hosts"][i % 3]
                     with torch.cuda.stream(pipe["s_in"]):
                         if sl["used"]:
                             pipe["s_in"].wait_event(sl["fwd"])       # the forward that read this slot's inputs has finished
@@ -288,21 +303,21 @@ class Engine:
                         sl["fwd"].record(pipe["s_fwd"])
                     with torch.cuda.stream(pipe["s_out"]):
                         pipe["s_out"].wait_event(sl["fwd"])
-                        sl["host"][0].copy_(sl["mesh"], non_blocking=True)
-                        sl["host"][1].copy_(sl["cam_pose"], non_blocking=True)
-                        sl["host"][2].copy_(sl["pose3d"], non_blocking=True)
+                        host[0].copy_(sl["mesh"], non_blocking=True)
+                        host[1].copy_(sl["cam_pose"], non_blocking=True)
+                        host[2].copy_(sl["pose3d"], non_blocking=True)
                         sl["d2h"].record(pipe["s_out"])
                     sl["used"] = True
-                    pending.append(sl)
+                    pending.append((sl["d2h"], host))     # the slot's event is re-recorded only after this entry was popped
                     i += 1
                     if len(pending) == 2:
-                        done = pending.pop(0)
-                        done["d2h"].synchronize()
-                        yield done["host"]
+                        ev, res = pending.pop(0)
+                        ev.synchronize()
+                        yield res
                 while pending:
-                    done = pending.pop(0)
-                    done["d2h"].synchronize()
-                    yield done["host"]
+                    ev, res = pending.pop(0)
+                    ev.synchronize()
+                    yield res
             finally:
                 # also on early exit (the consumer stopped iterating, or a batch was rejected): drain and rejoin the caller's stream
                 if pipe is not None:

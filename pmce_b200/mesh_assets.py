@@ -23,7 +23,7 @@ def load_downsampling(path):
 def _spmm_f32(d, x):
     d = d.tocoo()
     idx = torch.from_numpy(np.stack([d.row, d.col]).astype(np.int64))
-    m = torch.sparse_coo_tensor(idx, torch.from_numpy(d.data.astype(np.float32)), d.shape, check_invariants=False)
+    m = torch.sparse_coo_tensor(idx, torch.from_numpy(d.data.astype(np.float32)), d.shape, check_invariants=True)
     return torch.matmul(m, x)
 
 
@@ -31,7 +31,10 @@ def template_geometry(mean_vertices, D_list, J_regressor):
     """-> (init_vertices fp32 [431,3], vj_relation int64 [431])."""
     v = torch.as_tensor(np.asarray(mean_vertices), dtype=torch.float32)
     ds = v
-    for d in D_list:
+    # the reference applies exactly two levels, n1=0 -> n2=2 (CoevoDecoder.py:200-202: 6890 -> 1723 -> 431), whatever the npz holds
+    if len(D_list) < 2:
+        raise ValueError(f"mesh_downsampling.npz holds {len(D_list)} down-sampling levels; the decoder needs 2 (6890 -> 1723 -> 431)")
+    for d in D_list[:2]:
         ds = _spmm_f32(d, ds)
     joints_t = torch.matmul(torch.as_tensor(np.asarray(J_regressor), dtype=torch.float32), v).numpy()
     dsn = ds.numpy()

@@ -264,9 +264,78 @@ def test_sliding_windows_match_materialised_windows(base, N, stride):
         m.forward_sliding(pose_seq[:8].cuda(), feat_seq[:8].cuda())
 
 
+def test_repack_rebuilds_captured_pipelines(base):
+    """load_state_dict / refresh re-packs into a NEW blob; the single-shot graph and the two pipelined
+    graphs captured before must not be replayed against the old (freed) blob."""
+    g, sd, p2d, feat, (J, C, depth, T, B) = _case(os.path.join(GOLDEN, "pmce_J17_C256_T16_B2.npz"))
+    m = _model(sd, J, C, depth, T, graph=True)
+    hp, hf = p2d.pin_memory(), feat.pin_memory()
+    first = [tuple(t.clone() for t in o) for o in m.forward_host_iter(iter([(hp, hf)] * 3))]
+    sd2 = synth.make_state_dict(int(g["weight_seed"]) + 1, init_vertices=g["init_vertices"], lifter_out_scale=float(g["lifter_out_scale"]),
+                                num_joint=J, embed_dim=C, depth=depth, seqlen=T)
+    m.load_state_dict(sd2, strict=True)
+    junk = torch.full((m.engine().weight_bytes // 4,), float("nan"), device="cuda")      # recycle the freed blob's memory
+    ref = [t.cpu() for t in m(p2d.cuda(), feat.cuda())]
+    assert (ref[0] - first[0][0]).abs().max() > 1e-3                                      # the new weights really differ
+    for out in m.forward_host_iter(iter([(hp, hf)] * 3)):
+        for o, r in zip(out, ref):
+            assert torch.equal(o, r)
+    for o, r in zip(m.forward_host(hp, hf), ref):
+        assert torch.equal(o, r)
+    del junk
+
+
+def test_host_iter_results_stay_valid_for_one_more_request(base):
+    """a yielded triple may be kept while the NEXT result is requested (three pinned host sets)."""
+    m = base["m"]
+    eng = m.engine()
+    eng.use_graph = True
+    p2d, feat = base["p2d"], base["feat"]
+    batches = [(p2d.pin_memory(), (feat * (1.0 + 0.25 * i)).contiguous().pin_memory()) for i in range(6)]
+    refs = [tuple(t.cpu() for t in m(a.cuda(), b.cuda())) for a, b in batches]
+    prev = None
+    for i, out in enumerate(m.forward_host_iter(iter(batches))):
+        torch.cuda.synchronize()                      # every copy queued so far has landed: a clobbered buffer would show
+        if prev is not None:
+            for o, r in zip(prev, refs[i - 1]):
+                assert torch.equal(o, r), i
+        prev = out
+    eng.use_graph = False
+
+
+def test_concurrent_streams_are_independent(base):
+    """The C ABI is re-entrant across streams (include/pmce_b200.h): two eager forwards enqueued back to back on two
+    streams, each with its own engine workspace, interleave on the device and still return what a lone call returns."""
+    g, sd, p2d, feat, (J, C, depth, T, B) = _case(os.path.join(GOLDEN, "pmce_J17_C256_T16_B2.npz"))
+    ma, mb = _model(sd, J, C, depth, T, graph=False), _model(sd, J, C, depth, T, graph=False)
+    xa = (p2d.cuda(), feat.cuda())
+    xb = (p2d.flip(0).contiguous().cuda(), (feat.flip(0) * 1.5).contiguous().cuda())
+    ra, rb = [t.clone() for t in ma(*xa)], [t.clone() for t in mb(*xb)]
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for it in range(6):
+        with torch.cuda.stream(sa):
+            oa = ma(*xa)
+        with torch.cuda.stream(sb):
+            ob = mb(*xb)
+        outs.append((oa, ob))
+    torch.cuda.synchronize()
+    for oa, ob in outs:
+        for o, r in zip(oa, ra):
+            assert torch.equal(o, r)
+        for o, r in zip(ob, rb):
+            assert torch.equal(o, r)
+
+
 def test_input_validation(base):
     from pmce_b200._lib import PmceError
     m = base["m"]
+    # host-buffer calls validate shapes too (Tensor.copy_ into the graph's static buffers would broadcast [B,1,2048])
+    with pytest.raises(PmceError, match="shape"):
+        m.forward_host(base["p2d"], base["feat"][:, :1].contiguous())
+    with pytest.raises(PmceError, match="shape"):
+        list(m.forward_host_iter(iter([(base["p2d"][:, :8].contiguous(), base["feat"])])))
     with pytest.raises(PmceError, match="CUDA tensor"):
         m(base["p2d"], base["feat"])
     with pytest.raises(PmceError, match="shape"):
@@ -345,3 +414,22 @@ def test_forward_vs_oracle_other_shapes(assets_root, lib, J, C, T, B):
     e = (_maxabs(mesh, r_mesh), _maxabs(cam_pose, r_pose), _maxabs(pose3d, r_p3) / float(r_p3.abs().max()))
     print(f"J={J} C={C} T={T} B={B}: max|d mesh|={e[0]:.2e} max|d pose|={e[1]:.2e} rel|d pose3d|={e[2]:.2e}")
     assert e[0] < TOL and e[1] < TOL and e[2] < 1e-4
+
+
+@pytest.mark.parametrize("J,C,T,B", [(17, 512, 16, 64), (17, 512, 16, 256), (17, 512, 64, 32)])
+def test_headline_configs_vs_oracle(assets_root, lib, J, C, T, B):
+    """BASELINE.json configs[1], [2] and [4] at their FULL sizes, compared with the oracle directly (not through clip
+    independence): B=64 / 256 at C=512 run the CTA-pair GEMM instantiations and multi-item CTAs that B=2 never reaches."""
+    from oracle import pmce_oracle as po
+    g = np.load(os.path.join(GOLDEN, "pmce_J17_C256_T16_B2.npz"))
+    sd = synth.make_state_dict(5, init_vertices=g["init_vertices"], lifter_out_scale=300.0, num_joint=J, embed_dim=C, depth=3, seqlen=T)
+    p2d, feat = synth.make_inputs(B, T, J, seed=21)
+    with torch.no_grad():
+        r_mesh, r_pose, r_p3 = po.pmce_forward(sd, p2d, feat, g["vj_relation"])
+    for graph in (False, True):
+        m = _model(sd, J, C, 3, T, graph=graph)
+        mesh, cam_pose, pose3d = m(p2d.cuda(), feat.cuda())
+        e = (_maxabs(mesh, r_mesh), _maxabs(cam_pose, r_pose), _maxabs(pose3d, r_p3) / float(r_p3.abs().max()))
+        mpve = float((mesh.cpu() - r_mesh).norm(dim=-1).mean())
+        print(f"J={J} C={C} T={T} B={B} graph={graph}: max|d mesh|={e[0]:.2e} MPVE={mpve:.2e} max|d pose|={e[1]:.2e} rel|d pose3d|={e[2]:.2e}")
+        assert e[0] < TOL and e[1] < TOL and e[2] < 1e-4 and mpve < TOL
