@@ -38,46 +38,94 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason sampling through NVML (nvidia_ml_py) from a thread, every few milliseconds, started before
+    the warm-up and stopped after the last timed region; the summary covers the samples taken inside the timed windows
+    (`window()`), so even a 50 ms region holds >= 5 samples. Falls back to `nvidia-smi -lms` (B200_PROFILING.md recipe) when
+    NVML cannot be loaded. Works under torch.distributed.run: the device is looked up by the UUID of this rank's GPU."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"),
+               (0x80, "hw_power_brake_slowdown"))
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, torch_device_index, period_s=0.004):
+        self.rows, self.windows, self.period = [], [], period_s
+        self.idx, self.h, self.nv, self.th, self.stop_flag, self.proc = torch_device_index, None, None, None, False, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml as nv
+            import torch
+            nv.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            try:
+                self.h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nv = nv
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+        except Exception:
+            self.nv = None
+            self._start_smi()
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.perf_counter(), sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def _start_smi(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            self.mx = None
+
+            def rd():
+                for line in self.proc.stdout:
+                    r = [c.strip() for c in line.split(",")]
+                    try:
+                        bits = sum(b for (b, _), v in zip(((0x8, 0), (0x40, 0), (0x20, 0), (0x4, 0)), r[5:9]) if v.lower().startswith("active"))
+                        self.rows.append((time.perf_counter(), float(r[1]), bits, float(r[3])))
+                        self.mx = float(r[2])
+                    except Exception:
+                        continue
+            self.th = threading.Thread(target=rd, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def window(self, t0, t1):
+        """Register a timed region [t0, t1] (time.perf_counter values taken right around it on the host)."""
+        self.windows.append((t0, t1))
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        if self.th:
+            self.th.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
+        inside = [r for r in self.rows if any(a <= r[0] <= b for a, b in self.windows)] if self.windows else list(self.rows)
+        used = inside if len(inside) >= 3 else list(self.rows)
+        sm = sorted(r[1] for r in used)
+        bits = 0
+        for r in used:
+            bits |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.mx, "power_w_max": max(r[3] for r in used),
+                "samples": len(used), "samples_total": len(self.rows), "in_timed_regions": used is inside,
+                "source": "nvml" if self.nv else "nvidia-smi", "reasons": [n for b, n in self.REASONS if bits & b]}
 
 
 def build_model(device):
@@ -100,11 +148,24 @@ def build_model(device):
     return m.to(device).eval(), sd
 
 
-def best_cpu_threads(sd, vj):
+def _cpu_forward_fn(sd, vj_port):
+    """The reference's CPU implementation of the path: the UNMODIFIED reference module when it is importable here
+    (`/root/reference` in the build container, `oracle/_ref` - materialised by oracle/build_ref.py - on the GPU box), else the
+    oracle port. -> (callable(p2d, feat), kind)"""
+    import torch
+    from oracle import ref_harness as rh
+    if rh.which() is not None:
+        model = rh.build_pmce(J, C, DEPTH, T)            # models.PMCE.get_model of the reference, eval mode, CPU
+        model.load_state_dict(sd, strict=True)
+        return (lambda p2d, feat: model(p2d, feat)), "reference"
+    from oracle import pmce_oracle as po
+    return (lambda p2d, feat: po.pmce_forward(sd, p2d, feat, vj_port, depth=DEPTH)), "port"
+
+
+def best_cpu_threads(fwd):
     """The box may expose more logical CPUs than the container can use (oversubscription makes torch CPU slower, not
     faster): give the reference its best shot by calibrating the thread count on a small batch."""
     import torch
-    from oracle import pmce_oracle as po
     from pmce_b200 import synth
     try:
         avail = len(os.sched_getaffinity(0))
@@ -116,9 +177,9 @@ def best_cpu_threads(sd, vj):
     with torch.no_grad():
         for n in cands:
             torch.set_num_threads(n)
-            po.pmce_forward(sd, p2d, feat, vj, depth=DEPTH)
+            fwd(p2d, feat)
             t0 = time.perf_counter()
-            po.pmce_forward(sd, p2d, feat, vj, depth=DEPTH)
+            fwd(p2d, feat)
             dt = time.perf_counter() - t0
             if dt < best_t:
                 best, best_t = n, dt
@@ -126,62 +187,69 @@ def best_cpu_threads(sd, vj):
     return best, avail
 
 
-def cpu_oracle_clips_per_s(sd, vj, budget_s=20.0, batch=B_PER_GPU, max_iters=8):
-    """Time the oracle port (torch CPU fp32, best thread count) on the same B=64 batch; bounded to ~budget_s."""
-    import torch
-    from oracle import pmce_oracle as po
-    from pmce_b200 import synth
-    threads, avail = best_cpu_threads(sd, vj)
-    p2d, feat = synth.make_inputs(batch, T, J, seed=1)
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        po.pmce_forward(sd, p2d, feat, vj, depth=DEPTH)      # warm-up
-        warm = time.perf_counter() - t0
-        times = []
-        while len(times) < max_iters and (sum(times) + warm) < budget_s:
-            t0 = time.perf_counter()
-            po.pmce_forward(sd, p2d, feat, vj, depth=DEPTH)
-            times.append(time.perf_counter() - t0)
-    if not times:
-        times = [warm]
-    times.sort()
-    med = times[len(times) // 2]
-    return batch / med, len(times), threads, avail
-
-
 def run_reference(args, rank, world):
-    """--impl reference: the reference algorithm on the host CPU (oracle port; the Python reference cannot travel)."""
+    """--impl reference: the reference's own CPU implementation of PMCE.forward on the host cores (rank 0 only), on the same
+    workload (one B=64 batch per step), bounded to a few steps."""
     if rank != 0:
         return
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""        # this arm is the CPU implementation: the reference's hard-coded .cuda() calls stay on the host
     import numpy as np
+    import torch
     from pmce_b200 import synth
     g = np.load(os.path.join(REPO, "tests", "golden", f"pmce_J{J}_C{C}_T{T}_B2.npz"))
     sd = synth.make_state_dict(0, init_vertices=g["init_vertices"], lifter_out_scale=300.0, num_joint=J, embed_dim=C, depth=DEPTH, seqlen=T)
-    import torch
-    from oracle import pmce_oracle as po
-    cores, avail = best_cpu_threads(sd, g["vj_relation"])
+    fwd, kind = _cpu_forward_fn(sd, g["vj_relation"])
+    cores, avail = best_cpu_threads(fwd)
     p2d, feat = synth.make_inputs(B_PER_GPU, T, J, seed=1)
     steps = max(1, min(args.steps, 6))
     warm = max(1, min(args.warmup, 2))
     with torch.no_grad():
         for _ in range(warm):
-            po.pmce_forward(sd, p2d, feat, g["vj_relation"], depth=DEPTH)
+            out = fwd(p2d, feat)
         t0 = time.perf_counter()
         for _ in range(steps):
-            po.pmce_forward(sd, p2d, feat, g["vj_relation"], depth=DEPTH)
+            out = fwd(p2d, feat)
         dt = time.perf_counter() - t0
+    assert tuple(out[0].shape) == (B_PER_GPU, V, 3)
     val = B_PER_GPU * steps / dt
-    sample = (f"{steps} steps of the same B={B_PER_GPU} batch (bounded from --steps {args.steps}); torch CPU fp32, {cores} threads "
-              f"(best of a calibration sweep; {avail} logical CPUs visible)")
+    what = ("the unmodified reference module (lib/models/PMCE.py:15-26 via oracle/ref_harness.py)" if kind == "reference"
+            else "the oracle port (reference module not importable here)")
+    sample = (f"{steps} steps of the same B={B_PER_GPU} batch through {what} (bounded from --steps {args.steps}); torch CPU fp32, "
+              f"{cores} threads (best of a calibration sweep; {avail} logical CPUs visible)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU, "weights": "seeded random init (no checkpoints are published)",
-                   "note": "reference arm: the same B=64 batch through the reference algorithm on the host CPU (rank 0 only)"},
-        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config(args.gpus),      # the own arm's config, key for key
+        "note": "reference arm: one B=64 batch per step through the reference's CPU implementation on the host cores (rank 0 only)",
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def cpu_baseline_subprocess(steps=6, warmup=2, timeout=240):
+    """cpu_baseline of the own arm = the reference arm run in a CHILD process (no CUDA context, its own thread settings)."""
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup)],
+                       env=env, capture_output=True, text=True, timeout=timeout)
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)["cpu_baseline"]
+    raise RuntimeError("reference arm produced no JSON line: " + r.stderr[-500:])
+
+
+def bench_config(world, note=None):
+    """`config` of the JSON line; the reference arm prints the same keys as the own arm."""
+    cfg = {"workload": WORKLOAD, "global_batch": world * B_PER_GPU,
+           "parallelism": f"batch-shard x{world}" + (" + 1 all-gather" if world > 1 else ""),
+           "weights": "seeded random init (no checkpoints are published)",
+           "l2": "per-step working set (weights 0.46 GB + activations) exceeds the 126 MB L2; inputs rotate over 4 resident sets",
+           "cuda_graph": True}
+    if note:
+        cfg["note"] = note
+    return cfg
 
 
 def main():
@@ -258,13 +326,14 @@ def main():
     launches_per_step = int(lib.pmce_launch_count() - n0)
     eng.use_graph = True
 
-    for i in range(W):
-        step(i)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                  # sampling runs from the warm-up to the end of the last timed region
+    for i in range(W):
+        step(i)
+    t_a = time.perf_counter()
     ms = timed(step, K)
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.window(t_a, time.perf_counter())
     value = world * B * K / (ms * 1e-3)
 
     # e2e: the public host-buffer API, pipelined over the K batches (H2D of batch i+1 / D2H of batch i-1 overlap forward i);
@@ -288,7 +357,10 @@ def main():
         return float(t.item())
 
     run_e2e(W)
+    t_a = time.perf_counter()
     ms_e2e = timed_host(K)
+    sampler.window(t_a, time.perf_counter())
+    clocks = sampler.stop() if rank == 0 else None
     for i in range(W):
         step_e2e(i)
     ms_e2e_sync = timed(step_e2e, K)
@@ -306,10 +378,7 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"batch-shard x{world}" + (" + 1 all-gather" if world > 1 else ""),
-                   "weights": "seeded random init (no checkpoints are published)",
-                   "l2": "per-step working set (weights 0.46 GB + activations) exceeds the 126 MB L2; inputs rotate over 4 resident sets",
-                   "cuda_graph": True},
+        "config": bench_config(world),
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
                 "path": "models.PMCE.forward_host_iter: pinned host inputs -> H2D -> forward -> D2H of the 3 outputs, every step, copies of "
                         "neighbouring steps overlapped with the forward (the reference loop lib/core/base.py:218-238, pipelined)",
@@ -320,10 +389,7 @@ def main():
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            v, n, cores, avail = cpu_oracle_clips_per_s(sd, model.pose_mesh_coevo.vj_relation)
-            out["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
-                                   "sample": f"median of {n} forwards of the same B={B} batch through the oracle port (torch CPU fp32, "
-                                             f"{cores} threads = best of a calibration sweep; {avail} logical CPUs visible)"}
+            out["cpu_baseline"] = cpu_baseline_subprocess()
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

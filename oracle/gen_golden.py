@@ -24,7 +24,8 @@ from oracle import ref_harness as rh          # noqa: E402
 from oracle import pmce_oracle as po          # noqa: E402
 from pmce_b200 import synth                   # noqa: E402
 
-GOLDEN = os.path.join(REPO, "tests", "golden")
+# PMCE_GOLDEN_OUT redirects the output (tests/test_oracle_vs_reference.py regenerates into a scratch dir and diffs)
+GOLDEN = os.environ.get("PMCE_GOLDEN_OUT") or os.path.join(REPO, "tests", "golden")
 
 CONFIGS = [
     # name, J, C, T, B, lifter_out_scale

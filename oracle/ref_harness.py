@@ -1,11 +1,12 @@
 """Import the UNMODIFIED reference (`/root/reference`) on a CPU-only host.  TEST INFRASTRUCTURE.
 
-Only usable in the build container (the GPU box has no `/root/reference`): it is what
-`oracle/gen_golden.py` uses to produce `tests/golden/*.npz`, and what
-`tests/test_oracle_vs_reference.py` uses (skipped when the reference is absent) to pin the CPU
-restatement in `oracle/pmce_oracle.py`.
+In the build container it imports from `/root/reference`: this is what `oracle/gen_golden.py` uses to produce
+`tests/golden/*.npz`, and what `tests/test_oracle_vs_reference.py` re-runs (skipped when the reference is absent) to pin
+the CPU restatement in `oracle/pmce_oracle.py`. On the GPU box, where `/root/reference` does not exist, it imports from
+`oracle/_ref/` - the byte-identical copy `oracle/build_ref.py` materialises (git-ignored, travels with the snapshot) - so
+`bench.py --impl reference` times the reference module itself.
 
-No reference source is copied. A scratch "view" directory of *symlinks* to the read-only tree is
+No reference source enters the repository. A scratch "view" directory of *symlinks* to the read-only tree is
 built so that the reference's import-time `mkdir experiment/...` (lib/core/config.py:20-38, paths
 derived from `os.path.abspath(__file__)`, which does not resolve symlinks) lands in the scratch
 dir, and `data/base_data` (a dangling symlink in the reference) is replaced by seeded synthetic
@@ -22,6 +23,7 @@ import torch
 REFERENCE_ROOT = os.environ.get("PMCE_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
+REF_COPY = os.path.join(_HERE, "_ref")          # materialised by oracle/build_ref.py; travels to the GPU box (git-ignored)
 _state = {}
 
 
@@ -29,33 +31,17 @@ def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "lib", "models"))
 
 
-def setup(asset_seed=7):
-    """Build the view dir, chdir into it, patch `.cuda()` and put the reference on sys.path."""
-    if _state:
-        return _state
-    if not available():
-        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
-    if _REPO not in sys.path:
-        sys.path.insert(0, _REPO)
-    from pmce_b200 import synth
+def copy_available():
+    return os.path.isfile(os.path.join(REF_COPY, "MANIFEST.json"))
 
-    view = tempfile.mkdtemp(prefix="pmce_ref_view_")
-    # lib/ and lib/core/ must be real directories: config.py walks `<its dir>/../../` physically.
-    os.makedirs(os.path.join(view, "lib", "core"))
-    for name in os.listdir(os.path.join(REFERENCE_ROOT, "lib")):
-        if name != "core":
-            os.symlink(os.path.join(REFERENCE_ROOT, "lib", name), os.path.join(view, "lib", name))
-    for name in os.listdir(os.path.join(REFERENCE_ROOT, "lib", "core")):
-        os.symlink(os.path.join(REFERENCE_ROOT, "lib", "core", name), os.path.join(view, "lib", "core", name))
-    os.symlink(os.path.join(REFERENCE_ROOT, "smplpytorch"), os.path.join(view, "smplpytorch"))
-    os.makedirs(os.path.join(view, "data"))
-    os.makedirs(os.path.join(view, "experiment"))
-    for name in os.listdir(os.path.join(REFERENCE_ROOT, "data")):
-        if name == "base_data":
-            continue
-        os.symlink(os.path.join(REFERENCE_ROOT, "data", name), os.path.join(view, "data", name))
-    assets = synth.write_mesh_assets(view, seed=asset_seed)
 
+def which():
+    """'tree' (the read-only reference tree, through a symlink view), 'copy' (oracle/_ref) or None."""
+    return "tree" if available() else ("copy" if copy_available() else None)
+
+
+def _import_reference(view):
+    """chdir into `view`, neutralise `.cuda()` on CPU-only hosts, put the reference on sys.path and import `models`."""
     if not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self
         torch.nn.Module.cuda = lambda self, *a, **k: self
@@ -76,8 +62,42 @@ def setup(asset_seed=7):
         defaults[-1] = torch.device("cpu")
         ref_mesh.Mesh.__init__.__defaults__ = tuple(defaults)
     import models  # noqa: reference lib/models/__init__.py
+    return cfg, models
 
-    _state.update(view=view, cfg=cfg, models=models, assets=assets)
+
+def setup(asset_seed=7):
+    """Build the view dir (or use oracle/_ref), chdir into it, patch `.cuda()` and put the reference on sys.path."""
+    if _state:
+        return _state
+    if not available():
+        if not copy_available():
+            raise RuntimeError("reference tree not found at %s and no oracle/_ref copy (python oracle/build_ref.py)" % REFERENCE_ROOT)
+        # the materialised copy: real, writable files (the reference's import-time mkdirs land inside it)
+        cfg, models = _import_reference(REF_COPY)
+        _state.update(view=REF_COPY, cfg=cfg, models=models, assets=None, kind="copy")
+        return _state
+    if _REPO not in sys.path:
+        sys.path.insert(0, _REPO)
+    from pmce_b200 import synth
+
+    view = tempfile.mkdtemp(prefix="pmce_ref_view_")
+    # lib/ and lib/core/ must be real directories: config.py walks `<its dir>/../../` physically.
+    os.makedirs(os.path.join(view, "lib", "core"))
+    for name in os.listdir(os.path.join(REFERENCE_ROOT, "lib")):
+        if name != "core":
+            os.symlink(os.path.join(REFERENCE_ROOT, "lib", name), os.path.join(view, "lib", name))
+    for name in os.listdir(os.path.join(REFERENCE_ROOT, "lib", "core")):
+        os.symlink(os.path.join(REFERENCE_ROOT, "lib", "core", name), os.path.join(view, "lib", "core", name))
+    os.symlink(os.path.join(REFERENCE_ROOT, "smplpytorch"), os.path.join(view, "smplpytorch"))
+    os.makedirs(os.path.join(view, "data"))
+    os.makedirs(os.path.join(view, "experiment"))
+    for name in os.listdir(os.path.join(REFERENCE_ROOT, "data")):
+        if name == "base_data":
+            continue
+        os.symlink(os.path.join(REFERENCE_ROOT, "data", name), os.path.join(view, "data", name))
+    assets = synth.write_mesh_assets(view, seed=asset_seed)
+    cfg, models = _import_reference(view)
+    _state.update(view=view, cfg=cfg, models=models, assets=assets, kind="tree")
     return _state
 
 
