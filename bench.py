@@ -395,6 +395,18 @@ def main():
         dist.destroy_process_group()
 
 
+def ncu_traffic(key, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed ncu-derived table
+    `profiles/ncu_traffic.json` (written by profiles/collect.sh from one `ncu --set full` capture per kernel; never a literal
+    in this file). None when the table has no entry for (kernel, batch)."""
+    try:
+        tab = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
+        e = tab.get(f"{key}@B{B}")
+        return float(e["dram_read_bytes"] + e["dram_write_bytes"]) if e else None
+    except Exception:
+        return None
+
+
 def dominant_kernel_roofline(lib, dev, peaks, B):
     """The kernel with the largest share of the step: the tcgen05 split-bf16 GEMM, on the lifter fc1 shape
     (tokens x 2C x C, bias + GELU fused). Timed alone with CUDA events on the launch stream, operands pre-split and
@@ -433,9 +445,7 @@ def dominant_kernel_roofline(lib, dev, peaks, B):
     ach = flops / sec / 1e12
     return {"kernel": "linear_tc_kernel<256, TC_SPLIT_GELU, pair> (tcgen05 cta_group::2 / TMA / TMEM split-bf16 GEMM; lifter fc1 + bias + GELU)", "bound": "tensor", "achieved": ach,
             "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1p_linear_tc_fc1_pair_ncu_raw.csv:
-            # 37.8 MB read + 21.8 MB written; the rest of the 71 MB split output is still in L2 when the kernel ends)
-            "traffic": 59.5e6, "traffic_unit": "B", "frac_of_split_ceiling": 3.0 * ach / peaks["bf16_tflops"],
+            "traffic": ncu_traffic("linear_tc_kernel_fc1", B), "traffic_unit": "B", "frac_of_split_ceiling": 3.0 * ach / peaks["bf16_tflops"],
             "flops_per_launch": flops, "mma_flops_per_launch": 3 * flops, "us_per_launch": sec * 1e6, "shape_MNK": [M, N, K],
             "peak_source": peaks["source"], "note": "3 bf16 MMAs per product (bf16x3): frac ceiling is 1/3"}
 
@@ -445,7 +455,7 @@ def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):
     Timed alone with CUDA events over `nsets` rotating (xq, t) buffer sets whose total size exceeds the 126 MB L2, so every
     launch streams its query rows from HBM. achieved = ALGORITHMIC bytes / time with SURVEY.md §8(d)'s per-clip figure for the
     fused block (231,424 B: q/k/v streams in + q stream out + gamma/beta); `achieved_kernel_io` counts what this kernel's
-    contract really moves per clip (q in, q out, split-bf16 AdaLN_2 output, K, V, gamma/beta = 340,736 B)."""
+    contract really moves per clip (q in, q out, the per-clip folded operands KQ'|VPt' in split-bf16 and sb' = 253,696 B)."""
     import ctypes as Ct
     import torch
     Vd, D = 431, 64
@@ -453,8 +463,6 @@ def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):
     st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
     gen = torch.Generator(device=dev).manual_seed(5)
     xq = [torch.randn(B, Vd, D, device=dev, generator=gen) for _ in range(nsets)]
-    th = [torch.empty(B, Vd, D, dtype=torch.bfloat16, device=dev) for _ in range(nsets)]
-    tl = [torch.empty(B, Vd, D, dtype=torch.bfloat16, device=dev) for _ in range(nsets)]
     Kt = torch.randn(B, J, D, device=dev, generator=gen)
     Vt = torch.randn(B, J, D, device=dev, generator=gen)
     gb = torch.randn(B, lib.pmce_adaln_slots(), 2, D, device=dev, generator=gen)
@@ -462,7 +470,7 @@ def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):
     fold_ws = torch.empty(lib.pmce_ca_fold_bytes(B), dtype=torch.uint8, device=dev)
 
     def call(i, fold=0):
-        rc = lib.pmce_ca_vertex_fused(eng._dp, P(eng.weights), 1, P(xq[i]), P(Kt), P(Vt), P(gb), B, P(th[i]), P(tl[i]), P(fold_ws), fold,
+        rc = lib.pmce_ca_vertex_fused(eng._dp, P(eng.weights), 1, P(xq[i]), P(Kt), P(Vt), P(gb), B, Ct.c_void_p(0), Ct.c_void_p(0), P(fold_ws), fold,
                                       Ct.c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0, lib.pmce_last_error()
     call(0, fold=1)          # per-clip folded operands (a separate 64-CTA kernel in the forward), made once
@@ -490,13 +498,13 @@ def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):
     torch.cuda.synchronize(dev)
     sec = e0.elapsed_time(e1) * 1e-3 / (rounds * nsets)
     survey_bytes = ((J + Vd + Vd + J) * D * 4 + 2048) * B
-    io_bytes = (3 * Vd * D * 4 + 2 * J * D * 4 + 4 * D * 4) * B
+    io_bytes = (2 * Vd * D * 4 + 2 * (64 * 64 * 2 * 2) + 64 * 4) * B
     flops = (4 * 2 * Vd * J * 32 + 2 * 2 * Vd * D * D) * B       # attention core + Wq + Wp
     ach = survey_bytes / sec / 1e9
-    return {"kernel": "ca_vertex_fused_kernel (AdaLN_q + scores + softmax + P.V.Wp + residual + AdaLN_2 in one pass over the query stream)",
+    return {"kernel": "ca_vertex_fused_kernel (AdaLN_q + Wq + scores + softmax + P.V + Wp + bias + residual in one pass over the query stream; "
+                      "warp-specialised: 2 TMA producer warps, 2 consumer groups = 2 items in flight per CTA)",
             "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-            # ncu --set full at B=64 (profiles/r1p_ca_ncu_table.txt): 9.28 MB read, the 14 MB written stay in L2 past the kernel's end
-            "traffic": 9.29e6 if B == 64 else None, "traffic_unit": "B", "bytes_per_launch": survey_bytes, "us_per_launch": sec * 1e6,
+            "traffic": ncu_traffic("ca_vertex_fused_kernel", B), "traffic_unit": "B", "bytes_per_launch": survey_bytes, "us_per_launch": sec * 1e6,
             "achieved_kernel_io": io_bytes / sec / 1e9, "kernel_io_bytes_per_launch": io_bytes,
             "frac_kernel_io": io_bytes / sec / 1e9 / peaks["hbm_gbs"], "flops_per_launch": flops, "clips_per_launch": B,
             "l2": f"{nsets} rotating buffer sets ({nsets * io_bytes / 1e6:.0f} MB) > 126 MB L2", "peak_source": peaks["source"]}

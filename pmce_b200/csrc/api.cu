@@ -540,8 +540,8 @@ JointFoldArgs ca_fold_args(const Weights& W, const CoevoW* cw, const CaW& w, con
         a.wk = W.f + w.wk; a.bk = W.f + w.bk; a.wv = W.f + w.wv; a.bv = W.f + w.bv;
         a.xq_out = xq_out;
     }
-    a.wq = W.f + w.wq; a.bq = W.f + w.bq; a.wp = W.f + w.wp;
-    a.gb = gb; a.gb_ld = PMCE_ADALN_SLOTS * 128; a.slot_k = w.sk; a.slot_v = w.sv;
+    a.wq = W.f + w.wq; a.bq = W.f + w.bq; a.wp = W.f + w.wp; a.bp = W.f + w.bp;
+    a.gb = gb; a.gb_ld = PMCE_ADALN_SLOTS * 128; a.slot_k = w.sk; a.slot_v = w.sv; a.slot_q = w.sq;
     a.f = f; a.J = J; a.eps = 1e-6f; a.scale = 1.0f / sqrtf(64.0f / heads);
     return a;
 }
@@ -561,14 +561,13 @@ int ca_fold(const Weights& W, const CoevoW* cw, const CaW& w, const float* joint
     return ca_fold_launch(args, 1, B, st);
 }
 
-int ca_fused_launch(const Weights& W, const CaW& w, float* xq, int N1, int N2, const float* gb, int B, const SplitOut& t, const CaFolded& f,
-                    cudaStream_t st) {
+// xq += proj(MHA(...)) in one pass (ca_fused.cuh); AdaLN_q's gamma/beta, the output bias and log2e are inside the folded operands
+int ca_fused_launch(float* xq, int N1, int N2, int B, const CaFolded& f, cudaStream_t st) {
     CaFusedArgs a;
     memset(&a, 0, sizeof(a));
-    a.gb = gb; a.bp = W.f + w.bp; a.gb_ld = PMCE_ADALN_SLOTS * 128; a.slot_q = w.sq; a.slot_2 = w.s2;
     a.B = B; a.N1 = N1; a.N2 = N2; a.eps = 1e-6f;
     count_launch();
-    const int rc = launch_ca_vertex_fused(xq, t.hi, t.lo, f, a, st);
+    const int rc = launch_ca_vertex_fused(xq, f, a, st);
     if (rc) { pmce_set_error("ca_vertex_fused launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
     return 0;
 }
@@ -580,8 +579,9 @@ int cross_attn_query(const Weights& W, const CaW& w, int heads, float* xq, int N
     const int n1 = B * N1;
     if (ca_fused_ok(heads, N1, N2)) {
         if (!folded) RET(ca_fold(W, nullptr, w, nullptr, s.K, s.V, nullptr, gb, B, N2, heads, s.fold, st));
-        // one pass over the query stream: AdaLN_q, scores, softmax, P V Wp, residual, AdaLN_2 (ca_fused.cuh)
-        RET(ca_fused_launch(W, w, xq, N1, N2, gb, B, s.tq, s.fold, st));
+        // one pass over the query stream: AdaLN_q, scores, softmax, P V Wp, residual (ca_fused.cuh); then AdaLN_2 + Mlp
+        RET(ca_fused_launch(xq, N1, N2, B, s.fold, st));
+        RET(adaln(xq, B, N1, gb, w.s2, s.tq, st));
         { EpiOpt o; o.bias = W.f + w.fc1b; o.act = 1; o.outs = s.hid; o.ld_split = 256; RET(linear_tc(s.tq, 64, n1, 64, W, w.fc1w, 64, 256, o, st)); }
         { EpiOpt o; o.bias = W.f + w.fc2b; o.resid = xq; o.ld_resid = 64; o.out = xq; o.ld_out = 64; RET(linear_tc(s.hid, 256, n1, 256, W, w.fc2w, 256, 64, o, st)); }
         return 0;
@@ -851,7 +851,7 @@ extern "C" int pmce_ca_vertex_fused(const pmce_dims_t* dims, const void* weights
                                     const float* gb, int B, void* t_hi, void* t_lo, void* fold_ws, int fold, void* stream) {
     GET_LAYOUT();
     if (block < 1 || block > 3) { pmce_set_error("pmce_ca_vertex_fused: block must be 1..3 (got %d)", block); return 2; }
-    if (!xq || !K || !V || !gb || !t_hi || !t_lo || !fold_ws || B < 1) { pmce_set_error("pmce_ca_vertex_fused: bad argument"); return 2; }
+    if (!xq || !K || !V || !gb || !fold_ws || B < 1 || (t_hi == nullptr) != (t_lo == nullptr)) { pmce_set_error("pmce_ca_vertex_fused: bad argument"); return 2; }
     if ((uintptr_t)fold_ws & 255) { pmce_set_error("pmce_ca_vertex_fused: fold_ws must be 256-byte aligned"); return 2; }
     const int J = dims->num_joint, Vd = dims->num_vert_ds;
     if (!ca_vertex_fused_supported(VERTX_HEADS, J) || Vd < 128) { pmce_set_error("pmce_ca_vertex_fused: unsupported shape (J=%d, Vd=%d)", J, Vd); return 3; }
@@ -860,8 +860,12 @@ extern "C" int pmce_ca_vertex_fused(const pmce_dims_t* dims, const void* weights
     f.kq_hi = (bf16*)fold_ws; f.kq_lo = f.kq_hi + (size_t)B * CAF_NS * 64; f.vp_hi = f.kq_lo + (size_t)B * CAF_NS * 64;
     f.vp_lo = f.vp_hi + (size_t)B * 64 * 64; f.sb = (float*)(f.vp_lo + (size_t)B * 64 * 64);
     if (fold) RET(ca_fold(W, nullptr, w, nullptr, K, V, nullptr, gb, B, J, VERTX_HEADS, f, st));
-    SplitOut t{(bf16*)t_hi, (bf16*)t_lo};
-    return ca_fused_launch(W, w, xq, Vd, J, gb, B, t, f, st);
+    RET(ca_fused_launch(xq, Vd, J, B, f, st));
+    if (t_hi && t_lo) {          // optional: AdaLN_2 of the result, split-bf16 (the A operand of the block's fc1 when the Mlp is not fused)
+        SplitOut t{(bf16*)t_hi, (bf16*)t_lo};
+        RET(adaln(xq, B, Vd, gb, w.s2, t, st));
+    }
+    return 0;
 }
 
 extern "C" int pmce_self_attn_block(const pmce_dims_t* dims, const void* weights, int block, int which, const float* x, const float* gb,

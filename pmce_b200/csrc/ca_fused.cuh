@@ -1,18 +1,27 @@
-// Fused vertex<-joint CrossAttentionBlock front (CoevoDecoder.py:47-62 inside :82-86), one kernel per block:
+// Fused vertex<-joint CrossAttention of a CrossAttentionBlock (CoevoDecoder.py:47-62 inside :82-85), one kernel per block:
 //     xq' = xq + Wp . MHA( Wq AdaLN_q(xq) + bq ,  K ,  V ) + bp            (K, V: the 17/19 projected joint rows of the clip)
-//     t   = AdaLN_2(xq')  (split-bf16: the A operand of the block's fc1 GEMM)
-// replacing AdaLN -> Wq GEMM -> attention -> Wp GEMM(+residual) -> AdaLN (five launches, each a round trip of the
-// [B*431, 64] stream through HBM) with one pass: the stream is read once and written once.
+// replacing AdaLN -> Wq GEMM -> attention -> Wp GEMM(+residual) (four launches, each a round trip of the [B*431, 64] stream
+// through HBM) with one pass: the stream is read once and written once.  (AdaLN_2 + Mlp of the block: mlp_fused.cuh.)
 //
-// Work item = 128 query rows of one clip (TMA box [1][128][32 fp32] x2 out of the 3-D view [B][431][64]: rows past 431 are
-// zero-filled on load and clipped on store). 128 threads, thread r owns tile row r = TMEM lane r:
-//   TMA load (SW128)            -> row in registers -> AdaLN_q -> split-bf16 -> swizzled A tiles (hi, lo)
-//   tcgen05 128x64x64 (bf16x3)  -> Q in TMEM -> registers (+bq, *scale)
-//   attention on CUDA cores     : keys/values of the clip (<= 24 rows) broadcast from shared memory, softmax in registers
-//   O -> split-bf16 -> A tiles  -> tcgen05 128x64x64 with Wp -> TMEM -> + bp + xq (re-read from the swizzled input tile)
-//   xq' -> input tile (same swizzled slot) -> TMA store; AdaLN_2(xq') -> A tiles -> TMA store (hi, lo)
-// The four weight tiles ([64][64] bf16 hi/lo of Wq and Wp) are loaded once per CTA by TMA; CTAs are persistent over items,
-// two per SM (110 KB of shared memory, 128 TMEM columns each) so one CTA's loads/stores overlap the other's math.
+// Few keys => everything that is per clip is folded into two per-clip operands by ca_joint_fold_kernel (below):
+//   n        = (x - mean) / (std_unbiased + eps)                  per row, the only LayerNorm work left per element (1 FMA)
+//   S        = n KQ'^T + sb'      KQ'[32h+j][c] = log2e scale (K_h Wq_h)[j][c] gamma_q[c]
+//                                 sb' [32h+j]   = log2e (scale K_hj . bq_h + sum_c scale (K_h Wq_h)[j][c] beta_q[c])
+//   P_h      = 2^(S_h - max_j S_h) / sum                                   (softmax over the clip's NK keys, per head)
+//   xq'      = xq + P VPt'^T      VPt'[n][32h+j] = (V_h Wp[:, h]^T)[j][n] + bp[n] / 2     (rows of P_h sum to 1: 2 heads carry bp)
+// so a 128-row item is: TMA load -> row statistics -> one FMA per element -> split-bf16 A tiles -> tcgen05 128x64x64 ->
+// softmax of 2 x NK scores in registers -> P tiles -> tcgen05 128x64x64 -> + xq -> TMA store.
+//
+// Warp-specialised, persistent, ONE CTA per SM with CA2_G independent consumer groups (items in flight):
+//   warps 0-3 / 4-7   consumer group 0 / 1: thread r owns tile row r = TMEM lane r with the WHOLE 64-wide row in registers, so
+//                     the LayerNorm statistics are thread-local (no cross-thread reduction, no barrier); 4 group-wide named
+//                     barriers per item (A buffer free, A tiles written, P tiles written, output staged); the group's first
+//                     thread issues its MMAs and its TMA store.
+//   warp 8            producer of the x tiles (one lane): the group's IN buffer is released as soon as its 128 rows are in
+//                     registers, so the NEXT item's rows stream in under the whole chain of the current one.
+//   warp 9            producer of the per-clip operand tiles (KQ' | VPt', 32 KB, L2 hits for 3 of a clip's 4 tiles).
+// Shared memory per group: IN 32 KB (two [128][32 fp32] SW128 boxes) | A 32 KB (A tiles hi|lo, then P hi|lo, then the fp32
+// output boxes for the TMA store) | W 32 KB (KQ' hi|lo, VPt' hi|lo) = 96 KB; TMEM 128 columns per group (S | O).
 #pragma once
 #include "tc_common.cuh"
 #include "common.cuh"
@@ -20,18 +29,18 @@
 #include "attn_tc.cuh"
 #include "gemm_tc.cuh"
 
-constexpr int CAF_THREADS = 256;
 constexpr int CAF_KP = 32;                              // key slots per head (num_joint <= 24 live: 17 h36m, 19 coco; the rest are zero)
 constexpr int CAF_MAXJ = 24;
 constexpr int CAF_H = 2;                                // heads of the vertex stream (CoevoDecoder.py:140)
 constexpr int CAF_NS = CAF_H * CAF_KP;                  // 64 score columns: column 32 h + j = (head h, key j)
-constexpr int CAF_IN = 2 * 128 * 128;                   // two [128][32 fp32] boxes; the SAME 32 KB then hold the A tiles (hi | lo)
-constexpr int CAF_OFF_W = CAF_IN;                       // KQ hi | KQ lo | VPt hi | VPt lo ([64][64 bf16] each); later the t tiles (hi | lo)
-constexpr int CAF_OFF_GB = CAF_OFF_W + 4 * 8192;        // gamma_q beta_q gamma_2 beta_2 bp  (5 x 64 fp32)
-constexpr int CAF_OFF_PART = CAF_OFF_GB + 5 * 64 * 4;   // per-thread partial sums of the LayerNorm statistics (256 fp32)
-constexpr int CAF_OFF_BAR = CAF_OFF_PART + 256 * 4;
-constexpr int CAF_SMEM = CAF_OFF_BAR + 64 + 1024;       // + alignment slack  (68 KB: three CTAs per SM)
-constexpr int CAF_TX = CAF_IN + 2 * CAF_NS * 128 + 2 * 64 * 128;   // bytes per item arriving on bar_in
+constexpr int CA2_G = 2;                                // consumer groups = items in flight per CTA
+constexpr int CA2_THREADS = CA2_G * 128 + 64;           // + x-tile producer warp + operand producer warp
+constexpr int CA2_IN = 2 * 128 * 128;                   // two [128][32 fp32] boxes
+constexpr int CA2_A = 2 * AT_TILE;                      // A tiles hi | lo ([128][64 bf16] each) = the two fp32 output boxes later
+constexpr int CA2_W = 4 * 8192;                         // KQ' hi | KQ' lo | VPt' hi | VPt' lo ([64][64 bf16] each)
+constexpr int CA2_GBUF = CA2_IN + CA2_A + CA2_W;        // 96 KB per group
+constexpr int CA2_OFF_BAR = CA2_G * CA2_GBUF;
+constexpr int CA2_SMEM = CA2_OFF_BAR + 256 + 1024;      // barriers + alignment slack
 
 namespace tc {
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int crd0, int crd1, int crd2) {
@@ -47,249 +56,250 @@ __device__ __forceinline__ float4 lds16(uint32_t addr) {
 __device__ __forceinline__ void sts16f(uint32_t addr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {      // 2^x, rel. error 2^-22.5 (MUFU.EX2)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 }  // namespace tc
 
 struct CaFusedArgs {
-    const float* sb;         // [B, 64] folded score bias  scale * bq_h . K_hj
-    const float* gb;         // [B, gb_ld] AdaLN gamma/beta of every slot (pmce_adaln_gammabeta)
-    const float* bp;         // [64]
-    int gb_ld, slot_q, slot_2;
+    const float* sb;         // [B, 64] folded score bias sb' (log2 domain)
     int B, N1, N2, qtiles;
     float eps;
 };
 
-// read the 32 floats of one half row out of a swizzled [128][32 fp32] box
-__device__ __forceinline__ void caf_read_half(uint32_t rowaddr, int sw, float (&x)[32]) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 v = tc::lds16(rowaddr + ((j ^ sw) << 4));
-        x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
-    }
-}
-
-// AdaLayerNorm (CoevoDecoder.py:23-29: unbiased std, eps added to the std) of a 64-wide row owned by TWO threads (32 columns
-// each, in different warps): two-pass statistics, the halves' partial sums meet in shared memory (`part`, one float per
-// thread; partner = tid ^ 128). Contains two __syncthreads, the first of which also orders every thread's earlier shared-
-// memory reads before the tile writes below. Writes the normalised half as split-bf16 into swizzled [128][64 bf16] tiles.
-__device__ __forceinline__ void caf_adaln_pair(const float (&own)[32], float* part, int tid, const float* __restrict__ gam,
-                                               const float* __restrict__ bet, float eps, uint32_t t_hi, uint32_t t_lo, int r, int hf) {
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) { s0 += own[i]; s1 += own[i + 1]; }
-    part[tid] = s0 + s1;
-    __syncthreads();
-    const float mean = ((s0 + s1) + part[tid ^ 128]) * (1.0f / 64.0f);
-    float q0 = 0.f, q1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-        const float d0 = own[i] - mean, d1 = own[i + 1] - mean;
-        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
-    }
-    __syncthreads();                                   // every partner has read the sums before `part` is reused
-    part[tid] = q0 + q1;
-    __syncthreads();
-    const float inv = 1.0f / (sqrtf(((q0 + q1) + part[tid ^ 128]) * (1.0f / 63.0f)) + eps);
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-        const int c0 = hf * 32 + cc * 8;
-        const float4 g0 = ld4(gam + c0), g1 = ld4(gam + c0 + 4), b0 = ld4(bet + c0), b1 = ld4(bet + c0 + 4);
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float y[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = gg[i] * (own[cc * 8 + i] - mean) * inv + bb[i];
-        uint4 hh, ll;
-        tc::split8(y, hh, ll);
-        tc::sts16(t_hi, r, hf * 4 + cc, hh);
-        tc::sts16(t_lo, r, hf * 4 + cc, ll);
-    }
-}
-
-// Few-key cross-attention as two skinny GEMMs. With K_h, V_h the clip's projected keys/values of head h (NK <= 24 rows):
-//   scores_h = scale (xn Wq_h^T + bq_h) K_h^T = xn (scale K_h Wq_h)^T + scale K_h bq_h         -> KQ [64][64], sb [64]
-//   proj(concat_h P_h V_h) = sum_h P_h (V_h Wp[:, h]^T) + bp                                    -> VPt [64][64]
-// (row / column 32 h + j = head h, key j; slots j >= NK are zero) so per 128-row item: S = AdaLN_q(xq) KQ^T (tcgen05
-// 128x64x64), softmax per head in registers, out = P VPt^T (tcgen05 128x64x64). KQ / VPt / sb are per clip, made by
-// ca_joint_fold_kernel (split-bf16), and arrive by TMA.
-// Shared memory is two 32 KB regions that change roles through the item: X = {xq fp32 boxes -> A tiles (AdaLN_q(xq) split)
-// -> P split -> xq' fp32 boxes for the TMA store}, W = {KQ | VPt -> t tiles (AdaLN_2(xq') split) for the TMA store}; the
-// thread keeps its 32 xq values in registers for the residual. 68 KB and <= 80 registers: three CTAs (24 warps) per SM,
-// which is what hides the TMA / MMA / TMEM round trips of the per-item chain.
 template <int NK>
-__global__ void __launch_bounds__(CAF_THREADS, 3)
-ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_thi, const __grid_constant__ CUtensorMap tm_tlo,
-                       const __grid_constant__ CUtensorMap tm_kq_hi, const __grid_constant__ CUtensorMap tm_kq_lo,
-                       const __grid_constant__ CUtensorMap tm_vp_hi, const __grid_constant__ CUtensorMap tm_vp_lo, CaFusedArgs a) {
+__global__ void __launch_bounds__(CA2_THREADS, 1)
+ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_kq_hi,
+                       const __grid_constant__ CUtensorMap tm_kq_lo, const __grid_constant__ CUtensorMap tm_vp_hi,
+                       const __grid_constant__ CUtensorMap tm_vp_lo, CaFusedArgs a) {
     static_assert(NK <= CAF_MAXJ, "too many keys");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t sb = tc::smem_u32(smem);
-    const uint32_t s_ahi = sb, s_alo = sb + AT_TILE, s_w = sb + CAF_OFF_W;
-    float* gbs = reinterpret_cast<float*>(smem + CAF_OFF_GB);          // [0]=gamma_q [1]=beta_q [2]=gamma_2 [3]=beta_2 [4]=bp
-    float* part = reinterpret_cast<float*>(smem + CAF_OFF_PART);
-    uint64_t* bar_in = reinterpret_cast<uint64_t*>(smem + CAF_OFF_BAR);
-    uint64_t* bar_mma = bar_in + 1;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_in + 2);
+    const uint32_t sbase = tc::smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CA2_OFF_BAR);
+    uint64_t* in_full = bars;                    // [G] TMA bytes of the x tile
+    uint64_t* in_empty = bars + CA2_G;           // [G] 4 arrivals: every consumer warp has its rows in registers
+    uint64_t* w_full = bars + 2 * CA2_G;         // [G] TMA bytes of the operand tiles
+    uint64_t* w_empty = bars + 3 * CA2_G;        // [G] tcgen05.commit after the item's second MMA
+    uint64_t* mma_bar = bars + 4 * CA2_G;        // [G] tcgen05.commit: S complete / O complete
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5 * CA2_G);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        tc::tma_prefetch_desc(&tm_x); tc::tma_prefetch_desc(&tm_thi); tc::tma_prefetch_desc(&tm_tlo);
-        tc::tma_prefetch_desc(&tm_kq_hi); tc::tma_prefetch_desc(&tm_kq_lo); tc::tma_prefetch_desc(&tm_vp_hi); tc::tma_prefetch_desc(&tm_vp_lo);
-        tc::mbar_init(bar_in, 1); tc::mbar_init(bar_mma, 1);
+        tc::tma_prefetch_desc(&tm_x); tc::tma_prefetch_desc(&tm_kq_hi); tc::tma_prefetch_desc(&tm_kq_lo);
+        tc::tma_prefetch_desc(&tm_vp_hi); tc::tma_prefetch_desc(&tm_vp_lo);
+        for (int g = 0; g < CA2_G; ++g) {
+            tc::mbar_init(&in_full[g], 1); tc::mbar_init(&in_empty[g], 4);
+            tc::mbar_init(&w_full[g], 1); tc::mbar_init(&w_empty[g], 1); tc::mbar_init(&mma_bar[g], 1);
+        }
         tc::fence_barrier_init();
         tc::fence_proxy_async();
-        if ((int)blockIdx.x < a.B * a.qtiles) {        // the first item's loads fly while TMEM is allocated and the CTA assembles
-            const int b = blockIdx.x / a.qtiles, row0 = (blockIdx.x % a.qtiles) * 128;
-            tc::mbar_arrive_expect_tx(bar_in, CAF_TX);
-            tc::tma_load_3d(smem, &tm_x, bar_in, 0, row0, b);
-            tc::tma_load_3d(smem + 16384, &tm_x, bar_in, 32, row0, b);
-            tc::tma_load_2d(smem + CAF_OFF_W, &tm_kq_hi, bar_in, 0, b * CAF_NS);
-            tc::tma_load_2d(smem + CAF_OFF_W + 8192, &tm_kq_lo, bar_in, 0, b * CAF_NS);
-            tc::tma_load_2d(smem + CAF_OFF_W + 16384, &tm_vp_hi, bar_in, 0, b * 64);
-            tc::tma_load_2d(smem + CAF_OFF_W + 24576, &tm_vp_lo, bar_in, 0, b * 64);
-        }
     }
-    if (warp == 0) tc::tmem_alloc(tmem_ptr_smem, 128);
-    if (tid < 64) gbs[4 * 64 + tid] = a.bp[tid];
+    if (warp == CA2_G * 4) tc::tmem_alloc(tmem_ptr_smem, CA2_G * 128);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    const uint32_t tS = tmem_base, tO = tmem_base + 64;
-    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-
-    // thread = (tile row r, column half hf): hf selects the 32-column half of the 64-wide row it owns and the attention head
-    // whose softmax it runs
-    const int r = tid & 127, hf = tid >> 7;
-    const uint32_t row_own = sb + hf * 16384 + r * 128;                // this thread's half row inside the fp32 boxes
-    const int sw = r & 7;
     const int ntiles = a.B * a.qtiles;
-    uint32_t it = 0, mph = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
-        if (tid == 0 && it > 0) {                              // (the first item's loads were issued in the prologue)
-            tc::tma_store_wait_read<0>();                      // the previous item's stores have read both regions
-            tc::mbar_arrive_expect_tx(bar_in, CAF_TX);
-            tc::tma_load_3d(smem, &tm_x, bar_in, 0, row0, b);
-            tc::tma_load_3d(smem + 16384, &tm_x, bar_in, 32, row0, b);
-            tc::tma_load_2d(smem + CAF_OFF_W, &tm_kq_hi, bar_in, 0, b * CAF_NS);
-            tc::tma_load_2d(smem + CAF_OFF_W + 8192, &tm_kq_lo, bar_in, 0, b * CAF_NS);
-            tc::tma_load_2d(smem + CAF_OFF_W + 16384, &tm_vp_hi, bar_in, 0, b * 64);
-            tc::tma_load_2d(smem + CAF_OFF_W + 24576, &tm_vp_lo, bar_in, 0, b * 64);
-        }
-        {   // AdaLN parameters of clip b: gamma|beta of slot_q and slot_2 (the previous item's readers are past its last barrier)
-            const int arr = tid >> 6, c = tid & 63;
-            gbs[arr * 64 + c] = a.gb[(size_t)b * a.gb_ld + (arr < 2 ? a.slot_q : a.slot_2) * 128 + (arr & 1) * 64 + c];
-        }
-        float x[32];                                           // this thread's half of the xq row, kept for the residual
 
-        // ---- xq half row -> registers; AdaLN_q -> split A tiles over the same bytes ----
-        tc::mbar_wait(bar_in, it & 1);
-        caf_read_half(row_own, sw, x);
-        caf_adaln_pair(x, part, tid, gbs, gbs + 64, a.eps, s_ahi, s_alo, r, hf);   // first barrier inside also publishes gbs
-        tc::fence_proxy_async();
-        tc::tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc::tc_fence_after();
-            constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, CAF_NS);
-            const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
-            const uint64_t wh = tc::umma_desc_sw128(s_w), wl = tc::umma_desc_sw128(s_w + 8192);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                tc::umma_bf16(tS, tc::umma_desc_advance_k(al, k), tc::umma_desc_advance_k(wh, k), idesc, k != 0);
-                tc::umma_bf16(tS, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
-                tc::umma_bf16(tS, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
+    if (warp == CA2_G * 4) {
+        // ================= producer of the x tiles: item n of this CTA -> group n % G =================
+        if (lane == 0) {
+            uint32_t n = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+                const int g = n % CA2_G;
+                const uint32_t j = n / CA2_G;
+                const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
+                uint8_t* in = smem + g * CA2_GBUF;
+                tc::mbar_wait(&in_empty[g], (j & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&in_full[g], CA2_IN);
+                tc::tma_load_3d(in, &tm_x, &in_full[g], 0, row0, b);
+                tc::tma_load_3d(in + 16384, &tm_x, &in_full[g], 32, row0, b);
             }
-            tc::umma_commit(bar_mma);
         }
-        float p[CAF_MAXJ];                                     // folded score bias of this thread's head, then the probabilities
-#pragma unroll
-        for (int j = 0; j < CAF_MAXJ; j += 4) {
-            const float4 v = ld4(a.sb + (size_t)b * CAF_NS + hf * CAF_KP + j);
-            p[j] = v.x; p[j + 1] = v.y; p[j + 2] = v.z; p[j + 3] = v.w;
+    } else if (warp == CA2_G * 4 + 1) {
+        // ================= producer of the per-clip operand tiles =================
+        if (lane == 0) {
+            uint32_t n = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+                const int g = n % CA2_G;
+                const uint32_t j = n / CA2_G;
+                const int b = tile / a.qtiles;
+                uint8_t* w = smem + g * CA2_GBUF + CA2_IN + CA2_A;
+                tc::mbar_wait(&w_empty[g], (j & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&w_full[g], CA2_W);
+                tc::tma_load_2d(w, &tm_kq_hi, &w_full[g], 0, b * CAF_NS);
+                tc::tma_load_2d(w + 8192, &tm_kq_lo, &w_full[g], 0, b * CAF_NS);
+                tc::tma_load_2d(w + 16384, &tm_vp_hi, &w_full[g], 0, b * 64);
+                tc::tma_load_2d(w + 24576, &tm_vp_lo, &w_full[g], 0, b * 64);
+            }
         }
-        tc::mbar_wait(bar_mma, mph & 1);
-        ++mph;
-        tc::tc_fence_after();
+    } else {
+        // ================= consumers: group g = warp / 4, thread r owns tile row r =================
+        const int g = warp >> 2, r = tid & 127;
+        const uint32_t gbuf = sbase + g * CA2_GBUF;
+        const uint32_t s_in = gbuf, s_ahi = gbuf + CA2_IN, s_alo = s_ahi + AT_TILE, s_w = gbuf + CA2_IN + CA2_A;
+        const uint32_t tS = tmem_base + g * 128, tO = tS + 64;
+        const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+        const int sw = r & 7;
+        const uint32_t in_row = s_in + r * 128, out_row = s_ahi + r * 128;
+        const bool leader = r == 0;
+        bool store_pending = false;
+        uint32_t j = 0;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += CA2_G * gridDim.x, ++j) {
+            const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
 
-        // ---- softmax of head hf over the clip's NK keys; P (split) -> A tile columns [32 hf, 32 hf + 32) ----
-        {
-            uint32_t v[32];
-            tc::tmem_ld_32x32(tS + lane_sel + hf * CAF_KP, v);     // this head's 32 key slots
-            tc::tmem_ld_wait();
-            float m = -INFINITY;
+            // ---- the row -> registers (kept for the residual); the IN buffer goes back to the producer at once ----
+            float x[64];
+            tc::mbar_wait(&in_full[g], j & 1);
 #pragma unroll
-            for (int j = 0; j < NK; ++j) { p[j] += __uint_as_float(v[j]); m = fmaxf(m, p[j]); }
-            float l = 0.f;
+            for (int c = 0; c < 16; ++c) {
+                const float4 v = tc::lds16(in_row + (c >> 3) * 16384 + (((c & 7) ^ sw) << 4));
+                x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&in_empty[g]);
+
+            // ---- AdaLayerNorm statistics (CoevoDecoder.py:23-29: unbiased std, eps added to the std), thread-local ----
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int j = 0; j < NK; ++j) { p[j] = expf(p[j] - m); l += p[j]; }
-            const float inv = 1.0f / l;
+            for (int i = 0; i < 64; i += 4) { s0 += x[i]; s1 += x[i + 1]; s2 += x[i + 2]; s3 += x[i + 3]; }
+            const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / 64.0f);
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-            for (int j = 0; j < CAF_MAXJ; ++j) p[j] = j < NK ? p[j] * inv : 0.f;
+            for (int i = 0; i < 64; i += 4) {
+                const float d0 = x[i] - mean, d1 = x[i + 1] - mean, d2 = x[i + 2] - mean, d3 = x[i + 3] - mean;
+                q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+            }
+            const float inv = 1.0f / (sqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / 63.0f)) + a.eps);
+            const float nmi = -mean * inv;
+
+            // ---- the A buffer is free once the previous item's TMA store has read it ----
+            if (leader && store_pending) tc::tma_store_wait_read<0>();
+            tc::bar_sync_group(1 + g);
+
+            // ---- n = (x - mean) inv -> split-bf16 A tiles ----
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
+            for (int c = 0; c < 8; ++c) {
                 float y[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = p[cc * 8 + i];
+                for (int i = 0; i < 8; ++i) y[i] = fmaf(x[8 * c + i], inv, nmi);
                 uint4 hh, ll;
                 tc::split8(y, hh, ll);
-                tc::sts16(s_ahi, r, hf * 4 + cc, hh);
-                tc::sts16(s_alo, r, hf * 4 + cc, ll);
+                tc::sts16(s_ahi, r, c, hh);
+                tc::sts16(s_alo, r, c, ll);
             }
-            tc::sts16(s_ahi, r, hf * 4 + 3, make_uint4(0, 0, 0, 0));     // key slots 24..31 never hold a key
-            tc::sts16(s_alo, r, hf * 4 + 3, make_uint4(0, 0, 0, 0));
-        }
-        tc::fence_proxy_async();
-        tc::tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            tc::bar_sync_group(1 + g);
+            if (leader) {
+                tc::mbar_wait(&w_full[g], j & 1);
+                tc::tc_fence_after();
+                constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, CAF_NS);
+                const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
+                const uint64_t wh = tc::umma_desc_sw128(s_w), wl = tc::umma_desc_sw128(s_w + 8192);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    tc::umma_bf16(tS, tc::umma_desc_advance_k(al, k), tc::umma_desc_advance_k(wh, k), idesc, k != 0);
+                    tc::umma_bf16(tS, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
+                    tc::umma_bf16(tS, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
+                }
+                tc::umma_commit(&mma_bar[g]);
+            }
+            // folded score bias of both heads (the same 2 x NK floats for every row of the clip: L1/L2 broadcast), in flight
+            // while the MMA runs
+            constexpr int NKV = (NK + 3) / 4;                      // float4 loads per head
+            float4 sbv[2][NKV];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < NKV; ++i) sbv[h][i] = __ldg(reinterpret_cast<const float4*>(a.sb + (size_t)b * CAF_NS + h * CAF_KP) + i);
+            tc::mbar_wait(&mma_bar[g], 0);
             tc::tc_fence_after();
-            constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, 64);
-            const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
-            const uint64_t wh = tc::umma_desc_sw128(s_w + 16384), wl = tc::umma_desc_sw128(s_w + 24576);
-#pragma unroll
-            for (int k = 0; k < CAF_NS / 16; ++k) {
-                tc::umma_bf16(tO, tc::umma_desc_advance_k(al, k), tc::umma_desc_advance_k(wh, k), idesc, k != 0);
-                tc::umma_bf16(tO, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
-                tc::umma_bf16(tO, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
-            }
-            tc::umma_commit(bar_mma);
-        }
-        tc::mbar_wait(bar_mma, mph & 1);
-        ++mph;
-        tc::tc_fence_after();
 
-        // ---- xq' = (out + bp) + xq -> fp32 boxes (region X, free: both MMAs are complete); AdaLN_2(xq') -> t tiles (region W) ----
-        {
-            uint32_t v[32];
-            tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v);
-            tc::tmem_ld_wait();
+            // ---- softmax of each head over the clip's NK keys (log2 domain); P (split) -> A tile columns [32 h, 32 h + 32) ----
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 bpv = ld4(gbs + 4 * 64 + hf * 32 + i);
-                x[i] = (__uint_as_float(v[i]) + bpv.x) + x[i]; x[i + 1] = (__uint_as_float(v[i + 1]) + bpv.y) + x[i + 1];
-                x[i + 2] = (__uint_as_float(v[i + 2]) + bpv.z) + x[i + 2]; x[i + 3] = (__uint_as_float(v[i + 3]) + bpv.w) + x[i + 3];
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(tS + lane_sel + h * CAF_KP, v);
+                tc::tmem_ld_wait();
+                float p[CAF_MAXJ];
+                float m = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < NK; ++i) {
+                    const float4 t = sbv[h][i >> 2];
+                    const float bias = (i & 3) == 0 ? t.x : ((i & 3) == 1 ? t.y : ((i & 3) == 2 ? t.z : t.w));
+                    p[i] = __uint_as_float(v[i]) + bias;
+                    m = fmaxf(m, p[i]);
+                }
+                float l = 0.f;
+#pragma unroll
+                for (int i = 0; i < NK; ++i) { p[i] = tc::ex2_approx(p[i] - m); l += p[i]; }
+                const float il = 1.0f / l;
+#pragma unroll
+                for (int i = 0; i < CAF_MAXJ; ++i) p[i] = i < NK ? p[i] * il : 0.f;
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    float y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = p[cc * 8 + i];
+                    uint4 hh, ll;
+                    tc::split8(y, hh, ll);
+                    tc::sts16(s_ahi, r, h * 4 + cc, hh);
+                    tc::sts16(s_alo, r, h * 4 + cc, ll);
+                }
+                tc::sts16(s_ahi, r, h * 4 + 3, make_uint4(0, 0, 0, 0));     // key slots 24..31 never hold a key
+                tc::sts16(s_alo, r, h * 4 + 3, make_uint4(0, 0, 0, 0));
+            }
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            tc::bar_sync_group(1 + g);
+            if (leader) {
+                tc::tc_fence_after();
+                constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, 64);
+                const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
+                const uint64_t wh = tc::umma_desc_sw128(s_w + 16384), wl = tc::umma_desc_sw128(s_w + 24576);
+#pragma unroll
+                for (int k = 0; k < CAF_NS / 16; ++k) {
+                    tc::umma_bf16(tO, tc::umma_desc_advance_k(al, k), tc::umma_desc_advance_k(wh, k), idesc, k != 0);
+                    tc::umma_bf16(tO, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
+                    tc::umma_bf16(tO, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
+                }
+                tc::umma_commit(&mma_bar[g]);
+                tc::umma_commit(&w_empty[g]);                       // the operand tiles go back to their producer
+            }
+            tc::mbar_wait(&mma_bar[g], 1);
+            tc::tc_fence_after();
+
+            // ---- xq' = xq + P VPt'^T -> fp32 boxes in the A buffer (both MMAs have read it) -> TMA store ----
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    tc::sts16f(out_row + hf * 16384 + ((c ^ sw) << 4),
+                               make_float4(x[hf * 32 + 4 * c] + __uint_as_float(v[4 * c]), x[hf * 32 + 4 * c + 1] + __uint_as_float(v[4 * c + 1]),
+                                           x[hf * 32 + 4 * c + 2] + __uint_as_float(v[4 * c + 2]), x[hf * 32 + 4 * c + 3] + __uint_as_float(v[4 * c + 3])));
+            }
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            tc::bar_sync_group(1 + g);
+            if (leader) {
+                tc::tma_store_3d(&tm_x, smem + g * CA2_GBUF + CA2_IN, 0, row0, b);
+                tc::tma_store_3d(&tm_x, smem + g * CA2_GBUF + CA2_IN + 16384, 32, row0, b);
+                tc::tma_store_commit();
+                store_pending = true;
             }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            tc::sts16f(row_own + ((j ^ sw) << 4), make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
-        caf_adaln_pair(x, part, tid, gbs + 128, gbs + 192, a.eps, s_w, s_w + AT_TILE, r, hf);
-        tc::fence_proxy_async();
-        tc::tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc::tma_store_3d(&tm_x, smem, 0, row0, b);
-            tc::tma_store_3d(&tm_x, smem + 16384, 32, row0, b);
-            tc::tma_store_3d(&tm_thi, smem + CAF_OFF_W, 0, row0, b);
-            tc::tma_store_3d(&tm_tlo, smem + CAF_OFF_W + AT_TILE, 0, row0, b);
-            tc::tma_store_commit();
-        }
+        if (leader && store_pending) tc::tma_store_wait_read<0>();     // smem must outlive the reads; the grid boundary orders the writes
     }
-    if (tid == 0) tc::tma_store_wait_read<0>();          // smem must outlive the reads; the grid boundary orders the writes
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, 128);
+    if (warp == CA2_G * 4) tc::tmem_dealloc(tmem_base, CA2_G * 128);
 }
 
 // generic 3-D tiled map: dims/box innermost first, element strides ld1 / ld2 of dims 1 / 2, 128-byte swizzle
@@ -308,11 +318,11 @@ static inline int make_tmap_3d(CUtensorMap* m, const void* ptr, CUtensorMapDataT
 
 template <int NK>
 static inline int launch_ca_vertex_fused_t(const CUtensorMap* maps, const CaFusedArgs& a, cudaStream_t st) {
-    if (!pmce_configure_smem<ca_vertex_fused_kernel<NK>>(CAF_SMEM)) return 2;
+    if (!pmce_configure_smem<ca_vertex_fused_kernel<NK>>(CA2_SMEM)) return 2;
     const int ntiles = a.B * a.qtiles;
-    const int cap = 3 * tc_num_sms();
+    const int cap = tc_num_sms();                      // one CTA per SM (193 KB of shared memory), CA2_G items in flight each
     const int grid = ntiles < cap ? ntiles : cap;
-    ca_vertex_fused_kernel<NK><<<grid, CAF_THREADS, CAF_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], a);
+    ca_vertex_fused_kernel<NK><<<grid, CA2_THREADS, CA2_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], a);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
@@ -325,16 +335,14 @@ struct CaFolded {
     float* sb;
 };
 
-// xq [B, N1, 64] fp32 (updated in place), t_hi/t_lo [B, N1, 64] bf16 (AdaLN_2 of the result, split)
-static inline int launch_ca_vertex_fused(float* xq, __nv_bfloat16* t_hi, __nv_bfloat16* t_lo, const CaFolded& f, CaFusedArgs a, cudaStream_t st) {
-    CUtensorMap maps[7];
+// xq [B, N1, 64] fp32, updated in place
+static inline int launch_ca_vertex_fused(float* xq, const CaFolded& f, CaFusedArgs a, cudaStream_t st) {
+    CUtensorMap maps[5];
     a.qtiles = (a.N1 + 127) / 128;
     a.sb = f.sb;
     if (make_tmap_3d(&maps[0], xq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 64, a.N1, a.B, 64, 64LL * a.N1, 32, 128, 1) ||
-        make_tmap_3d(&maps[1], t_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64, a.N1, a.B, 64, 64LL * a.N1, 64, 128, 1) ||
-        make_tmap_3d(&maps[2], t_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64, a.N1, a.B, 64, 64LL * a.N1, 64, 128, 1) ||
-        make_tmap_bf16(&maps[3], f.kq_hi, a.B * CAF_NS, 64, 64, CAF_NS) || make_tmap_bf16(&maps[4], f.kq_lo, a.B * CAF_NS, 64, 64, CAF_NS) ||
-        make_tmap_bf16(&maps[5], f.vp_hi, a.B * 64, 64, 64, 64) || make_tmap_bf16(&maps[6], f.vp_lo, a.B * 64, 64, 64, 64))
+        make_tmap_bf16(&maps[1], f.kq_hi, a.B * CAF_NS, 64, 64, CAF_NS) || make_tmap_bf16(&maps[2], f.kq_lo, a.B * CAF_NS, 64, 64, CAF_NS) ||
+        make_tmap_bf16(&maps[3], f.vp_hi, a.B * 64, 64, 64, 64) || make_tmap_bf16(&maps[4], f.vp_lo, a.B * 64, 64, 64, 64))
         return 1;
     if (a.N2 == 17) return launch_ca_vertex_fused_t<17>(maps, a, st);
     if (a.N2 == 19) return launch_ca_vertex_fused_t<19>(maps, a, st);
@@ -346,7 +354,9 @@ static inline int launch_ca_vertex_fused(float* xq, __nv_bfloat16* t_hi, __nv_bf
 //   Jf = W_jp P + b + jpos                       (CoevoDecoder.py:177)      [-> xq_out = Jf + jQ when asked, :182]
 //   xk = W_j2v Jf + b + j2v_K                    (:184)
 //   K  = Wk AdaLN_k(xk) + bk ;  V = Wv AdaLN_v(Jf) + bv     (:53-55 with :84)
-//   KQ = scale K_h Wq_h, sb = scale K_h bq_h, VPt = (V_h Wp[:, h]^T)^T       (the folded operands of ca_vertex_fused_kernel)
+//   KQ' = log2e scale (K_h Wq_h) diag(gamma_q), sb' = log2e (scale K_h bq_h + scale (K_h Wq_h) beta_q),
+//   VPt' = (V_h Wp[:, h]^T)^T + bp / 2 on the live key slots     (the folded operands of ca_vertex_fused_kernel: AdaLN_q's
+//   per-clip gamma / beta, the softmax's log2e and the output bias all live in them)
 // replacing six launches (embed, key projection, 2 x AdaLN, 2 x projection GEMM with 17 live rows per 128-row tile).
 // With joints == nullptr the kernel starts from given K / V [B,J,64] (pmce_cross_attn_block on arbitrary key/value streams).
 // Thread n (of 64 per row group) keeps row n of a 64x64 weight in registers; activations are broadcast from shared memory.
@@ -360,8 +370,8 @@ struct JointFoldArgs {
     const float *wjp, *bjp, *jpos, *jq;          // [64,3], [64], [J,64], [J,64] (jq optional)
     const float *wj2v, *bj2v, *j2vk;             // [64,64], [64], [J,64]
     const float *wk, *bk, *wv, *bv;              // [64,64], [64]
-    const float *wq, *bq, *wp;                   // [64,64], [64], [64,64] of the vertex cross-attention
-    const float* gb; int gb_ld, slot_k, slot_v;
+    const float *wq, *bq, *wp, *bp;              // [64,64], [64], [64,64], [64] of the vertex cross-attention
+    const float* gb; int gb_ld, slot_k, slot_v, slot_q;
     float* xq_out;                               // optional [B, J, 64]: Jf + jQ (query stream of the joint branch)
     CaFolded f;
     int J; float eps, scale;
@@ -467,8 +477,12 @@ ca_joint_fold_kernel(const __grid_constant__ JointFoldArgs3 args) {
             st4(Vs + idx * 4, ld4(a.V_in + (size_t)b * J * 64 + idx * 4));
         }
     }
+    __shared__ float sbacc[CAF_NS];              // sum_c KQ[s][c] beta_q[c]: two warps (c = 0..31, 32..63) add into each slot
+    if (tid < CAF_NS) sbacc[tid] = 0.f;
     cp_async_wait<0>();
     __syncthreads();
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float gq = a.gb[(size_t)b * a.gb_ld + a.slot_q * 128 + n], bq_ = a.gb[(size_t)b * a.gb_ld + a.slot_q * 128 + 64 + n];
     // ---- fold: KQ[32h+j][c] = scale sum_d K[j][32h+d] Wq[32h+d][c]  (thread = output channel c, coalesced weight columns) ----
 #pragma unroll 1
     for (int h = 0; h < CAF_H; ++h) {
@@ -487,18 +501,23 @@ ca_joint_fold_kernel(const __grid_constant__ JointFoldArgs3 args) {
                 }
                 acc = (a0 + a1) * a.scale;
             }
+            // (a + b == b + a: the two warps' contributions commute, the sum is deterministic)
+            const float part = warp_sum(acc * bq_);
+            if ((tid & 31) == 0 && j < J) atomicAdd(&sbacc[h * CAF_KP + j], part);
+            acc *= gq * LOG2E;
             __nv_bfloat16 hi, lo;
             tc::split_bf16(acc, hi, lo);
             const size_t o = ((size_t)b * CAF_NS + h * CAF_KP + j) * 64 + n;
             a.f.kq_hi[o] = hi; a.f.kq_lo[o] = lo;
         }
     }
-    if (tid < CAF_NS) {                          // sb[32h+j] = scale sum_d bq[32h+d] K[j][32h+d]
+    __syncthreads();                             // sbacc complete
+    if (tid < CAF_NS) {                          // sb'[32h+j] = log2e (scale sum_d bq[32h+d] K[j][32h+d] + sum_c KQ[32h+j][c] beta_q[c])
         const int h = tid / CAF_KP, j = tid % CAF_KP;
         float acc = 0.f;
         if (j < J)
             for (int d = 0; d < 32; ++d) acc = fmaf(a.bq[h * 32 + d], Ks[j * 64 + h * 32 + d], acc);
-        a.f.sb[(size_t)b * CAF_NS + tid] = acc * a.scale;
+        a.f.sb[(size_t)b * CAF_NS + tid] = (acc * a.scale + sbacc[tid]) * LOG2E;
     }
     // ---- fold: VPt[n][32h+j] = sum_d V[j][32h+d] Wp[n][32h+d]  (thread = output channel n, weight row in registers) ----
     {
@@ -523,7 +542,7 @@ ca_joint_fold_kernel(const __grid_constant__ JointFoldArgs3 args) {
                         a0 = fmaf(v.x, w[32 + d], a0); a1 = fmaf(v.y, w[32 + d + 1], a1); a0 = fmaf(v.z, w[32 + d + 2], a0); a1 = fmaf(v.w, w[32 + d + 3], a1);
                     }
                 }
-                acc = a0 + a1;
+                acc = (a0 + a1) + 0.5f * a.bp[n];           // every softmax row sums to 1: the two heads carry the output bias
             }
             VPs[idx * 65 + n] = acc;            // Jf/Xk/Nk (aliased) were last read before the barrier that published Ks/Vs
         }

@@ -22,12 +22,13 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 // two floats -> packed hi pair and lo pair (element 0 in the low half-word)
+// One packed conversion per pair (cvt.rn.bf16x2.f32 = F2FP.BF16.F32.PACK_AB on the ALU pipe): the scalar
+// __float2bfloat16_rn compiles to F2F.BF16.F32, a quarter-rate XU-pipe instruction shared with ex2/rcp - two of those per
+// element made every split-producing epilogue XU-bound. Same round-to-nearest-even results, bit for bit.
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
-    __nv_bfloat16 ah, al, bh, bl;
-    split_bf16(a, ah, al);
-    split_bf16(b, bh, bl);
-    hi2 = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-    lo2 = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(b), "f"(a));               // first source -> upper half
+    const float ah = __uint_as_float(hi2 << 16), bh = __uint_as_float(hi2 & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(b - bh), "f"(a - ah));
 }
 
 // ---- mbarrier ------------------------------------------------------------------------------------------
