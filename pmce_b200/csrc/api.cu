@@ -22,6 +22,7 @@
 #include "attn_tc.cuh"
 #include "attn_flash_tc.cuh"
 #include "ca_fused.cuh"
+#include "mlp_fused.cuh"
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -479,15 +480,54 @@ int adaln_gammabeta(const Layout& L, const Weights& W, const float* g, int B, fl
     return linear_tc(g_s, F, B, F, W, L.adaln_w, F, N, o, st);
 }
 
-// residual-stream tail shared by CrossAttentionBlock and Block: x += proj(att); x += fc2(gelu(fc1(AdaLN_2(x))))
-int attn_tail(const Weights& W, size_t wp, size_t bp, int s2, size_t fc1w, size_t fc1b, size_t fc2w, size_t fc2b, float* x, const SplitOut& att,
-              const SplitOut& tmp, const SplitOut& hid, const float* gb, int B, int ntok, cudaStream_t st) {
+bool mlp_fused_enabled() {
+    static int on = -1;      // PMCE_MLP_FUSED=0: keep AdaLN-apply + fc1 GEMM + fc2 GEMM as separate launches (A/B profiling, tests)
+    if (on < 0) on = pmce_env_int("PMCE_MLP_FUSED", 1) ? 1 : 0;
+    return on == 1;
+}
+
+// How the fused Mlp kernel closes the block (mlp_fused.cuh): nothing extra, the feature -> coordinate projection + residual
+// (CoevoDecoder.py:189), or the NEXT AdaLayerNorm as the split-bf16 operand of the next projection.
+struct MlpTail {
+    int epi = MLP_EPI_X;
+    size_t f2cw = 0, f2cb = 0; const float* coords_in = nullptr; float* coords_out = nullptr;     // MLP_EPI_F2C
+    int slot_next = 0; SplitOut t{nullptr, nullptr};                                              // MLP_EPI_T
+};
+
+// x += fc2(gelu(fc1(AdaLN_s2(x)))) over x [B*ntok, 64]   (CoevoDecoder.py:86 / :104)
+int adaln_mlp(const Weights& W, int s2, size_t fc1w, size_t fc1b, size_t fc2w, size_t fc2b, float* x, const SplitOut& tmp, const SplitOut& hid,
+              const float* gb, int B, int ntok, const MlpTail& tail, cudaStream_t st) {
     const int M = B * ntok;
-    { EpiOpt o; o.bias = W.f + bp; o.resid = x; o.ld_resid = 64; o.out = x; o.ld_out = 64; RET(linear_tc(att, 64, M, 64, W, wp, 64, 64, o, st)); }
+    if (mlp_fused_enabled()) {
+        MlpFusedArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x = x; a.gb = gb; a.gb_ld = PMCE_ADALN_SLOTS * 128; a.slot = s2; a.slot_next = tail.slot_next;
+        a.b1 = W.f + fc1b; a.b2 = W.f + fc2b; a.rows = M; a.ntok = ntok; a.eps = 1e-6f;
+        if (tail.epi == MLP_EPI_F2C) { a.wc = W.f + tail.f2cw; a.bc = W.f + tail.f2cb; a.coords_in = tail.coords_in; a.coords_out = tail.coords_out; }
+        MlpWeights w{W.hi + fc1w, W.lo + fc1w, W.hi + fc2w, W.lo + fc2w};
+        count_launch();
+        const int rc = launch_mlp64_fused(tail.epi, w, tail.t, a, st);
+        if (rc) { pmce_set_error("mlp64_fused launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
+        return 0;
+    }
     RET(adaln(x, B, ntok, gb, s2, tmp, st));
     { EpiOpt o; o.bias = W.f + fc1b; o.act = 1; o.outs = hid; o.ld_split = 256; RET(linear_tc(tmp, 64, M, 64, W, fc1w, 64, 256, o, st)); }
     { EpiOpt o; o.bias = W.f + fc2b; o.resid = x; o.ld_resid = 64; o.out = x; o.ld_out = 64; RET(linear_tc(hid, 256, M, 256, W, fc2w, 256, 64, o, st)); }
+    if (tail.epi == MLP_EPI_F2C) {
+        feat2coor_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, M, W.f + tail.f2cw, W.f + tail.f2cb, tail.coords_in, tail.coords_out);
+        CKL();
+    } else if (tail.epi == MLP_EPI_T) {
+        RET(adaln(x, B, ntok, gb, tail.slot_next, tail.t, st));
+    }
     return 0;
+}
+
+// residual-stream tail shared by CrossAttentionBlock and Block: x += proj(att); x += fc2(gelu(fc1(AdaLN_2(x))))
+int attn_tail(const Weights& W, size_t wp, size_t bp, int s2, size_t fc1w, size_t fc1b, size_t fc2w, size_t fc2b, float* x, const SplitOut& att,
+              const SplitOut& tmp, const SplitOut& hid, const float* gb, int B, int ntok, cudaStream_t st, const MlpTail& tail = MlpTail()) {
+    const int M = B * ntok;
+    { EpiOpt o; o.bias = W.f + bp; o.resid = x; o.ld_resid = 64; o.out = x; o.ld_out = 64; RET(linear_tc(att, 64, M, 64, W, wp, 64, 64, o, st)); }
+    return adaln_mlp(W, s2, fc1w, fc1b, fc2w, fc2b, x, tmp, hid, gb, B, ntok, tail, st);
 }
 
 int proj64(const SplitOut& a, int M, const Weights& W, size_t w, size_t b, float* out, cudaStream_t st, const float* rowadd = nullptr, int period = 1,
@@ -575,37 +615,36 @@ int ca_fused_launch(float* xq, int N1, int N2, int B, const CaFolded& f, cudaStr
 // the query side of a CrossAttentionBlock: xq [B,N1,64] updated in place. Needs projected K / V in s.K / s.V, or (folded) the
 // folded operands in s.fold when the fused kernel applies.
 int cross_attn_query(const Weights& W, const CaW& w, int heads, float* xq, int N1, int N2, const float* gb, int B, const AttnScratch& s, bool folded,
-                     cudaStream_t st) {
+                     cudaStream_t st, const MlpTail& tail = MlpTail()) {
     const int n1 = B * N1;
     if (ca_fused_ok(heads, N1, N2)) {
         if (!folded) RET(ca_fold(W, nullptr, w, nullptr, s.K, s.V, nullptr, gb, B, N2, heads, s.fold, st));
-        // one pass over the query stream: AdaLN_q, scores, softmax, P V Wp, residual (ca_fused.cuh); then AdaLN_2 + Mlp
+        // one pass over the query stream: AdaLN_q, scores, softmax, P V Wp, residual (ca_fused.cuh); then AdaLN_2 + Mlp (mlp_fused.cuh)
         RET(ca_fused_launch(xq, N1, N2, B, s.fold, st));
-        RET(adaln(xq, B, N1, gb, w.s2, s.tq, st));
-        { EpiOpt o; o.bias = W.f + w.fc1b; o.act = 1; o.outs = s.hid; o.ld_split = 256; RET(linear_tc(s.tq, 64, n1, 64, W, w.fc1w, 64, 256, o, st)); }
-        { EpiOpt o; o.bias = W.f + w.fc2b; o.resid = xq; o.ld_resid = 64; o.out = xq; o.ld_out = 64; RET(linear_tc(s.hid, 256, n1, 256, W, w.fc2w, 256, 64, o, st)); }
-        return 0;
+        return adaln_mlp(W, w.s2, w.fc1w, w.fc1b, w.fc2w, w.fc2b, xq, s.tq, s.hid, gb, B, N1, tail, st);
     }
     RET(adaln(xq, B, N1, gb, w.sq, s.tq, st));
     RET(proj64(s.tq, n1, W, w.wq, w.bq, s.Q, st));
     RET(mha_core(heads, s.Q, 64, s.K, s.V, 64, s.att, B, N1, N2, st));
-    return attn_tail(W, w.wp, w.bp, w.s2, w.fc1w, w.fc1b, w.fc2w, w.fc2b, xq, s.att, s.tq, s.hid, gb, B, N1, st);
+    return attn_tail(W, w.wp, w.bp, w.s2, w.fc1w, w.fc1b, w.fc2w, w.fc2b, xq, s.att, s.tq, s.hid, gb, B, N1, st, tail);
 }
 
 // a6 CrossAttentionBlock.forward (CoevoDecoder.py:82-87): xq [B,N1,64] updated in place; xk, xv [B,N2,64]
 int cross_attn_block(const Weights& W, const CaW& w, int heads, float* xq, int N1, const float* xk, const float* xv, int N2, const float* gb, int B,
-                     const AttnScratch& s, cudaStream_t st) {
+                     const AttnScratch& s, cudaStream_t st, const MlpTail& tail = MlpTail()) {
     RET(cross_attn_kv(W, w, xk, xv, N2, gb, B, s, st));
-    return cross_attn_query(W, w, heads, xq, N1, N2, gb, B, s, false, st);
+    return cross_attn_query(W, w, heads, xq, N1, N2, gb, B, s, false, st, tail);
 }
 
-// a7 Block.forward (CoevoDecoder.py:102-105): x [B,N,64] updated in place
-int self_attn_block(const Weights& W, const SaW& w, int heads, float* x, int N, const float* gb, int B, const AttnScratch& s, cudaStream_t st) {
+// a7 Block.forward (CoevoDecoder.py:102-105): x [B,N,64] updated in place. t_ready: s.tq already holds AdaLN_1(x) (split), written
+// by the previous block's fused Mlp epilogue. tail: how the block's Mlp kernel closes (e.g. the feature -> coordinate projection).
+int self_attn_block(const Weights& W, const SaW& w, int heads, float* x, int N, const float* gb, int B, const AttnScratch& s, cudaStream_t st,
+                    bool t_ready = false, const MlpTail& tail = MlpTail()) {
     const int n = B * N;
-    RET(adaln(x, B, N, gb, w.s1, s.tq, st));
+    if (!t_ready) RET(adaln(x, B, N, gb, w.s1, s.tq, st));
     RET(proj64(s.tq, n, W, w.qkvw, w.qkvb, s.Q, st, nullptr, 1, 192));
     RET(mha_core(heads, s.Q, 192, s.Q + 64, s.Q + 128, 192, s.att, B, N, N, st));
-    return attn_tail(W, w.wp, w.bp, w.s2, w.fc1w, w.fc1b, w.fc2w, w.fc2b, x, s.att, s.tq, s.hid, gb, B, N, st);
+    return attn_tail(W, w.wp, w.bp, w.s2, w.fc1w, w.fc1b, w.fc2w, w.fc2b, x, s.att, s.tq, s.hid, gb, B, N, st, tail);
 }
 
 AttnScratch vertex_scratch(const Workspace& ws) {   // query stream = the 431 vertices
@@ -664,19 +703,21 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
         }
         const AttnScratch s = joint_scratch(ws);
         // joint cross-attention block: q = joints (J), k/v = vertices (431); 8 heads x 8; then joint self-attention
-        RET(cross_attn_block(W, w.jca, JOINT_HEADS, ws.xqj, J, ws.xkv, ws.Vf, Vd, gb, B, s, sj));
-        RET(self_attn_block(W, w.jsa, JOINT_HEADS, ws.xqj, J, gb, B, s, sj));
-        feat2coor_kernel<<<cdiv(nj, 8), 256, 0, sj>>>(ws.xqj, nj, W.f + w.jf2cw, W.f + w.jf2cb, joints, joints_out);
-        CKL();
+        MlpTail tj_ca, tj_sa;                                  // the Mlp kernels also produce the next AdaLN / the coordinates
+        tj_ca.epi = MLP_EPI_T; tj_ca.slot_next = w.jsa.s1; tj_ca.t = s.tq;
+        tj_sa.epi = MLP_EPI_F2C; tj_sa.f2cw = w.jf2cw; tj_sa.f2cb = w.jf2cb; tj_sa.coords_in = joints; tj_sa.coords_out = joints_out;
+        RET(cross_attn_block(W, w.jca, JOINT_HEADS, ws.xqj, J, ws.xkv, ws.Vf, Vd, gb, B, s, sj, tj_ca));
+        RET(self_attn_block(W, w.jsa, JOINT_HEADS, ws.xqj, J, gb, B, s, sj, true, tj_sa));
         if (aux) CK(cudaEventRecord(aux->join2, aux->side));
     }
 
     // vertex cross-attention block: q = vertices (431), k/v = joints (J); 2 heads x 32; then vertex self-attention 431 x 431
     if (!fused) RET(cross_attn_kv(W, w.vca, ws.xkj, ws.Jf, J, gb, B, sv, st));
-    RET(cross_attn_query(W, w.vca, VERTX_HEADS, ws.xqv, Vd, J, gb, B, sv, fused, st));
-    RET(self_attn_block(W, w.vsa, VERTX_HEADS, ws.xqv, Vd, gb, B, sv, st));
-    feat2coor_kernel<<<cdiv(nv, 8), 256, 0, st>>>(ws.xqv, nv, W.f + w.vf2cw, W.f + w.vf2cb, verts_in, verts_out);
-    CKL();
+    MlpTail tv_ca, tv_sa;
+    tv_ca.epi = MLP_EPI_T; tv_ca.slot_next = w.vsa.s1; tv_ca.t = sv.tq;
+    tv_sa.epi = MLP_EPI_F2C; tv_sa.f2cw = w.vf2cw; tv_sa.f2cb = w.vf2cb; tv_sa.coords_in = verts_in; tv_sa.coords_out = verts_out;
+    RET(cross_attn_query(W, w.vca, VERTX_HEADS, ws.xqv, Vd, J, gb, B, sv, fused, st, tv_ca));
+    RET(self_attn_block(W, w.vsa, VERTX_HEADS, ws.xqv, Vd, gb, B, sv, st, true, tv_sa));
     if (ja && aux) CK(cudaStreamWaitEvent(st, aux->join2, 0));
     return 0;
 }

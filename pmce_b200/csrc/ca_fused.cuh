@@ -19,7 +19,9 @@
 //                     thread issues its MMAs and its TMA store.
 //   warp 8            producer of the x tiles (one lane): the group's IN buffer is released as soon as its 128 rows are in
 //                     registers, so the NEXT item's rows stream in under the whole chain of the current one.
-//   warp 9            producer of the per-clip operand tiles (KQ' | VPt', 32 KB, L2 hits for 3 of a clip's 4 tiles).
+//   warp 9 / 10       producers of the per-clip operand tiles KQ' / VPt' (16 KB each, L2 hits for 3 of a clip's 4 tiles): KQ' is
+//                     released by the commit of the first MMA and VPt' by the second, so the next item's KQ' is resident long
+//                     before its rows are normalised.
 // Shared memory per group: IN 32 KB (two [128][32 fp32] SW128 boxes) | A 32 KB (A tiles hi|lo, then P hi|lo, then the fp32
 // output boxes for the TMA store) | W 32 KB (KQ' hi|lo, VPt' hi|lo) = 96 KB; TMEM 128 columns per group (S | O).
 #pragma once
@@ -34,7 +36,7 @@ constexpr int CAF_MAXJ = 24;
 constexpr int CAF_H = 2;                                // heads of the vertex stream (CoevoDecoder.py:140)
 constexpr int CAF_NS = CAF_H * CAF_KP;                  // 64 score columns: column 32 h + j = (head h, key j)
 constexpr int CA2_G = 2;                                // consumer groups = items in flight per CTA
-constexpr int CA2_THREADS = CA2_G * 128 + 64;           // + x-tile producer warp + operand producer warp
+constexpr int CA2_THREADS = CA2_G * 128 + 96;           // + x-tile producer warp + two operand producer warps
 constexpr int CA2_IN = 2 * 128 * 128;                   // two [128][32 fp32] boxes
 constexpr int CA2_A = 2 * AT_TILE;                      // A tiles hi | lo ([128][64 bf16] each) = the two fp32 output boxes later
 constexpr int CA2_W = 4 * 8192;                         // KQ' hi | KQ' lo | VPt' hi | VPt' lo ([64][64 bf16] each)
@@ -65,8 +67,10 @@ __device__ __forceinline__ float ex2_approx(float x) {      // 2^x, rel. error 2
 
 struct CaFusedArgs {
     const float* sb;         // [B, 64] folded score bias sb' (log2 domain)
+    float* xq;               // [B, N1, 64] the stream itself (rows are stored straight from registers)
     int B, N1, N2, qtiles;
     float eps;
+    int tma_out;             // 1: stage the output rows in shared memory and TMA-store them (A/B knob PMCE_CA_TMA_OUT)
 };
 
 template <int NK>
@@ -81,34 +85,52 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CA2_OFF_BAR);
     uint64_t* in_full = bars;                    // [G] TMA bytes of the x tile
     uint64_t* in_empty = bars + CA2_G;           // [G] 4 arrivals: every consumer warp has its rows in registers
-    uint64_t* w_full = bars + 2 * CA2_G;         // [G] TMA bytes of the operand tiles
-    uint64_t* w_empty = bars + 3 * CA2_G;        // [G] tcgen05.commit after the item's second MMA
-    uint64_t* mma_bar = bars + 4 * CA2_G;        // [G] tcgen05.commit: S complete / O complete
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 5 * CA2_G);
+    uint64_t* kq_full = bars + 2 * CA2_G;        // [G] TMA bytes of KQ' hi|lo
+    uint64_t* kq_empty = bars + 3 * CA2_G;       // [G] tcgen05.commit after the item's first MMA
+    uint64_t* vp_full = bars + 4 * CA2_G;        // [G] TMA bytes of VPt' hi|lo
+    uint64_t* vp_empty = bars + 5 * CA2_G;       // [G] tcgen05.commit after the item's second MMA
+    uint64_t* mma_bar = bars + 6 * CA2_G;        // [G] tcgen05.commit: S complete / O complete
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 7 * CA2_G);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = a.B * a.qtiles;
     if (tid == 0) {
-        tc::tma_prefetch_desc(&tm_x); tc::tma_prefetch_desc(&tm_kq_hi); tc::tma_prefetch_desc(&tm_kq_lo);
-        tc::tma_prefetch_desc(&tm_vp_hi); tc::tma_prefetch_desc(&tm_vp_lo);
         for (int g = 0; g < CA2_G; ++g) {
             tc::mbar_init(&in_full[g], 1); tc::mbar_init(&in_empty[g], 4);
-            tc::mbar_init(&w_full[g], 1); tc::mbar_init(&w_empty[g], 1); tc::mbar_init(&mma_bar[g], 1);
+            tc::mbar_init(&kq_full[g], 1); tc::mbar_init(&kq_empty[g], 1); tc::mbar_init(&vp_full[g], 1); tc::mbar_init(&vp_empty[g], 1);
+            tc::mbar_init(&mma_bar[g], 1);
         }
         tc::fence_barrier_init();
         tc::fence_proxy_async();
+        // the first item of every group is requested here, before TMEM is allocated and the CTA assembles: at small batches
+        // (one or two items per CTA) this DRAM round trip is a third of the kernel
+        for (int g = 0; g < CA2_G; ++g) {
+            const int tile = blockIdx.x + g * gridDim.x;
+            if (tile >= ntiles) break;
+            const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
+            uint8_t* gbuf = smem + g * CA2_GBUF;
+            tc::mbar_arrive_expect_tx(&in_full[g], CA2_IN);
+            tc::tma_load_3d(gbuf, &tm_x, &in_full[g], 0, row0, b);
+            tc::tma_load_3d(gbuf + 16384, &tm_x, &in_full[g], 32, row0, b);
+            tc::mbar_arrive_expect_tx(&kq_full[g], CA2_W / 2);
+            tc::tma_load_2d(gbuf + CA2_IN + CA2_A, &tm_kq_hi, &kq_full[g], 0, b * CAF_NS);
+            tc::tma_load_2d(gbuf + CA2_IN + CA2_A + 8192, &tm_kq_lo, &kq_full[g], 0, b * CAF_NS);
+            tc::mbar_arrive_expect_tx(&vp_full[g], CA2_W / 2);
+            tc::tma_load_2d(gbuf + CA2_IN + CA2_A + 16384, &tm_vp_hi, &vp_full[g], 0, b * 64);
+            tc::tma_load_2d(gbuf + CA2_IN + CA2_A + 24576, &tm_vp_lo, &vp_full[g], 0, b * 64);
+        }
     }
     if (warp == CA2_G * 4) tc::tmem_alloc(tmem_ptr_smem, CA2_G * 128);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    const int ntiles = a.B * a.qtiles;
 
     if (warp == CA2_G * 4) {
         // ================= producer of the x tiles: item n of this CTA -> group n % G =================
         if (lane == 0) {
-            uint32_t n = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+            uint32_t n = CA2_G;                         // (the first round was requested in the prologue)
+            for (int tile = blockIdx.x + CA2_G * gridDim.x; tile < ntiles; tile += gridDim.x, ++n) {
                 const int g = n % CA2_G;
                 const uint32_t j = n / CA2_G;
                 const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
@@ -120,20 +142,33 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             }
         }
     } else if (warp == CA2_G * 4 + 1) {
-        // ================= producer of the per-clip operand tiles =================
+        // ================= producer of the KQ' tiles =================
         if (lane == 0) {
-            uint32_t n = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+            uint32_t n = CA2_G;
+            for (int tile = blockIdx.x + CA2_G * gridDim.x; tile < ntiles; tile += gridDim.x, ++n) {
                 const int g = n % CA2_G;
                 const uint32_t j = n / CA2_G;
                 const int b = tile / a.qtiles;
                 uint8_t* w = smem + g * CA2_GBUF + CA2_IN + CA2_A;
-                tc::mbar_wait(&w_empty[g], (j & 1) ^ 1);
-                tc::mbar_arrive_expect_tx(&w_full[g], CA2_W);
-                tc::tma_load_2d(w, &tm_kq_hi, &w_full[g], 0, b * CAF_NS);
-                tc::tma_load_2d(w + 8192, &tm_kq_lo, &w_full[g], 0, b * CAF_NS);
-                tc::tma_load_2d(w + 16384, &tm_vp_hi, &w_full[g], 0, b * 64);
-                tc::tma_load_2d(w + 24576, &tm_vp_lo, &w_full[g], 0, b * 64);
+                tc::mbar_wait(&kq_empty[g], (j & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&kq_full[g], CA2_W / 2);
+                tc::tma_load_2d(w, &tm_kq_hi, &kq_full[g], 0, b * CAF_NS);
+                tc::tma_load_2d(w + 8192, &tm_kq_lo, &kq_full[g], 0, b * CAF_NS);
+            }
+        }
+    } else if (warp == CA2_G * 4 + 2) {
+        // ================= producer of the VPt' tiles =================
+        if (lane == 0) {
+            uint32_t n = CA2_G;
+            for (int tile = blockIdx.x + CA2_G * gridDim.x; tile < ntiles; tile += gridDim.x, ++n) {
+                const int g = n % CA2_G;
+                const uint32_t j = n / CA2_G;
+                const int b = tile / a.qtiles;
+                uint8_t* w = smem + g * CA2_GBUF + CA2_IN + CA2_A + CA2_W / 2;
+                tc::mbar_wait(&vp_empty[g], (j & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&vp_full[g], CA2_W / 2);
+                tc::tma_load_2d(w, &tm_vp_hi, &vp_full[g], 0, b * 64);
+                tc::tma_load_2d(w + 8192, &tm_vp_lo, &vp_full[g], 0, b * 64);
             }
         }
     } else {
@@ -177,8 +212,10 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             const float nmi = -mean * inv;
 
             // ---- the A buffer is free once the previous item's TMA store has read it ----
-            if (leader && store_pending) tc::tma_store_wait_read<0>();
-            tc::bar_sync_group(1 + g);
+            if (a.tma_out) {
+                if (leader && store_pending) tc::tma_store_wait_read<0>();
+                tc::bar_sync_group(1 + g);
+            }
 
             // ---- n = (x - mean) inv -> split-bf16 A tiles ----
 #pragma unroll
@@ -195,7 +232,7 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             tc::tc_fence_before();
             tc::bar_sync_group(1 + g);
             if (leader) {
-                tc::mbar_wait(&w_full[g], j & 1);
+                tc::mbar_wait(&kq_full[g], j & 1);
                 tc::tc_fence_after();
                 constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, CAF_NS);
                 const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
@@ -207,6 +244,7 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
                     tc::umma_bf16(tS, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
                 }
                 tc::umma_commit(&mma_bar[g]);
+                tc::umma_commit(&kq_empty[g]);                      // KQ' goes back to its producer: the next item's tiles arrive early
             }
             // folded score bias of both heads (the same 2 x NK floats for every row of the clip: L1/L2 broadcast), in flight
             // while the MMA runs
@@ -257,6 +295,7 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             tc::tc_fence_before();
             tc::bar_sync_group(1 + g);
             if (leader) {
+                tc::mbar_wait(&vp_full[g], j & 1);
                 tc::tc_fence_after();
                 constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, 64);
                 const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
@@ -268,31 +307,52 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
                     tc::umma_bf16(tO, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
                 }
                 tc::umma_commit(&mma_bar[g]);
-                tc::umma_commit(&w_empty[g]);                       // the operand tiles go back to their producer
+                tc::umma_commit(&vp_empty[g]);
             }
             tc::mbar_wait(&mma_bar[g], 1);
             tc::tc_fence_after();
 
             // ---- xq' = xq + P VPt'^T -> fp32 boxes in the A buffer (both MMAs have read it) -> TMA store ----
+            if (a.tma_out) {
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                uint32_t v[32];
-                tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v);
-                tc::tmem_ld_wait();
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32];
+                    tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    tc::sts16f(out_row + hf * 16384 + ((c ^ sw) << 4),
-                               make_float4(x[hf * 32 + 4 * c] + __uint_as_float(v[4 * c]), x[hf * 32 + 4 * c + 1] + __uint_as_float(v[4 * c + 1]),
-                                           x[hf * 32 + 4 * c + 2] + __uint_as_float(v[4 * c + 2]), x[hf * 32 + 4 * c + 3] + __uint_as_float(v[4 * c + 3])));
-            }
-            tc::fence_proxy_async();
-            tc::tc_fence_before();
-            tc::bar_sync_group(1 + g);
-            if (leader) {
-                tc::tma_store_3d(&tm_x, smem + g * CA2_GBUF + CA2_IN, 0, row0, b);
-                tc::tma_store_3d(&tm_x, smem + g * CA2_GBUF + CA2_IN + 16384, 32, row0, b);
-                tc::tma_store_commit();
-                store_pending = true;
+                    for (int c = 0; c < 8; ++c)
+                        tc::sts16f(out_row + hf * 16384 + ((c ^ sw) << 4),
+                                   make_float4(x[hf * 32 + 4 * c] + __uint_as_float(v[4 * c]), x[hf * 32 + 4 * c + 1] + __uint_as_float(v[4 * c + 1]),
+                                               x[hf * 32 + 4 * c + 2] + __uint_as_float(v[4 * c + 2]), x[hf * 32 + 4 * c + 3] + __uint_as_float(v[4 * c + 3])));
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                tc::bar_sync_group(1 + g);
+                if (leader) {
+                    tc::tma_store_3d(&tm_x, smem + g * CA2_GBUF + CA2_IN, 0, row0, b);
+                    tc::tma_store_3d(&tm_x, smem + g * CA2_GBUF + CA2_IN + 16384, 32, row0, b);
+                    tc::tma_store_commit();
+                    store_pending = true;
+                }
+            } else {
+                // the thread's 256-byte row goes straight to global memory: no staging, no proxy fence, no group barrier, and the
+                // next item's A tiles never wait for a TMA store to drain the buffer
+                float* orow = a.xq + ((size_t)b * a.N1 + row0 + r) * 64;
+                const bool live = row0 + r < a.N1;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32];
+                    tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v);
+                    tc::tmem_ld_wait();
+                    if (live) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            __stcs(reinterpret_cast<float4*>(orow + hf * 32 + 4 * c),
+                                   make_float4(x[hf * 32 + 4 * c] + __uint_as_float(v[4 * c]), x[hf * 32 + 4 * c + 1] + __uint_as_float(v[4 * c + 1]),
+                                               x[hf * 32 + 4 * c + 2] + __uint_as_float(v[4 * c + 2]), x[hf * 32 + 4 * c + 3] + __uint_as_float(v[4 * c + 3])));
+                    }
+                }
+                tc::tc_fence_before();       // orders the TMEM reads above before the group barrier that precedes the next item's MMA
             }
         }
         if (leader && store_pending) tc::tma_store_wait_read<0>();     // smem must outlive the reads; the grid boundary orders the writes
@@ -340,6 +400,10 @@ static inline int launch_ca_vertex_fused(float* xq, const CaFolded& f, CaFusedAr
     CUtensorMap maps[5];
     a.qtiles = (a.N1 + 127) / 128;
     a.sb = f.sb;
+    a.xq = xq;
+    static int tma_out = -1;
+    if (tma_out < 0) tma_out = pmce_env_int("PMCE_CA_TMA_OUT", 1) ? 1 : 0;   // measured: direct row stores 27.6 us vs 23.8 us staged + TMA (B=256)
+    a.tma_out = tma_out;
     if (make_tmap_3d(&maps[0], xq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 64, a.N1, a.B, 64, 64LL * a.N1, 32, 128, 1) ||
         make_tmap_bf16(&maps[1], f.kq_hi, a.B * CAF_NS, 64, 64, CAF_NS) || make_tmap_bf16(&maps[2], f.kq_lo, a.B * CAF_NS, 64, 64, CAF_NS) ||
         make_tmap_bf16(&maps[3], f.vp_hi, a.B * 64, 64, 64, 64) || make_tmap_bf16(&maps[4], f.vp_lo, a.B * 64, 64, 64, 64))
