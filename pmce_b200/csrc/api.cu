@@ -23,6 +23,7 @@
 #include "attn_flash_tc.cuh"
 #include "ca_fused.cuh"
 #include "mlp_fused.cuh"
+#include "attn_rows_tc.cuh"
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -213,6 +214,13 @@ const SplitOut NO_SPLIT{nullptr, nullptr};
 int flash_attn32(const float* Q, AttnAddr aq, const float* K, const float* V, AttnAddr akv, const SplitOut& Os, AttnAddr ao, int nseq, int H, int N1,
                  int N2, cudaStream_t st) {
     count_launch();
+    static int rows_on = -1;      // PMCE_ATTN_ROWS=0: keep the chunked online-softmax kernel (A/B profiling; also the path for N2 > 448)
+    if (rows_on < 0) rows_on = pmce_env_int("PMCE_ATTN_ROWS", 1) ? 1 : 0;
+    if (rows_on && attn_rows_tc_supported(N2)) {
+        const int rc = launch_attn_rows_tc(Q, aq, K, V, akv, Os, ao, nseq, H, N1, N2, st);
+        if (rc) { pmce_set_error("attn_rows_tc launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
+        return 0;
+    }
     const int rc = launch_attn_flash_tc(Q, aq, K, V, akv, Os, ao, nseq, H, N1, N2, st);
     if (rc) { pmce_set_error("attn_flash_tc launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
     return 0;
