@@ -103,7 +103,7 @@ Workspace carve(const pmce_dims_t& d, int B, void* base) {
     for (int i = 0; i < 3; ++i) w.verts[i] = c.f32((size_t)B * Vd * 3);
     const size_t nv = (size_t)B * Vd, nj = (size_t)B * J;
     w.Jf = c.f32(nj * D); w.Vf = c.f32(nv * D); w.xqv = c.f32(nv * D);
-    w.xkj = c.f32(nj * D); w.Kj = c.f32(nj * D); w.Vj = c.f32(nj * D); w.qkv_d = c.f32(nv * 3 * D);
+    w.xkj = c.f32(nj * D); w.Kj = c.f32(nj * D); w.Vj = c.f32(nj * D); w.qkv_d = c.f32(nv * 4 * D);      /* fp32 qkv [nv,192] or the bf16 [nv,512] attention records */
     w.xqj = c.f32(nj * D); w.xkv = c.f32(nv * D); w.Kv = c.f32(nv * D); w.Vv = c.f32(nv * D); w.qkvj = c.f32(nj * 3 * D);
     w.Jf_s = c.split(nj * D); w.Vf_s = c.split(nv * D); w.tA_s = c.split(nv * D); w.tA2_s = c.split(nv * D); w.tJ_s = c.split(nj * D);
     w.att_ds = c.split(nv * D); w.hid_ds = c.split(nv * 4 * D); w.attj_s = c.split(nj * D); w.hidj_s = c.split(nj * 4 * D);
@@ -152,6 +152,7 @@ struct EpiOpt {
     const float* rowadd = nullptr; int period = 1;
     float* out = nullptr; int ld_out = 0;
     SplitOut outs{nullptr, nullptr}; int ld_split = 0;
+    bf16* att = nullptr; float qscale = 1.0f;       // TC_ATTN32: operand records of attn_rows_tc_kernel (gemm_tc.cuh)
     bool mapped = false; RowMap rmap{1, 0, 0}, cmap{1, 0, 0};
 };
 
@@ -164,6 +165,7 @@ int linear_tc(const SplitOut& A, int lda, int M, int K, const Weights& W, size_t
     e.bias = o.bias; e.act = o.act; e.resid = o.resid; e.ld_resid = o.ld_resid; e.rowadd = o.rowadd; e.rowadd_period = o.period;
     e.out_f32 = o.out; e.ld_out = o.ld_out; e.out_hi = o.outs.hi; e.out_lo = o.outs.lo; e.ld_split = o.ld_split;
     e.mapped = o.mapped ? 1 : 0; e.rmap = o.rmap; e.cmap = o.cmap;
+    e.out_att = o.att; e.qscale = o.qscale;
     count_launch();
     const int rc = launch_linear_tc(a, w, e, st);
     if (rc) { pmce_set_error("tensor-core GEMM launch failed (%d; M=%d N=%d K=%d): %s", rc, M, N, K, cudaGetErrorString(cudaGetLastError())); return 10; }
@@ -214,13 +216,6 @@ const SplitOut NO_SPLIT{nullptr, nullptr};
 int flash_attn32(const float* Q, AttnAddr aq, const float* K, const float* V, AttnAddr akv, const SplitOut& Os, AttnAddr ao, int nseq, int H, int N1,
                  int N2, cudaStream_t st) {
     count_launch();
-    static int rows_on = -1;      // PMCE_ATTN_ROWS=0: keep the chunked online-softmax kernel (A/B profiling; also the path for N2 > 448)
-    if (rows_on < 0) rows_on = pmce_env_int("PMCE_ATTN_ROWS", 1) ? 1 : 0;
-    if (rows_on && attn_rows_tc_supported(N2)) {
-        const int rc = launch_attn_rows_tc(Q, aq, K, V, akv, Os, ao, nseq, H, N1, N2, st);
-        if (rc) { pmce_set_error("attn_rows_tc launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
-        return 0;
-    }
     const int rc = launch_attn_flash_tc(Q, aq, K, V, akv, Os, ao, nseq, H, N1, N2, st);
     if (rc) { pmce_set_error("attn_flash_tc launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
     return 0;
@@ -549,6 +544,7 @@ struct AttnScratch {
     SplitOut tq, tk, tv;     // AdaLN outputs (split): [n1,64], [n2,64], [n2,64]   (self-attention uses tq only)
     float *Q, *K, *V;        // projected q/k/v fp32 [n1,64], [n2,64], [n2,64]    (self-attention: Q = qkv [n1,192])
     SplitOut att, hid;       // attention output [n1,64], MLP hidden [n1,256] (split)
+    bf16* att_rec;           // [n1, 512] operand records of attn_rows_tc_kernel (vertex stream only; aliases the fp32 qkv buffer)
     CaFolded fold;           // folded per-clip operands (fused vertex cross-attention only)
 };
 
@@ -650,8 +646,19 @@ int self_attn_block(const Weights& W, const SaW& w, int heads, float* x, int N, 
                     bool t_ready = false, const MlpTail& tail = MlpTail()) {
     const int n = B * N;
     if (!t_ready) RET(adaln(x, B, N, gb, w.s1, s.tq, st));
-    RET(proj64(s.tq, n, W, w.qkvw, w.qkvb, s.Q, st, nullptr, 1, 192));
-    RET(mha_core(heads, s.Q, 192, s.Q + 64, s.Q + 128, 192, s.att, B, N, N, st));
+    static int rows_on = -1;      // PMCE_ATTN_ROWS=0: fp32 qkv + the chunked online-softmax kernel (A/B profiling; also the path for N > 448)
+    if (rows_on < 0) rows_on = pmce_env_int("PMCE_ATTN_ROWS", 1) ? 1 : 0;
+    if (rows_on && s.att_rec && attn_rows_tc_supported(heads, N)) {
+        // the qkv projection writes the attention kernel's operand tiles (TC_ATTN32 epilogue); whole score rows in TMEM (attn_rows_tc.cuh)
+        EpiOpt o; o.bias = W.f + w.qkvb; o.att = s.att_rec; o.qscale = attn_rows_qscale();
+        RET(linear_tc(s.tq, 64, n, 64, W, w.qkvw, 64, 192, o, st));
+        count_launch();
+        const int rc = launch_attn_rows_tc(s.att_rec, s.att, addr_plain(N, 64), B, heads, N, st);
+        if (rc) { pmce_set_error("attn_rows_tc launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
+    } else {
+        RET(proj64(s.tq, n, W, w.qkvw, w.qkvb, s.Q, st, nullptr, 1, 192));
+        RET(mha_core(heads, s.Q, 192, s.Q + 64, s.Q + 128, 192, s.att, B, N, N, st));
+    }
     return attn_tail(W, w.wp, w.bp, w.s2, w.fc1w, w.fc1b, w.fc2w, w.fc2b, x, s.att, s.tq, s.hid, gb, B, N, st, tail);
 }
 
@@ -659,12 +666,14 @@ AttnScratch vertex_scratch(const Workspace& ws) {   // query stream = the 431 ve
     AttnScratch s;
     s.tq = ws.tA_s; s.tk = ws.tJ_s; s.tv = ws.tJ_s; s.Q = ws.qkv_d; s.K = ws.Kj; s.V = ws.Vj; s.att = ws.att_ds; s.hid = ws.hid_ds;
     s.fold = ws.fold[0];
+    s.att_rec = reinterpret_cast<bf16*>(ws.qkv_d);       // nv * 512 bf16 = nv * 1024 B <= the fp32 qkv buffer's nv * 192 * 4 B... (see carve)
     return s;
 }
 AttnScratch joint_scratch(const Workspace& ws) {    // query stream = the J joints
     AttnScratch s;
     s.tq = ws.tJ2_s; s.tk = ws.tB_s; s.tv = ws.tA2_s; s.Q = ws.qkvj; s.K = ws.Kv; s.V = ws.Vv; s.att = ws.attj_s; s.hid = ws.hidj_s;
     memset(&s.fold, 0, sizeof(s.fold));
+    s.att_rec = nullptr;
     return s;
 }
 constexpr int JOINT_HEADS = 8, VERTX_HEADS = 2;      // CoevoDecoder.py:139-140

@@ -20,7 +20,16 @@
 #include "common.cuh"
 #include "host_once.h"
 
-enum TcMode { TC_F32 = 0, TC_F32_RESID = 1, TC_SPLIT_GELU = 2, TC_GENERIC = 3, TC_NULL = 4, TC_SPLIT = 5 };
+enum TcMode { TC_F32 = 0, TC_F32_RESID = 1, TC_SPLIT_GELU = 2, TC_GENERIC = 3, TC_NULL = 4, TC_SPLIT = 5, TC_ATTN32 = 6 };
+
+// TC_ATTN32: the fused qkv projection of a 64-wide stream with 2 heads of 32 (N = 192 = q|k|v) writes the operand tiles of
+// attn_rows_tc_kernel directly, as one bf16 tensor [M, 512] of 128-byte (row, head) records, so the attention kernel takes them
+// by TMA in the layout its MMAs read (head_dim 32 = 64-byte operand rows: hi|lo halves are CONCATENATED into 128-byte rows):
+//   cols [  0,128): QC = per head [q_hi | q_lo] (q already times softmax-scale * log2e)
+//   cols [128,256): K1 = per head [k_hi | k_hi]
+//   cols [256,384): K2 = per head [k_lo | k_lo]
+//   cols [384,512): VC = per head [v_hi | v_lo]
+constexpr int TC_ATT_LD = 512;
 
 struct TcEpi {
     const float* bias;      // [N] or null
@@ -32,9 +41,11 @@ struct TcEpi {
     float* out_f32;         // fp32 [M, ld_out] or null
     __nv_bfloat16* out_hi;  // split output [M, ld_split] or null (both hi and lo, or neither)
     __nv_bfloat16* out_lo;
+    __nv_bfloat16* out_att; // TC_ATTN32: [M, TC_ATT_LD] operand records (N must be 192)
     int ld_out, ld_split;
     int mapped;             // out_f32 / resid are addressed as rmap(row) + cmap(col) instead of row*ld + col
     RowMap rmap, cmap;
+    float qscale;           // TC_ATTN32: factor applied to the q columns before the split
     int dbg;                // profiling only (PMCE_TC_DBG): 1 = stage but do not issue TMA stores, 2 = no staging either
     int pair_relaxed;       // CTA pairs: release the accumulator with a relaxed cluster-scope arrive (PMCE_TC_PAIR_RELAXED=1)
 };
@@ -125,7 +136,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA_hi); tc::tma_prefetch_desc(&tmA_lo);
         tc::tma_prefetch_desc(&tmW_hi); tc::tma_prefetch_desc(&tmW_lo);
-        if (MODE == TC_F32 || MODE == TC_F32_RESID || MODE == TC_SPLIT_GELU || MODE == TC_SPLIT) tc::tma_prefetch_desc(&om.out);
+        if (MODE == TC_F32 || MODE == TC_F32_RESID || MODE == TC_SPLIT_GELU || MODE == TC_SPLIT || MODE == TC_ATTN32) tc::tma_prefetch_desc(&om.out);
         if (MODE == TC_SPLIT_GELU || MODE == TC_SPLIT) tc::tma_prefetch_desc(&om.out_lo);
         if (MODE == TC_F32_RESID) tc::tma_prefetch_desc(&om.resid);
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
@@ -296,14 +307,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if (e.dbg == 1) continue;
                     if (lane == 0) { tc::tma_store_2d(&om.out, stg, col0, row0); tc::tma_store_commit(); }
                     store_pending = true;
-                } else if (MODE == TC_SPLIT_GELU || MODE == TC_SPLIT) {
+                } else if (MODE == TC_SPLIT_GELU || MODE == TC_SPLIT || MODE == TC_ATTN32) {
                     uint32_t hi[TC_CW / 2], lo[TC_CW / 2];
+                    const float qs = (MODE == TC_ATTN32 && col0 < 64) ? e.qscale : 1.0f;
 #pragma unroll
                     for (int i = 0; i < TC_CW; i += 4) {
                         const float4 b = ld4(e.bias + col0 + i);
                         float x0 = __uint_as_float(v[i]) + b.x, x1 = __uint_as_float(v[i + 1]) + b.y;
                         float x2 = __uint_as_float(v[i + 2]) + b.z, x3 = __uint_as_float(v[i + 3]) + b.w;
                         if (MODE == TC_SPLIT_GELU) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
+                        if (MODE == TC_ATTN32) { x0 *= qs; x1 *= qs; x2 *= qs; x3 *= qs; }
                         tc::split_bf16x2(x0, x1, hi[i / 2], lo[i / 2]);
                         tc::split_bf16x2(x2, x3, hi[i / 2 + 1], lo[i / 2 + 1]);
                     }
@@ -320,8 +333,25 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     tc::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tc::tma_store_2d(&om.out, stg, col0, row0);
-                        tc::tma_store_2d(&om.out_lo, stg + 1024, col0, row0);
+                        if (MODE == TC_ATTN32) {
+                            // col0 = 64 * which + 32 * head + d0 (d0 = 0 or 16) -> record column 64 * head + d0 (+ 32 for the second half)
+                            const int which = col0 >> 6, rc = ((col0 >> 5) & 1) * 64 + (col0 & 31);
+                            if (which == 0) {            // q: [hi | lo]
+                                tc::tma_store_2d(&om.out, stg, rc, row0);
+                                tc::tma_store_2d(&om.out, stg + 1024, rc + 32, row0);
+                            } else if (which == 1) {     // k: K1 = [hi | hi], K2 = [lo | lo]
+                                tc::tma_store_2d(&om.out, stg, 128 + rc, row0);
+                                tc::tma_store_2d(&om.out, stg, 128 + rc + 32, row0);
+                                tc::tma_store_2d(&om.out, stg + 1024, 256 + rc, row0);
+                                tc::tma_store_2d(&om.out, stg + 1024, 256 + rc + 32, row0);
+                            } else {                     // v: [hi | lo]
+                                tc::tma_store_2d(&om.out, stg, 384 + rc, row0);
+                                tc::tma_store_2d(&om.out, stg + 1024, 384 + rc + 32, row0);
+                            }
+                        } else {
+                            tc::tma_store_2d(&om.out, stg, col0, row0);
+                            tc::tma_store_2d(&om.out_lo, stg + 1024, col0, row0);
+                        }
                         tc::tma_store_commit();
                     }
                     store_pending = true;
@@ -466,6 +496,11 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
             if (make_tmap(&om.resid, e.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_resid, TC_CW, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
             return launch_linear_tc_mode<BN, TC_F32_RESID>(ta, tw, om, M, N, K, e, st);
         }
+    }
+    if (e.out_att) {
+        if (!plain || N != 192 || e.out_f32 || e.out_hi || e.resid || e.act || !a16(e.out_att)) return 4;
+        if (make_tmap(&om.out, e.out_att, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, TC_ATT_LD, TC_ATT_LD, TC_CW, 32, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+        return launch_linear_tc_mode<BN, TC_ATTN32>(ta, tw, om, M, N, K, e, st);
     }
     if (plain && e.out_hi && !e.out_f32 && !e.resid && a16(e.out_hi) && a16(e.out_lo) && e.ld_split % 8 == 0) {
         if (make_tmap(&om.out, e.out_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, e.ld_split, TC_CW, 32, CU_TENSOR_MAP_SWIZZLE_NONE) ||
