@@ -288,12 +288,15 @@ def main():
     sets = [tuple(t.to(dev) for t in synth.make_inputs(B, T, J, seed=100 + rank * NSETS + i)) for i in range(NSETS)]
     host_sets = [tuple(t.pin_memory() for t in synth.make_inputs(B, T, J, seed=100 + rank * NSETS + i)) for i in range(NSETS)]
 
+    # N > 1: the forward writes straight into this rank's row of an all-gather buffer; the single collective of the path (an
+    # in-place all-gather of the per-rank outputs) runs on a communication stream under the next step's forward
+    sf = pdist.ShardedForward(model, B, J, dev) if world > 1 else None
+
     def step(i):
         p2d, feat = sets[i % NSETS]
-        mesh, cam_pose, pose3d = model(p2d, feat)
-        if world > 1:   # the single collective of the path: all-gather of the per-rank packed outputs
-            return pdist.all_gather_blocks(pdist.pack_outputs(mesh, cam_pose, pose3d, B))
-        return mesh
+        if sf is not None:
+            return sf.step(p2d, feat)
+        return model(p2d, feat)[0]
 
     host_out = (torch.empty(B, V, 3).pin_memory(), torch.empty(B, J, 3).pin_memory(), torch.empty(B, J, 3).pin_memory())
 
@@ -338,10 +341,17 @@ def main():
 
     # e2e: the public host-buffer API, pipelined over the K batches (H2D of batch i+1 / D2H of batch i-1 overlap forward i);
     # every step copies its own inputs from pinned host memory and its three outputs back, and the consumer reads them
+    hooks = {}
+    if sf is not None:        # e2e at N > 1 includes the all-gather of every step (issued from the pipeline's forward stream)
+        hooks = dict(out_slots=[sf.views(sf.bufs[k], rank) for k in range(2)], before_forward=sf.wait_slot_free, after_forward=sf.gather_async)
+
     def run_e2e(k):
         acc = 0.0
-        for mesh_h, pose_h, p3_h in model.forward_host_iter(host_sets[i % NSETS] for i in range(k)):
+        for mesh_h, pose_h, p3_h in model.forward_host_iter((host_sets[i % NSETS] for i in range(k)), **hooks):
             acc += float(mesh_h[0, 0, 0]) + float(pose_h[0, 0, 0])      # the host really reads each step's result
+        if sf is not None:
+            for k2 in range(2):
+                sf.result(k2)                                           # the last gathers are part of the timed region
         return acc
 
     def timed_host(k):
@@ -368,6 +378,20 @@ def main():
     h2d = B * (T * J * 2 + T * 2048) * 4
     d2h = B * (V * 3 + 2 * J * 3) * 4
 
+    # BASELINE.json configs[3]: B=1024 sharded over 8 GPUs (128 clips per GPU) + the all-gather, beside the weak-scaling line
+    b1024 = None
+    if world == 8:
+        Bs = 1024 // world
+        sets_s = [tuple(t.to(dev) for t in synth.make_inputs(Bs, T, J, seed=500 + rank * NSETS + i)) for i in range(NSETS)]
+        sfs = pdist.ShardedForward(model, Bs, J, dev)
+        fn = lambda i: sfs.step(*sets_s[i % NSETS])
+        for i in range(W):
+            fn(i)
+        ms_s = timed(fn, K)
+        b1024 = {"workload": f"B=1024 T={T} C={C} batch-sharded over 8 GPUs ({Bs} clips per GPU) + 1 all-gather", "value": 1024 * K / (ms_s * 1e-3),
+                 "unit": "clips/s", "ms_per_step": ms_s / K}
+        del sfs, sets_s
+
     # roofline of the dominant kernel, timed alone with CUDA events on the launch stream
     roof = dominant_kernel_roofline(lib, dev, peaks, B)
     roof_ca = cross_attn_roofline(lib, eng, dev, peaks, B)
@@ -385,7 +409,7 @@ def main():
                 "unpipelined": {"value": world * B * K / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync / K,
                                 "path": "models.PMCE.forward_host: H2D -> forward -> D2H -> sync per step"}},
         "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
-        "clocks": clocks, "roofline": roof, "roofline_cross_attn": roof_ca, "peaks": peaks,
+        "config3_B1024_x8": b1024, "clocks": clocks, "roofline": roof, "roofline_cross_attn": roof_ca, "peaks": peaks,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -63,13 +63,17 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + ep
 constexpr int TC_CW = 16;            // epilogue chunk width in columns
 constexpr int TC_STG = 2048;         // staging bytes per epilogue warp: [32][16] fp32, or [32][16] bf16 hi + lo
 
-template <int BN, int NCTA = 1>
+// NBUF: staging tiles per epilogue warp. A warp may only refill a staging tile once the TMA store that reads it has drained; with
+// one tile per warp the epilogue's pace is (staging bytes in flight) / (store drain latency), with two the warp fills tile b while
+// the store of tile b^1 drains (cp.async.bulk.wait_group.read 1).
+template <int BN, int NCTA = 1, int NBUF = 1>
 struct TcCfg {
     static constexpr int A_TILE = TC_BM * 128;          // bytes per A half (hi or lo)
     static constexpr int W_TILE = (BN / NCTA) * 128;    // per CTA: a CTA pair holds half of the tile's W rows each
     static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;
-    static constexpr int STG_BYTES = TC_EPI_WARPS * TC_STG;          // per-warp epilogue staging tiles (1024-B aligned)
-    static constexpr int STAGES = (196 * 1024) / STAGE_BYTES >= 4 ? 4 : (196 * 1024) / STAGE_BYTES;
+    static constexpr int STG_BYTES = TC_EPI_WARPS * TC_STG * NBUF;   // per-warp epilogue staging tiles (1024-B aligned)
+    static constexpr int RING_BYTES = 227 * 1024 - 1024 - 256 - STG_BYTES;
+    static constexpr int STAGES = RING_BYTES / STAGE_BYTES >= 4 ? 4 : RING_BYTES / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // two accumulators
     static_assert(STAGES >= 2, "tile too large");
@@ -109,12 +113,12 @@ __device__ __forceinline__ void tc_epilogue_generic(const TcEpi& e, const uint32
 // NCTA == 2: the same kernel on CTA pairs (cluster of 2, tcgen05 cta_group::2): one 256 x 256 tile per pair, each CTA loads
 // its 128 rows of A and HALF of the tile's W rows (a third less operand traffic L2->SM and smem per FLOP than two 128 x 256
 // tiles), the leader issues the MMAs for both, each CTA drains its own 128 accumulator rows.
-template <int BN, int MODE, int NCTA>
+template <int BN, int MODE, int NCTA, int NBUF = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                  const __grid_constant__ TcOutMaps om, int M, int N, int K, TcEpi e) {
-    using Cfg = TcCfg<BN, NCTA>;
+    using Cfg = TcCfg<BN, NCTA, NBUF>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -222,9 +226,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int q = warp & 3;
         const int cg = ew >> 2;
         constexpr int CH = BN / TC_CW;                        // 16-column chunks per tile
-        uint8_t* stg = stg_all + ew * TC_STG;                 // this warp's staging tile
-        const uint32_t stg_u32 = tc::smem_u32(stg);
-        uint32_t tcount = 0, rcount = 0;
+        uint8_t* const stg_base = stg_all + ew * TC_STG * NBUF;   // this warp's staging tile(s)
+        uint32_t tcount = 0, rcount = 0, ccount = 0;
         bool store_pending = false;
         // accumulator-drained arrivals go to the leader's barrier (its MMA thread is the only waiter)
         const uint32_t te_bar[2] = {tc::mapa_rank(tc::smem_u32(&tmem_empty_bar[0]), 0), tc::mapa_rank(tc::smem_u32(&tmem_empty_bar[1]), 0)};
@@ -249,10 +252,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             for (int c = cg; c < CH; c += 4) {
                 const int col0 = n0 + c * TC_CW;
                 const bool live = row0 < M && col0 < N;          // warp-uniform
+                uint8_t* const stg = stg_base + (NBUF > 1 ? (ccount % NBUF) * TC_STG : 0);
+                const uint32_t stg_u32 = tc::smem_u32(stg);
+                if (live) ++ccount;
                 if (MODE == TC_F32_RESID && live) {
                     // the staging tile is about to be overwritten by the residual load: the previous store must have read it
                     if (lane == 0) {
-                        if (store_pending) tc::tma_store_wait_read<0>();
+                        if (store_pending) tc::tma_store_wait_read<NBUF - 1>();
                         tc::mbar_arrive_expect_tx(&resid_bar[ew], TC_STG);
                         tc::tma_load_2d(stg, &om.resid, &resid_bar[ew], col0, row0);
                     }
@@ -295,7 +301,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
                         }
                     } else {
-                        if (store_pending) { if (lane == 0) tc::tma_store_wait_read<0>(); __syncwarp(); }
+                        if (store_pending) { if (lane == 0) tc::tma_store_wait_read<NBUF - 1>(); __syncwarp(); }
                     }
                     if (e.dbg == 2) { if (f[0] == 123.456f) e.out_f32[0] = f[1]; continue; }
 #pragma unroll
@@ -320,7 +326,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         tc::split_bf16x2(x0, x1, hi[i / 2], lo[i / 2]);
                         tc::split_bf16x2(x2, x3, hi[i / 2 + 1], lo[i / 2 + 1]);
                     }
-                    if (store_pending) { if (lane == 0) tc::tma_store_wait_read<0>(); __syncwarp(); }
+                    if (store_pending) { if (lane == 0) tc::tma_store_wait_read<NBUF - 1>(); __syncwarp(); }
                     // two dense [32 rows][16 bf16] tiles (32-byte rows, no swizzle): hi at +0, lo at +1024
                     const uint32_t rowaddr = stg_u32 + lane * 32;
 #pragma unroll
@@ -448,16 +454,24 @@ static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap
                                         cudaStream_t st) {
     if (BN == 256 && tc_pair_enabled(M, N, K)) {
         constexpr int BNP = BN == 256 ? 256 : 256;
-        if (!pmce_configure_smem<linear_tc_kernel<BNP, MODE, 2>>(TcCfg<BNP, 2>::SMEM_BYTES)) return 2;
+        static int nbuf = -1;     // PMCE_TC_NBUF=2: two staging tiles per epilogue warp and a two-stage operand ring (A/B knob)
+        if (nbuf < 0) nbuf = pmce_env_int("PMCE_TC_NBUF", 1);
         const long long tiles = (long long)((N + 255) / 256) * ((M + 2 * TC_BM - 1) / (2 * TC_BM));
         const int pairs = (int)(tiles < tc_num_sms() / 2 ? tiles : tc_num_sms() / 2);
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BNP, 2>::SMEM_BYTES; cfg.stream = st;
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
+        if (nbuf == 2 && MODE != TC_GENERIC && MODE != TC_NULL) {
+            if (!pmce_configure_smem<linear_tc_kernel<BNP, MODE, 2, 2>>(TcCfg<BNP, 2, 2>::SMEM_BYTES)) return 2;
+            cfg.dynamicSmemBytes = TcCfg<BNP, 2, 2>::SMEM_BYTES;
+            return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 2, 2>, ta[0], ta[1], tw[0], tw[1], om, M, N, K, e) == cudaSuccess ? 0 : 3;
+        }
+        if (!pmce_configure_smem<linear_tc_kernel<BNP, MODE, 2>>(TcCfg<BNP, 2>::SMEM_BYTES)) return 2;
+        cfg.dynamicSmemBytes = TcCfg<BNP, 2>::SMEM_BYTES;
         return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 2>, ta[0], ta[1], tw[0], tw[1], om, M, N, K, e) == cudaSuccess ? 0 : 3;
     }
     if (!pmce_configure_smem<linear_tc_kernel<BN, MODE, 1>>(TcCfg<BN>::SMEM_BYTES)) return 2;

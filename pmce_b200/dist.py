@@ -73,3 +73,75 @@ def sharded_forward(forward_fn, pose2d, img_feat, num_vert=6890, group=None, gat
             return e.reshape(0, num_vert, 3), e.reshape(0, J, 3), e.reshape(0, J, 3)
         block = pose2d.new_zeros(per, width)
     return unpack_outputs(all_gather_blocks(block, group), B, num_vert, J)
+
+
+class ShardedForward:
+    """The multi-GPU step of the path, without staging copies and with the collective off the critical path.
+
+    Every rank owns `slots` gather buffers of shape [world, per * width]. Row `rank` of a buffer is three contiguous sections
+    `cam_mesh [per,6890,3] | cam_pose [per,J,3] | pose3d [per,J,3]`, and the forward writes its outputs STRAIGHT into them
+    (`forward_fn(pose2d, img_feat, out=...)`, no pack kernel). The single collective, an in-place all-gather of the rank rows,
+    is issued on a communication stream: step i+1's forward (other slot) runs under step i's gather. `result(i)` waits for the
+    gather of step i and returns per-rank views (rank-major; `unpack` concatenates them when one global tensor is wanted).
+    """
+
+    def __init__(self, forward_fn, per, num_joint, device, num_vert=6890, group=None, slots=2):
+        self.fn, self.per, self.J, self.V, self.group = forward_fn, per, num_joint, num_vert, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.sizes = (per * num_vert * 3, per * num_joint * 3, per * num_joint * 3)
+        self.width = sum(self.sizes)
+        self.bufs = [torch.zeros(self.world, self.width, device=device) for _ in range(slots)]
+        self.cuda = torch.device(device).type == "cuda"
+        if self.cuda:
+            self.comm = torch.cuda.Stream(device=device)
+            self.ev_fwd = [torch.cuda.Event() for _ in range(slots)]
+            self.ev_comm = [torch.cuda.Event() for _ in range(slots)]
+        self.steps = 0
+
+    def views(self, buf, r):
+        a, b, _ = self.sizes
+        row = buf[r]
+        return (row[:a].view(self.per, self.V, 3), row[a:a + b].view(self.per, self.J, 3), row[a + b:].view(self.per, self.J, 3))
+
+    def step(self, pose2d, img_feat):
+        """One forward on this rank's `per` clips + the (asynchronous) all-gather of the step. Returns the slot index."""
+        k = self.steps % len(self.bufs)
+        self.steps += 1
+        buf = self.bufs[k]
+        out = self.views(buf, self.rank)
+        if self.cuda:
+            self.wait_slot_free(k)
+            self.fn(pose2d, img_feat, out=out)
+            self.gather_async(k)
+        else:                                              # gloo / CPU: same data flow, synchronous
+            self.fn(pose2d, img_feat, out=out)
+            chunks = [torch.empty_like(buf[0]) for _ in range(self.world)]
+            dist.all_gather(chunks, buf[self.rank].clone(), group=self.group)
+            for r, c in enumerate(chunks):
+                buf[r].copy_(c)
+        return k
+
+    def wait_slot_free(self, k):
+        """Make the current stream wait until the previous gather out of slot k has finished (before writing the slot again)."""
+        torch.cuda.current_stream().wait_event(self.ev_comm[k])
+
+    def gather_async(self, k):
+        """Issue slot k's in-place all-gather on the communication stream, after everything queued on the current stream."""
+        buf = self.bufs[k]
+        self.ev_fwd[k].record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ev_fwd[k])
+            dist.all_gather_into_tensor(buf.view(-1), buf[self.rank], group=self.group)     # in place: row `rank` is the send buffer
+            self.ev_comm[k].record(self.comm)
+
+    def result(self, k):
+        """Per-rank (cam_mesh, cam_pose, pose3d) views of slot k, valid once its gather has completed (waited for here)."""
+        if self.cuda:
+            torch.cuda.current_stream().wait_event(self.ev_comm[k])
+        return [self.views(self.bufs[k], r) for r in range(self.world)]
+
+    def unpack(self, k, total=None):
+        """Global (cam_mesh [B,6890,3], cam_pose [B,J,3], pose3d [B,J,3]) of slot k (a concatenating copy), padding dropped."""
+        parts = self.result(k)
+        total = self.world * self.per if total is None else total
+        return tuple(torch.cat([p[i] for p in parts], dim=0)[:total] for i in range(3))

@@ -113,8 +113,12 @@ class Engine:
                                     _ptr(mesh), _ptr(cam_pose), _ptr(pose3d), _ptr(ws), ws.numel(), _stream()),
               "pmce_forward")
 
-    def forward(self, pose2d, img_feat):
-        """PMCE.forward: ([B,T,J,2], [B,T,2048]) -> (cam_mesh [B,6890,3], cam_pose [B,J,3], pose3d [B,J,3])."""
+    def forward(self, pose2d, img_feat, out=None):
+        """PMCE.forward: ([B,T,J,2], [B,T,2048]) -> (cam_mesh [B,6890,3], cam_pose [B,J,3], pose3d [B,J,3]).
+
+        `out` = (cam_mesh, cam_pose, pose3d) caller-owned contiguous CUDA tensors: the kernels write straight into them (in
+        graph mode a graph is captured per (B, output buffers) and replayed without the final clones) - e.g. a rank's slot of an
+        all-gather buffer (`pmce_b200.dist.ShardedForward`)."""
         self._ready(need_vj=True)
         d = self.dims
         B = pose2d.shape[0] if isinstance(pose2d, torch.Tensor) and pose2d.dim() == 4 else -1
@@ -123,28 +127,36 @@ class Engine:
         dev = pose2d.device
         if dev != self.weights.device:
             raise PmceError(f"inputs on {dev} but weights on {self.weights.device}")
+        if out is not None:
+            shapes = ((B, d.num_vert, 3), (B, d.num_joint, 3), (B, d.num_joint, 3))
+            for t, n, sh in zip(out, ("cam_mesh", "cam_pose", "pose3d"), shapes):
+                if _require_cuda_f32(t, "out." + n, sh) is not t or t.device != dev:
+                    raise PmceError(f"out.{n}: must be a contiguous float32 tensor of shape {sh} on {dev}")
         with torch.cuda.device(dev):
             if not self.use_graph or torch.cuda.is_current_stream_capturing():
-                mesh = torch.empty(B, d.num_vert, 3, device=dev)
-                cam_pose = torch.empty(B, d.num_joint, 3, device=dev)
-                pose3d = torch.empty(B, d.num_joint, 3, device=dev)
+                mesh, cam_pose, pose3d = out if out is not None else (
+                    torch.empty(B, d.num_vert, 3, device=dev), torch.empty(B, d.num_joint, 3, device=dev), torch.empty(B, d.num_joint, 3, device=dev))
                 self._forward_eager(pose2d, img_feat, mesh, cam_pose, pose3d)
                 return mesh, cam_pose, pose3d
-            g = self._graphs.get(B)
+            key = B if out is None else (B,) + tuple(t.data_ptr() for t in out)
+            g = self._graphs.get(key)
             if g is None:
-                g = self._capture(B, dev)
+                g = self._capture(B, dev, key, out)
             g["p2d"].copy_(pose2d)
             g["feat"].copy_(img_feat)
             g["graph"].replay()
+            if out is not None:
+                return out
             return g["mesh"].clone(), g["cam_pose"].clone(), g["pose3d"].clone()
 
-    def _capture(self, B, dev):
+    def _capture(self, B, dev, key=None, out=None):
         d = self.dims
+        key = B if key is None else key
+        mesh, cam_pose, pose3d = out if out is not None else (
+            torch.empty(B, d.num_vert, 3, device=dev), torch.empty(B, d.num_joint, 3, device=dev), torch.empty(B, d.num_joint, 3, device=dev))
         st = dict(p2d=torch.zeros(B, d.seqlen, d.num_joint, 2, device=dev),
                   feat=torch.zeros(B, d.seqlen, d.feat_dim, device=dev),
-                  mesh=torch.empty(B, d.num_vert, 3, device=dev),
-                  cam_pose=torch.empty(B, d.num_joint, 3, device=dev),
-                  pose3d=torch.empty(B, d.num_joint, 3, device=dev))
+                  mesh=mesh, cam_pose=cam_pose, pose3d=pose3d)
         self._workspace(B, dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
@@ -156,7 +168,7 @@ class Engine:
         with torch.cuda.graph(graph):
             self._forward_eager(st["p2d"], st["feat"], st["mesh"], st["cam_pose"], st["pose3d"])
         st["graph"] = graph
-        self._graphs[B] = st
+        self._graphs[key] = st
         return st
 
     def _require_host(self, pose2d_cpu, img_feat_cpu, what):
@@ -227,20 +239,23 @@ class Engine:
         return mesh, cam_pose, pose3d
 
     # ---- pipelined host loop ---------------------------------------------------------------------------
-    def _pipeline(self, B, dev):
+    def _pipeline(self, B, dev, out_slots=None):
         """Two slots of static device buffers + captured graphs + pinned host outputs, three streams (H2D / forward / D2H).
-        Both graphs replay on the one forward stream, so they share the workspace."""
+        Both graphs replay on the one forward stream, so they share the workspace. `out_slots`: two caller-owned
+        (cam_mesh, cam_pose, pose3d) triples the two graphs write into (e.g. the rank's rows of two all-gather buffers)."""
         ws = self._workspace(B, dev)
-        baked = (ws.data_ptr(), self.weights.data_ptr(), self.vj.data_ptr())       # pointers the captured graphs hold
+        baked = (ws.data_ptr(), self.weights.data_ptr(), self.vj.data_ptr()) + (        # pointers the captured graphs hold
+            tuple(t.data_ptr() for sl in out_slots for t in sl) if out_slots is not None else ())
         pipe = self._pipe.get(B)
         if pipe is not None and pipe["baked"] == baked:
             return pipe
         d = self.dims
         slots = []
-        for _ in range(2):
+        for k in range(2):
+            o = out_slots[k] if out_slots is not None else (torch.empty(B, d.num_vert, 3, device=dev), torch.empty(B, d.num_joint, 3, device=dev),
+                                                            torch.empty(B, d.num_joint, 3, device=dev))
             sl = dict(p2d=torch.zeros(B, d.seqlen, d.num_joint, 2, device=dev), feat=torch.zeros(B, d.seqlen, d.feat_dim, device=dev),
-                      mesh=torch.empty(B, d.num_vert, 3, device=dev), cam_pose=torch.empty(B, d.num_joint, 3, device=dev),
-                      pose3d=torch.empty(B, d.num_joint, 3, device=dev),
+                      mesh=o[0], cam_pose=o[1], pose3d=o[2],
                       h2d=torch.cuda.Event(), fwd=torch.cuda.Event(), d2h=torch.cuda.Event(), used=False)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
@@ -262,7 +277,7 @@ class Engine:
         self._pipe[B] = pipe
         return pipe
 
-    def forward_host_iter(self, batches):
+    def forward_host_iter(self, batches, out_slots=None, before_forward=None, after_forward=None):
         """Pipelined form of the reference's test loop (lib/core/base.py:218-238: `.cuda()` -> forward -> `.cpu()` per batch).
 
         `batches` yields (pose2d [B,T,J,2], img_feat [B,T,2048]) contiguous float32 CPU tensors (pinned for asynchronous
@@ -271,7 +286,11 @@ class Engine:
         (three streams, two device buffer slots with one captured graph each, three pinned host output sets). A yielded
         triple stays valid while the NEXT result is requested and consumed; it is overwritten once the result after next is
         requested, so consume (or copy) it before asking for the batch after next. `list(forward_host_iter(...))` therefore
-        aliases buffers: copy each triple as it arrives."""
+        aliases buffers: copy each triple as it arrives.
+
+        Multi-GPU hooks (pmce_b200.dist.ShardedForward): `out_slots` = the two device output triples the forwards write into;
+        `before_forward(k)` / `after_forward(k)` run on the forward stream around the replay of slot k (wait until the slot's
+        previous all-gather has finished / issue this step's all-gather on the communication stream)."""
         self._ready(need_vj=True)
         dev = self.weights.device
         with torch.cuda.device(dev):
@@ -282,7 +301,7 @@ class Engine:
                     self._require_host(hp, hf, "forward_host_iter")
                     if pipe is None:
                         B = hp.shape[0]
-                        pipe = self._pipeline(B, dev)
+                        pipe = self._pipeline(B, dev, out_slots)
                         for s in (pipe["s_in"], pipe["s_fwd"], pipe["s_out"]):
                             s.wait_stream(cur)
                     elif hp.shape[0] != B:
@@ -299,8 +318,12 @@ class Engine:
                         pipe["s_fwd"].wait_event(sl["h2d"])
                         if sl["used"]:
                             pipe["s_fwd"].wait_event(sl["d2h"])      # this slot's previous outputs have left the device
+                        if before_forward is not None:
+                            before_forward(i & 1)
                         sl["graph"].replay()
                         sl["fwd"].record(pipe["s_fwd"])
+                        if after_forward is not None:
+                            after_forward(i & 1)
                     with torch.cuda.stream(pipe["s_out"]):
                         pipe["s_out"].wait_event(sl["fwd"])
                         host[0].copy_(sl["mesh"], non_blocking=True)

@@ -26,9 +26,10 @@ class PMCE(EngineModule):
         return self.pose_mesh_coevo.vj_relation
 
     @torch.no_grad()
-    def forward(self, pose2d, img_feat):
-        """pose2d [B,T,J,2], img_feat [B,T,2048] -> (cam_mesh [B,6890,3], cam_pose [B,J,3], pose3d [B,J,3])."""
-        return self.engine().forward(pose2d, img_feat)
+    def forward(self, pose2d, img_feat, out=None):
+        """pose2d [B,T,J,2], img_feat [B,T,2048] -> (cam_mesh [B,6890,3], cam_pose [B,J,3], pose3d [B,J,3]).
+        `out` (extension, optional): caller-owned output tensors the kernels write into directly (Engine.forward)."""
+        return self.engine().forward(pose2d, img_feat, out)
 
 
     @torch.no_grad()
@@ -47,10 +48,10 @@ class PMCE(EngineModule):
         return self.engine().forward_sliding(pose2d_seq, img_feat_seq, stride)
 
     @torch.no_grad()
-    def forward_host_iter(self, batches):
+    def forward_host_iter(self, batches, **hooks):
         """Pipelined `forward_host` over an iterable of (pose2d, img_feat) pinned CPU batches: copies of neighbouring batches
         overlap the forward (Engine.forward_host_iter). Yields (cam_mesh, cam_pose, pose3d) pinned CPU tensors in order."""
-        return self.engine().forward_host_iter(batches)
+        return self.engine().forward_host_iter(batches, **hooks)
 
 
 def get_model(num_joint, embed_dim, depth):

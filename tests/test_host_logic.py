@@ -109,3 +109,44 @@ def test_sharded_forward_gloo_world2(total):
         assert p.exitcode == 0
     for rank, ok, shape in res:
         assert ok and shape == (total, 6890, 3)
+
+
+def _fake_forward_out(p2d, feat, out=None):
+    m, a, b = _fake_forward(p2d, feat)
+    out[0].copy_(m); out[1].copy_(a); out[2].copy_(b)
+    return out
+
+
+def _worker_direct(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pmce_b200.dist import ShardedForward
+        per = 3
+        sf = ShardedForward(_fake_forward_out, per, 17, "cpu")
+        ok = True
+        for step in range(3):                       # three steps over two slots: slot reuse
+            p2d, feat = synth.make_inputs(world * per, 16, 17, seed=40 + step)
+            k = sf.step(p2d[rank * per:(rank + 1) * per].contiguous(), feat[rank * per:(rank + 1) * per].contiguous())
+            out = sf.unpack(k)
+            ref = _fake_forward(p2d, feat)
+            ok = ok and all(torch.equal(a, b) for a, b in zip(out, ref))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_forward_direct_outputs_gloo_world2():
+    """ShardedForward: outputs written straight into the rank's row of the gather buffer, in-place all-gather, slot rotation."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_direct, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
