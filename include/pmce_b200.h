@@ -196,6 +196,22 @@ int pmce_linear_tc_presplit(const void* x_hi, const void* x_lo, const void* w_hi
                             void* out_hi, void* out_lo /* split bf16 [M,N] or NULL */, const float* resid /* [M,N] or NULL */,
                             void* stream);
 
+/* ---- (f)2, the step before the path: the SPIN / HMR ResNet-50 feature extractor, lib/models/spin.py:129-143
+ * (`HMR.feature_extractor`, called on the frame crops at main/run_demo.py:315) -> the 2048-d per-frame features PMCE.forward
+ * consumes.  frames [B,3,224,224] fp32 NCHW -> feat [B,2048].  Convolutions run as NHWC GEMMs on the tensor cores; BatchNorm
+ * (eval) is folded at pack time.  `convs`: HOST array of the 53 convolutions in execution order (stem; per bottleneck conv1,
+ * conv2, conv3, then the first block's downsample), each a [cout, k] matrix (k = kh*kw*cin in (kh, kw, cin) order, the stem's
+ * 147 padded to 152) at float offset w_off of the three weight views (fp32 / bf16 hi / bf16 lo) with its folded bias at b_off of
+ * the fp32 view.  pmce_b200/spin.py builds them from the reference state_dict. */
+typedef struct pmce_spin_conv {
+    int64_t w_off, b_off;
+    int32_t cout, k;
+} pmce_spin_conv_t;
+int pmce_spin_num_convs(void);
+size_t pmce_spin_workspace_bytes(int B);
+int pmce_spin_features(const float* w_f32, const void* w_hi, const void* w_lo, const pmce_spin_conv_t* convs, int nconv,
+                       const float* frames, int B, float* feat, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Cumulative number of kernels this library has launched in this process (for the bench's gpu_launches). */
 unsigned long long pmce_launch_count(void);
 

@@ -169,8 +169,36 @@ def gen_eval():
                         mesh_mean_error=np.float64(s_err), pred_pose=pred_pose.numpy())
 
 
+def gen_spin():
+    """(f)2 golden: the reference's own `HMR.feature_extractor` (lib/models/spin.py:129-143) on seeded trunk weights and frames."""
+    from oracle import spin_oracle as so
+    model = rh.build_spin_trunk()
+    ref_sd = model.state_dict()
+    schema = synth.spin_state_dict_schema()
+    assert set(schema) == set(ref_sd) and all(tuple(ref_sd[k].shape) == tuple(v) for k, v in schema.items()), "spin schema mismatch"
+    sd = synth.make_spin_state_dict(17)
+    model.load_state_dict(sd, strict=True)
+    x = synth.make_frames(2, 19)
+    cap = {}
+    hooks = [getattr(model, f"layer{i}").register_forward_hook(lambda m, i_, o, i=i: cap.__setitem__(f"layer{i}", o.detach().clone())) for i in (1, 2, 3, 4)]
+    with torch.no_grad():
+        xf = model.feature_extractor(x)
+        oxf, inter = so.feature_extractor(sd, x, return_intermediates=True)
+    for h in hooks:
+        h.remove()
+    errs = {k: float((inter[k] - cap[k]).abs().max()) for k in cap}
+    errs["xf"] = float((oxf - xf).abs().max())
+    print("spin oracle-vs-reference max abs:", errs, "| max|xf| = %.3f" % float(xf.abs().max()))
+    assert max(errs.values()) < 1e-4
+    # layer outputs are large: keep a strided sub-sample (every 7th position of both spatial axes) next to the full feature vector
+    np.savez_compressed(os.path.join(GOLDEN, "spin_B2.npz"), weight_seed=np.int64(17), input_seed=np.int64(19), xf=xf.numpy(),
+                        layer1=cap["layer1"][:, :, ::7, ::7].numpy(), layer2=cap["layer2"][:, :, ::7, ::7].numpy(),
+                        layer3=cap["layer3"][:, :, ::7, ::7].numpy(), layer4=cap["layer4"][:, ::8].numpy())
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    gen_spin()
     gen_jregressors()
     gen_smpl()
     gen_eval()

@@ -126,3 +126,25 @@ def build_smpl_layer(buffers):
     layer.kintree_parents = list(buffers["kintree_parents"])
     layer.num_joints = len(layer.kintree_parents)
     return layer.eval()
+
+
+def build_spin_trunk():
+    """The reference's SPIN/HMR ResNet-50 TRUNK (lib/models/spin.py): `HMR.__init__` needs the licensed SMPL body model
+    (spin.py:90-94) and `smpl_mean_params.npz` (:103), so the constructor is bypassed and only its trunk lines (:66-77) are
+    replayed through the reference's own `_make_layer` / `Bottleneck`; `feature_extractor` (:129-143) then runs verbatim."""
+    setup()
+    import torch.nn as nn
+    from models import spin as sp            # the reference module (smplx comes from oracle/shims)
+    m = sp.HMR.__new__(sp.HMR)
+    nn.Module.__init__(m)
+    m.inplanes = 64
+    m.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+    m.bn1 = nn.BatchNorm2d(64)
+    m.relu = nn.ReLU(inplace=True)
+    m.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+    m.layer1 = m._make_layer(sp.Bottleneck, 64, 3)
+    m.layer2 = m._make_layer(sp.Bottleneck, 128, 4, stride=2)
+    m.layer3 = m._make_layer(sp.Bottleneck, 256, 6, stride=2)
+    m.layer4 = m._make_layer(sp.Bottleneck, 512, 3, stride=2)
+    m.avgpool = nn.AvgPool2d(7, stride=1)
+    return m.eval()

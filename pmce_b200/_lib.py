@@ -20,6 +20,10 @@ class PmceDims(C.Structure):
         return tuple(getattr(self, n) for n, _ in self._fields_)
 
 
+class PmceSpinConv(C.Structure):
+    _fields_ = [("w_off", C.c_int64), ("b_off", C.c_int64), ("cout", C.c_int32), ("k", C.c_int32)]
+
+
 class PmceSlot(C.Structure):
     _fields_ = [("offset", C.c_uint64), ("rows", C.c_int64), ("cols", C.c_int64), ("ld", C.c_int64)]
 
@@ -59,6 +63,9 @@ SIGNATURES = {
     "pmce_split_bf16": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "pmce_linear_tc_presplit": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "pmce_launch_count": (C.c_ulonglong, []),
+    "pmce_spin_num_convs": (C.c_int, []),
+    "pmce_spin_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "pmce_spin_features": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "smpl_blend_ld": (C.c_int, []),
     "smpl_workspace_bytes": (C.c_size_t, [C.c_int]),
     "smpl_lbs_forward_scaled": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_float, _P, _P, _P, C.c_size_t, _P]),

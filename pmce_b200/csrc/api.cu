@@ -24,6 +24,7 @@
 #include "ca_fused.cuh"
 #include "mlp_fused.cuh"
 #include "attn_rows_tc.cuh"
+#include "spin.cuh"
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -1172,4 +1173,108 @@ extern "C" int smpl_lbs_forward(const float* blend, const float* v_template, con
                                 void* stream) {
     return smpl_lbs_forward_scaled(blend, nullptr, nullptr, v_template, j_template, j_shapedirs, skin_weights, parents, pose, betas, trans, B,
                                    1.0f, verts, joints, workspace, workspace_bytes, stream);
+}
+
+// ---- (f)2: SPIN / HMR ResNet-50 feature extractor (lib/models/spin.py:129-143) -------------------------------------------
+namespace {
+struct SpinWs {
+    SplitOut col, xs, c1s, c2s, sub;      // im2col rows; split copy of the block input; conv1 / conv2 outputs; strided rows
+    float *xa, *xb, *rs;                  // block input / output (fp32 NHWC), down-sampled residual
+    size_t bytes;
+};
+SpinWs spin_carve(int B, void* base) {
+    SpinWs w;
+    Carver c{(char*)base, 0};
+    const size_t b = (size_t)B;
+    w.col = c.split(b * 12544 * SPIN_STEM_K);      // >= 3136 * 576 (layer1 conv2), 784 * 1152, ...
+    w.xs = c.split(b * 3136 * 256);
+    w.c1s = c.split(b * 3136 * 128);               // layer2.0 conv1 runs at 56 x 56 with 128 planes
+    w.c2s = c.split(b * 3136 * 64);                // = 784 * 256 = 196 * 1024 ...: rows x planes never exceeds 3136 x 64
+    w.sub = c.split(b * 784 * 256);
+    w.xa = c.f32(b * 3136 * 256); w.xb = c.f32(b * 3136 * 256); w.rs = c.f32(b * 3136 * 256);
+    w.bytes = c.cur;
+    return w;
+}
+const int SPIN_PLANES[4] = {64, 128, 256, 512}, SPIN_BLOCKS[4] = {3, 4, 6, 3}, SPIN_STRIDE[4] = {1, 2, 2, 2};
+}  // namespace
+
+extern "C" int pmce_spin_num_convs(void) { return 1 + 3 * 16 + 4; }
+extern "C" size_t pmce_spin_workspace_bytes(int B) { return B < 1 ? 0 : spin_carve(B, nullptr).bytes; }
+
+extern "C" int pmce_spin_features(const float* w_f32, const void* w_hi, const void* w_lo, const pmce_spin_conv_t* convs, int nconv,
+                                  const float* frames, int B, float* feat, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!w_f32 || !w_hi || !w_lo || !convs || !frames || !feat || !workspace) { pmce_set_error("pmce_spin_features: NULL argument"); return 2; }
+    if (B < 1) { pmce_set_error("batch size %d < 1", B); return 2; }
+    if (nconv != pmce_spin_num_convs()) { pmce_set_error("pmce_spin_features: expected %d convolutions, got %d", pmce_spin_num_convs(), nconv); return 2; }
+    if (((uintptr_t)workspace & 255) || workspace_bytes < pmce_spin_workspace_bytes(B)) { pmce_set_error("pmce_spin_features: workspace too small or unaligned"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const SpinWs ws = spin_carve(B, workspace);
+    const Weights W{w_f32, (const bf16*)w_hi, (const bf16*)w_lo};
+    int ci = 0;
+    auto conv = [&](const SplitOut& A, int M, int K, int N, const EpiOpt& o) -> int {
+        const pmce_spin_conv_t& c = convs[ci++];
+        if (c.cout != N || c.k != K) { pmce_set_error("pmce_spin_features: convolution %d is [%d,%d], expected [%d,%d]", ci - 1, c.cout, c.k, N, K); return 2; }
+        EpiOpt e = o;
+        e.bias = W.f + c.b_off;
+        return linear_tc(A, K, M, K, W, (size_t)c.w_off, K, N, e, st);
+    };
+    // stem: conv 7x7 / 2 (+ folded BN) -> ReLU -> max-pool 3x3 / 2   (spin.py:131-134)
+    {
+        const size_t n = (size_t)B * 12544 * (SPIN_STEM_K / 8);
+        spin_stem_im2col_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>(frames, B, ws.col);
+        CKL();
+        EpiOpt o; o.out = ws.xb; o.ld_out = 64;
+        RET(conv(ws.col, B * 12544, SPIN_STEM_K, 64, o));
+        spin_relu_maxpool_kernel<<<cdiv((long long)B * 3136 * 16, 256), 256, 0, st>>>(ws.xb, B, ws.xa, ws.xs);
+        CKL();
+    }
+    float *x = ws.xa, *y = ws.xb;
+    int H = 56, Cin = 64;
+    for (int li = 0; li < 4; ++li) {
+        const int planes = SPIN_PLANES[li];
+        for (int bi = 0; bi < SPIN_BLOCKS[li]; ++bi) {
+            const int s = bi == 0 ? SPIN_STRIDE[li] : 1;
+            const int Ho = H / s, M = B * H * H, Mo = B * Ho * Ho;
+            // conv1 1x1 + BN + ReLU   (Bottleneck.forward, spin.py:41-43)
+            { EpiOpt o; o.act = 2; o.outs = ws.c1s; o.ld_split = planes; RET(conv(ws.xs, M, Cin, planes, o)); }
+            // conv2 3x3 (stride s) + BN + ReLU   (:45-47)
+            {
+                const size_t n = (size_t)Mo * 9 * (planes / 8);
+                spin_im2col3_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>(ws.c1s, B, H, H, planes, s, Ho, Ho, ws.col);
+                CKL();
+                EpiOpt o; o.act = 2; o.outs = ws.c2s; o.ld_split = planes;
+                RET(conv(ws.col, Mo, 9 * planes, planes, o));
+            }
+            // conv3 1x1 + BN, + residual (identity, or the first block's 1x1 / stride s conv + BN, :116-120), ReLU   (:49-55)
+            const float* resid = x;
+            {
+                EpiOpt o; o.out = y; o.ld_out = 4 * planes; o.ld_resid = 4 * planes;
+                const int i3 = ci++;                          // conv3 comes before the downsample in the pack order
+                if (bi == 0) {
+                    SplitOut a = ws.xs;
+                    if (s != 1) {
+                        const size_t n = (size_t)Mo * (Cin / 8);
+                        spin_subsample_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>(ws.xs, B, H, H, Cin, s, Ho, Ho, ws.sub);
+                        CKL();
+                        a = ws.sub;
+                    }
+                    EpiOpt od; od.out = ws.rs; od.ld_out = 4 * planes;
+                    RET(conv(a, Mo, Cin, 4 * planes, od));
+                    resid = ws.rs;
+                }
+                const int after = ci;
+                ci = i3;
+                o.resid = resid;
+                RET(conv(ws.c2s, Mo, planes, 4 * planes, o));
+                ci = after > ci ? after : ci;
+            }
+            spin_relu_split_kernel<<<cdiv((long long)Mo * planes, 256), 256, 0, st>>>(y, (size_t)Mo * planes, ws.xs);
+            CKL();
+            float* t = x; x = y; y = t;
+            H = Ho; Cin = 4 * planes;
+        }
+    }
+    spin_avgpool_kernel<<<cdiv(B * 2048, 256), 256, 0, st>>>(x, B, 2048, feat);
+    CKL();
+    return 0;
 }

@@ -37,7 +37,7 @@ struct TcEpi {
     const float* rowadd;    // [period, N] or null (added at row % period)
     int rowadd_period;
     int ld_resid;
-    int act;                // 0 none, 1 exact GELU
+    int act;                // 0 none, 1 exact GELU, 2 ReLU (split-bf16 outputs and the generic path)
     float* out_f32;         // fp32 [M, ld_out] or null
     __nv_bfloat16* out_hi;  // split output [M, ld_split] or null (both hi and lo, or neither)
     __nv_bfloat16* out_lo;
@@ -92,6 +92,7 @@ __device__ __forceinline__ void tc_epilogue_generic(const TcEpi& e, const uint32
         float x = __uint_as_float(v[i]);
         if (e.bias) x += e.bias[col];
         if (e.act == 1) x = gelu_erf(x);
+        if (e.act == 2) x = fmaxf(x, 0.f);
         if (radd) x += radd[col];
         if (e.mapped) {
             const long long off = e.rmap(row) + e.cmap(col);
@@ -322,6 +323,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         float x0 = __uint_as_float(v[i]) + b.x, x1 = __uint_as_float(v[i + 1]) + b.y;
                         float x2 = __uint_as_float(v[i + 2]) + b.z, x3 = __uint_as_float(v[i + 3]) + b.w;
                         if (MODE == TC_SPLIT_GELU) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
+                        if (MODE == TC_SPLIT && e.act == 2) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }   // ReLU
                         if (MODE == TC_ATTN32) { x0 *= qs; x1 *= qs; x2 *= qs; x3 *= qs; }
                         tc::split_bf16x2(x0, x1, hi[i / 2], lo[i / 2]);
                         tc::split_bf16x2(x2, x3, hi[i / 2 + 1], lo[i / 2 + 1]);

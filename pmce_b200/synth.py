@@ -276,3 +276,57 @@ def prepare_data_root(root, sparse_regressors_npz, asset_seed=7):
     os.makedirs(os.path.join(root, "data", "Human36M"), exist_ok=True)
     np.save(os.path.join(root, "data", "Human36M", "J_regressor_h36m_correct.npy"), J)
     return root
+
+
+# ---- (f)2: SPIN / HMR ResNet-50 trunk (reference lib/models/spin.py:66-77) --------------------------------------------------
+SPIN_LAYERS = ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2))      # (planes, blocks, stride) of layer1..4
+
+
+def spin_state_dict_schema():
+    """name -> shape of the trunk's tensors (the keys `HMR.state_dict()` has for conv1/bn1/layer1-4)."""
+    sch = {"conv1.weight": (64, 3, 7, 7)}
+
+    def bn(prefix, c):
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            sch[f"{prefix}.{k}"] = (c,)
+        sch[f"{prefix}.num_batches_tracked"] = ()
+    bn("bn1", 64)
+    inpl = 64
+    for li, (planes, blocks, stride) in enumerate(SPIN_LAYERS, 1):
+        for bi in range(blocks):
+            p = f"layer{li}.{bi}"
+            sch[p + ".conv1.weight"] = (planes, inpl, 1, 1); bn(p + ".bn1", planes)
+            sch[p + ".conv2.weight"] = (planes, planes, 3, 3); bn(p + ".bn2", planes)
+            sch[p + ".conv3.weight"] = (planes * 4, planes, 1, 1); bn(p + ".bn3", planes * 4)
+            if bi == 0:
+                sch[p + ".downsample.0.weight"] = (planes * 4, inpl, 1, 1); bn(p + ".downsample.1", planes * 4)
+            inpl = planes * 4
+    return sch
+
+
+def make_spin_state_dict(seed):
+    """Seeded trunk weights at a trained-like scale: He-normal convolutions, BatchNorm running statistics / affine parameters
+    away from the identity, so BN folding, ReLU sparsity and the residual adds are all exercised."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in spin_state_dict_schema().items():
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.tensor(100, dtype=torch.int64)
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(shp, generator=g) * 1.0 + 0.5
+        elif k.endswith("running_mean"):
+            sd[k] = torch.randn(shp, generator=g) * 0.1
+        elif k.endswith("bias"):
+            sd[k] = torch.randn(shp, generator=g) * 0.1
+        elif len(shp) == 1:                                  # BN weight: the last BN of a bottleneck is damped like a trained net's
+            sd[k] = (torch.rand(shp, generator=g) * 0.5 + 0.75) * (0.2 if ".bn3." in k else 1.0)
+        else:
+            fan_in = shp[1] * shp[2] * shp[3]
+            sd[k] = torch.randn(shp, generator=g) * (2.0 / fan_in) ** 0.5
+    return sd
+
+
+def make_frames(B, seed):
+    """[B,3,224,224] crops, normalised-image-like values."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, 3, 224, 224, generator=g)
