@@ -479,7 +479,7 @@ def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):
     Timed alone with CUDA events over `nsets` rotating (xq, t) buffer sets whose total size exceeds the 126 MB L2, so every
     launch streams its query rows from HBM. achieved = ALGORITHMIC bytes / time with SURVEY.md §8(d)'s per-clip figure for the
     fused block (231,424 B: q/k/v streams in + q stream out + gamma/beta); `achieved_kernel_io` counts what this kernel's
-    contract really moves per clip (q in, q out, the per-clip folded operands KQ'|VPt' in split-bf16 and sb' = 253,696 B)."""
+    contract really moves per clip (q in, q out, the per-clip folded operands KQ'|VP' in split-bf16 and sb' = 245,440 B)."""
     import ctypes as Ct
     import torch
     Vd, D = 431, 64
@@ -522,11 +522,11 @@ def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):
     torch.cuda.synchronize(dev)
     sec = e0.elapsed_time(e1) * 1e-3 / (rounds * nsets)
     survey_bytes = ((J + Vd + Vd + J) * D * 4 + 2048) * B
-    io_bytes = (2 * Vd * D * 4 + 2 * (64 * 64 * 2 * 2) + 64 * 4) * B
+    io_bytes = (2 * Vd * D * 4 + 4 * (48 * 64 * 2) + 48 * 4) * B
     flops = (4 * 2 * Vd * J * 32 + 2 * 2 * Vd * D * D) * B       # attention core + Wq + Wp
     ach = survey_bytes / sec / 1e9
     return {"kernel": "ca_vertex_fused_kernel (AdaLN_q + Wq + scores + softmax + P.V + Wp + bias + residual in one pass over the query stream; "
-                      "warp-specialised: 2 TMA producer warps, 2 consumer groups = 2 items in flight per CTA)",
+                      "4 independent 4-warp groups = 4 items in flight per CTA, in-place buffers, residual held in the TMEM accumulator)",
             "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
             "traffic": ncu_traffic("ca_vertex_fused_kernel", B), "traffic_unit": "B", "bytes_per_launch": survey_bytes, "us_per_launch": sec * 1e6,
             "achieved_kernel_io": io_bytes / sec / 1e9, "kernel_io_bytes_per_launch": io_bytes,

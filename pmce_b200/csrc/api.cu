@@ -112,7 +112,7 @@ Workspace carve(const pmce_dims_t& d, int B, void* base) {
     w.tB_s = c.split(nv * D); w.tJ2_s = c.split(nj * D);
     w.lc_mesh = c.f32((size_t)B * d.num_vert * 3);
     for (int k = 0; k < 3; ++k) {
-        SplitOut kq = c.split((size_t)B * CAF_NS * 64), vp = c.split((size_t)B * 64 * 64);
+        SplitOut kq = c.split((size_t)B * CAF_NS * 64), vp = c.split((size_t)B * CAF_NS * 64);
         w.fold[k].kq_hi = kq.hi; w.fold[k].kq_lo = kq.lo; w.fold[k].vp_hi = vp.hi; w.fold[k].vp_lo = vp.lo;
         w.fold[k].sb = c.f32((size_t)B * CAF_NS);
     }
@@ -904,7 +904,7 @@ extern "C" int pmce_cross_attn_block(const pmce_dims_t* dims, const void* weight
                  : cross_attn_block(W, w.jca, JOINT_HEADS, out, N1, xk, xv, N2, gb, B, joint_scratch(ws), st);
 }
 
-extern "C" size_t pmce_ca_fold_bytes(int B) { return B < 1 ? 0 : (size_t)B * (2 * (CAF_NS + 64) * 64 * 2 + CAF_NS * 4); }
+extern "C" size_t pmce_ca_fold_bytes(int B) { return B < 1 ? 0 : (size_t)B * (4 * CAF_NS * 64 * 2 + CAF_NS * 4); }
 
 extern "C" int pmce_ca_vertex_fused(const pmce_dims_t* dims, const void* weights, int block, float* xq, const float* K, const float* V,
                                     const float* gb, int B, void* t_hi, void* t_lo, void* fold_ws, int fold, void* stream) {
@@ -917,7 +917,7 @@ extern "C" int pmce_ca_vertex_fused(const pmce_dims_t* dims, const void* weights
     const CaW& w = L.blk[block - 1].vca;
     CaFolded f;
     f.kq_hi = (bf16*)fold_ws; f.kq_lo = f.kq_hi + (size_t)B * CAF_NS * 64; f.vp_hi = f.kq_lo + (size_t)B * CAF_NS * 64;
-    f.vp_lo = f.vp_hi + (size_t)B * 64 * 64; f.sb = (float*)(f.vp_lo + (size_t)B * 64 * 64);
+    f.vp_lo = f.vp_hi + (size_t)B * CAF_NS * 64; f.sb = (float*)(f.vp_lo + (size_t)B * CAF_NS * 64);
     if (fold) RET(ca_fold(W, nullptr, w, nullptr, K, V, nullptr, gb, B, J, VERTX_HEADS, f, st));
     RET(ca_fused_launch(xq, Vd, J, B, f, st));
     if (t_hi && t_lo) {          // optional: AdaLN_2 of the result, split-bf16 (the A operand of the block's fc1 when the Mlp is not fused)

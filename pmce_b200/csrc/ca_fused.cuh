@@ -5,25 +5,26 @@
 //
 // Few keys => everything that is per clip is folded into two per-clip operands by ca_joint_fold_kernel (below):
 //   n        = (x - mean) / (std_unbiased + eps)                  per row, the only LayerNorm work left per element (1 FMA)
-//   S        = n KQ'^T + sb'      KQ'[32h+j][c] = log2e scale (K_h Wq_h)[j][c] gamma_q[c]
-//                                 sb' [32h+j]   = log2e (scale K_hj . bq_h + sum_c scale (K_h Wq_h)[j][c] beta_q[c])
+//   S        = n KQ'^T + sb'      KQ'[24h+j][c] = log2e scale (K_h Wq_h)[j][c] gamma_q[c]
+//                                 sb' [24h+j]   = log2e (scale K_hj . bq_h + sum_c scale (K_h Wq_h)[j][c] beta_q[c])
 //   P_h      = 2^(S_h - max_j S_h) / sum                                   (softmax over the clip's NK keys, per head)
-//   xq'      = xq + P VPt'^T      VPt'[n][32h+j] = (V_h Wp[:, h]^T)[j][n] + bp[n] / 2     (rows of P_h sum to 1: 2 heads carry bp)
-// so a 128-row item is: TMA load -> row statistics -> one FMA per element -> split-bf16 A tiles -> tcgen05 128x64x64 ->
-// softmax of 2 x NK scores in registers -> P tiles -> tcgen05 128x64x64 -> + xq -> TMA store.
+//   xq'      = xq + P VP'         VP'[24h+j][n] = (V_h Wp[:, h]^T)[j][n] + bp[n] / 2     (rows of P_h sum to 1: 2 heads carry bp)
+// so a 128-row item is: TMA load -> row statistics -> one FMA per element -> split-bf16 A tiles -> tcgen05 128x48x64 ->
+// softmax of 2 x NK scores in registers -> P tiles -> tcgen05 128x64x48 ON TOP of xq (preloaded into the accumulator) -> TMA store.
 //
-// Warp-specialised, persistent, ONE CTA per SM with CA2_G independent consumer groups (items in flight):
-//   warps 0-3 / 4-7   consumer group 0 / 1: thread r owns tile row r = TMEM lane r with the WHOLE 64-wide row in registers, so
-//                     the LayerNorm statistics are thread-local (no cross-thread reduction, no barrier); 4 group-wide named
-//                     barriers per item (A buffer free, A tiles written, P tiles written, output staged); the group's first
-//                     thread issues its MMAs and its TMA store.
-//   warp 8            producer of the x tiles (one lane): the group's IN buffer is released as soon as its 128 rows are in
-//                     registers, so the NEXT item's rows stream in under the whole chain of the current one.
-//   warp 9 / 10       producers of the per-clip operand tiles KQ' / VPt' (16 KB each, L2 hits for 3 of a clip's 4 tiles): KQ' is
-//                     released by the commit of the first MMA and VPt' by the second, so the next item's KQ' is resident long
-//                     before its rows are normalised.
-// Shared memory per group: IN 32 KB (two [128][32 fp32] SW128 boxes) | A 32 KB (A tiles hi|lo, then P hi|lo, then the fp32
-// output boxes for the TMA store) | W 32 KB (KQ' hi|lo, VPt' hi|lo) = 96 KB; TMEM 128 columns per group (S | O).
+// The per-item chain (load, two MMA round trips, store drain) is ~7 us of latency against ~1 us of issue work, so throughput
+// comes from items in flight: ONE CTA per SM with CA_G = 4 independent groups of 4 warps, each walking its own items:
+//   * thread r of a group owns tile row r = TMEM lane r; the whole 64-wide row passes through its registers once, so the
+//     LayerNorm statistics are thread-local (no cross-thread reduction);
+//   * ONE 32 KB buffer per group changes roles in place - the two [128][32 fp32] TMA boxes of x -> the A tiles hi|lo (row r of
+//     a tile occupies exactly the bytes of row r of a box: no hazard between threads, no barrier) -> the P tiles -> the fp32
+//     output boxes for the TMA store; the residual x does not stay in registers either: it is written into the output
+//     accumulator (tcgen05.st) and the second MMA accumulates onto it;
+//   * the operands are compact (48 key slots: KQ' [48][64] K-major, VP' [48][64] MN-major, 24 KB with hi|lo), per group;
+//   * no producer warps: the group's first thread issues the group's TMA loads at the moment it learns a buffer is free
+//     (KQ' after the first MMA's commit, VP' after the second's, x after the store has drained) and its MMAs;
+//   * three group-wide named barriers per item (A tiles written, P tiles written, output staged).
+// Shared memory: 4 x (32 + 24) KB = 224 KB; TMEM: 4 x (64 + 64) columns.
 #pragma once
 #include "tc_common.cuh"
 #include "common.cuh"
@@ -31,18 +32,20 @@
 #include "attn_tc.cuh"
 #include "gemm_tc.cuh"
 
-constexpr int CAF_KP = 32;                              // key slots per head (num_joint <= 24 live: 17 h36m, 19 coco; the rest are zero)
+constexpr int CAF_KP = 24;                              // key slots per head (num_joint <= 24: 17 h36m, 19 coco; the rest are zero)
 constexpr int CAF_MAXJ = 24;
 constexpr int CAF_H = 2;                                // heads of the vertex stream (CoevoDecoder.py:140)
-constexpr int CAF_NS = CAF_H * CAF_KP;                  // 64 score columns: column 32 h + j = (head h, key j)
-constexpr int CA2_G = 2;                                // consumer groups = items in flight per CTA
-constexpr int CA2_THREADS = CA2_G * 128 + 96;           // + x-tile producer warp + two operand producer warps
-constexpr int CA2_IN = 2 * 128 * 128;                   // two [128][32 fp32] boxes
-constexpr int CA2_A = 2 * AT_TILE;                      // A tiles hi | lo ([128][64 bf16] each) = the two fp32 output boxes later
-constexpr int CA2_W = 4 * 8192;                         // KQ' hi | KQ' lo | VPt' hi | VPt' lo ([64][64 bf16] each)
-constexpr int CA2_GBUF = CA2_IN + CA2_A + CA2_W;        // 96 KB per group
-constexpr int CA2_OFF_BAR = CA2_G * CA2_GBUF;
-constexpr int CA2_SMEM = CA2_OFF_BAR + 256 + 1024;      // barriers + alignment slack
+constexpr int CAF_NS = CAF_H * CAF_KP;                  // 48 score columns / key slots: slot 24 h + j = (head h, key j)
+constexpr int CA_G = 4;                                 // groups = items in flight per CTA
+constexpr int CA_THREADS = CA_G * 128;
+constexpr int CA_X = 2 * 128 * 128;                     // x boxes = A tiles hi|lo = P tiles = output boxes (32 KB, in place)
+constexpr int CA_WT = CAF_NS * 128;                     // one operand tile [48][64 bf16]: 6 KB
+constexpr int CA_W = 4 * CA_WT;                         // KQ' hi | KQ' lo | VP' hi | VP' lo
+constexpr int CA_GBUF = CA_X + CA_W;                    // 56 KB per group (1024-byte aligned pieces)
+constexpr int CA_OFF_BAR = CA_G * CA_GBUF;
+constexpr int CA_SMEM = CA_OFF_BAR + 256 + 1024;        // barriers + alignment slack
+static_assert(CA_SMEM <= 227 * 1024, "shared memory");
+static_assert(CA_WT % 1024 == 0, "operand tiles must stay 1024-byte aligned");
 
 namespace tc {
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int crd0, int crd1, int crd2) {
@@ -63,18 +66,35 @@ __device__ __forceinline__ float ex2_approx(float x) {      // 2^x, rel. error 2
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// TMEM -> registers: this warp's 32 lanes (rows) x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes (rows) x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+          "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]),
+          "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 }  // namespace tc
 
 struct CaFusedArgs {
-    const float* sb;         // [B, 64] folded score bias sb' (log2 domain)
-    float* xq;               // [B, N1, 64] the stream itself (rows are stored straight from registers)
+    const float* sb;         // [B, 48] folded score bias sb' (log2 domain)
     int B, N1, N2, qtiles;
     float eps;
-    int tma_out;             // 1: stage the output rows in shared memory and TMA-store them (A/B knob PMCE_CA_TMA_OUT)
 };
 
 template <int NK>
-__global__ void __launch_bounds__(CA2_THREADS, 1)
+__global__ void __launch_bounds__(CA_THREADS, 1)
 ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_kq_hi,
                        const __grid_constant__ CUtensorMap tm_kq_lo, const __grid_constant__ CUtensorMap tm_vp_hi,
                        const __grid_constant__ CUtensorMap tm_vp_lo, CaFusedArgs a) {
@@ -82,122 +102,72 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = tc::smem_u32(smem);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CA2_OFF_BAR);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CA_OFF_BAR);
     uint64_t* in_full = bars;                    // [G] TMA bytes of the x tile
-    uint64_t* in_empty = bars + CA2_G;           // [G] 4 arrivals: every consumer warp has its rows in registers
-    uint64_t* kq_full = bars + 2 * CA2_G;        // [G] TMA bytes of KQ' hi|lo
-    uint64_t* kq_empty = bars + 3 * CA2_G;       // [G] tcgen05.commit after the item's first MMA
-    uint64_t* vp_full = bars + 4 * CA2_G;        // [G] TMA bytes of VPt' hi|lo
-    uint64_t* vp_empty = bars + 5 * CA2_G;       // [G] tcgen05.commit after the item's second MMA
-    uint64_t* mma_bar = bars + 6 * CA2_G;        // [G] tcgen05.commit: S complete / O complete
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 7 * CA2_G);
+    uint64_t* kq_full = bars + CA_G;             // [G] TMA bytes of KQ' hi|lo
+    uint64_t* vp_full = bars + 2 * CA_G;         // [G] TMA bytes of VP' hi|lo
+    uint64_t* mma_bar = bars + 3 * CA_G;         // [G] tcgen05.commit: S complete / O complete
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 4 * CA_G);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int g = warp >> 2, r = tid & 127;
+    const bool leader = r == 0;
     const int ntiles = a.B * a.qtiles;
-    if (tid == 0) {
-        for (int g = 0; g < CA2_G; ++g) {
-            tc::mbar_init(&in_full[g], 1); tc::mbar_init(&in_empty[g], 4);
-            tc::mbar_init(&kq_full[g], 1); tc::mbar_init(&kq_empty[g], 1); tc::mbar_init(&vp_full[g], 1); tc::mbar_init(&vp_empty[g], 1);
-            tc::mbar_init(&mma_bar[g], 1);
-        }
+    uint8_t* gptr = smem + g * CA_GBUF;
+    const int tile0 = blockIdx.x + g * gridDim.x, tstep = CA_G * gridDim.x;       // this group's items
+    if (leader) {
+        tc::mbar_init(&in_full[g], 1); tc::mbar_init(&kq_full[g], 1); tc::mbar_init(&vp_full[g], 1); tc::mbar_init(&mma_bar[g], 1);
         tc::fence_barrier_init();
         tc::fence_proxy_async();
-        // the first item of every group is requested here, before TMEM is allocated and the CTA assembles: at small batches
-        // (one or two items per CTA) this DRAM round trip is a third of the kernel
-        for (int g = 0; g < CA2_G; ++g) {
-            const int tile = blockIdx.x + g * gridDim.x;
-            if (tile >= ntiles) break;
-            const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
-            uint8_t* gbuf = smem + g * CA2_GBUF;
-            tc::mbar_arrive_expect_tx(&in_full[g], CA2_IN);
-            tc::tma_load_3d(gbuf, &tm_x, &in_full[g], 0, row0, b);
-            tc::tma_load_3d(gbuf + 16384, &tm_x, &in_full[g], 32, row0, b);
-            tc::mbar_arrive_expect_tx(&kq_full[g], CA2_W / 2);
-            tc::tma_load_2d(gbuf + CA2_IN + CA2_A, &tm_kq_hi, &kq_full[g], 0, b * CAF_NS);
-            tc::tma_load_2d(gbuf + CA2_IN + CA2_A + 8192, &tm_kq_lo, &kq_full[g], 0, b * CAF_NS);
-            tc::mbar_arrive_expect_tx(&vp_full[g], CA2_W / 2);
-            tc::tma_load_2d(gbuf + CA2_IN + CA2_A + 16384, &tm_vp_hi, &vp_full[g], 0, b * 64);
-            tc::tma_load_2d(gbuf + CA2_IN + CA2_A + 24576, &tm_vp_lo, &vp_full[g], 0, b * 64);
+        if (tile0 < ntiles) {       // the group's first item is requested before TMEM is allocated and the CTA assembles
+            const int b = tile0 / a.qtiles, row0 = (tile0 % a.qtiles) * 128;
+            tc::mbar_arrive_expect_tx(&in_full[g], CA_X);
+            tc::tma_load_3d(gptr, &tm_x, &in_full[g], 0, row0, b);
+            tc::tma_load_3d(gptr + 16384, &tm_x, &in_full[g], 32, row0, b);
+            tc::mbar_arrive_expect_tx(&kq_full[g], 2 * CA_WT);
+            tc::tma_load_2d(gptr + CA_X, &tm_kq_hi, &kq_full[g], 0, b * CAF_NS);
+            tc::tma_load_2d(gptr + CA_X + CA_WT, &tm_kq_lo, &kq_full[g], 0, b * CAF_NS);
+            tc::mbar_arrive_expect_tx(&vp_full[g], 2 * CA_WT);
+            tc::tma_load_2d(gptr + CA_X + 2 * CA_WT, &tm_vp_hi, &vp_full[g], 0, b * CAF_NS);
+            tc::tma_load_2d(gptr + CA_X + 3 * CA_WT, &tm_vp_lo, &vp_full[g], 0, b * CAF_NS);
         }
     }
-    if (warp == CA2_G * 4) tc::tmem_alloc(tmem_ptr_smem, CA2_G * 128);
+    if (warp == 0) tc::tmem_alloc(tmem_ptr_smem, CA_G * 128);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == CA2_G * 4) {
-        // ================= producer of the x tiles: item n of this CTA -> group n % G =================
-        if (lane == 0) {
-            uint32_t n = CA2_G;                         // (the first round was requested in the prologue)
-            for (int tile = blockIdx.x + CA2_G * gridDim.x; tile < ntiles; tile += gridDim.x, ++n) {
-                const int g = n % CA2_G;
-                const uint32_t j = n / CA2_G;
-                const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
-                uint8_t* in = smem + g * CA2_GBUF;
-                tc::mbar_wait(&in_empty[g], (j & 1) ^ 1);
-                tc::mbar_arrive_expect_tx(&in_full[g], CA2_IN);
-                tc::tma_load_3d(in, &tm_x, &in_full[g], 0, row0, b);
-                tc::tma_load_3d(in + 16384, &tm_x, &in_full[g], 32, row0, b);
-            }
-        }
-    } else if (warp == CA2_G * 4 + 1) {
-        // ================= producer of the KQ' tiles =================
-        if (lane == 0) {
-            uint32_t n = CA2_G;
-            for (int tile = blockIdx.x + CA2_G * gridDim.x; tile < ntiles; tile += gridDim.x, ++n) {
-                const int g = n % CA2_G;
-                const uint32_t j = n / CA2_G;
-                const int b = tile / a.qtiles;
-                uint8_t* w = smem + g * CA2_GBUF + CA2_IN + CA2_A;
-                tc::mbar_wait(&kq_empty[g], (j & 1) ^ 1);
-                tc::mbar_arrive_expect_tx(&kq_full[g], CA2_W / 2);
-                tc::tma_load_2d(w, &tm_kq_hi, &kq_full[g], 0, b * CAF_NS);
-                tc::tma_load_2d(w + 8192, &tm_kq_lo, &kq_full[g], 0, b * CAF_NS);
-            }
-        }
-    } else if (warp == CA2_G * 4 + 2) {
-        // ================= producer of the VPt' tiles =================
-        if (lane == 0) {
-            uint32_t n = CA2_G;
-            for (int tile = blockIdx.x + CA2_G * gridDim.x; tile < ntiles; tile += gridDim.x, ++n) {
-                const int g = n % CA2_G;
-                const uint32_t j = n / CA2_G;
-                const int b = tile / a.qtiles;
-                uint8_t* w = smem + g * CA2_GBUF + CA2_IN + CA2_A + CA2_W / 2;
-                tc::mbar_wait(&vp_empty[g], (j & 1) ^ 1);
-                tc::mbar_arrive_expect_tx(&vp_full[g], CA2_W / 2);
-                tc::tma_load_2d(w, &tm_vp_hi, &vp_full[g], 0, b * 64);
-                tc::tma_load_2d(w + 8192, &tm_vp_lo, &vp_full[g], 0, b * 64);
-            }
-        }
-    } else {
-        // ================= consumers: group g = warp / 4, thread r owns tile row r =================
-        const int g = warp >> 2, r = tid & 127;
-        const uint32_t gbuf = sbase + g * CA2_GBUF;
-        const uint32_t s_in = gbuf, s_ahi = gbuf + CA2_IN, s_alo = s_ahi + AT_TILE, s_w = gbuf + CA2_IN + CA2_A;
-        const uint32_t tS = tmem_base + g * 128, tO = tS + 64;
-        const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-        const int sw = r & 7;
-        const uint32_t in_row = s_in + r * 128, out_row = s_ahi + r * 128;
-        const bool leader = r == 0;
-        bool store_pending = false;
-        uint32_t j = 0;
-        for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += CA2_G * gridDim.x, ++j) {
-            const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
+    const uint32_t s_x = sbase + g * CA_GBUF, s_ahi = s_x, s_alo = s_x + AT_TILE, s_w = s_x + CA_X;
+    const uint32_t tS = tmem_base + g * 128, tO = tS + 64;
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    const int sw = r & 7;
+    const uint32_t row_addr = s_x + r * 128;
+    uint32_t j = 0;
+    for (int tile = tile0; tile < ntiles; tile += tstep, ++j) {
+        const int b = tile / a.qtiles, row0 = (tile % a.qtiles) * 128;
+        const int next = tile + tstep;
+        const bool has_next = next < ntiles;
+        const int nb = has_next ? next / a.qtiles : 0, nrow0 = has_next ? (next % a.qtiles) * 128 : 0;
 
-            // ---- the row -> registers (kept for the residual); the IN buffer goes back to the producer at once ----
+        // ---- the row: shared memory -> registers -> (a) the output accumulator (residual), (b) statistics, (c) A tiles in place ----
+        tc::mbar_wait(&in_full[g], j & 1);
+        float inv, nmi;
+        {
             float x[64];
-            tc::mbar_wait(&in_full[g], j & 1);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                const float4 v = tc::lds16(in_row + (c >> 3) * 16384 + (((c & 7) ^ sw) << 4));
+                const float4 v = tc::lds16(row_addr + (c >> 3) * 16384 + (((c & 7) ^ sw) << 4));
                 x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
             }
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&in_empty[g]);
-
-            // ---- AdaLayerNorm statistics (CoevoDecoder.py:23-29: unbiased std, eps added to the std), thread-local ----
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(x[hf * 32 + i]);
+                tc::tmem_st_32x32(tO + lane_sel + hf * 32, v);
+            }
+            // AdaLayerNorm statistics (CoevoDecoder.py:23-29: unbiased std, eps added to the std), thread-local
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
             for (int i = 0; i < 64; i += 4) { s0 += x[i]; s1 += x[i + 1]; s2 += x[i + 2]; s3 += x[i + 3]; }
@@ -208,16 +178,9 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
                 const float d0 = x[i] - mean, d1 = x[i + 1] - mean, d2 = x[i + 2] - mean, d3 = x[i + 3] - mean;
                 q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
             }
-            const float inv = 1.0f / (sqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / 63.0f)) + a.eps);
-            const float nmi = -mean * inv;
-
-            // ---- the A buffer is free once the previous item's TMA store has read it ----
-            if (a.tma_out) {
-                if (leader && store_pending) tc::tma_store_wait_read<0>();
-                tc::bar_sync_group(1 + g);
-            }
-
-            // ---- n = (x - mean) inv -> split-bf16 A tiles ----
+            inv = 1.0f / (sqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / 63.0f)) + a.eps);
+            nmi = -mean * inv;
+            // n = (x - mean) inv -> split-bf16 A tiles over the SAME bytes (row r of the hi / lo tile = row r of box 0 / 1)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 float y[8];
@@ -228,138 +191,131 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
                 tc::sts16(s_ahi, r, c, hh);
                 tc::sts16(s_alo, r, c, ll);
             }
-            tc::fence_proxy_async();
-            tc::tc_fence_before();
-            tc::bar_sync_group(1 + g);
-            if (leader) {
-                tc::mbar_wait(&kq_full[g], j & 1);
-                tc::tc_fence_after();
-                constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, CAF_NS);
-                const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
-                const uint64_t wh = tc::umma_desc_sw128(s_w), wl = tc::umma_desc_sw128(s_w + 8192);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    tc::umma_bf16(tS, tc::umma_desc_advance_k(al, k), tc::umma_desc_advance_k(wh, k), idesc, k != 0);
-                    tc::umma_bf16(tS, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
-                    tc::umma_bf16(tS, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
-                }
-                tc::umma_commit(&mma_bar[g]);
-                tc::umma_commit(&kq_empty[g]);                      // KQ' goes back to its producer: the next item's tiles arrive early
-            }
-            // folded score bias of both heads (the same 2 x NK floats for every row of the clip: L1/L2 broadcast), in flight
-            // while the MMA runs
-            constexpr int NKV = (NK + 3) / 4;                      // float4 loads per head
-            float4 sbv[2][NKV];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int i = 0; i < NKV; ++i) sbv[h][i] = __ldg(reinterpret_cast<const float4*>(a.sb + (size_t)b * CAF_NS + h * CAF_KP) + i);
-            tc::mbar_wait(&mma_bar[g], 0);
+        }
+        tc::tmem_st_wait();
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        tc::bar_sync_group(1 + g);
+        if (leader) {
+            tc::mbar_wait(&kq_full[g], j & 1);
             tc::tc_fence_after();
-
-            // ---- softmax of each head over the clip's NK keys (log2 domain); P (split) -> A tile columns [32 h, 32 h + 32) ----
+            constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, CAF_NS);
+            const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
+            const uint64_t wh = tc::umma_desc_sw128(s_w), wl = tc::umma_desc_sw128(s_w + CA_WT);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t v[32];
-                tc::tmem_ld_32x32(tS + lane_sel + h * CAF_KP, v);
+            for (int k = 0; k < 4; ++k) {
+                tc::umma_bf16(tS, tc::umma_desc_advance_k(al, k), tc::umma_desc_advance_k(wh, k), idesc, k != 0);
+                tc::umma_bf16(tS, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
+                tc::umma_bf16(tS, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
+            }
+            tc::umma_commit(&mma_bar[g]);
+        }
+        // folded score bias of both heads (the same 2 x NK floats for every row of the clip: L1/L2 broadcast), in flight while the MMA runs
+        constexpr int NKV = (NK + 3) / 4;
+        float4 sbv[2][NKV];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < NKV; ++i) sbv[h][i] = __ldg(reinterpret_cast<const float4*>(a.sb + (size_t)b * CAF_NS + h * CAF_KP) + i);
+        tc::mbar_wait(&mma_bar[g], 0);
+        tc::tc_fence_after();
+        if (leader && has_next) {                 // KQ' is free: the next item's tiles arrive under the rest of this item
+            tc::mbar_arrive_expect_tx(&kq_full[g], 2 * CA_WT);
+            tc::tma_load_2d(gptr + CA_X, &tm_kq_hi, &kq_full[g], 0, nb * CAF_NS);
+            tc::tma_load_2d(gptr + CA_X + CA_WT, &tm_kq_lo, &kq_full[g], 0, nb * CAF_NS);
+        }
+
+        // ---- softmax of each head over the clip's NK keys (log2 domain); P (split) -> A tile columns [24 h, 24 h + 24) ----
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float p[CAF_KP];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                uint32_t v[8];
+                tc::tmem_ld_32x8(tS + lane_sel + h * CAF_KP + q * 8, v);
                 tc::tmem_ld_wait();
-                float p[CAF_MAXJ];
-                float m = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < NK; ++i) {
-                    const float4 t = sbv[h][i >> 2];
-                    const float bias = (i & 3) == 0 ? t.x : ((i & 3) == 1 ? t.y : ((i & 3) == 2 ? t.z : t.w));
-                    p[i] = __uint_as_float(v[i]) + bias;
-                    m = fmaxf(m, p[i]);
-                }
-                float l = 0.f;
-#pragma unroll
-                for (int i = 0; i < NK; ++i) { p[i] = tc::ex2_approx(p[i] - m); l += p[i]; }
-                const float il = 1.0f / l;
-#pragma unroll
-                for (int i = 0; i < CAF_MAXJ; ++i) p[i] = i < NK ? p[i] * il : 0.f;
-#pragma unroll
-                for (int cc = 0; cc < 3; ++cc) {
-                    float y[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = p[cc * 8 + i];
-                    uint4 hh, ll;
-                    tc::split8(y, hh, ll);
-                    tc::sts16(s_ahi, r, h * 4 + cc, hh);
-                    tc::sts16(s_alo, r, h * 4 + cc, ll);
-                }
-                tc::sts16(s_ahi, r, h * 4 + 3, make_uint4(0, 0, 0, 0));     // key slots 24..31 never hold a key
-                tc::sts16(s_alo, r, h * 4 + 3, make_uint4(0, 0, 0, 0));
+                for (int i = 0; i < 8; ++i) p[q * 8 + i] = __uint_as_float(v[i]);
             }
-            tc::fence_proxy_async();
-            tc::tc_fence_before();
-            tc::bar_sync_group(1 + g);
-            if (leader) {
-                tc::mbar_wait(&vp_full[g], j & 1);
-                tc::tc_fence_after();
-                constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, 64);
-                const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
-                const uint64_t wh = tc::umma_desc_sw128(s_w + 16384), wl = tc::umma_desc_sw128(s_w + 24576);
+            float m = -INFINITY;
 #pragma unroll
-                for (int k = 0; k < CAF_NS / 16; ++k) {
-                    tc::umma_bf16(tO, tc::umma_desc_advance_k(al, k), tc::umma_desc_advance_k(wh, k), idesc, k != 0);
-                    tc::umma_bf16(tO, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
-                    tc::umma_bf16(tO, tc::umma_desc_advance_k(ah, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
-                }
-                tc::umma_commit(&mma_bar[g]);
-                tc::umma_commit(&vp_empty[g]);
+            for (int i = 0; i < NK; ++i) {
+                const float4 t = sbv[h][i >> 2];
+                p[i] += (i & 3) == 0 ? t.x : ((i & 3) == 1 ? t.y : ((i & 3) == 2 ? t.z : t.w));
+                m = fmaxf(m, p[i]);
             }
-            tc::mbar_wait(&mma_bar[g], 1);
-            tc::tc_fence_after();
-
-            // ---- xq' = xq + P VPt'^T -> fp32 boxes in the A buffer (both MMAs have read it) -> TMA store ----
-            if (a.tma_out) {
+            float l = 0.f;
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t v[32];
-                    tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v);
-                    tc::tmem_ld_wait();
+            for (int i = 0; i < NK; ++i) { p[i] = tc::ex2_approx(p[i] - m); l += p[i]; }
+            const float il = 1.0f / l;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        tc::sts16f(out_row + hf * 16384 + ((c ^ sw) << 4),
-                                   make_float4(x[hf * 32 + 4 * c] + __uint_as_float(v[4 * c]), x[hf * 32 + 4 * c + 1] + __uint_as_float(v[4 * c + 1]),
-                                               x[hf * 32 + 4 * c + 2] + __uint_as_float(v[4 * c + 2]), x[hf * 32 + 4 * c + 3] + __uint_as_float(v[4 * c + 3])));
-                }
-                tc::fence_proxy_async();
-                tc::tc_fence_before();
-                tc::bar_sync_group(1 + g);
-                if (leader) {
-                    tc::tma_store_3d(&tm_x, smem + g * CA2_GBUF + CA2_IN, 0, row0, b);
-                    tc::tma_store_3d(&tm_x, smem + g * CA2_GBUF + CA2_IN + 16384, 32, row0, b);
-                    tc::tma_store_commit();
-                    store_pending = true;
-                }
-            } else {
-                // the thread's 256-byte row goes straight to global memory: no staging, no proxy fence, no group barrier, and the
-                // next item's A tiles never wait for a TMA store to drain the buffer
-                float* orow = a.xq + ((size_t)b * a.N1 + row0 + r) * 64;
-                const bool live = row0 + r < a.N1;
+            for (int i = 0; i < CAF_KP; ++i) p[i] = i < NK ? p[i] * il : 0.f;
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t v[32];
-                    tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v);
-                    tc::tmem_ld_wait();
-                    if (live) {
+            for (int cc = 0; cc < 3; ++cc) {
+                float y[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            __stcs(reinterpret_cast<float4*>(orow + hf * 32 + 4 * c),
-                                   make_float4(x[hf * 32 + 4 * c] + __uint_as_float(v[4 * c]), x[hf * 32 + 4 * c + 1] + __uint_as_float(v[4 * c + 1]),
-                                               x[hf * 32 + 4 * c + 2] + __uint_as_float(v[4 * c + 2]), x[hf * 32 + 4 * c + 3] + __uint_as_float(v[4 * c + 3])));
-                    }
-                }
-                tc::tc_fence_before();       // orders the TMEM reads above before the group barrier that precedes the next item's MMA
+                for (int i = 0; i < 8; ++i) y[i] = p[cc * 8 + i];
+                uint4 hh, ll;
+                tc::split8(y, hh, ll);
+                tc::sts16(s_ahi, r, h * 3 + cc, hh);
+                tc::sts16(s_alo, r, h * 3 + cc, ll);
             }
         }
-        if (leader && store_pending) tc::tma_store_wait_read<0>();     // smem must outlive the reads; the grid boundary orders the writes
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        tc::bar_sync_group(1 + g);
+        if (leader) {
+            tc::mbar_wait(&vp_full[g], j & 1);
+            tc::tc_fence_after();
+            constexpr uint32_t idesc = tc::umma_idesc_bf16_f32_bmn(128, 64);
+            const uint64_t ah = tc::umma_desc_sw128(s_ahi), al = tc::umma_desc_sw128(s_alo);
+            const uint64_t wh = tc::umma_desc_sw128(s_w + 2 * CA_WT), wl = tc::umma_desc_sw128(s_w + 3 * CA_WT);
+#pragma unroll
+            for (int k = 0; k < CAF_NS / 16; ++k) {          // every MMA ACCUMULATES: the accumulator already holds xq
+                const uint64_t bh = wh + (uint64_t)(k * 2048 >> 4), bl = wl + (uint64_t)(k * 2048 >> 4);     // 16 key slots = two 8-row groups
+                tc::umma_bf16(tO, tc::umma_desc_advance_k(al, k), bh, idesc, 1);
+                tc::umma_bf16(tO, tc::umma_desc_advance_k(ah, k), bl, idesc, 1);
+                tc::umma_bf16(tO, tc::umma_desc_advance_k(ah, k), bh, idesc, 1);
+            }
+            tc::umma_commit(&mma_bar[g]);
+        }
+        tc::mbar_wait(&mma_bar[g], 1);
+        tc::tc_fence_after();
+        if (leader && has_next) {                 // VP' is free
+            tc::mbar_arrive_expect_tx(&vp_full[g], 2 * CA_WT);
+            tc::tma_load_2d(gptr + CA_X + 2 * CA_WT, &tm_vp_hi, &vp_full[g], 0, nb * CAF_NS);
+            tc::tma_load_2d(gptr + CA_X + 3 * CA_WT, &tm_vp_lo, &vp_full[g], 0, nb * CAF_NS);
+        }
+
+        // ---- xq' = accumulator -> fp32 boxes over the same buffer (both MMAs have read it) -> TMA store ----
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tO + lane_sel + hf * 32, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                tc::sts16f(row_addr + hf * 16384 + ((c ^ sw) << 4), make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
+                                                                                   __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3])));
+        }
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        tc::bar_sync_group(1 + g);
+        if (leader) {
+            tc::tma_store_3d(&tm_x, gptr, 0, row0, b);
+            tc::tma_store_3d(&tm_x, gptr + 16384, 32, row0, b);
+            tc::tma_store_commit();
+            tc::tma_store_wait_read<0>();         // the buffer has been read: the next item's rows may land in it
+            if (has_next) {
+                tc::mbar_arrive_expect_tx(&in_full[g], CA_X);
+                tc::tma_load_3d(gptr, &tm_x, &in_full[g], 0, nrow0, nb);
+                tc::tma_load_3d(gptr + 16384, &tm_x, &in_full[g], 32, nrow0, nb);
+            }
+        }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == CA2_G * 4) tc::tmem_dealloc(tmem_base, CA2_G * 128);
+    if (warp == 0) tc::tmem_dealloc(tmem_base, CA_G * 128);
 }
 
 // generic 3-D tiled map: dims/box innermost first, element strides ld1 / ld2 of dims 1 / 2, 128-byte swizzle
@@ -378,18 +334,19 @@ static inline int make_tmap_3d(CUtensorMap* m, const void* ptr, CUtensorMapDataT
 
 template <int NK>
 static inline int launch_ca_vertex_fused_t(const CUtensorMap* maps, const CaFusedArgs& a, cudaStream_t st) {
-    if (!pmce_configure_smem<ca_vertex_fused_kernel<NK>>(CA2_SMEM)) return 2;
+    if (!pmce_configure_smem<ca_vertex_fused_kernel<NK>>(CA_SMEM)) return 2;
     const int ntiles = a.B * a.qtiles;
-    const int cap = tc_num_sms();                      // one CTA per SM (193 KB of shared memory), CA2_G items in flight each
+    const int cap = tc_num_sms();                      // one CTA per SM (225 KB of shared memory), CA_G items in flight each
     const int grid = ntiles < cap ? ntiles : cap;
-    ca_vertex_fused_kernel<NK><<<grid, CA2_THREADS, CA2_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], a);
+    ca_vertex_fused_kernel<NK><<<grid, CA_THREADS, CA_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], a);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
 // true when the fused kernel covers (heads, keys): the reference's vertex stream has 2 heads; 17 (h36m) / 19 (coco) joints
 static inline bool ca_vertex_fused_supported(int heads, int nkeys) { return heads == CAF_H && (nkeys == 17 || nkeys == 19); }
 
-// Per-clip folded operands (made by ca_joint_fold_kernel): kq [B*64, 64], vpt [B*64, 64] split bf16, sb [B, 64] fp32
+// Per-clip folded operands (made by ca_joint_fold_kernel): kq [B*48, 64] (row = key slot, K-major over the channel c),
+// vp [B*48, 64] (row = key slot, MN-major over the output channel n), split bf16; sb [B, 48] fp32
 struct CaFolded {
     __nv_bfloat16 *kq_hi, *kq_lo, *vp_hi, *vp_lo;
     float* sb;
@@ -400,13 +357,9 @@ static inline int launch_ca_vertex_fused(float* xq, const CaFolded& f, CaFusedAr
     CUtensorMap maps[5];
     a.qtiles = (a.N1 + 127) / 128;
     a.sb = f.sb;
-    a.xq = xq;
-    static int tma_out = -1;
-    if (tma_out < 0) tma_out = pmce_env_int("PMCE_CA_TMA_OUT", 1) ? 1 : 0;   // measured: direct row stores 27.6 us vs 23.8 us staged + TMA (B=256)
-    a.tma_out = tma_out;
     if (make_tmap_3d(&maps[0], xq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 64, a.N1, a.B, 64, 64LL * a.N1, 32, 128, 1) ||
         make_tmap_bf16(&maps[1], f.kq_hi, a.B * CAF_NS, 64, 64, CAF_NS) || make_tmap_bf16(&maps[2], f.kq_lo, a.B * CAF_NS, 64, 64, CAF_NS) ||
-        make_tmap_bf16(&maps[3], f.vp_hi, a.B * 64, 64, 64, 64) || make_tmap_bf16(&maps[4], f.vp_lo, a.B * 64, 64, 64, 64))
+        make_tmap_bf16(&maps[3], f.vp_hi, a.B * CAF_NS, 64, 64, CAF_NS) || make_tmap_bf16(&maps[4], f.vp_lo, a.B * CAF_NS, 64, 64, CAF_NS))
         return 1;
     if (a.N2 == 17) return launch_ca_vertex_fused_t<17>(maps, a, st);
     if (a.N2 == 19) return launch_ca_vertex_fused_t<19>(maps, a, st);
@@ -419,7 +372,7 @@ static inline int launch_ca_vertex_fused(float* xq, const CaFolded& f, CaFusedAr
 //   xk = W_j2v Jf + b + j2v_K                    (:184)
 //   K  = Wk AdaLN_k(xk) + bk ;  V = Wv AdaLN_v(Jf) + bv     (:53-55 with :84)
 //   KQ' = log2e scale (K_h Wq_h) diag(gamma_q), sb' = log2e (scale K_h bq_h + scale (K_h Wq_h) beta_q),
-//   VPt' = (V_h Wp[:, h]^T)^T + bp / 2 on the live key slots     (the folded operands of ca_vertex_fused_kernel: AdaLN_q's
+//   VP' = V_h Wp[:, h]^T + bp / 2 on the live key slots     (the folded operands of ca_vertex_fused_kernel: AdaLN_q's
 //   per-clip gamma / beta, the softmax's log2e and the output bias all live in them)
 // replacing six launches (embed, key projection, 2 x AdaLN, 2 x projection GEMM with 17 live rows per 128-row tile).
 // With joints == nullptr the kernel starts from given K / V [B,J,64] (pmce_cross_attn_block on arbitrary key/value streams).
@@ -496,8 +449,6 @@ ca_joint_fold_kernel(const __grid_constant__ JointFoldArgs3 args) {
     constexpr int RS = JKV_ROWS * 64;            // floats per [24][64] buffer
     __shared__ __align__(16) float buf[6 * RS];
     float *Jf = buf, *Xk = buf + RS, *Nk = buf + 2 * RS, *Nv = buf + 3 * RS, *Ks = buf + 4 * RS, *Vs = buf + 5 * RS;
-    float* VPs = buf;                            // [64][65] staging of VPt^T, aliases Jf/Xk/Nk once K and V are final
-    static_assert(CAF_NS * 65 <= 3 * RS, "VPs must not reach Ks/Vs");
     extern __shared__ __align__(16) float wsm[];   // the five 64x64 weights, all in flight from the first instruction
     float *Wj2v = wsm, *Wk = wsm + JKV_WMAT, *Wv = wsm + 2 * JKV_WMAT, *Wp = wsm + 3 * JKV_WMAT, *Wq = wsm;   // Wq reuses W_j2v's slot
     const int b = blockIdx.x, tid = threadIdx.x, J = a.J;
@@ -547,7 +498,7 @@ ca_joint_fold_kernel(const __grid_constant__ JointFoldArgs3 args) {
     __syncthreads();
     constexpr float LOG2E = 1.4426950408889634f;
     const float gq = a.gb[(size_t)b * a.gb_ld + a.slot_q * 128 + n], bq_ = a.gb[(size_t)b * a.gb_ld + a.slot_q * 128 + 64 + n];
-    // ---- fold: KQ[32h+j][c] = scale sum_d K[j][32h+d] Wq[32h+d][c]  (thread = output channel c, coalesced weight columns) ----
+    // ---- fold: KQ[24h+j][c] = scale sum_d K[j][32h+d] Wq[32h+d][c]  (thread = output channel c, coalesced weight columns) ----
 #pragma unroll 1
     for (int h = 0; h < CAF_H; ++h) {
         float wc[32];
@@ -576,14 +527,14 @@ ca_joint_fold_kernel(const __grid_constant__ JointFoldArgs3 args) {
         }
     }
     __syncthreads();                             // sbacc complete
-    if (tid < CAF_NS) {                          // sb'[32h+j] = log2e (scale sum_d bq[32h+d] K[j][32h+d] + sum_c KQ[32h+j][c] beta_q[c])
+    if (tid < CAF_NS) {                          // sb'[24h+j] = log2e (scale sum_d bq[32h+d] K[j][32h+d] + sum_c KQ[32h+j][c] beta_q[c])
         const int h = tid / CAF_KP, j = tid % CAF_KP;
         float acc = 0.f;
         if (j < J)
             for (int d = 0; d < 32; ++d) acc = fmaf(a.bq[h * 32 + d], Ks[j * 64 + h * 32 + d], acc);
         a.f.sb[(size_t)b * CAF_NS + tid] = (acc * a.scale + sbacc[tid]) * LOG2E;
     }
-    // ---- fold: VPt[n][32h+j] = sum_d V[j][32h+d] Wp[n][32h+d]  (thread = output channel n, weight row in registers) ----
+    // ---- fold: VP'[24h+j][n] = sum_d V[j][32h+d] Wp[n][32h+d] + bp[n]/2  (thread = output channel n, weight row in registers) ----
     {
         float w[64];
 #pragma unroll
@@ -608,17 +559,10 @@ ca_joint_fold_kernel(const __grid_constant__ JointFoldArgs3 args) {
                 }
                 acc = (a0 + a1) + 0.5f * a.bp[n];           // every softmax row sums to 1: the two heads carry the output bias
             }
-            VPs[idx * 65 + n] = acc;            // Jf/Xk/Nk (aliased) were last read before the barrier that published Ks/Vs
+            __nv_bfloat16 hi, lo;                // VP' row = key slot, the 64 threads of a row group write 64 consecutive channels
+            tc::split_bf16(acc, hi, lo);
+            const size_t o = ((size_t)b * CAF_NS + idx) * 64 + n;
+            a.f.vp_hi[o] = hi; a.f.vp_lo[o] = lo;
         }
-    }
-    __syncthreads();
-    for (int e = tid; e < 64 * 32; e += JKV_THREADS) {       // VPt rows [64][64], split-bf16, coalesced
-        const int row = e >> 5, c = (e & 31) * 2;
-        const float v0 = VPs[c * 65 + row], v1 = VPs[(c + 1) * 65 + row];
-        uint32_t h2, l2;
-        tc::split_bf16x2(v0, v1, h2, l2);
-        const size_t o = ((size_t)b * 64 + row) * 64 + c;
-        *reinterpret_cast<uint32_t*>(a.f.vp_hi + o) = h2;
-        *reinterpret_cast<uint32_t*>(a.f.vp_lo + o) = l2;
     }
 }

@@ -47,6 +47,8 @@ struct TcEpi {
     RowMap rmap, cmap;
     float qscale;           // TC_ATTN32: factor applied to the q columns before the split
     int dbg;                // profiling only (PMCE_TC_DBG): 1 = stage but do not issue TMA stores, 2 = no staging either
+    int direct;             // epilogue stores straight from registers with 256-bit st.global (one full 32-byte sector per thread and
+                            // instruction) instead of shared-memory staging + TMA store (PMCE_TC_DIRECT=1, A/B knob)
     int pair_relaxed;       // CTA pairs: release the accumulator with a relaxed cluster-scope arrive (PMCE_TC_PAIR_RELAXED=1)
 };
 
@@ -305,6 +307,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         if (store_pending) { if (lane == 0) tc::tma_store_wait_read<NBUF - 1>(); __syncwarp(); }
                     }
                     if (e.dbg == 2) { if (f[0] == 123.456f) e.out_f32[0] = f[1]; continue; }
+                    if (MODE == TC_F32 && e.direct) {
+                        if (row < M) {
+                            float* o = e.out_f32 + (size_t)row * e.ld_out + col0;
+                            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]),
+                                         "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
+                            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + 8), "f"(f[8]), "f"(f[9]), "f"(f[10]), "f"(f[11]),
+                                         "f"(f[12]), "f"(f[13]), "f"(f[14]), "f"(f[15]) : "memory");
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + ((j ^ sw) << 4)), "f"(f[4 * j]), "f"(f[4 * j + 1]),
@@ -327,6 +339,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         if (MODE == TC_ATTN32) { x0 *= qs; x1 *= qs; x2 *= qs; x3 *= qs; }
                         tc::split_bf16x2(x0, x1, hi[i / 2], lo[i / 2]);
                         tc::split_bf16x2(x2, x3, hi[i / 2 + 1], lo[i / 2 + 1]);
+                    }
+                    if ((MODE == TC_SPLIT_GELU || MODE == TC_SPLIT) && e.direct) {
+                        if (row < M) {
+                            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(e.out_hi + (size_t)row * e.ld_split + col0), "r"(hi[0]),
+                                         "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+                            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(e.out_lo + (size_t)row * e.ld_split + col0), "r"(lo[0]),
+                                         "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+                        }
+                        continue;
                     }
                     if (store_pending) { if (lane == 0) tc::tma_store_wait_read<NBUF - 1>(); __syncwarp(); }
                     // two dense [32 rows][16 bf16] tiles (32-byte rows, no swizzle): hi at +0, lo at +1024
@@ -500,6 +521,12 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
     static int relaxed = -1;   // ncu shows the release.cluster arrive (a cluster-scope fence per accumulator release) at 15 % of the pair kernel's stall samples
     if (relaxed < 0) relaxed = pmce_env_int("PMCE_TC_PAIR_RELAXED", 0) ? 1 : 0;
     const_cast<TcEpi&>(e).pair_relaxed = relaxed;
+    static int direct = -1;
+    if (direct < 0) direct = pmce_env_int("PMCE_TC_DIRECT", 0);
+    // 256-bit stores need 32-byte aligned rows: leading dimensions in multiples of 16 bf16 / 8 fp32 and 32-byte aligned bases
+    auto a32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+    const_cast<TcEpi&>(e).direct = (direct && ((e.out_hi && a32(e.out_hi) && a32(e.out_lo) && e.ld_split % 16 == 0) ||
+                                               (e.out_f32 && !e.resid && a32(e.out_f32) && e.ld_out % 8 == 0))) ? 1 : 0;
     TcOutMaps om;
     memset(&om, 0, sizeof(om));
     if (null_epi) return launch_linear_tc_mode<BN, TC_NULL>(ta, tw, om, M, N, K, e, st);

@@ -98,7 +98,7 @@ def test_new_entry_points_validate_before_touching_the_gpu(lib):
     rc = lib.pmce_forward_sliding(dp, None, None, None, None, 64, 17, None, None, None, None, 0, None)
     assert rc != 0 and b"stride" in lib.pmce_last_error()
     assert lib.pmce_ca_fold_bytes(0) == 0
-    assert lib.pmce_ca_fold_bytes(2) == 2 * (2 * (64 + 64) * 64 * 2 + 64 * 4)
+    assert lib.pmce_ca_fold_bytes(2) == 2 * (4 * 48 * 64 * 2 + 48 * 4)      # KQ' | VP' (48 key slots x 64, bf16 hi + lo each) + sb' fp32
     blob = C.c_void_p(256)                               # non-NULL, never dereferenced: every call below fails in validation
     rc = lib.pmce_cross_attn_block(dp, blob, 4, 1, None, None, None, None, 1, None, None, 0, None)
     assert rc != 0 and b"block must be 1..3" in lib.pmce_last_error()
