@@ -399,6 +399,9 @@ def main():
     roof_ca["at_B256"] = {k: big[k] for k in ("achieved", "frac", "us_per_launch", "achieved_kernel_io", "frac_kernel_io", "bytes_per_launch",
                                               "kernel_io_bytes_per_launch", "clips_per_launch")}
 
+    roof_lbs = lbs_roofline(lib, dev, peaks) if rank == 0 else None
+    spin = spin_leg(lib, dev, peaks, cpu=(world == 1 and not args.no_cpu_baseline)) if rank == 0 else None
+
     out = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -409,7 +412,8 @@ def main():
                 "unpipelined": {"value": world * B * K / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync / K,
                                 "path": "models.PMCE.forward_host: H2D -> forward -> D2H -> sync per step"}},
         "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
-        "config3_B1024_x8": b1024, "clocks": clocks, "roofline": roof, "roofline_cross_attn": roof_ca, "peaks": peaks,
+        "config3_B1024_x8": b1024, "clocks": clocks, "roofline": roof, "roofline_cross_attn": roof_ca, "roofline_lbs": roof_lbs, "spin_feature_extractor": spin,
+        "peaks": peaks,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -472,6 +476,124 @@ def dominant_kernel_roofline(lib, dev, peaks, B):
             "traffic": ncu_traffic("linear_tc_kernel_fc1", B), "traffic_unit": "B", "frac_of_split_ceiling": 3.0 * ach / peaks["bf16_tflops"],
             "flops_per_launch": flops, "mma_flops_per_launch": 3 * flops, "us_per_launch": sec * 1e6, "shape_MNK": [M, N, K],
             "peak_source": peaks["source"], "note": "3 bf16 MMAs per product (bf16x3): frac ceiling is 1/3"}
+
+
+def _graph_time(fns, dev, rounds=5):
+    """seconds per call of the zero-argument callables `fns` (one per rotating buffer set), timed as CUDA-graph replays."""
+    import torch
+    for f in fns:
+        f()
+    torch.cuda.synchronize(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for f in fns:
+                f()
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rounds):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) * 1e-3 / (rounds * len(fns))
+
+
+def lbs_roofline(lib, dev, peaks, B=256):
+    """north_star's LBS-bandwidth roofline: `SMPL_Layer.forward` (smpl_layer.py:65-158) = smpl_pose_kernel + blend-shape GEMM +
+    the sparse skinning kernel, timed as one call (`smpl_lbs_forward_sparse`) over rotating output sets larger than L2.
+    achieved = SURVEY §8(d)'s algorithmic bytes (340 B in + 82,968 B out per sample) / time; `kernel_io` adds the v_posed
+    intermediate the GEMM writes and the skinning kernel reads (82,688 B each way per sample)."""
+    import ctypes as Ct
+    import torch
+    from pmce_b200 import synth
+    from pmce_b200.smpl_layer import SMPL_Layer
+    layer = SMPL_Layer.from_buffers(synth.make_smpl_buffers(11)).to(dev)
+    p = layer._pack()
+    pose, betas, trans = [t.to(dev) for t in synth.make_smpl_inputs(B, seed=13)]
+    nsets = 8
+    verts = [torch.empty(B, 6890, 3, device=dev) for _ in range(nsets)]
+    joints = torch.empty(B, 24, 3, device=dev)
+    ws = torch.empty(lib.smpl_workspace_bytes(B), dtype=torch.uint8, device=dev)
+    P = lambda t: Ct.c_void_p(t.data_ptr()) if t is not None else Ct.c_void_p(0)
+
+    def call(i):
+        rc = lib.smpl_lbs_forward_sparse(P(p["blend"]), P(p["blend_hi"]), P(p["blend_lo"]), P(p["vt_pad"]), P(p["jt"]), P(p["js"]), P(p["weights"]),
+                                         P(p["idx4"]), P(p["w4"]), P(p["parents"]), P(pose), P(betas), P(trans), B, 1.0, P(verts[i]), P(joints),
+                                         P(ws), ws.numel(), Ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, lib.pmce_last_error()
+    sec = _graph_time([lambda i=i: call(i) for i in range(nsets)], dev)
+    alg = B * (340 + 82968)
+    io = alg + B * 2 * 82688
+    return {"kernel": "smpl_lbs_forward_sparse (smpl_pose_kernel + blend-shape GEMM on tcgen05 + smpl_skin4_kernel: <= 4 joints per vertex)",
+            "bound": "hbm", "achieved": alg / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg / sec / 1e9 / peaks["hbm_gbs"],
+            "traffic": ncu_traffic("smpl_skin_kernel", B), "traffic_unit": "B", "bytes_per_launch": alg, "us_per_launch": sec * 1e6,
+            "achieved_kernel_io": io / sec / 1e9, "frac_kernel_io": io / sec / 1e9 / peaks["hbm_gbs"], "samples_per_launch": B,
+            "peak_source": peaks["source"]}
+
+
+def spin_leg(lib, dev, peaks, cpu=False, frames=16):
+    """(f)2, the step before the path: the SPIN ResNet-50 feature extractor (lib/models/spin.py:129-143) on one clip's 16 frame
+    crops; algorithmic FLOPs 2 x 4.09 GMAC per frame. Also the 3x3 convolution of layer1 as the GEMM it runs as (explicit
+    im2col rows [frames*3136, 576] x [64, 576]^T) on the tcgen05 GEMM, timed alone."""
+    import ctypes as Ct
+    import torch
+    from pmce_b200 import synth
+    from pmce_b200.spin import HMR
+    m = HMR()
+    sd = synth.make_spin_state_dict(17)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    x = synth.make_frames(frames, 3).to(dev)
+    for _ in range(3):
+        m.feature_extractor(x)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        m.feature_extractor(x)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sec = e0.elapsed_time(e1) * 1e-3 / n
+    flops = frames * 2 * 4.09e9
+    out = {"frames_per_s": frames / sec, "ms_per_clip_of_16_frames": sec * 1e3 * 16 / frames, "tflops_algorithmic": flops / sec / 1e12,
+           "frac_of_bf16_peak": flops / sec / 1e12 / peaks["bf16_tflops"], "note": "split-bf16 (3 MMAs per product) GEMMs, explicit im2col"}
+    # the 3x3 convolution of layer1 as a GEMM
+    M, N, K = frames * 3136, 64, 576
+    P = lambda t: Ct.c_void_p(t.data_ptr())
+    a = [torch.empty(M, K, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    w = [torch.empty(N, K, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.pmce_split_bf16(P(torch.randn(M, K, device=dev)), M, K, P(a[0]), P(a[1]), st) == 0
+    assert lib.pmce_split_bf16(P(torch.randn(N, K, device=dev) * 0.05), N, K, P(w[0]), P(w[1]), st) == 0
+    b = torch.randn(N, device=dev)
+    o = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    Z = Ct.c_void_p(0)
+
+    def conv():
+        assert lib.pmce_linear_tc_presplit(P(a[0]), P(a[1]), P(w[0]), P(w[1]), P(b), M, N, K, 2, Z, P(o[0]), P(o[1]), Z,
+                                           Ct.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+    sec_c = _graph_time([conv] * 4, dev)
+    fl = 2.0 * M * N * K
+    out["conv3x3_layer1"] = {"shape_MNK": [M, N, K], "us_per_launch": sec_c * 1e6, "tflops_algorithmic": fl / sec_c / 1e12,
+                             "frac": fl / sec_c / 1e12 / peaks["bf16_tflops"], "bound": "hbm (N = 64: 231 MB of im2col rows per launch)",
+                             "achieved_gbs": (M * K * 4 + M * N * 4) / sec_c / 1e9, "frac_hbm": (M * K * 4 + M * N * 4) / sec_c / 1e9 / peaks["hbm_gbs"]}
+    if cpu:
+        from oracle import spin_oracle as so
+        xc = synth.make_frames(4, 3)
+        with torch.no_grad():
+            so.feature_extractor(sd, xc)
+            t0 = time.perf_counter()
+            so.feature_extractor(sd, xc)
+            dt = time.perf_counter() - t0
+        out["cpu_frames_per_s"] = 4 / dt
+        out["cpu_sample"] = f"4 frames through the oracle restatement (torch CPU fp32, {torch.get_num_threads()} threads)"
+    return out
 
 
 def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):

@@ -238,6 +238,13 @@ int smpl_lbs_forward_scaled(const float* blend, const void* blend_hi, const void
                             const int32_t* parents, const float* pose, const float* betas, const float* trans, int B,
                             float out_scale, float* verts, float* joints, void* workspace, size_t workspace_bytes,
                             void* stream);
+/* Same with the skinning weights in sparse form: skin_idx4 / skin_w4 [6890,4] = the (joint, weight) pairs of each vertex in
+ * ascending joint order, zero-weight padded (every shipped SMPL model binds a vertex to <= 4 joints; smpl_layer.py:134 sums
+ * over all 24, the other 20 terms being exact zeros). NULL for both selects the dense [6890,24] skin_weights. */
+int smpl_lbs_forward_sparse(const float* blend, const void* blend_hi, const void* blend_lo, const float* v_template,
+                            const float* j_template, const float* j_shapedirs, const float* skin_weights, const int32_t* skin_idx4,
+                            const float* skin_w4, const int32_t* parents, const float* pose, const float* betas, const float* trans,
+                            int B, float out_scale, float* verts, float* joints, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,7 @@ SIGNATURES = {
     "smpl_blend_ld": (C.c_int, []),
     "smpl_workspace_bytes": (C.c_size_t, [C.c_int]),
     "smpl_lbs_forward_scaled": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_float, _P, _P, _P, C.c_size_t, _P]),
+    "smpl_lbs_forward_sparse": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_float, _P, _P, _P, C.c_size_t, _P]),
     "smpl_lbs_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
 }
 

@@ -1128,11 +1128,25 @@ extern "C" size_t smpl_workspace_bytes(int B) {
     return al((size_t)B * SMPL_LDK * 4) + al((size_t)B * 288 * 4) + al((size_t)B * SMPL_NPAD * 4) + 2 * al((size_t)B * SMPL_LDK * 2);
 }
 
+extern "C" int smpl_lbs_forward_sparse(const float* blend, const void* blend_hi, const void* blend_lo, const float* v_template,
+                                       const float* j_template, const float* j_shapedirs, const float* skin_weights, const int32_t* skin_idx4,
+                                       const float* skin_w4, const int32_t* parents, const float* pose, const float* betas, const float* trans,
+                                       int B, float out_scale, float* verts, float* joints, void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int smpl_lbs_forward_scaled(const float* blend, const void* blend_hi, const void* blend_lo, const float* v_template,
                                        const float* j_template, const float* j_shapedirs, const float* skin_weights, const int32_t* parents,
                                        const float* pose, const float* betas, const float* trans, int B, float out_scale, float* verts,
                                        float* joints, void* workspace, size_t workspace_bytes, void* stream) {
-    if ((!blend && !blend_hi) || (blend_hi && !blend_lo) || !v_template || !j_template || !j_shapedirs || !skin_weights || !parents || !pose || !betas ||
+    return smpl_lbs_forward_sparse(blend, blend_hi, blend_lo, v_template, j_template, j_shapedirs, skin_weights, nullptr, nullptr, parents, pose,
+                                   betas, trans, B, out_scale, verts, joints, workspace, workspace_bytes, stream);
+}
+
+extern "C" int smpl_lbs_forward_sparse(const float* blend, const void* blend_hi, const void* blend_lo, const float* v_template,
+                                       const float* j_template, const float* j_shapedirs, const float* skin_weights, const int32_t* skin_idx4,
+                                       const float* skin_w4, const int32_t* parents, const float* pose, const float* betas, const float* trans,
+                                       int B, float out_scale, float* verts, float* joints, void* workspace, size_t workspace_bytes, void* stream) {
+    if ((!blend && !blend_hi) || (blend_hi && !blend_lo) || !v_template || !j_template || !j_shapedirs || (!skin_weights && !skin_idx4) ||
+        ((skin_idx4 == nullptr) != (skin_w4 == nullptr)) || !parents || !pose || !betas ||
         !verts || !joints) {
         pmce_set_error("smpl_lbs_forward: NULL argument"); return 2;
     }
@@ -1162,7 +1176,11 @@ extern "C" int smpl_lbs_forward_scaled(const float* blend, const void* blend_hi,
         ld_vp = SMPL_V * 3;
     }
     dim3 grid(cdiv(SMPL_V, 256), cdiv(B, SMPL_SKIN_NB));
-    smpl_skin_kernel<<<grid, 256, 0, st>>>(vposed, Amat, skin_weights, trans, SMPL_V, B, ld_vp, verts, out_scale);
+    if (skin_idx4)      // <= 4 joints per vertex (every shipped SMPL model): the sparse stream kernel, one thread per vertex pair
+        smpl_skin4_kernel<<<dim3(cdiv((SMPL_V + 1) / 2, 256), cdiv(B, SMPL_SKIN_NB)), 256, 0, st>>>(vposed, Amat, reinterpret_cast<const int4*>(skin_idx4), reinterpret_cast<const float4*>(skin_w4), trans,
+                                                SMPL_V, B, ld_vp, verts, out_scale);
+    else
+        smpl_skin_kernel<<<grid, 256, 0, st>>>(vposed, Amat, skin_weights, trans, SMPL_V, B, ld_vp, verts, out_scale);
     CKL();
     return 0;
 }

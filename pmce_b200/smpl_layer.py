@@ -96,8 +96,16 @@ class SMPL_Layer(Module):
         j_shapedirs = torch.einsum("jv,vck->jck", Jreg, self.th_shapedirs.double()).float().contiguous()  # [24,3,10]
         parents = torch.as_tensor(np.array([max(p, 0) if i else 0 for i, p in enumerate(self.kintree_parents)],
                                            dtype=np.int32) % 24, device=dev)
+        # sparse skinning table: the <= 4 (joint, weight) pairs of each vertex, ascending joint order (dense fallback otherwise)
+        wts = self.th_weights
+        idx4 = w4 = None
+        if int((wts != 0).sum(dim=1).max()) <= 4:
+            order = torch.argsort((wts == 0).to(torch.int8), dim=1, stable=True)[:, :4]      # non-zeros first, joint order kept
+            order, _ = torch.sort(order, dim=1)
+            w4 = torch.gather(wts, 1, order).contiguous()
+            idx4 = order.to(torch.int32).contiguous()
         packed = dict(dev=dev, lib=lib, blend=blend, vt=vt, jt=j_template, js=j_shapedirs, parents=parents,
-                      weights=self.th_weights.contiguous(), ws=None, blend_hi=blend_hi, blend_lo=blend_lo, vt_pad=vt_pad)
+                      weights=self.th_weights.contiguous(), ws=None, blend_hi=blend_hi, blend_lo=blend_lo, vt_pad=vt_pad, idx4=idx4, w4=w4)
         object.__setattr__(self, "_packed", packed)
         return packed
 
@@ -131,8 +139,10 @@ class SMPL_Layer(Module):
             verts = torch.empty(B, 6890, 3, device=dev)
             joints = torch.empty(B, 24, 3, device=dev)
             tcp = os.environ.get("PMCE_SMPL_FP32", "0") != "1"      # PMCE_SMPL_FP32=1: exact fp32 CUDA-core blend-shape GEMM
-            check(lib.smpl_lbs_forward_scaled(_ptr(p["blend"]), _ptr(p["blend_hi"] if tcp else None), _ptr(p["blend_lo"] if tcp else None),
+            dense = os.environ.get("PMCE_SMPL_DENSE_SKIN", "0") == "1"    # A/B knob: the dense 24-joint blend
+            check(lib.smpl_lbs_forward_sparse(_ptr(p["blend"]), _ptr(p["blend_hi"] if tcp else None), _ptr(p["blend_lo"] if tcp else None),
                                               _ptr(p["vt_pad"] if tcp else p["vt"]), _ptr(p["jt"]), _ptr(p["js"]), _ptr(p["weights"]),
+                                              _ptr(None if dense else p["idx4"]), _ptr(None if dense else p["w4"]),
                                               _ptr(p["parents"]), _ptr(pose), _ptr(betas), _ptr(trans), B, float(_out_scale),
                                               _ptr(verts), _ptr(joints), _ptr(p["ws"]), p["ws"].numel(), _stream()),
                   "smpl_lbs_forward")

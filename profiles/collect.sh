@@ -19,11 +19,12 @@ cap() {  # name, kernel regex, skip, count, command...
 if [ "${FULL:-1}" = "1" ]; then
     cap ca_b64 ca_vertex_fused 20 2 python tools/ca_check.py 64
     cap ca_b256 ca_vertex_fused 8 2 python tools/ca_check.py 256
-    cap fc1 linear_tc_kernel 4 2 python tools/gemm_one.py 17408 1024 512 1
+    cap fc1 linear_tc_kernel 1 2 python tools/gemm_one.py 17408 1024 512 1
     cap mlp mlp64_fused 2 2 python tools/one_forward.py
-    cap flash attn_flash 2 2 python tools/one_forward.py
+    cap attn_rows attn_rows 2 2 python tools/one_forward.py
     cap gru gru_ 4 2 python tools/one_forward.py
     cap smpl smpl_skin 1 2 python tools/hbm_kernels.py 256
+    cap attn_tile attn_tile 2 2 python tools/one_forward.py
     python profiles/ncu_to_json.py $TAG $OUT > $OUT/${TAG}_ncu_traffic.json
 fi
 tail -30 $OUT/${TAG}_launches_summary.txt

@@ -8,7 +8,8 @@ import subprocess
 import sys
 
 KEYS = {"ca_b64": ("ca_vertex_fused_kernel", 64), "ca_b256": ("ca_vertex_fused_kernel", 256), "fc1": ("linear_tc_kernel_fc1", 64),
-        "mlp": ("mlp64_fused_kernel", 64), "flash": ("attn_flash_tc_kernel", 64), "gru": ("gru_kernel", 64), "smpl": ("smpl_skin_kernel", 256)}
+        "mlp": ("mlp64_fused_kernel", 64), "attn_rows": ("attn_rows_tc_kernel", 64), "attn_tile": ("attn_tile_tc_kernel", 64),
+        "qkv": ("linear_tc_kernel_qkv", 64), "gru": ("gru_kernel", 64), "smpl": ("smpl_skin_kernel", 256)}
 
 
 def table(path):
