@@ -73,8 +73,9 @@ struct Workspace {
     float *imgemb, *x, *qkv, *r3, *joints_m;
     SplitOut xn_s, att_s, hid_s;
     // gru
-    float *gi0, *y0, *gi1f, *gi1b, *h1[2][2], *g;
-    SplitOut y0_s, g_s, gr_s, h1_s[2][2];
+    float *gi0, *y0, *gi1f, *gi1b, *h1[2][2], *g, *y1;
+    SplitOut y0_s, g_s, gr_s, h1_s[2][2], y1_s;
+    unsigned* gru_counters;                            // step-barrier counters of the persistent GRU layer kernel (2 layers x 2 directions)
     // decoder
     float *gb, *verts[3], *Jf, *Vf, *xqv, *xkj, *Kj, *Vj, *qkv_d;
     float *xqj, *xkv, *Kv, *Vv, *qkvj;
@@ -100,6 +101,8 @@ Workspace carve(const pmce_dims_t& d, int B, void* base) {
     w.g = c.f32((size_t)B * F);
     w.y0_s = c.split((size_t)T * B * 2 * H); w.g_s = c.split((size_t)B * F); w.gr_s = c.split((size_t)B * F);
     for (int dir = 0; dir < 2; ++dir) for (int i = 0; i < 2; ++i) w.h1_s[dir][i] = c.split((size_t)B * H);
+    w.y1 = c.f32((size_t)(T + 1) * B * H); w.y1_s = c.split((size_t)(T + 1) * B * H);     // layer-1 hidden states of the (T/2+1) + (T-T/2) live steps
+    w.gru_counters = (unsigned*)c.take_bytes(2 * 2 * GRU_MAX_CTAS * sizeof(unsigned));     // step flags: 2 layers x 2 directions x 64 CTAs
     w.gb = c.f32((size_t)B * PMCE_ADALN_SLOTS * 2 * D);
     for (int i = 0; i < 3; ++i) w.verts[i] = c.f32((size_t)B * Vd * 3);
     const size_t nv = (size_t)B * Vd, nj = (size_t)B * J;
@@ -387,6 +390,38 @@ int gru_step(const GruStep* s, int ndir, const Weights& W, int B, int H, cudaStr
     return 0;
 }
 
+bool gru_persistent_enabled() {
+    // PMCE_GRU_PERSISTENT=1: one persistent launch per GRU layer (gru_layer_tc_kernel) instead of one launch per time step.
+    // Measured (B=64, same box): gru_mid 583 us persistent vs 514 us per step, whole forward 24.3k vs 25.3k clips/s - a step is
+    // bound by what ONE SM must ingest from L2 (its 192 KB W_hh slice + the whole 256 KB h_prev, ~8 us at ~57 GB/s per SM), not by
+    // the launch; the persistent form adds the step barrier's release/poll latency on top and pins 128 SMs. Off by default.
+    static int on = -1;
+    if (on < 0) on = pmce_env_int("PMCE_GRU_PERSISTENT", 0) ? 1 : 0;
+    return on == 1;
+}
+
+// one persistent launch per batch tile of 128 rows for a whole GRU layer (gru_tc.cuh)
+int gru_layer(const GruLayerDir* dd, int ndir, const SplitOut* hs, const int* nblk, const Weights& W, const size_t* whh_off, int B, int H,
+              unsigned* counters, cudaStream_t st) {
+    GruTcMaps maps[2];
+    for (int i = 0; i < 2; ++i) {
+        const int k = i < ndir ? i : 0;
+        if (make_tmap_bf16_3d(&maps[i].h_hi, hs[k].hi, dd[k].ld_y, B, nblk[k], dd[k].ld_y, (long long)B * dd[k].ld_y, 128, 1) ||
+            make_tmap_bf16_3d(&maps[i].h_lo, hs[k].lo, dd[k].ld_y, B, nblk[k], dd[k].ld_y, (long long)B * dd[k].ld_y, 128, 1) ||
+            make_tmap_bf16(&maps[i].w_hi, W.hi + whh_off[k], 3 * H, H, H, GRU_U) || make_tmap_bf16(&maps[i].w_lo, W.lo + whh_off[k], 3 * H, H, H, GRU_U)) {
+            pmce_set_error("gru_layer: cuTensorMapEncodeTiled failed");
+            return 10;
+        }
+    }
+    if (!pmce_configure_smem<gru_layer_tc_kernel>(GRU_SMEM)) { pmce_set_error("gru_layer: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); return 10; }
+    for (int b0 = 0; b0 < B; b0 += 128) {          // all CTAs of a launch must be co-resident: one 128-row batch tile at a time
+        CK(cudaMemsetAsync(counters, 0, 2 * GRU_MAX_CTAS * sizeof(unsigned), st));
+        gru_layer_tc_kernel<<<dim3(H / GRU_U, ndir), 192, GRU_SMEM, st>>>(maps[0], maps[1], dd[0], dd[ndir > 1 ? 1 : 0], B, H, b0, counters);
+        CKL();
+    }
+    return 0;
+}
+
 // nfr / fstride as in lifter(): the layer-0 input projection is a per-frame product, so overlapping windows share it.
 int gru_mid(const Layout& L, const Weights& W, int B, int nfr, int fstride, float* g, const Workspace& ws, cudaStream_t st) {
     const pmce_dims_t& d = L.d;
@@ -395,6 +430,52 @@ int gru_mid(const Layout& L, const Weights& W, int B, int nfr, int fstride, floa
     {   // layer-0 input projections, every frame, both directions: gi0[frame][6H] (the step kernels stride over windows with fstride*6H)
         EpiOpt o; o.bias = W.f + L.bih0; o.out = ws.gi0; o.ld_out = 6 * H;
         RET(linear_tc(ws.feat_s, F, nfr, F, W, L.wih0, F, 6 * H, o, st));
+    }
+    if (gru_persistent_enabled() && H % 64 == 0 && H / GRU_U <= 64) {
+        const int nf = mid + 1, nb = T - mid;
+        {   // layer 0: y0 [T, B, 2H]; forward direction writes blocks 0..T-1, backward T-1..0 (block = frame)
+            GruLayerDir dd[2];
+            memset(dd, 0, sizeof(dd));
+            for (int dir = 0; dir < 2; ++dir) {
+                GruLayerDir& x = dd[dir];
+                x.gi = ws.gi0 + (dir == 0 ? 0 : (size_t)(T - 1) * 6 * H) + dir * 3 * H;
+                x.gi_step = dir == 0 ? 6 * H : -6 * H; x.ld_gi = fstride * 6 * H;
+                x.y = ws.y0; x.ys = ws.y0_s; x.ld_y = 2 * H; x.col0 = dir * H;
+                x.blk0 = dir == 0 ? 0 : T - 1; x.blk_step = dir == 0 ? 1 : -1; x.nsteps = T;
+                x.bhh = W.f + L.bhh0[dir];
+            }
+            const SplitOut hs[2] = {ws.y0_s, ws.y0_s};
+            const int nblk[2] = {T, T};
+            const size_t wo[2] = {L.whh0[0], L.whh0[1]};
+            RET(gru_layer(dd, 2, hs, nblk, W, wo, B, H, ws.gru_counters, st));
+        }
+        {
+            EpiOpt o; o.bias = W.f + L.bih1[0]; o.out = ws.gi1f; o.ld_out = 3 * H;
+            RET(linear_tc(ws.y0_s, 2 * H, nf * B, 2 * H, W, L.wih1[0], 2 * H, 3 * H, o, st));
+        }
+        {
+            EpiOpt o; o.bias = W.f + L.bih1[1]; o.out = ws.gi1b; o.ld_out = 3 * H;
+            SplitOut a{ws.y0_s.hi + (size_t)mid * B * 2 * H, ws.y0_s.lo + (size_t)mid * B * 2 * H};
+            RET(linear_tc(a, 2 * H, nb * B, 2 * H, W, L.wih1[1], 2 * H, 3 * H, o, st));
+        }
+        {   // layer 1: only the steps y[T//2] depends on; y1 [nf + nb, B, H]: forward blocks 0..nf-1, backward nf..nf+nb-1
+            GruLayerDir dd[2];
+            memset(dd, 0, sizeof(dd));
+            for (int dir = 0; dir < 2; ++dir) {
+                GruLayerDir& x = dd[dir];
+                x.gi = dir == 0 ? ws.gi1f : ws.gi1b + (size_t)(nb - 1) * B * 3 * H;      // gi1b row block i = frame mid + i; step s reads frame T-1-s
+                x.gi_step = dir == 0 ? (long long)B * 3 * H : -(long long)B * 3 * H; x.ld_gi = 3 * H;
+                x.y = ws.y1; x.ys = ws.y1_s; x.ld_y = H; x.col0 = 0;
+                x.blk0 = dir == 0 ? 0 : nf; x.blk_step = 1; x.nsteps = dir == 0 ? nf : nb;
+                x.bhh = W.f + L.bhh1[dir];
+                x.last_out = g + dir * H; x.ld_last = 2 * H;
+            }
+            const SplitOut hs[2] = {ws.y1_s, ws.y1_s};
+            const int nblk[2] = {nf + nb, nf + nb};
+            const size_t wo[2] = {L.whh1[0], L.whh1[1]};
+            RET(gru_layer(dd, 2, hs, nblk, W, wo, B, H, ws.gru_counters + 2 * GRU_MAX_CTAS, st));
+        }
+        return 0;
     }
     for (int s = 0; s < T; ++s) {
         GruStep dd[2];

@@ -144,3 +144,216 @@ gru_step_tc_kernel(const __grid_constant__ GruTcMaps m0_, const __grid_constant_
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem_base, 64);
 }
+
+// ------------------------------------------------------------------------------------------------------
+// One GRU LAYER (up to two directions) as ONE persistent launch: the per-step kernel above paid a launch, a pipeline fill and a
+// TMEM allocation per time step (41 launches per forward, 17 us each for ~6 us of L2 streaming). Here the CTAs stay resident
+// over all steps of the layer: CTA (x, dir) owns hidden units [16 x, 16 x + 16) of direction dir for every step,
+//   warp 0   TMA producer: per step streams the 16 k-blocks of h_prev (all hidden units of the previous step, written by the
+//            OTHER CTAs of this direction) and of its own W_hh rows (L2 hits); W_hh tiles of the first stages are requested
+//            BEFORE the step barrier, the h_prev tiles after it
+//   warp 1   MMA issuer, one TMEM accumulator (128 x 48), handed back by the epilogue through an mbarrier
+//   warps 2-5 epilogue: gate math in registers (h_prev of the CTA's own units is its own output of the previous step), h' as
+//            fp32 + split-bf16 into the layer's hidden-state tensor, then the step barrier: every CTA owns ONE flag word and
+//            publishes "step s done" with st.release.gpu (no atomics, no __threadfence: a first version with one atomic counter
+//            per direction spent 12 us per step in the fence behind 64 CTAs polling the same L2 line); the producer warp of every
+//            CTA polls the direction's 64 flags (two ld.acquire.gpu per lane, __all_sync), then fence.proxy.async before its TMA
+//            reads of h'.
+// The two directions of a layer are independent chains with their own flags. All CTAs of a launch must be co-resident
+// (64 per direction, 1 per SM: 128 <= 148 SMs); the host launches one batch tile of 128 rows at a time.
+// Hidden states live in [nblk][B][ld] tensors (a block per time step) so the TMA boxes zero-fill the rows past B.
+// ------------------------------------------------------------------------------------------------------
+struct GruLayerDir {
+    const float* gi;          // input projections: row b of step s at gi + s * gi_step + b * ld_gi (+ gate * H + unit)
+    long long gi_step;
+    int ld_gi;
+    float* y;                 // hidden states fp32 [nblk, B, ld_y]; this direction's units start at column col0
+    SplitOut ys;              // the same, split-bf16 (the A operand of the next step, read by TMA)
+    int ld_y, col0;
+    int blk0, blk_step;       // step s writes block blk0 + s * blk_step and reads block blk0 + (s - 1) * blk_step
+    int nsteps;
+    const float* bhh;         // [3H]
+    float* last_out;          // optional [B, ld_last]: the last step's h' is also written here (columns = unit index)
+    int ld_last;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr int GRU_MAX_CTAS = 64;     // CTAs (flags) per direction: H / 16 <= 64
+
+__global__ void __launch_bounds__(192, 1)
+gru_layer_tc_kernel(const __grid_constant__ GruTcMaps m0_, const __grid_constant__ GruTcMaps m1_, GruLayerDir d0, GruLayerDir d1, int B, int H, int b0,
+                    unsigned* __restrict__ counters) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GRU_STAGES * GRU_STAGE);
+    uint64_t* empty_bar = full_bar + GRU_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + GRU_STAGES;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.y;
+    const GruTcMaps& mp = dir == 0 ? m0_ : m1_;
+    const GruLayerDir d = dir == 0 ? d0 : d1;
+    const int j0 = blockIdx.x * GRU_U;
+    const int nkb = H / 64;
+    unsigned* flags = counters + dir * GRU_MAX_CTAS;     // flags[x] = number of steps CTA x of this direction has published
+    const int nx = gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&mp.h_hi); tc::tma_prefetch_desc(&mp.h_lo);
+        tc::tma_prefetch_desc(&mp.w_hi); tc::tma_prefetch_desc(&mp.w_lo);
+        for (int s = 0; s < GRU_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+        tc::mbar_init(tmem_full_bar, 1); tc::mbar_init(tmem_empty_bar, 4);
+        tc::fence_barrier_init();
+        tc::fence_proxy_async();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr_smem, 64);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        uint32_t it = 0;
+        for (int s = 1; s < d.nsteps; ++s) {
+            const int blkp = d.blk0 + (s - 1) * d.blk_step;
+            const int pre = nkb < GRU_STAGES ? nkb : GRU_STAGES;
+            if (lane == 0) {
+                // W_hh tiles of the first stages do not depend on the previous step: request them before the step barrier
+                for (int kb = 0; kb < pre; ++kb) {
+                    const int st_i = (it + kb) % GRU_STAGES;
+                    tc::mbar_wait(&empty_bar[st_i], (((it + kb) / GRU_STAGES) & 1) ^ 1);
+                    uint8_t* st = smem + st_i * GRU_STAGE;
+                    tc::mbar_arrive_expect_tx(&full_bar[st_i], GRU_STAGE);
+                    uint8_t* wh = st + 2 * GRU_A_TILE;
+                    uint8_t* wl = wh + GRU_W_TILE;
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        tc::tma_load_2d(wh + g * GRU_U * 128, &mp.w_hi, &full_bar[st_i], kb * 64, g * H + j0);
+                        tc::tma_load_2d(wl + g * GRU_U * 128, &mp.w_lo, &full_bar[st_i], kb * 64, g * H + j0);
+                    }
+                }
+            }
+            // step barrier: every CTA of this direction has published its h' of step s-1 (whole warp polls: 2 flags per lane)
+            for (;;) {
+                const unsigned fa = lane < nx ? ld_acquire_gpu(flags + lane) : (unsigned)s;
+                const unsigned fb = lane + 32 < nx ? ld_acquire_gpu(flags + lane + 32) : (unsigned)s;
+                if (__all_sync(0xffffffffu, fa >= (unsigned)s && fb >= (unsigned)s)) break;
+                __nanosleep(100);
+            }
+            if (lane == 0) {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int st_i = it % GRU_STAGES;
+                    uint8_t* st = smem + st_i * GRU_STAGE;
+                    if (kb >= pre) {
+                        tc::mbar_wait(&empty_bar[st_i], ((it / GRU_STAGES) & 1) ^ 1);
+                        tc::mbar_arrive_expect_tx(&full_bar[st_i], GRU_STAGE);
+                        uint8_t* wh = st + 2 * GRU_A_TILE;
+                        uint8_t* wl = wh + GRU_W_TILE;
+#pragma unroll
+                        for (int g = 0; g < 3; ++g) {
+                            tc::tma_load_2d(wh + g * GRU_U * 128, &mp.w_hi, &full_bar[st_i], kb * 64, g * H + j0);
+                            tc::tma_load_2d(wl + g * GRU_U * 128, &mp.w_lo, &full_bar[st_i], kb * 64, g * H + j0);
+                        }
+                    }
+                    tc::tma_load_3d(st, &mp.h_hi, &full_bar[st_i], d.col0 + kb * 64, b0, blkp);
+                    tc::tma_load_3d(st + GRU_A_TILE, &mp.h_lo, &full_bar[st_i], d.col0 + kb * 64, b0, blkp);
+                }
+            }
+            it = __shfl_sync(0xffffffffu, it, 0);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, GRU_N);
+            uint32_t it = 0;
+            for (int s = 1; s < d.nsteps; ++s) {
+                tc::mbar_wait(tmem_empty_bar, ((s - 1) & 1) ^ 1);            // the epilogue has read the previous step's accumulator
+                tc::tc_fence_after();
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int st_i = it % GRU_STAGES;
+                    tc::mbar_wait(&full_bar[st_i], (it / GRU_STAGES) & 1);
+                    tc::tc_fence_after();
+                    const uint32_t st = tc::smem_u32(smem + st_i * GRU_STAGE);
+                    const uint64_t a_hi = tc::umma_desc_sw128(st), a_lo = tc::umma_desc_sw128(st + GRU_A_TILE);
+                    const uint64_t w_hi = tc::umma_desc_sw128(st + 2 * GRU_A_TILE), w_lo = tc::umma_desc_sw128(st + 2 * GRU_A_TILE + GRU_W_TILE);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        tc::umma_bf16(tmem_base, tc::umma_desc_advance_k(a_lo, k), tc::umma_desc_advance_k(w_hi, k), idesc, (kb | k) != 0);
+                        tc::umma_bf16(tmem_base, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_lo, k), idesc, 1);
+                        tc::umma_bf16(tmem_base, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_hi, k), idesc, 1);
+                    }
+                    tc::umma_commit(&empty_bar[st_i]);
+                }
+                tc::umma_commit(tmem_full_bar);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = b0 + q * 32 + lane;
+        const bool live = row < B;
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int s = 0; s < d.nsteps; ++s) {
+            uint32_t ar[16], az[16], an[16];
+            if (s > 0) {
+                tc::mbar_wait(tmem_full_bar, (s - 1) & 1);
+                tc::tc_fence_after();
+                tc::tmem_ld_32x16(t0, ar);
+                tc::tmem_ld_32x16(t0 + GRU_U, az);
+                tc::tmem_ld_32x16(t0 + 2 * GRU_U, an);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tmem_empty_bar);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) ar[u] = az[u] = an[u] = 0u;      // h_0 = 0: W_hh h = 0
+            }
+            const int blk = d.blk0 + s * d.blk_step;
+            if (live) {
+                const float* gi = d.gi + (long long)s * d.gi_step + (size_t)row * d.ld_gi + j0;
+                const size_t yo = ((size_t)blk * B + row) * d.ld_y + d.col0 + j0;
+                const size_t yp = ((size_t)(blk - d.blk_step) * B + row) * d.ld_y + d.col0 + j0;
+                float hn[16];
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    const float4 gr = ld4(gi + u), gz = ld4(gi + H + u), gn = ld4(gi + 2 * H + u);
+                    const float4 hv = s > 0 ? ld4(d.y + yp + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 br = ld4(d.bhh + j0 + u), bz = ld4(d.bhh + H + j0 + u), bn = ld4(d.bhh + 2 * H + j0 + u);
+                    const float grr[4] = {gr.x, gr.y, gr.z, gr.w}, gzz[4] = {gz.x, gz.y, gz.z, gz.w}, gnn[4] = {gn.x, gn.y, gn.z, gn.w};
+                    const float hh[4] = {hv.x, hv.y, hv.z, hv.w}, brr[4] = {br.x, br.y, br.z, br.w}, bzz[4] = {bz.x, bz.y, bz.z, bz.w}, bnn[4] = {bn.x, bn.y, bn.z, bn.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float r = sigmoid_f(grr[i] + (__uint_as_float(ar[u + i]) + brr[i]));
+                        const float z = sigmoid_f(gzz[i] + (__uint_as_float(az[u + i]) + bzz[i]));
+                        const float n = tanhf(gnn[i] + r * (__uint_as_float(an[u + i]) + bnn[i]));
+                        hn[u + i] = (1.0f - z) * n + z * hh[i];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    const float4 v = make_float4(hn[u], hn[u + 1], hn[u + 2], hn[u + 3]);
+                    st4(d.y + yo + u, v);
+                    store_split4(d.ys, yo + u, v);
+                    if (d.last_out && s == d.nsteps - 1) st4(d.last_out + (size_t)row * d.ld_last + j0 + u, v);
+                }
+            }
+            // publish this CTA's h' of step s (the last step has no reader inside the kernel)
+            if (s + 1 < d.nsteps) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps' stores are ordered before the release below
+                if (threadIdx.x == 64) st_release_gpu(flags + blockIdx.x, (unsigned)(s + 1));
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 64);
+}
