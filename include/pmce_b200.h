@@ -124,7 +124,9 @@ int pmce_coevo_block(const pmce_dims_t* dims, const void* weights, int block, co
  * timm Mlp).  `which` selects the instance of coevoblock<block>: 0 = joint_CA_FFN (:167; queries = J joints, keys/values =
  * 431 vertices, 8 heads), 1 = vertx_CA_FFN (:169; queries = 431 vertices, keys/values = J joints, 2 heads).
  * xq [B,N1,64], xk / xv [B,N2,64], gb from pmce_adaln_gammabeta -> out [B,N1,64] (may alias xq).  The vertex instance
- * runs the fused kernel (one pass over the query stream: AdaLN_q, Wq, attention, Wp, residual, AdaLN_2). */
+ * runs the fused kernels: one pass over the query stream for AdaLN_q + Wq + attention + Wp + residual (ca_fused.cuh), one for
+ * AdaLN_2 + fc1 + GELU + fc2 + residual with the hidden activations on chip (mlp_fused.cuh); the joint instance uses the
+ * second one too. */
 int pmce_cross_attn_block(const pmce_dims_t* dims, const void* weights, int block, int which, const float* xq,
                           const float* xk, const float* xv, const float* gb, int B, float* out, void* workspace,
                           size_t workspace_bytes, void* stream);
@@ -132,9 +134,10 @@ int pmce_cross_attn_block(const pmce_dims_t* dims, const void* weights, int bloc
 /* Kernel-level entry of the fused vertex cross-attention (measurement / tests; the kernels pmce_cross_attn_block(which=1)
  * and pmce_coevo_block launch): with K / V [B,J,64] = the projected AdaLN'd joint rows (CoevoDecoder.py:53-55),
  *   xq [B,431,64] <- xq + proj(MHA(wq(AdaLN_q(xq)), K, V))   in place                     (:56-62, :84)
- *   t_hi / t_lo [B,431,64] bf16 <- split-bf16 of AdaLN_2(xq)                               (:86, input of the Mlp)
+ *   t_hi / t_lo [B,431,64] bf16 (optional, both or neither; NULL = skip) <- split-bf16 of AdaLN_2(xq) (:86), by a second launch
  * using the weights of coevoblock<block>.vertx_CA_FFN.  fold_ws: pmce_ca_fold_bytes(B) bytes, 256-byte aligned, holds the
- * per-clip folded operands (scale K_h Wq_h, V_h Wp_h^T, score bias); fold != 0 recomputes them from K / V first (a second,
+ * per-clip folded operands KQ' [B,48,64] | VP' [B,48,64] (bf16 hi, lo) | sb' [B,48] - AdaLN_q's gamma/beta (from gb), the softmax
+ * scale * log2e and the projection bias are folded into them; fold != 0 recomputes them from K / V / gb first (a second,
  * per-clip kernel), fold == 0 reuses what a previous call left there (times the streaming kernel alone). */
 size_t pmce_ca_fold_bytes(int B);
 int pmce_ca_vertex_fused(const pmce_dims_t* dims, const void* weights, int block, float* xq, const float* K,

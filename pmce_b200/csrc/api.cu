@@ -12,6 +12,7 @@
 #include <map>
 #include <mutex>
 #include <utility>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/pmce_b200.h"
 #include "layout.h"
 #include "common.cuh"
@@ -37,6 +38,13 @@
 #define CKL() do { count_launch(); CK(cudaGetLastError()); } while (0)
 #define CKG(expr) do { count_launch(); CK(expr); } while (0)
 #define RET(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+// NVTX ranges (header-only NVTX3; a no-op unless a profiler is attached) around the stages of the forward, so nsys / ncu
+// --nvtx timelines read "pmce/lifter", "pmce/image-feature stream", "pmce/decoder" ... instead of 100+ anonymous launches.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 static std::atomic<unsigned long long> g_launches{0};
 static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -306,6 +314,7 @@ int vit_block(const pmce_dims_t& d, const Weights& W, const VitBlockW& w, const 
 // into the window-major token order by the LayerNorm that follows it.
 int lifter(const Layout& L, const Weights& W, const float* pose2d, int B, int nfr, int fstride, float* pose3d, const Workspace& ws,
            cudaStream_t st) {
+    NvtxRange nvtx("pmce/lifter (pose stream)");
     const pmce_dims_t& d = L.d;
     const int J = d.num_joint, C = d.embed_dim, T = d.seqlen, F = d.feat_dim;
     const int N = B * T * J;
@@ -766,6 +775,7 @@ bool coevo_fused(const pmce_dims_t& d) { return ca_fused_ok(VERTX_HEADS, d.num_v
 // by decoder_fold_all (the joint side of all three blocks depends only on the lifter's joints and on gb).
 int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, const float* verts_in, const float* gb, int B,
                 float* joints_out, float* verts_out, const Workspace& ws, cudaStream_t st, Aux* aux = nullptr, bool prefolded = false) {
+    NvtxRange nvtx(k == 0 ? "pmce/coevoblock1" : (k == 1 ? "pmce/coevoblock2" : "pmce/coevoblock3"));
     const pmce_dims_t& d = L.d;
     const CoevoW& w = L.blk[k];
     const int J = d.num_joint, Vd = d.num_vert_ds;
@@ -860,6 +870,7 @@ int prepare_feat(const Layout& L, const float* img_feat, int nfr, const Workspac
 
 // image-feature stream of the two-stream encoder: GRU -> y[T//2] -> all AdaLN gamma/beta (independent of the pose stream)
 int decoder_front(const Layout& L, const Weights& W, int B, int nfr, int fstride, const Workspace& ws, cudaStream_t st) {
+    NvtxRange nvtx("pmce/image-feature stream (GRU + AdaLN gamma/beta + linear_cur)");
     RET(gru_mid(L, W, B, nfr, fstride, ws.g, ws, st));
     RET(adaln_gammabeta(L, W, ws.g, B, ws.gb, ws.g_s, st));
     return mesh_residual(L, W, ws.g, B, ws, st);
@@ -867,6 +878,7 @@ int decoder_front(const Layout& L, const Weights& W, int B, int nfr, int fstride
 
 int decoder_back(const Layout& L, const Weights& W, const float* joints, const int32_t* vj, int B, float* cam_pose, float* cam_mesh,
                  float* verts0_out, const Workspace& ws, cudaStream_t st, Aux* aux = nullptr) {
+    NvtxRange nvtx("pmce/decoder (3 co-evolution blocks + up-sampling)");
     const pmce_dims_t& d = L.d;
     const int J = d.num_joint, Vd = d.num_vert_ds;
     float* v0 = verts0_out ? verts0_out : ws.verts[2];
@@ -1306,6 +1318,7 @@ extern "C" int pmce_spin_features(const float* w_f32, const void* w_hi, const vo
     if (B < 1) { pmce_set_error("batch size %d < 1", B); return 2; }
     if (nconv != pmce_spin_num_convs()) { pmce_set_error("pmce_spin_features: expected %d convolutions, got %d", pmce_spin_num_convs(), nconv); return 2; }
     if (((uintptr_t)workspace & 255) || workspace_bytes < pmce_spin_workspace_bytes(B)) { pmce_set_error("pmce_spin_features: workspace too small or unaligned"); return 2; }
+    NvtxRange nvtx("pmce/spin feature extractor");
     cudaStream_t st = (cudaStream_t)stream;
     const SpinWs ws = spin_carve(B, workspace);
     const Weights W{w_f32, (const bf16*)w_hi, (const bf16*)w_lo};

@@ -433,3 +433,17 @@ def test_headline_configs_vs_oracle(assets_root, lib, J, C, T, B):
         mpve = float((mesh.cpu() - r_mesh).norm(dim=-1).mean())
         print(f"J={J} C={C} T={T} B={B} graph={graph}: max|d mesh|={e[0]:.2e} MPVE={mpve:.2e} max|d pose|={e[1]:.2e} rel|d pose3d|={e[2]:.2e}")
         assert e[0] < TOL and e[1] < TOL and e[2] < 1e-4 and mpve < TOL
+
+
+@pytest.mark.parametrize("env", [{"PMCE_GRU_PERSISTENT": "1"},
+                                 {"PMCE_MLP_FUSED": "0", "PMCE_ATTN_ROWS": "0", "PMCE_CA_FUSED": "0"},
+                                 {"PMCE_TC_DIRECT": "1", "PMCE_TC_NBUF": "2", "PMCE_TC_PAIR_RELAXED": "1"}])
+def test_alternative_paths_in_subprocess(env):
+    """The opt-in / A-B variants stay parity-green: the persistent GRU layer kernel, the unfused launch sequences the fused
+    kernels replaced, and the GEMM epilogue variants (the library reads its knobs once per process, hence the subprocess)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k",
+                        "forward_vs_reference_golden or coevo_blocks_vs_oracle or gru_mid_vs_oracle or attention_blocks_vs_oracle"],
+                       env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
