@@ -116,7 +116,10 @@ __device__ __forceinline__ void tc_epilogue_generic(const TcEpi& e, const uint32
 // NCTA == 2: the same kernel on CTA pairs (cluster of 2, tcgen05 cta_group::2): one 256 x 256 tile per pair, each CTA loads
 // its 128 rows of A and HALF of the tile's W rows (a third less operand traffic L2->SM and smem per FLOP than two 128 x 256
 // tiles), the leader issues the MMAs for both, each CTA drains its own 128 accumulator rows.
-template <int BN, int MODE, int NCTA, int NBUF = 1>
+// CL > 1 (with NCTA == 1): a cluster of CL CTAs works on CL consecutive 128-row m-tiles of the SAME n-tile; every CTA loads its own
+// A rows and ONE CL-th of the W tile, multicast to all CTAs of the cluster - W leaves L2 once per cluster instead of once per CTA
+// (the GEMMs are bound by L2->SMEM operand bytes): 48 KB per CTA and k-block instead of 64 KB on a CTA pair.
+template <int BN, int MODE, int NCTA, int NBUF = 1, int CL = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -135,10 +138,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (K + TC_BK - 1) / TC_BK;
-    const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + NCTA * TC_BM - 1) / (NCTA * TC_BM);
+    static_assert(CL == 1 || (NCTA == 1 && BN % CL == 0), "W multicast clusters are built from single-CTA tiles");
+    const int tiles_n = (N + BN - 1) / BN, tiles_m = ((M + NCTA * TC_BM - 1) / (NCTA * TC_BM) + CL - 1) / CL;   // CL > 1: groups of CL m-tiles
     const int num_tiles = tiles_n * tiles_m;
-    const uint32_t rank = NCTA == 2 ? tc::cluster_ctarank() : 0;          // position in the CTA pair
-    const int tile0 = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;    // tiles are dealt to pairs
+    const uint32_t crank = (NCTA == 2 || CL > 1) ? tc::cluster_ctarank() : 0;
+    const uint32_t rank = NCTA == 2 ? crank : 0;                          // position in the CTA pair
+    const int tile0 = blockIdx.x / (NCTA * CL), tile_step = gridDim.x / (NCTA * CL);    // tiles are dealt to pairs / clusters
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA_hi); tc::tma_prefetch_desc(&tmA_lo);
@@ -146,7 +152,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (MODE == TC_F32 || MODE == TC_F32_RESID || MODE == TC_SPLIT_GELU || MODE == TC_SPLIT || MODE == TC_ATTN32) tc::tma_prefetch_desc(&om.out);
         if (MODE == TC_SPLIT_GELU || MODE == TC_SPLIT) tc::tma_prefetch_desc(&om.out_lo);
         if (MODE == TC_F32_RESID) tc::tma_prefetch_desc(&om.resid);
-        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], CL); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], NCTA * TC_EPI_WARPS); }
         for (int w = 0; w < TC_EPI_WARPS; ++w) tc::mbar_init(&resid_bar[w], 1);
         tc::fence_barrier_init();
@@ -155,7 +161,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (warp == 1) { if (NCTA == 2) tc::tmem_alloc_pair(tmem_ptr_smem, Cfg::TMEM_COLS); else tc::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); }
     tc::tc_fence_before();
     __syncthreads();
-    if (NCTA == 2) tc::cluster_sync_all();               // the peer's barriers are initialised before anything signals them
+    if (NCTA == 2 || CL > 1) tc::cluster_sync_all();     // the peers' barriers are initialised before anything signals them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -163,13 +169,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (lane == 0) {
             uint32_t it = 0;                                    // global k-block counter across tiles
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-                const int m0 = (tile / tiles_n) * (NCTA * TC_BM) + (int)rank * TC_BM, n0 = (tile % tiles_n) * BN + (int)rank * (BN / NCTA);
+                const int m0 = ((tile / tiles_n) * CL + (CL > 1 ? (int)crank : 0)) * (NCTA * TC_BM) + (int)rank * TC_BM,
+                          n0 = (tile % tiles_n) * BN + (int)rank * (BN / NCTA);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     tc::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-                    if (NCTA == 1) {
+                    if (CL > 1) {
+                        // own A rows; this CTA's CL-th of the W tile goes to every CTA of the cluster (all CTAs' MMAs have released the stage)
+                        constexpr int WQ = Cfg::W_TILE / CL;
+                        tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                        tc::tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
+                        tc::tma_load_2d(st + Cfg::A_TILE, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
+                        tc::tma_load_2d_mcast(st + 2 * Cfg::A_TILE + crank * WQ, &tmW_hi, &full_bar[s], kb * TC_BK, n0 + (int)crank * (BN / CL), CMASK);
+                        tc::tma_load_2d_mcast(st + 2 * Cfg::A_TILE + Cfg::W_TILE + crank * WQ, &tmW_lo, &full_bar[s], kb * TC_BK, n0 + (int)crank * (BN / CL), CMASK);
+                    } else if (NCTA == 1) {
                         tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                         tc::tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
                         tc::tma_load_2d(st + Cfg::A_TILE, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
@@ -217,7 +232,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             tc::umma_bf16_pair(tmem_d, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_hi, k), idesc, 1);
                         }
                     }
-                    if (NCTA == 1) tc::umma_commit(&empty_bar[s]); else tc::umma_commit_pair(&empty_bar[s]);   // smem slot free once these MMAs have read it
+                    if (CL > 1) tc::umma_commit_mcast(&empty_bar[s], CMASK);                       // every CTA of the cluster may refill its share of the stage
+                    else if (NCTA == 1) tc::umma_commit(&empty_bar[s]); else tc::umma_commit_pair(&empty_bar[s]);   // smem slot free once these MMAs have read it
                 }
                 if (NCTA == 1) tc::umma_commit(&tmem_full_bar[acc]); else tc::umma_commit_pair(&tmem_full_bar[acc]);   // accumulator complete
             }
@@ -235,7 +251,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         // accumulator-drained arrivals go to the leader's barrier (its MMA thread is the only waiter)
         const uint32_t te_bar[2] = {tc::mapa_rank(tc::smem_u32(&tmem_empty_bar[0]), 0), tc::mapa_rank(tc::smem_u32(&tmem_empty_bar[1]), 0)};
         for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
-            const int m0 = (tile / tiles_n) * (NCTA * TC_BM) + (int)rank * TC_BM, n0 = (tile % tiles_n) * BN;
+            const int m0 = ((tile / tiles_n) * CL + (CL > 1 ? (int)crank : 0)) * (NCTA * TC_BM) + (int)rank * TC_BM, n0 = (tile % tiles_n) * BN;
             const uint32_t acc = tcount & 1;
             const int row0 = m0 + q * 32;
             const int row = row0 + lane;
@@ -391,7 +407,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (NCTA == 2) tc::cluster_sync_all();               // neither CTA leaves (or frees TMEM) while its peer may still touch it
+    if (NCTA == 2 || CL > 1) tc::cluster_sync_all();     // no CTA leaves (or frees TMEM) while a peer may still touch it
     if (warp == 1) { if (NCTA == 2) tc::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
@@ -472,9 +488,32 @@ static inline bool tc_pair_enabled(int M, int N, int K) {
     return mode >= 2 || (N >= 512 && K >= 512);
 }
 
+constexpr int TC_CL = 4;      // CTAs per W-multicast cluster
+// PMCE_TC_MCAST=1: 256-wide tiles of large GEMMs run on clusters of 4 single-CTA tiles with the W tile multicast (instead of CTA pairs)
+static inline bool tc_mcast_enabled(int M, int N, int K) {
+    static int mode = -1;
+    if (mode < 0) mode = pmce_env_int("PMCE_TC_MCAST", 0);
+    return mode != 0 && M > TC_CL * TC_BM && N >= 512 && K >= 512;
+}
+
 template <int BN, int MODE>
 static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap* tw, const TcOutMaps& om, int M, int N, int K, const TcEpi& e,
                                         cudaStream_t st) {
+    if (BN == 256 && MODE != TC_GENERIC && MODE != TC_NULL && tc_mcast_enabled(M, N, K)) {
+        constexpr int BNP = BN == 256 ? 256 : 256;
+        using K4 = TcCfg<BNP, 1, 1>;
+        if (!pmce_configure_smem<linear_tc_kernel<BNP, MODE, 1, 1, TC_CL>>(K4::SMEM_BYTES)) return 2;
+        const long long tiles = (long long)((N + 255) / 256) * (((M + TC_BM - 1) / TC_BM + TC_CL - 1) / TC_CL);
+        const int clusters = (int)(tiles < tc_num_sms() / TC_CL ? tiles : tc_num_sms() / TC_CL);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(TC_CL * clusters); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = K4::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = TC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 1, 1, TC_CL>, ta[0], ta[1], tw[4], tw[5], om, M, N, K, e) == cudaSuccess ? 0 : 3;
+    }
     if (BN == 256 && tc_pair_enabled(M, N, K)) {
         constexpr int BNP = BN == 256 ? 256 : 256;
         static int nbuf = -1;     // PMCE_TC_NBUF=2: two staging tiles per epilogue warp and a two-stage operand ring (A/B knob)
@@ -491,11 +530,11 @@ static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap
         if (nbuf == 2 && MODE != TC_GENERIC && MODE != TC_NULL) {
             if (!pmce_configure_smem<linear_tc_kernel<BNP, MODE, 2, 2>>(TcCfg<BNP, 2, 2>::SMEM_BYTES)) return 2;
             cfg.dynamicSmemBytes = TcCfg<BNP, 2, 2>::SMEM_BYTES;
-            return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 2, 2>, ta[0], ta[1], tw[0], tw[1], om, M, N, K, e) == cudaSuccess ? 0 : 3;
+            return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 2, 2>, ta[0], ta[1], tw[2], tw[3], om, M, N, K, e) == cudaSuccess ? 0 : 3;
         }
         if (!pmce_configure_smem<linear_tc_kernel<BNP, MODE, 2>>(TcCfg<BNP, 2>::SMEM_BYTES)) return 2;
         cfg.dynamicSmemBytes = TcCfg<BNP, 2>::SMEM_BYTES;
-        return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 2>, ta[0], ta[1], tw[0], tw[1], om, M, N, K, e) == cudaSuccess ? 0 : 3;
+        return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 2>, ta[0], ta[1], tw[2], tw[3], om, M, N, K, e) == cudaSuccess ? 0 : 3;
     }
     if (!pmce_configure_smem<linear_tc_kernel<BN, MODE, 1>>(TcCfg<BN>::SMEM_BYTES)) return 2;
     const long long tiles = (long long)((N + BN - 1) / BN) * ((M + TC_BM - 1) / TC_BM);
@@ -506,10 +545,14 @@ static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap
 
 template <int BN>
 static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, const TcEpi& e, cudaStream_t st) {
-    CUtensorMap ta[2], tw[2];
-    const int wbox = (BN == 256 && tc_pair_enabled(A.rows, W.rows, A.cols)) ? BN / 2 : BN;    // a CTA of a pair loads half of the W rows
+    // W maps: [0,1] whole-tile box, [2,3] half (a CTA of a pair loads half of the W rows), [4,5] quarter (a CTA of a multicast
+    // cluster loads a quarter); launch_linear_tc_mode picks the pair that matches the kernel variant it launches
+    CUtensorMap ta[2], tw[6];
     if (make_tmap_bf16(&ta[0], A.hi, A.rows, A.cols, A.ld, TC_BM) || make_tmap_bf16(&ta[1], A.lo, A.rows, A.cols, A.ld, TC_BM) ||
-        make_tmap_bf16(&tw[0], W.hi, W.rows, W.cols, W.ld, wbox) || make_tmap_bf16(&tw[1], W.lo, W.rows, W.cols, W.ld, wbox))
+        make_tmap_bf16(&tw[0], W.hi, W.rows, W.cols, W.ld, BN) || make_tmap_bf16(&tw[1], W.lo, W.rows, W.cols, W.ld, BN))
+        return 1;
+    if (BN == 256 && (make_tmap_bf16(&tw[2], W.hi, W.rows, W.cols, W.ld, BN / 2) || make_tmap_bf16(&tw[3], W.lo, W.rows, W.cols, W.ld, BN / 2) ||
+                      make_tmap_bf16(&tw[4], W.hi, W.rows, W.cols, W.ld, BN / TC_CL) || make_tmap_bf16(&tw[5], W.lo, W.rows, W.cols, W.ld, BN / TC_CL)))
         return 1;
     const int M = A.rows, N = W.rows, K = A.cols;
     auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };

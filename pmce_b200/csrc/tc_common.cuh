@@ -166,6 +166,19 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// ---- cluster multicast (cta_group::1): one TMA load delivers the box to the SAME shared-memory offset of every CTA in `mask`
+// and signals complete_tx on the mbarrier at the same offset in each of them; one tcgen05.commit arrives on every CTA's barrier
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int crd0, int crd1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes (rows) x 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
