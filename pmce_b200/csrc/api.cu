@@ -1270,7 +1270,7 @@ extern "C" int smpl_lbs_forward_sparse(const float* blend, const void* blend_hi,
     }
     dim3 grid(cdiv(SMPL_V, 256), cdiv(B, SMPL_SKIN_NB));
     if (skin_idx4)      // <= 4 joints per vertex (every shipped SMPL model): the sparse stream kernel, one thread per vertex pair
-        smpl_skin4_kernel<<<dim3(cdiv((SMPL_V + 1) / 2, 256), cdiv(B, SMPL_SKIN_NB)), 256, 0, st>>>(vposed, Amat, reinterpret_cast<const int4*>(skin_idx4), reinterpret_cast<const float4*>(skin_w4), trans,
+        smpl_skin4_kernel<<<dim3(cdiv((SMPL_V + 1) / 2, 256), B), 256, 0, st>>>(vposed, Amat, reinterpret_cast<const int4*>(skin_idx4), reinterpret_cast<const float4*>(skin_w4), trans,
                                                 SMPL_V, B, ld_vp, verts, out_scale);
     else
         smpl_skin_kernel<<<grid, 256, 0, st>>>(vposed, Amat, skin_weights, trans, SMPL_V, B, ld_vp, verts, out_scale);

@@ -688,12 +688,12 @@ smpl_skin_kernel(const float* __restrict__ v_posed, const float* __restrict__ Am
 __global__ void __launch_bounds__(256)
 smpl_skin4_kernel(const float* __restrict__ v_posed, const float* __restrict__ Amat, const int4* __restrict__ idx4, const float4* __restrict__ w4,
                   const float* __restrict__ trans, int V, int B, int ld_vp, float* __restrict__ verts, float out_scale) {
-    // thread = a PAIR of consecutive vertices: their 6 coordinates are three aligned 8-byte words in v_posed (row stride ld_vp,
-    // even) and in verts (V * 3 floats per sample with V even), so all global traffic is float2
-    __shared__ __align__(16) float As[SMPL_SKIN_NB][24 * 12];
-    const int b0 = blockIdx.y * SMPL_SKIN_NB;
-    const int nb = B - b0 < SMPL_SKIN_NB ? B - b0 : SMPL_SKIN_NB;
-    for (int i = threadIdx.x; i < nb * 288; i += blockDim.x) As[i / 288][i % 288] = Amat[(size_t)b0 * 288 + i];
+    // thread = (a PAIR of consecutive vertices, one sample): the pair's 6 coordinates are three aligned 8-byte words in v_posed
+    // (row stride ld_vp, even) and in verts (V * 3 floats per sample with V even), so all global traffic is float2; the sparse
+    // table (32 B per vertex) is re-read per sample from L2 - cheap next to what the dense kernel's sample loop saved
+    __shared__ __align__(16) float As[24 * 12];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < 288; i += blockDim.x) As[i] = Amat[(size_t)b * 288 + i];
     __syncthreads();
     const int v = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (v >= V) return;
@@ -702,40 +702,36 @@ smpl_skin4_kernel(const float* __restrict__ v_posed, const float* __restrict__ A
     const float4 wa = w4[v], wb = two ? w4[v + 1] : wa;
     const int ids[2][4] = {{ia.x, ia.y, ia.z, ia.w}, {ib.x, ib.y, ib.z, ib.w}};
     const float ws[2][4] = {{wa.x, wa.y, wa.z, wa.w}, {wb.x, wb.y, wb.z, wb.w}};
-#pragma unroll 2
-    for (int s = 0; s < nb; ++s) {
-        const int b = b0 + s;
-        const float2* vp = reinterpret_cast<const float2*>(v_posed + (size_t)b * ld_vp + (size_t)v * 3);
-        float2 p0 = vp[0], p1 = make_float2(0.f, 0.f), p2 = p1;
-        if (two) { p1 = vp[1]; p2 = vp[2]; } else { p1.x = v_posed[(size_t)b * ld_vp + (size_t)v * 3 + 2]; }
-        const float xyz[2][3] = {{p0.x, p0.y, p1.x}, {p1.y, p2.x, p2.y}};
-        float o[2][3];
-        const float tx = trans ? trans[(size_t)b * 3] : 0.f, ty = trans ? trans[(size_t)b * 3 + 1] : 0.f, tz = trans ? trans[(size_t)b * 3 + 2] : 0.f;
+    const float2* vp = reinterpret_cast<const float2*>(v_posed + (size_t)b * ld_vp + (size_t)v * 3);
+    float2 p0 = vp[0], p1 = make_float2(0.f, 0.f), p2 = p1;
+    if (two) { p1 = vp[1]; p2 = vp[2]; } else { p1.x = v_posed[(size_t)b * ld_vp + (size_t)v * 3 + 2]; }
+    const float xyz[2][3] = {{p0.x, p0.y, p1.x}, {p1.y, p2.x, p2.y}};
+    float o[2][3];
+    const float tx = trans ? trans[(size_t)b * 3] : 0.f, ty = trans ? trans[(size_t)b * 3 + 1] : 0.f, tz = trans ? trans[(size_t)b * 3 + 2] : 0.f;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
+    for (int q = 0; q < 2; ++q) {
+        float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 a0 = ld4(&As[s][ids[q][i] * 12]), a1 = ld4(&As[s][ids[q][i] * 12 + 4]), a2 = ld4(&As[s][ids[q][i] * 12 + 8]);
-                const float w = ws[q][i];
-                T0.x = fmaf(w, a0.x, T0.x); T0.y = fmaf(w, a0.y, T0.y); T0.z = fmaf(w, a0.z, T0.z); T0.w = fmaf(w, a0.w, T0.w);
-                T1.x = fmaf(w, a1.x, T1.x); T1.y = fmaf(w, a1.y, T1.y); T1.z = fmaf(w, a1.z, T1.z); T1.w = fmaf(w, a1.w, T1.w);
-                T2.x = fmaf(w, a2.x, T2.x); T2.y = fmaf(w, a2.y, T2.y); T2.z = fmaf(w, a2.z, T2.z); T2.w = fmaf(w, a2.w, T2.w);
-            }
-            const float x = xyz[q][0], y = xyz[q][1], z = xyz[q][2];
-            float ox = ((T0.x * x + T0.y * y) + T0.z * z) + T0.w;
-            float oy = ((T1.x * x + T1.y * y) + T1.z * z) + T1.w;
-            float oz = ((T2.x * x + T2.y * y) + T2.z * z) + T2.w;
-            if (trans) { ox += tx; oy += ty; oz += tz; }
-            o[q][0] = ox * out_scale; o[q][1] = oy * out_scale; o[q][2] = oz * out_scale;
+        for (int i = 0; i < 4; ++i) {
+            const float4 a0 = ld4(&As[ids[q][i] * 12]), a1 = ld4(&As[ids[q][i] * 12 + 4]), a2 = ld4(&As[ids[q][i] * 12 + 8]);
+            const float w = ws[q][i];
+            T0.x = fmaf(w, a0.x, T0.x); T0.y = fmaf(w, a0.y, T0.y); T0.z = fmaf(w, a0.z, T0.z); T0.w = fmaf(w, a0.w, T0.w);
+            T1.x = fmaf(w, a1.x, T1.x); T1.y = fmaf(w, a1.y, T1.y); T1.z = fmaf(w, a1.z, T1.z); T1.w = fmaf(w, a1.w, T1.w);
+            T2.x = fmaf(w, a2.x, T2.x); T2.y = fmaf(w, a2.y, T2.y); T2.z = fmaf(w, a2.z, T2.z); T2.w = fmaf(w, a2.w, T2.w);
         }
-        float* op = verts + ((size_t)b * V + v) * 3;
-        if (two && (V & 1) == 0) {
-            float2* o2 = reinterpret_cast<float2*>(op);
-            o2[0] = make_float2(o[0][0], o[0][1]); o2[1] = make_float2(o[0][2], o[1][0]); o2[2] = make_float2(o[1][1], o[1][2]);
-        } else {
-            op[0] = o[0][0]; op[1] = o[0][1]; op[2] = o[0][2];
-            if (two) { op[3] = o[1][0]; op[4] = o[1][1]; op[5] = o[1][2]; }
-        }
+        const float x = xyz[q][0], y = xyz[q][1], z = xyz[q][2];
+        float ox = ((T0.x * x + T0.y * y) + T0.z * z) + T0.w;
+        float oy = ((T1.x * x + T1.y * y) + T1.z * z) + T1.w;
+        float oz = ((T2.x * x + T2.y * y) + T2.z * z) + T2.w;
+        if (trans) { ox += tx; oy += ty; oz += tz; }
+        o[q][0] = ox * out_scale; o[q][1] = oy * out_scale; o[q][2] = oz * out_scale;
+    }
+    float* op = verts + ((size_t)b * V + v) * 3;
+    if (two && (V & 1) == 0) {
+        float2* o2 = reinterpret_cast<float2*>(op);
+        o2[0] = make_float2(o[0][0], o[0][1]); o2[1] = make_float2(o[0][2], o[1][0]); o2[2] = make_float2(o[1][1], o[1][2]);
+    } else {
+        op[0] = o[0][0]; op[1] = o[0][1]; op[2] = o[0][2];
+        if (two) { op[3] = o[1][0]; op[4] = o[1][1]; op[5] = o[1][2]; }
     }
 }

@@ -103,7 +103,7 @@ mlp64_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     uint64_t* x_full = bars + 1;        // x tile landed
     uint64_t* x_empty = bars + 2;       // 4 arrivals: the owner warps hold their rows in registers
     uint64_t* fc1_done = bars + 3;      // [4] tcgen05.commit per hidden chunk
-    uint64_t* h_free = bars + 7;        // [2] tcgen05.commit: the fc2 MMAs have read hidden buffer 0 / 1
+    uint64_t* h_free = bars + 7;        // [2] tcgen05.commit: the fc2 MMAs of chunk 0 / 1 have read hidden buffer 0 / 1
     uint64_t* fc2_done = bars + 9;      // tcgen05.commit: output accumulator complete
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
 
@@ -183,7 +183,7 @@ mlp64_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         tc::umma_bf16(tO, tc::umma_desc_advance_k(hh, k), tc::umma_desc_advance_k(wl, k), idesc, 1);
                         tc::umma_bf16(tO, tc::umma_desc_advance_k(hh, k), tc::umma_desc_advance_k(wh, k), idesc, 1);
                     }
-                    tc::umma_commit(&h_free[c & 1]);
+                    if (c < 2) tc::umma_commit(&h_free[c]);        // hidden buffer c is rewritten by chunk c + 2 (the only waiter)
                     if (c == 3) tc::umma_commit(fc2_done);
                 }
                 __syncwarp();
@@ -232,7 +232,7 @@ mlp64_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 // buffer c & 1 must be free: buffer 0 (H) after the fc2 MMAs of chunk c-2; buffer 1 (A) after ALL fc1 MMAs (they
                 // read the A tiles) and, from chunk 3 on, after the fc2 MMAs of chunk 1
                 if (c == 1) tc::mbar_wait(&fc1_done[3], it & 1);
-                if (c >= 2) tc::mbar_wait(&h_free[c & 1], 0);          // per item: chunk c-2 is the first commit (parity 0) on that buffer...
+                if (c >= 2) tc::mbar_wait(&h_free[c & 1], it & 1);     // the fc2 MMAs of chunk c - 2 have read the buffer (one commit per item)
                 const uint32_t hb = sb + ((c & 1) ? MLP_OFF_A : MLP_OFF_H);
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {

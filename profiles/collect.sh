@@ -26,5 +26,13 @@ if [ "${FULL:-1}" = "1" ]; then
     cap smpl smpl_skin 1 2 python tools/hbm_kernels.py 256
     cap attn_tile attn_tile 2 2 python tools/one_forward.py
     python profiles/ncu_to_json.py $TAG $OUT > $OUT/${TAG}_ncu_traffic.json
+    for k in ca_b64 ca_b256 fc1 mlp attn_rows gru smpl attn_tile; do
+        [ -f $OUT/${TAG}_$k.ncu-rep ] && python profiles/ncu_kernels.py $OUT/${TAG}_$k.ncu-rep 6553.9 > $OUT/${TAG}_${k}_ncu_table.txt 2>/dev/null
+    done
+    python tools/ncu_walk.py $OUT/${TAG}_ca_b256.ncu-rep ca_vertex 25 > $OUT/${TAG}_ca_b256_stall_walk.txt 2>/dev/null
+    python tools/ncu_walk.py $OUT/${TAG}_attn_rows.ncu-rep attn_rows 25 > $OUT/${TAG}_attn_rows_stall_walk.txt 2>/dev/null
+    python tools/ncu_walk.py $OUT/${TAG}_mlp.ncu-rep mlp64 25 > $OUT/${TAG}_mlp_stall_walk.txt 2>/dev/null
+    # gpurun brings back at most 64 MiB: keep the graded kernel's report, drop the rest (their tables / JSON rows stay)
+    [ "${KEEP_REPS:-0}" = "1" ] || find $OUT -name "${TAG}_*.ncu-rep" ! -name "${TAG}_ca_b256.ncu-rep" -delete
 fi
 tail -30 $OUT/${TAG}_launches_summary.txt

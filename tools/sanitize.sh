@@ -9,6 +9,7 @@ mkdir -p "$OUT"
 CS=${CS:-/usr/local/cuda/bin/compute-sanitizer}
 TC_TESTS="tests/test_gpu_tc.py -k test_linear_tc_matches_fp64"
 ATTN_TESTS="tests/test_gpu_parity.py -k 'test_attention_blocks_vs_oracle or test_gru_mid_vs_oracle or test_coevo_blocks_vs_oracle or test_lifter_vs_oracle'"
+SPIN_TESTS="tests/test_spin.py -k test_spin_features_vs_reference_golden"
 PER=${PER:-240}
 
 run() {  # tool, set name, extra env, tests
@@ -31,7 +32,7 @@ run() {  # tool, set name, extra env, tests
 }
 
 # (tool, set) pairs: memcheck everywhere; racecheck / synccheck where the protocol is hand-rolled across warps / CTAs
-PASSES=${PASSES:-"memcheck:gemm memcheck:gemm_pair memcheck:attn_gru_ca racecheck:gemm_pair_relaxed racecheck:attn_gru_ca synccheck:gemm_pair synccheck:attn_gru_ca"}
+PASSES=${PASSES:-"memcheck:gemm memcheck:gemm_pair memcheck:attn_gru_ca memcheck:gru_persistent memcheck:spin racecheck:gemm_pair racecheck:gemm_pair_relaxed racecheck:attn_gru_ca synccheck:gemm_pair synccheck:attn_gru_ca synccheck:gru_persistent"}
 for p in $PASSES; do
     tool=${p%%:*}; name=${p##*:}
     case $name in
@@ -39,5 +40,7 @@ for p in $PASSES; do
         gemm_pair) run $tool gemm_pair "PMCE_TC_PAIR=2 PMCE_TC_BN=256" "$TC_TESTS" ;;
         gemm_pair_relaxed) run $tool gemm_pair_relaxed "PMCE_TC_PAIR=2 PMCE_TC_BN=256 PMCE_TC_PAIR_RELAXED=1" "$TC_TESTS" ;;
         attn_gru_ca) run $tool attn_gru_ca "" "$ATTN_TESTS" ;;
+        gru_persistent) run $tool gru_persistent "PMCE_GRU_PERSISTENT=1" "tests/test_gpu_parity.py -k test_gru_mid_vs_oracle" ;;
+        spin) run $tool spin "" "$SPIN_TESTS" ;;
     esac
 done
