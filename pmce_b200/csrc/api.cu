@@ -373,7 +373,87 @@ struct GruStep {
     size_t whh_off;      // float offset of W_hh [3H,H] in the weight blob
 };
 
-int gru_step(const GruStep* s, int ndir, const Weights& W, int B, int H, cudaStream_t st) {
+// Few-CTA recurrent steps (gru_step_multi_kernel, gru_tc.cuh) while the image-feature stream runs beside the pose lifter: an
+// EXPERIMENT that did not pay, kept behind knobs (default off). Measured at 64 clips (tools/forward_breakdown.py, overlap_probe.py):
+// the forward is 2,547 us, 2,116 us without the image-feature stream (580 us alone): only ~150 us of it hide under the 1,585 us
+// lifter. Hypothesis: a 128-CTA step delays the lifter's persistent GEMM (static tile schedule) it collides with by the whole
+// step, so run the first steps on 12 CTAs = the 6 TPCs the balanced GEMM grids leave free (tc_balanced_grid / tc_sm_reserve).
+// Result: a 12-CTA step takes ~60-70 us (per-SM L2 ingest ~64 GB/s x 3.8 MB of W_hh + h per CTA) and costs the lifter as much
+// as the 128-CTA step it replaces (forward 2,538 / 2,549 / 2,627 / 2,780 us with 0 / 12 / 19 / 22 such steps): the GEMMs are bound
+// by L2 operand bandwidth and a step moves ~50 MB through L2 however many SMs it uses.
+//   PMCE_GRU_FEW_STEPS  how many of the first recurrent steps run on few CTAs (default 0; -1 = a host-side estimate of what fits
+//                       under the lifter)
+//   PMCE_GRU_FEW        CTAs of such a step (default 12)
+struct GruFew { int ctas, steps; };
+GruFew gru_few_plan(const pmce_dims_t& d, int B) {
+    static int ctas = -1, steps = -2;
+    if (ctas < 0) { ctas = pmce_env_int("PMCE_GRU_FEW", 12) & ~1; steps = pmce_env_int("PMCE_GRU_FEW_STEPS", 0); }
+    GruFew f{ctas, steps};
+    if (ctas <= 0) { f.steps = 0; return f; }
+    if (steps < 0) {
+        const double c = d.embed_dim / 512.0, h = d.gru_hidden / 1024.0;
+        const double lifter_us = 1590.0 * ((double)B * d.seqlen * d.num_joint / 17408.0) * c * c * (d.depth / 3.0);
+        const double step_us = 60.0 * h * h * (double)cdiv(B, 128) * (12.0 / ctas);
+        const double room = 0.85 * lifter_us - 200.0;      // the stream's GEMMs (input projections) take ~200 us
+        f.steps = room > 0 ? (int)(room / step_us) : 0;
+        if (f.steps < 4) f.steps = 0;
+    }
+    return f;
+}
+
+template <int U, int S>
+int launch_gru_multi(const GruStep* s, int ndir, const Weights& W, int B, int H, int ctas, cudaStream_t st) {
+    using Cfg = GruMultiCfg<U, S>;
+    GruTcMaps maps[2];
+    GruTcDir dirs[2];
+    for (int i = 0; i < 2; ++i) {
+        const GruStep& x = s[i < ndir ? i : 0];
+        if (make_tmap_bf16(&maps[i].h_hi, x.hprev_s.hi, B, H, x.ld_hs, 128) || make_tmap_bf16(&maps[i].h_lo, x.hprev_s.lo, B, H, x.ld_hs, 128) ||
+            make_tmap_bf16(&maps[i].w_hi, W.hi + x.whh_off, 3 * H, H, H, U) || make_tmap_bf16(&maps[i].w_lo, W.lo + x.whh_off, 3 * H, H, H, U)) {
+            pmce_set_error("gru_step: cuTensorMapEncodeTiled failed");
+            return 10;
+        }
+        dirs[i].gi = x.d.gi; dirs[i].hprev = x.d.hprev; dirs[i].bhh = x.d.bhh; dirs[i].hout = x.d.hout; dirs[i].hs = x.d.hs;
+        dirs[i].ld_gi = x.d.ld_gi; dirs[i].ld_h = x.d.ld_h; dirs[i].ld_o = x.d.ld_o; dirs[i].ld_s = x.d.ld_s;
+    }
+    if (!pmce_configure_smem<gru_step_multi_kernel<U, S>>(Cfg::SMEM)) { pmce_set_error("gru_step: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); return 10; }
+    const int ntiles = (H / U) * ndir * cdiv(B, 128);
+    int grid = ctas < ntiles ? ctas : ntiles;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    int nattr = 0;
+    if (grid >= 2) {       // CTA pairs land on whole TPCs, so the lifter's pair GEMMs find their TPCs whole as well
+        grid &= ~1;
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        nattr = 1;
+    }
+    cfg.gridDim = dim3(grid); cfg.attrs = attr; cfg.numAttrs = nattr;
+    count_launch();
+    if (cudaLaunchKernelEx(&cfg, gru_step_multi_kernel<U, S>, maps[0], maps[1], dirs[0], dirs[1], B, H, ndir) != cudaSuccess) {
+        pmce_set_error("gru_step_multi launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 10;
+    }
+    return 0;
+}
+
+// PMCE_SKIP (profiling build only, results are garbage): bit 0 = no recurrent GRU steps, bit 1 = no image-feature stream at all,
+// bit 2 = no lifter, bit 3 = no decoder - tools/forward_breakdown.py times the forward with parts removed
+static int skip_mask() {
+    static int m = -1;
+    if (m < 0) m = pmce_profiling_knob("PMCE_SKIP");
+    return m;
+}
+
+int gru_step(const GruStep* s, int ndir, const Weights& W, int B, int H, int few, cudaStream_t st) {
+    if (skip_mask() & 1) return 0;
+    if (s[0].d.hprev && few > 0 && H % 64 == 0) {
+        static int u = -1;
+        if (u < 0) u = pmce_env_int("PMCE_GRU_FEW_U", 32);
+        return u == 64 ? launch_gru_multi<64, 2>(s, ndir, W, B, H, few, st) : launch_gru_multi<32, 4>(s, ndir, W, B, H, few, st);
+    }
     if (!s[0].d.hprev) {   // first step of both directions (they always start together)
         dim3 grid(H / 16, cdiv(B, 64), ndir);
         gru_step_kernel<<<grid, 256, 0, st>>>(s[0].d, s[ndir > 1 ? 1 : 0].d, B, H);
@@ -432,7 +512,7 @@ int gru_layer(const GruLayerDir* dd, int ndir, const SplitOut* hs, const int* nb
 }
 
 // nfr / fstride as in lifter(): the layer-0 input projection is a per-frame product, so overlapping windows share it.
-int gru_mid(const Layout& L, const Weights& W, int B, int nfr, int fstride, float* g, const Workspace& ws, cudaStream_t st) {
+int gru_mid(const Layout& L, const Weights& W, int B, int nfr, int fstride, float* g, const Workspace& ws, cudaStream_t st, GruFew few = GruFew{0, 0}) {
     const pmce_dims_t& d = L.d;
     const int T = d.seqlen, H = d.gru_hidden, F = d.feat_dim;
     const int mid = T / 2;
@@ -501,7 +581,7 @@ int gru_mid(const Layout& L, const Weights& W, int B, int nfr, int fstride, floa
             x.hprev_s.hi = s > 0 ? ws.y0_s.hi + offp : nullptr; x.hprev_s.lo = s > 0 ? ws.y0_s.lo + offp : nullptr; x.ld_hs = 2 * H;
             x.whh_off = L.whh0[dir];
         }
-        RET(gru_step(dd, 2, W, B, H, st));
+        RET(gru_step(dd, 2, W, B, H, (s > 0 && few.steps-- > 0) ? few.ctas : 0, st));
     }
     // layer 1: only the steps y[T//2] depends on (fwd t = 0..mid, bwd t = T-1..mid)
     const int nf = mid + 1, nb = T - mid;
@@ -531,7 +611,7 @@ int gru_mid(const Layout& L, const Weights& W, int B, int nfr, int fstride, floa
             if (s == nd - 1) { x.d.hout = g + dir * H; x.d.ld_o = 2 * H; x.d.hs = NO_SPLIT; x.d.ld_s = 0; }
             else { x.d.hout = ws.h1[dir][s & 1]; x.d.ld_o = H; x.d.hs = ws.h1_s[dir][s & 1]; x.d.ld_s = H; }
         }
-        RET(gru_step(dd, n, W, B, H, st));
+        RET(gru_step(dd, n, W, B, H, (s > 0 && few.steps-- > 0) ? few.ctas : 0, st));
     }
     return 0;
 }
@@ -555,7 +635,11 @@ Aux* get_aux(cudaStream_t caller) {
     std::lock_guard<std::mutex> lock(mu);
     Aux& a = table[std::make_pair(dev, caller)];           // std::map nodes are address-stable
     if (!a.join2) {
-        if (!a.side && cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (!a.side) {       // highest priority: its few-CTA kernels take the first SMs any lifter kernel frees
+            int lo = 0, hi = 0;
+            if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
+            if (cudaStreamCreateWithPriority(&a.side, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+        }
         if (!a.fork && cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (!a.join && cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (!a.fork2 && cudaEventCreateWithFlags(&a.fork2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -869,9 +953,9 @@ int prepare_feat(const Layout& L, const float* img_feat, int nfr, const Workspac
 }
 
 // image-feature stream of the two-stream encoder: GRU -> y[T//2] -> all AdaLN gamma/beta (independent of the pose stream)
-int decoder_front(const Layout& L, const Weights& W, int B, int nfr, int fstride, const Workspace& ws, cudaStream_t st) {
+int decoder_front(const Layout& L, const Weights& W, int B, int nfr, int fstride, const Workspace& ws, cudaStream_t st, GruFew few = GruFew{0, 0}) {
     NvtxRange nvtx("pmce/image-feature stream (GRU + AdaLN gamma/beta + linear_cur)");
-    RET(gru_mid(L, W, B, nfr, fstride, ws.g, ws, st));
+    RET(gru_mid(L, W, B, nfr, fstride, ws.g, ws, st, few));
     RET(adaln_gammabeta(L, W, ws.g, B, ws.gb, ws.g_s, st));
     return mesh_residual(L, W, ws.g, B, ws, st);
 }
@@ -949,7 +1033,10 @@ extern "C" int pmce_gru_mid(const pmce_dims_t* dims, const void* weights, const 
     Workspace ws;
     RET(check_ws(*dims, B, workspace, workspace_bytes, &ws));
     RET(prepare_feat(L, img_feat, B * dims->seqlen, ws, st));
-    return gru_mid(L, W, B, B * dims->seqlen, dims->seqlen, g, ws, st);
+    // standalone: 128-CTA steps unless PMCE_GRU_FEW_STEPS asks for few-CTA ones (tests, tools/stage_times.py)
+    GruFew few = gru_few_plan(L.d, B);
+    if (pmce_env_int("PMCE_GRU_FEW_STEPS", 0) < 0) few.steps = 0;
+    return gru_mid(L, W, B, B * dims->seqlen, dims->seqlen, g, ws, st, few);
 }
 
 extern "C" int pmce_adaln_gammabeta(const pmce_dims_t* dims, const void* weights, const float* g, int B, float* gb, void* workspace,
@@ -1066,10 +1153,15 @@ static int forward_windows(const pmce_dims_t* dims, const void* weights, const f
     if (!aux) { pmce_set_error("could not create the side stream/events: %s", cudaGetErrorString(cudaGetLastError())); return 10; }
     CK(cudaEventRecord(aux->fork, st));
     CK(cudaStreamWaitEvent(aux->side, aux->fork, 0));
-    RET(decoder_front(L, W, B, nfr, fstride, ws, aux->side));
+    const GruFew few = gru_few_plan(L.d, B);
+    if (!(skip_mask() & 2)) RET(decoder_front(L, W, B, nfr, fstride, ws, aux->side, few));
     CK(cudaEventRecord(aux->join, aux->side));
-    RET(lifter(L, W, pose2d, B, nfr, fstride, pose3d, ws, st));
+    tc_sm_reserve = few.steps > 0 ? few.ctas : 0;
+    const int lrc = (skip_mask() & 4) ? 0 : lifter(L, W, pose2d, B, nfr, fstride, pose3d, ws, st);
+    tc_sm_reserve = 0;
+    if (lrc) return lrc;
     CK(cudaStreamWaitEvent(st, aux->join, 0));
+    if (skip_mask() & 8) return 0;
     return decoder_back(L, W, ws.joints_m, vj_relation, B, cam_pose, cam_mesh, nullptr, ws, st, aux);
 }
 

@@ -496,6 +496,20 @@ static inline bool tc_mcast_enabled(int M, int N, int K) {
     return mode != 0 && M > TC_CL * TC_BM && N >= 512 && K >= 512;
 }
 
+// SMs the persistent grids leave alone. pmce_forward sets it while the image-feature stream's few-CTA GRU steps run beside the
+// pose lifter (api.cu): the GEMM CTAs then never wait behind a GRU CTA and vice versa. Host-side, per calling thread.
+static thread_local int tc_sm_reserve = 0;
+
+// Persistent grid for `tiles` equal work items dealt round-robin to at most max_units CTAs (pairs): the SMALLEST grid with the
+// same number of waves. 272 tiles on 74 pairs take 4 waves, so do 68 pairs - the 6 TPCs left over cost nothing and are free for
+// a concurrent stream.
+static inline int tc_balanced_grid(long long tiles, int max_units) {
+    if (max_units < 1) max_units = 1;
+    if (tiles <= max_units) return (int)tiles;
+    const long long waves = (tiles + max_units - 1) / max_units;
+    return (int)((tiles + waves - 1) / waves);
+}
+
 template <int BN, int MODE>
 static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap* tw, const TcOutMaps& om, int M, int N, int K, const TcEpi& e,
                                         cudaStream_t st) {
@@ -519,7 +533,7 @@ static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap
         static int nbuf = -1;     // PMCE_TC_NBUF=2: two staging tiles per epilogue warp and a two-stage operand ring (A/B knob)
         if (nbuf < 0) nbuf = pmce_env_int("PMCE_TC_NBUF", 1);
         const long long tiles = (long long)((N + 255) / 256) * ((M + 2 * TC_BM - 1) / (2 * TC_BM));
-        const int pairs = (int)(tiles < tc_num_sms() / 2 ? tiles : tc_num_sms() / 2);
+        const int pairs = tc_balanced_grid(tiles, (tc_num_sms() - tc_sm_reserve) / 2);
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.stream = st;
@@ -538,7 +552,7 @@ static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap
     }
     if (!pmce_configure_smem<linear_tc_kernel<BN, MODE, 1>>(TcCfg<BN>::SMEM_BYTES)) return 2;
     const long long tiles = (long long)((N + BN - 1) / BN) * ((M + TC_BM - 1) / TC_BM);
-    const int grid = (int)(tiles < tc_num_sms() ? tiles : tc_num_sms());
+    const int grid = tc_balanced_grid(tiles, tc_num_sms() - tc_sm_reserve);
     linear_tc_kernel<BN, MODE, 1><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta[0], ta[1], tw[0], tw[1], om, M, N, K, e);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }

@@ -146,6 +146,163 @@ gru_step_tc_kernel(const __grid_constant__ GruTcMaps m0_, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------------
+// The same step on a FEW SMs (opt-in experiment, api.cu::gru_few_plan has the measurements): the kernel above spreads a step over
+// H/16 x ndir = 128 CTAs for ~17 us. This variant runs it on `gridDim.x` CTAs (launched as CTA pairs so they fill whole TPCs):
+// every CTA walks tiles of U hidden units x 3 gates (N = 3U) of one direction, two TMEM accumulators so the gate math of tile i
+// overlaps the MMAs of tile i+1. On 12 CTAs a step takes ~60-70 us (per-SM L2 ingest) and, beside the lifter, costs the forward
+// as much as the 128-CTA step - both are L2-bandwidth, not SM-count, problems.
+// ------------------------------------------------------------------------------------------------------
+template <int U, int S>
+struct GruMultiCfg {
+    static constexpr int N = 3 * U;
+    static constexpr int W_TILE = N * 128;
+    static constexpr int STAGE = 2 * GRU_A_TILE + 2 * W_TILE;
+    static constexpr int SMEM = S * STAGE + 1024 + 256;
+    static constexpr int ACC_STRIDE = N <= 128 ? 128 : 256;
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+};
+
+template <int U, int S>
+__global__ void __launch_bounds__(192, 1)
+gru_step_multi_kernel(const __grid_constant__ GruTcMaps m0_, const __grid_constant__ GruTcMaps m1_, GruTcDir d0, GruTcDir d1, int B, int H, int ndir) {
+    using Cfg = GruMultiCfg<U, S>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE);
+    uint64_t* empty_bar = full_bar + S;
+    uint64_t* tmem_full_bar = empty_bar + S;         // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = H / 64, jtiles = H / U;
+    const int ntiles = jtiles * ndir * ((B + 127) / 128);     // tile = (batch block, direction, unit tile), unit tile fastest
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&m0_.h_hi); tc::tma_prefetch_desc(&m0_.h_lo); tc::tma_prefetch_desc(&m0_.w_hi); tc::tma_prefetch_desc(&m0_.w_lo);
+        if (ndir > 1) { tc::tma_prefetch_desc(&m1_.h_hi); tc::tma_prefetch_desc(&m1_.h_lo); tc::tma_prefetch_desc(&m1_.w_hi); tc::tma_prefetch_desc(&m1_.w_lo); }
+        for (int s = 0; s < S; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], 4); }
+        tc::fence_barrier_init();
+        tc::fence_proxy_async();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int jt = tile % jtiles, dir = (tile / jtiles) % ndir, b0 = (tile / (jtiles * ndir)) * 128;
+                const GruTcMaps& mp = dir == 0 ? m0_ : m1_;
+                const int j0 = jt * U;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % S;
+                    tc::mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
+                    uint8_t* st = smem + s * Cfg::STAGE;
+                    tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
+                    tc::tma_load_2d(st, &mp.h_hi, &full_bar[s], kb * 64, b0);
+                    tc::tma_load_2d(st + GRU_A_TILE, &mp.h_lo, &full_bar[s], kb * 64, b0);
+                    uint8_t* wh = st + 2 * GRU_A_TILE;
+                    uint8_t* wl = wh + Cfg::W_TILE;
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        tc::tma_load_2d(wh + g * U * 128, &mp.w_hi, &full_bar[s], kb * 64, g * H + j0);
+                        tc::tma_load_2d(wl + g * U * 128, &mp.w_lo, &full_bar[s], kb * 64, g * H + j0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(128, Cfg::N);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+                const uint32_t acc = tcount & 1;
+                tc::mbar_wait(&tmem_empty_bar[acc], ((tcount >> 1) & 1) ^ 1);     // the gate math of tile tcount-2 has read this accumulator
+                tc::tc_fence_after();
+                const uint32_t dt = tmem_base + acc * Cfg::ACC_STRIDE;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % S;
+                    tc::mbar_wait(&full_bar[s], (it / S) & 1);
+                    tc::tc_fence_after();
+                    const uint32_t st = tc::smem_u32(smem + s * Cfg::STAGE);
+                    const uint64_t a_hi = tc::umma_desc_sw128(st), a_lo = tc::umma_desc_sw128(st + GRU_A_TILE);
+                    const uint64_t w_hi = tc::umma_desc_sw128(st + 2 * GRU_A_TILE), w_lo = tc::umma_desc_sw128(st + 2 * GRU_A_TILE + Cfg::W_TILE);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        tc::umma_bf16(dt, tc::umma_desc_advance_k(a_lo, k), tc::umma_desc_advance_k(w_hi, k), idesc, (kb | k) != 0);
+                        tc::umma_bf16(dt, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_lo, k), idesc, 1);
+                        tc::umma_bf16(dt, tc::umma_desc_advance_k(a_hi, k), tc::umma_desc_advance_k(w_hi, k), idesc, 1);
+                    }
+                    tc::umma_commit(&empty_bar[s]);
+                }
+                tc::umma_commit(&tmem_full_bar[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const int jt = tile % jtiles, dir = (tile / jtiles) % ndir, b0 = (tile / (jtiles * ndir)) * 128;
+            const GruTcDir& d = dir == 0 ? d0 : d1;
+            const uint32_t acc = tcount & 1;
+            const int row = b0 + q * 32 + lane;
+            tc::mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t t0 = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+            if (b0 + q * 32 < B) {          // warps whose 32 rows are all padding only hand the accumulator back
+#pragma unroll 1
+                for (int u0 = 0; u0 < U; u0 += 16) {
+                    uint32_t ar[16], az[16], an[16];
+                    tc::tmem_ld_32x16(t0 + u0, ar);
+                    tc::tmem_ld_32x16(t0 + U + u0, az);
+                    tc::tmem_ld_32x16(t0 + 2 * U + u0, an);
+                    tc::tmem_ld_wait();
+                    if (row < B) {
+                        const int j0 = jt * U + u0;
+                        const float* gi = d.gi + (size_t)row * d.ld_gi + j0;
+                        const float* hp = d.hprev + (size_t)row * d.ld_h + j0;
+                        float hn[16];
+#pragma unroll
+                        for (int u = 0; u < 16; u += 4) {
+                            const float4 gr = ld4(gi + u), gz = ld4(gi + H + u), gn = ld4(gi + 2 * H + u), hv = ld4(hp + u);
+                            const float4 br = ld4(d.bhh + j0 + u), bz = ld4(d.bhh + H + j0 + u), bn = ld4(d.bhh + 2 * H + j0 + u);
+                            const float grr[4] = {gr.x, gr.y, gr.z, gr.w}, gzz[4] = {gz.x, gz.y, gz.z, gz.w}, gnn[4] = {gn.x, gn.y, gn.z, gn.w};
+                            const float hh[4] = {hv.x, hv.y, hv.z, hv.w}, brr[4] = {br.x, br.y, br.z, br.w}, bzz[4] = {bz.x, bz.y, bz.z, bz.w}, bnn[4] = {bn.x, bn.y, bn.z, bn.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float r = sigmoid_f(grr[i] + (__uint_as_float(ar[u + i]) + brr[i]));
+                                const float z = sigmoid_f(gzz[i] + (__uint_as_float(az[u + i]) + bzz[i]));
+                                const float n = tanhf(gnn[i] + r * (__uint_as_float(an[u + i]) + bnn[i]));
+                                hn[u + i] = (1.0f - z) * n + z * hh[i];
+                            }
+                        }
+                        float* ho = d.hout + (size_t)row * d.ld_o + j0;
+#pragma unroll
+                        for (int u = 0; u < 16; u += 4) st4(ho + u, make_float4(hn[u], hn[u + 1], hn[u + 2], hn[u + 3]));
+                        if (d.hs.hi) {
+                            const size_t si = (size_t)row * d.ld_s + j0;
+#pragma unroll
+                            for (int u = 0; u < 16; u += 4) store_split4(d.hs, si + u, make_float4(hn[u], hn[u + 1], hn[u + 2], hn[u + 3]));
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // One GRU LAYER (up to two directions) as ONE persistent launch: the per-step kernel above paid a launch, a pipeline fill and a
 // TMEM allocation per time step (41 launches per forward, 17 us each for ~6 us of L2 streaming). Here the CTAs stay resident
 // over all steps of the layer: CTA (x, dir) owns hidden units [16 x, 16 x + 16) of direction dir for every step,

@@ -436,10 +436,13 @@ def test_headline_configs_vs_oracle(assets_root, lib, J, C, T, B):
 
 
 @pytest.mark.parametrize("env", [{"PMCE_GRU_PERSISTENT": "1"},
+                                 {"PMCE_GRU_FEW_STEPS": "100"},
+                                 {"PMCE_GRU_FEW": "6", "PMCE_GRU_FEW_STEPS": "7", "PMCE_GRU_FEW_U": "64"},
                                  {"PMCE_MLP_FUSED": "0", "PMCE_ATTN_ROWS": "0", "PMCE_CA_FUSED": "0"},
                                  {"PMCE_TC_DIRECT": "1", "PMCE_TC_NBUF": "2", "PMCE_TC_PAIR_RELAXED": "1"}])
 def test_alternative_paths_in_subprocess(env):
-    """The opt-in / A-B variants stay parity-green: the persistent GRU layer kernel, the unfused launch sequences the fused
+    """The opt-in / A-B variants stay parity-green: the persistent GRU layer kernel, the few-CTA GRU step kernel (all steps / the
+    first 7 on 6 CTAs with 64-unit tiles), the unfused launch sequences the fused
     kernels replaced, and the GEMM epilogue variants (the library reads its knobs once per process, hence the subprocess)."""
     import subprocess
     import sys
