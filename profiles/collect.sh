@@ -12,6 +12,9 @@ mkdir -p $OUT
 NCU="ncu --clock-control none"
 timeout 400 $NCU --metrics gpu__time_duration.sum --profile-from-start off --csv --log-file $OUT/${TAG}_launches.csv python tools/one_forward.py > $OUT/${TAG}_launches.log 2>&1
 python profiles/summarize_launches.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches_summary.txt 2>&1
+# the SMPL LBS call's own kernels (pose kernel, blend-shape GEMM, skinning), B=256
+timeout 300 $NCU --metrics gpu__time_duration.sum -k regex:"smpl|linear_tc" -c 60 --csv --log-file $OUT/${TAG}_lbs_launches.csv python tools/hbm_kernels.py 256 > /dev/null 2>&1
+python profiles/summarize_launches.py $OUT/${TAG}_lbs_launches.csv > $OUT/${TAG}_lbs_launches_summary.txt 2>&1
 cap() {  # name, kernel regex, skip, count, command...
     local name=$1 re=$2 skip=$3 cnt=$4; shift 4
     timeout 400 $NCU --set full --import-source on -k regex:$re -s $skip -c $cnt -o $OUT/${TAG}_$name "$@" > $OUT/${TAG}_$name.log 2>&1
