@@ -1343,14 +1343,14 @@ extern "C" int smpl_lbs_forward_sparse(const float* blend, const void* blend_hi,
     float* Amat = c.f32((size_t)B * 288);
     float* vposed = c.f32((size_t)B * SMPL_NPAD);
     SplitOut coef_s = c.split((size_t)B * SMPL_LDK);
-    smpl_pose_kernel<<<B, 32, 0, st>>>(pose, betas, trans, j_template, j_shapedirs, parents, B, SMPL_LDK, coef, Amat, joints, out_scale);
+    smpl_pose_kernel<<<B, 32, 0, st>>>(pose, betas, trans, j_template, j_shapedirs, parents, B, SMPL_LDK, coef, Amat, joints, out_scale,
+                                       blend_hi ? coef_s : NO_SPLIT);
     CKL();
     // v_posed[b, v*3+c] = v_template + [shapedirs | posedirs] . [betas | pose_map]   (smpl_layer.py:93-99)
     int ld_vp;
     if (blend_hi) {
         // tensor cores (bf16x3, as every projection of the forward): blend_hi/lo and v_template are padded to SMPL_NPAD rows
-        RET(split_rows(coef, B, SMPL_LDK, SMPL_LDK, false, coef_s, SMPL_LDK, st));
-        Weights Wb{nullptr, (const bf16*)blend_hi, (const bf16*)blend_lo};
+        Weights Wb{nullptr, (const bf16*)blend_hi, (const bf16*)blend_lo};      // coef_s: written by the pose kernel
         EpiOpt o; o.bias = v_template; o.out = vposed; o.ld_out = SMPL_NPAD;
         RET(linear_tc(coef_s, SMPL_LDK, B, SMPL_LDK, Wb, 0, SMPL_LDK, SMPL_NPAD, o, st));
         ld_vp = SMPL_NPAD;

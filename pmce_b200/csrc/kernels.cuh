@@ -14,6 +14,12 @@ __device__ __forceinline__ void store_split4(const SplitOut& o, size_t idx, floa
     *reinterpret_cast<uint2*>(o.hi + idx) = h;
     *reinterpret_cast<uint2*>(o.lo + idx) = l;
 }
+__device__ __forceinline__ void store_split1(const SplitOut& o, size_t idx, float a) {
+    uint32_t h, l;
+    tc::split_bf16x2(a, 0.f, h, l);          // first element sits in the low half
+    *reinterpret_cast<unsigned short*>(o.hi + idx) = (unsigned short)(h & 0xffffu);
+    *reinterpret_cast<unsigned short*>(o.lo + idx) = (unsigned short)(l & 0xffffu);
+}
 __device__ __forceinline__ void store_split2(const SplitOut& o, size_t idx, float a, float b) {
     uint32_t h, l;
     tc::split_bf16x2(a, b, h, l);
@@ -567,7 +573,7 @@ __global__ void __launch_bounds__(32)
 smpl_pose_kernel(const float* __restrict__ pose, const float* __restrict__ betas, const float* __restrict__ trans,
                  const float* __restrict__ j_template, const float* __restrict__ j_shapedirs,
                  const int32_t* __restrict__ parents, int B, int ldc, float* __restrict__ coef, float* __restrict__ Aout,
-                 float* __restrict__ joints, float out_scale) {
+                 float* __restrict__ joints, float out_scale, SplitOut coef_s) {
     const int b = blockIdx.x, lane = threadIdx.x;
     __shared__ float R[24][9];
     __shared__ float Jr[24][3];
@@ -575,6 +581,10 @@ smpl_pose_kernel(const float* __restrict__ pose, const float* __restrict__ betas
     float* cf = coef + (size_t)b * ldc;
     if (lane < 10) cf[lane] = betas[(size_t)b * 10 + lane];
     if (lane < ldc - 217) cf[217 + lane] = 0.f;
+    if (coef_s.hi) {      // the split-bf16 copy the tensor-core blend-shape GEMM reads (saves a split_rows launch)
+        if (lane < 10) store_split1(coef_s, (size_t)b * ldc + lane, betas[(size_t)b * 10 + lane]);
+        if (lane < ldc - 217) store_split1(coef_s, (size_t)b * ldc + 217 + lane, 0.f);
+    }
     if (lane < 24) {
         // batch_rodrigues (rodrigues_layer.py:41-52): theta = |a + 1e-8|, axis = a / theta, quaternion -> matrix
         const float ax = pose[(size_t)b * 72 + lane * 3], ay = pose[(size_t)b * 72 + lane * 3 + 1], az = pose[(size_t)b * 72 + lane * 3 + 2];
@@ -600,29 +610,32 @@ smpl_pose_kernel(const float* __restrict__ pose, const float* __restrict__ betas
         }
         if (lane >= 1) {
 #pragma unroll
-            for (int e = 0; e < 9; ++e) cf[10 + (lane - 1) * 9 + e] = R[lane][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
-        }
-    }
-    __syncwarp();
-    if (lane == 0) {
-        // forward kinematics (smpl_layer.py:105-119); G = [R | t] 3x4, row-major
-        for (int i = 0; i < 24; ++i) {
-            float t[3];
-            if (i == 0) { t[0] = Jr[0][0]; t[1] = Jr[0][1]; t[2] = Jr[0][2]; }
-            else { const int p = parents[i]; t[0] = Jr[i][0] - Jr[p][0]; t[1] = Jr[i][1] - Jr[p][1]; t[2] = Jr[i][2] - Jr[p][2]; }
-            if (i == 0) {
-                for (int r = 0; r < 3; ++r) { G[0][r * 4 + 0] = R[0][r * 3]; G[0][r * 4 + 1] = R[0][r * 3 + 1]; G[0][r * 4 + 2] = R[0][r * 3 + 2]; G[0][r * 4 + 3] = t[r]; }
-            } else {
-                const int p = parents[i];
-                for (int r = 0; r < 3; ++r) {
-                    const float g0 = G[p][r * 4], g1 = G[p][r * 4 + 1], g2 = G[p][r * 4 + 2], g3 = G[p][r * 4 + 3];
-                    for (int c = 0; c < 3; ++c) G[i][r * 4 + c] = (g0 * R[i][c] + g1 * R[i][3 + c]) + g2 * R[i][6 + c];
-                    G[i][r * 4 + 3] = ((g0 * t[0] + g1 * t[1]) + g2 * t[2]) + g3;
-                }
+            for (int e = 0; e < 9; ++e) {
+                const float v = R[lane][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+                cf[10 + (lane - 1) * 9 + e] = v;
+                if (coef_s.hi) store_split1(coef_s, (size_t)b * ldc + 10 + (lane - 1) * 9 + e, v);
             }
         }
     }
     __syncwarp();
+    {
+        // forward kinematics (smpl_layer.py:105-119); G = [R | t] 3x4, row-major. Element (r, c) of a joint depends only on row r
+        // of its parent: lanes 0..11 own one element each and walk the chain together (same expression order as a serial loop)
+        const int r = lane >> 2, c = lane & 3;
+        for (int i = 0; i < 24; ++i) {
+            if (lane < 12) {
+                if (i == 0) {
+                    G[0][lane] = c < 3 ? R[0][r * 3 + c] : Jr[0][r];
+                } else {
+                    const int p = parents[i];
+                    const float g0 = G[p][r * 4], g1 = G[p][r * 4 + 1], g2 = G[p][r * 4 + 2], g3 = G[p][r * 4 + 3];
+                    if (c < 3) G[i][lane] = (g0 * R[i][c] + g1 * R[i][3 + c]) + g2 * R[i][6 + c];
+                    else G[i][lane] = ((g0 * (Jr[i][0] - Jr[p][0]) + g1 * (Jr[i][1] - Jr[p][1])) + g2 * (Jr[i][2] - Jr[p][2])) + g3;
+                }
+            }
+            __syncwarp();
+        }
+    }
     if (lane < 24) {
         const float tx = trans ? trans[(size_t)b * 3] : 0.f, ty = trans ? trans[(size_t)b * 3 + 1] : 0.f, tz = trans ? trans[(size_t)b * 3 + 2] : 0.f;
         joints[((size_t)b * 24 + lane) * 3 + 0] = (G[lane][3] + tx) * out_scale;
@@ -690,10 +703,13 @@ smpl_skin4_kernel(const float* __restrict__ v_posed, const float* __restrict__ A
                   const float* __restrict__ trans, int V, int B, int ld_vp, float* __restrict__ verts, float out_scale) {
     // thread = (a PAIR of consecutive vertices, one sample): the pair's 6 coordinates are three aligned 8-byte words in v_posed
     // (row stride ld_vp, even) and in verts (V * 3 floats per sample with V even), so all global traffic is float2; the sparse
-    // table (32 B per vertex) is re-read per sample from L2 - cheap next to what the dense kernel's sample loop saved
-    __shared__ __align__(16) float As[24 * 12];
+    // table (32 B per vertex) is re-read per sample from L2 - cheap next to what the dense kernel's sample loop saved.
+    // The sample's 24 transforms sit in shared memory TRANSPOSED, As[k][joint] (k = 0..11): a warp's lanes read element k of
+    // 32 different joints from 32 different banks (joint < 24 < 32), whatever the joints are - the natural [joint][12] layout read
+    // with 16-byte loads had 42 % of its wavefronts in bank conflicts on vertices whose neighbours use unrelated joints
+    __shared__ float As[12 * 24];
     const int b = blockIdx.y;
-    for (int i = threadIdx.x; i < 288; i += blockDim.x) As[i] = Amat[(size_t)b * 288 + i];
+    for (int i = threadIdx.x; i < 288; i += blockDim.x) As[(i % 12) * 24 + i / 12] = Amat[(size_t)b * 288 + i];
     __syncthreads();
     const int v = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (v >= V) return;
@@ -710,19 +726,20 @@ smpl_skin4_kernel(const float* __restrict__ v_posed, const float* __restrict__ A
     const float tx = trans ? trans[(size_t)b * 3] : 0.f, ty = trans ? trans[(size_t)b * 3 + 1] : 0.f, tz = trans ? trans[(size_t)b * 3 + 2] : 0.f;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
+        float T[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) T[k] = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float4 a0 = ld4(&As[ids[q][i] * 12]), a1 = ld4(&As[ids[q][i] * 12 + 4]), a2 = ld4(&As[ids[q][i] * 12 + 8]);
             const float w = ws[q][i];
-            T0.x = fmaf(w, a0.x, T0.x); T0.y = fmaf(w, a0.y, T0.y); T0.z = fmaf(w, a0.z, T0.z); T0.w = fmaf(w, a0.w, T0.w);
-            T1.x = fmaf(w, a1.x, T1.x); T1.y = fmaf(w, a1.y, T1.y); T1.z = fmaf(w, a1.z, T1.z); T1.w = fmaf(w, a1.w, T1.w);
-            T2.x = fmaf(w, a2.x, T2.x); T2.y = fmaf(w, a2.y, T2.y); T2.z = fmaf(w, a2.z, T2.z); T2.w = fmaf(w, a2.w, T2.w);
+            const float* a = As + ids[q][i];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) T[k] = fmaf(w, a[k * 24], T[k]);
         }
         const float x = xyz[q][0], y = xyz[q][1], z = xyz[q][2];
-        float ox = ((T0.x * x + T0.y * y) + T0.z * z) + T0.w;
-        float oy = ((T1.x * x + T1.y * y) + T1.z * z) + T1.w;
-        float oz = ((T2.x * x + T2.y * y) + T2.z * z) + T2.w;
+        float ox = ((T[0] * x + T[1] * y) + T[2] * z) + T[3];
+        float oy = ((T[4] * x + T[5] * y) + T[6] * z) + T[7];
+        float oz = ((T[8] * x + T[9] * y) + T[10] * z) + T[11];
         if (trans) { ox += tx; oy += ty; oz += tz; }
         o[q][0] = ox * out_scale; o[q][1] = oy * out_scale; o[q][2] = oz * out_scale;
     }

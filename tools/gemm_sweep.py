@@ -16,6 +16,9 @@ SHAPES = [(17408, 1024, 512, 1), (17408, 512, 1024, 2), (17408, 1536, 512, 0), (
 
 
 def main():
+    if os.environ.get("PMCE_SWEEP_SHAPES"):      # "M,N,K,act;M,N,K,act;..."
+        global SHAPES
+        SHAPES = [tuple(int(v) for v in t.split(",")) for t in os.environ["PMCE_SWEEP_SHAPES"].split(";")]
     lib = _lib.load()
     dev = torch.device("cuda")
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
