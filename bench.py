@@ -396,7 +396,7 @@ def main():
     roof = dominant_kernel_roofline(lib, dev, peaks, B)
     roof_ca = cross_attn_roofline(lib, eng, dev, peaks, B)
     big = cross_attn_roofline(lib, eng, dev, peaks, 256, nsets=4)      # BASELINE.json configs[2] batch: 3.5 items per CTA
-    roof_ca["at_B256"] = {k: big[k] for k in ("achieved", "frac", "us_per_launch", "achieved_kernel_io", "frac_kernel_io", "bytes_per_launch",
+    roof_ca["at_B256"] = {k: big[k] for k in ("achieved", "frac", "us_per_launch", "achieved_kernel_io", "frac_kernel_io", "bytes_per_launch", "embed_mode",
                                               "kernel_io_bytes_per_launch", "clips_per_launch")}
 
     roof_lbs = lbs_roofline(lib, dev, peaks) if rank == 0 else None
@@ -598,53 +598,65 @@ def spin_leg(lib, dev, peaks, cpu=False, frames=16):
 
 def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):
     """north_star's graded kernel: the fused vertex<-joint cross-attention (ca_vertex_fused_kernel, csrc/ca_fused.cuh), HBM-bound.
-    Timed alone with CUDA events over `nsets` rotating (xq, t) buffer sets whose total size exceeds the 126 MB L2, so every
-    launch streams its query rows from HBM. achieved = ALGORITHMIC bytes / time with SURVEY.md §8(d)'s per-clip figure for the
-    fused block (231,424 B: q/k/v streams in + q stream out + gamma/beta); `achieved_kernel_io` counts what this kernel's
-    contract really moves per clip (q in, q out, the per-clip folded operands KQ'|VP' in split-bf16 and sb' = 245,440 B)."""
+    Timed alone with CUDA events over `nsets` rotating buffer sets whose total size exceeds the 126 MB L2, so every launch
+    streams its query rows from HBM (`pmce_ca_vertex_fused`, the mode the forward runs); `embed_mode` = the opt-in variant that
+    builds the stream from the [B,431,3] coordinates (`pmce_ca_vertex_fused_embed`). achieved = ALGORITHMIC bytes / time with SURVEY.md
+    §8(d)'s per-clip figure for the fused block (231,424 B: q/k/v streams in + q stream out + gamma/beta);
+    `achieved_kernel_io` counts what the launch really moves per clip through HBM."""
     import ctypes as Ct
     import torch
     Vd, D = 431, 64
     P = lambda t: Ct.c_void_p(t.data_ptr())
-    st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
     gen = torch.Generator(device=dev).manual_seed(5)
     xq = [torch.randn(B, Vd, D, device=dev, generator=gen) for _ in range(nsets)]
+    coords = [torch.randn(B, Vd, 3, device=dev, generator=gen) * 0.3 for _ in range(nsets)]
     Kt = torch.randn(B, J, D, device=dev, generator=gen)
     Vt = torch.randn(B, J, D, device=dev, generator=gen)
     gb = torch.randn(B, lib.pmce_adaln_slots(), 2, D, device=dev, generator=gen)
-
     fold_ws = torch.empty(lib.pmce_ca_fold_bytes(B), dtype=torch.uint8, device=dev)
+    table_ws = torch.empty(Vd * D, device=dev)
 
-    def call(i, fold=0):
+    def call_inplace(i, fold=0):
         rc = lib.pmce_ca_vertex_fused(eng._dp, P(eng.weights), 1, P(xq[i]), P(Kt), P(Vt), P(gb), B, Ct.c_void_p(0), Ct.c_void_p(0), P(fold_ws), fold,
                                       Ct.c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0, lib.pmce_last_error()
-    call(0, fold=1)          # per-clip folded operands (a separate 64-CTA kernel in the forward), made once
-    for i in range(nsets):
-        call(i)
-    torch.cuda.synchronize(dev)
-    # one CUDA graph holding a full rotation over the buffer sets: the timed region is device time only, as in the forward
-    # (which replays a captured graph); eager launches from Python would be bounded by the host at this kernel size
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream())
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
-        st = Ct.c_void_p(side.cuda_stream)
-        with torch.cuda.graph(graph, stream=side):
-            for i in range(nsets):
-                call(i)          # in place: xq[i] keeps being updated (values stay finite: every pass re-normalises the row)
-    torch.cuda.current_stream().wait_stream(side)
-    graph.replay()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(rounds):
+
+    def call_embed(i, fold=0):
+        rc = lib.pmce_ca_vertex_fused_embed(eng._dp, P(eng.weights), 1, P(coords[i]), P(xq[i]), P(Kt), P(Vt), P(gb), B, P(fold_ws), fold, P(table_ws),
+                                            Ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, lib.pmce_last_error()
+
+    def timed(call):
+        call(0, fold=1)          # per-clip folded operands (+ the table): separate small kernels in the forward, made once here
+        for i in range(nsets):
+            call(i)
+        torch.cuda.synchronize(dev)
+        # one CUDA graph holding a full rotation over the buffer sets: the timed region is device time only, as in the forward
+        # (which replays a captured graph); eager launches from Python would be bounded by the host at this kernel size
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(nsets):
+                    call(i)      # in-place mode: xq[i] keeps being updated (values stay finite: every pass re-normalises the row)
+        torch.cuda.current_stream().wait_stream(side)
         graph.replay()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    sec = e0.elapsed_time(e1) * 1e-3 / (rounds * nsets)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(rounds):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) * 1e-3 / (rounds * nsets)
+
+    sec = timed(call_inplace)
+    sec_e = timed(call_embed)
     survey_bytes = ((J + Vd + Vd + J) * D * 4 + 2048) * B
-    io_bytes = (2 * Vd * D * 4 + 4 * (48 * 64 * 2) + 48 * 4) * B
+    folded = 4 * (48 * 64 * 2) + 48 * 4
+    io_bytes = (2 * Vd * D * 4 + folded) * B
+    io_e = (Vd * 3 * 4 + Vd * D * 4 + folded) * B                 # coordinates in, stream out, folded operands in (the table stays in L2)
     flops = (4 * 2 * Vd * J * 32 + 2 * 2 * Vd * D * D) * B       # attention core + Wq + Wp
     ach = survey_bytes / sec / 1e9
     return {"kernel": "ca_vertex_fused_kernel (AdaLN_q + Wq + scores + softmax + P.V + Wp + bias + residual in one pass over the query stream; "
@@ -653,6 +665,9 @@ def cross_attn_roofline(lib, eng, dev, peaks, B, nsets=16, rounds=6):
             "traffic": ncu_traffic("ca_vertex_fused_kernel", B), "traffic_unit": "B", "bytes_per_launch": survey_bytes, "us_per_launch": sec * 1e6,
             "achieved_kernel_io": io_bytes / sec / 1e9, "kernel_io_bytes_per_launch": io_bytes,
             "frac_kernel_io": io_bytes / sec / 1e9 / peaks["hbm_gbs"], "flops_per_launch": flops, "clips_per_launch": B,
+            "embed_mode": {"us_per_launch": sec_e * 1e6, "frac": survey_bytes / sec_e / 1e9 / peaks["hbm_gbs"], "kernel_io_bytes_per_launch": io_e,
+                           "note": "PMCE_CA_EMBED=1 (off by default): the kernel also embeds the coordinates and only WRITES the stream - half "
+                                   "the HBM bytes, slower: the kernel is latency / instruction bound, not byte bound"},
             "l2": f"{nsets} rotating buffer sets ({nsets * io_bytes / 1e6:.0f} MB) > 126 MB L2", "peak_source": peaks["source"]}
 
 

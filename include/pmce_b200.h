@@ -144,6 +144,18 @@ int pmce_ca_vertex_fused(const pmce_dims_t* dims, const void* weights, int block
                          const float* V, const float* gb, int B, void* t_hi, void* t_lo, void* fold_ws, int fold,
                          void* stream);
 
+/* The same kernel in EMBED mode (what pmce_forward / pmce_coevo_block run under PMCE_CA_EMBED=1; off by default because it
+ * measured slower, see api.cu::ca_embed_enabled): the vertex query stream of a block does not exist
+ * yet when the block starts - it is  xq[b,i,:] = W_e coords[b,i,:] + b_e + pos[i,:] + Q_embed[i,:]  (CoevoDecoder.py:178,182) -
+ * so the kernel takes coords [B,431,3], loads tiles of the per-block table E = b_e + pos + Q_embed [431,64] (shared by all
+ * clips, L2-resident) where it would load xq, adds the 3-term product per element, and WRITES xq_out [B,431,64]: no separate
+ * embedding launch and no read of the stream.  table_ws: 431*64 floats, 256-byte aligned; fold != 0 (re)computes the folded
+ * operands and the table, fold == 0 reuses them.  Same result as embedding first and calling pmce_ca_vertex_fused (up to the
+ * rounding order of the embedding's sums). */
+int pmce_ca_vertex_fused_embed(const pmce_dims_t* dims, const void* weights, int block, const float* coords, float* xq_out,
+                               const float* K, const float* V, const float* gb, int B, void* fold_ws, int fold,
+                               float* table_ws, void* stream);
+
 /* ---- a7: Block.forward, lib/models/CoevoDecoder.py:102-105 (Attention :119-131).  `which`: 0 = joint_SA_FFN (:166),
  * 1 = vertx_SA_FFN (:168).  x [B,N,64] -> out [B,N,64] (may alias x). */
 int pmce_self_attn_block(const pmce_dims_t* dims, const void* weights, int block, int which, const float* x,

@@ -52,6 +52,7 @@ SIGNATURES = {
     "pmce_cross_attn_block": (C.c_int, [_DP, _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_ca_fold_bytes": (C.c_size_t, [C.c_int]),
     "pmce_ca_vertex_fused": (C.c_int, [_DP, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, _P]),
+    "pmce_ca_vertex_fused_embed": (C.c_int, [_DP, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P]),
     "pmce_self_attn_block": (C.c_int, [_DP, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_mesh_epilogue": (C.c_int, [_DP, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "pmce_decoder_forward": (C.c_int, [_DP, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),

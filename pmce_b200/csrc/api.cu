@@ -90,6 +90,7 @@ struct Workspace {
     SplitOut Jf_s, Vf_s, tA_s, tA2_s, tB_s, tJ_s, tJ2_s, att_ds, hid_ds, attj_s, hidj_s, im2col_s;
     float* lc_mesh;
     CaFolded fold[3];                                  // per-clip folded operands of the fused vertex cross-attention, per block
+    float* etab[3];                                    // per block: E = b_e + vpos + vQ [Vd, 64], the embed-mode table of that kernel
     size_t bytes;
 };
 
@@ -127,6 +128,7 @@ Workspace carve(const pmce_dims_t& d, int B, void* base) {
         w.fold[k].kq_hi = kq.hi; w.fold[k].kq_lo = kq.lo; w.fold[k].vp_hi = vp.hi; w.fold[k].vp_lo = vp.lo;
         w.fold[k].sb = c.f32((size_t)B * CAF_NS);
     }
+    for (int k = 0; k < 3; ++k) w.etab[k] = c.f32(Vd * D);
     w.bytes = c.cur;
     return w;
 }
@@ -781,12 +783,12 @@ int ca_fold(const Weights& W, const CoevoW* cw, const CaW& w, const float* joint
 }
 
 // xq += proj(MHA(...)) in one pass (ca_fused.cuh); AdaLN_q's gamma/beta, the output bias and log2e are inside the folded operands
-int ca_fused_launch(float* xq, int N1, int N2, int B, const CaFolded& f, cudaStream_t st) {
+int ca_fused_launch(float* xq, int N1, int N2, int B, const CaFolded& f, cudaStream_t st, const CaEmbed* embed = nullptr) {
     CaFusedArgs a;
     memset(&a, 0, sizeof(a));
     a.B = B; a.N1 = N1; a.N2 = N2; a.eps = 1e-6f;
     count_launch();
-    const int rc = launch_ca_vertex_fused(xq, f, a, st);
+    const int rc = launch_ca_vertex_fused(xq, f, a, st, embed);
     if (rc) { pmce_set_error("ca_vertex_fused launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return 10; }
     return 0;
 }
@@ -794,12 +796,12 @@ int ca_fused_launch(float* xq, int N1, int N2, int B, const CaFolded& f, cudaStr
 // the query side of a CrossAttentionBlock: xq [B,N1,64] updated in place. Needs projected K / V in s.K / s.V, or (folded) the
 // folded operands in s.fold when the fused kernel applies.
 int cross_attn_query(const Weights& W, const CaW& w, int heads, float* xq, int N1, int N2, const float* gb, int B, const AttnScratch& s, bool folded,
-                     cudaStream_t st, const MlpTail& tail = MlpTail()) {
+                     cudaStream_t st, const MlpTail& tail = MlpTail(), const CaEmbed* embed = nullptr) {
     const int n1 = B * N1;
     if (ca_fused_ok(heads, N1, N2)) {
         if (!folded) RET(ca_fold(W, nullptr, w, nullptr, s.K, s.V, nullptr, gb, B, N2, heads, s.fold, st));
         // one pass over the query stream: AdaLN_q, scores, softmax, P V Wp, residual (ca_fused.cuh); then AdaLN_2 + Mlp (mlp_fused.cuh)
-        RET(ca_fused_launch(xq, N1, N2, B, s.fold, st));
+        RET(ca_fused_launch(xq, N1, N2, B, s.fold, st, embed));
         return adaln_mlp(W, w.s2, w.fc1w, w.fc1b, w.fc2w, w.fc2b, xq, s.tq, s.hid, gb, B, N1, tail, st);
     }
     RET(adaln(xq, B, N1, gb, w.sq, s.tq, st));
@@ -855,6 +857,32 @@ constexpr int JOINT_HEADS = 8, VERTX_HEADS = 2;      // CoevoDecoder.py:139-140
 
 bool coevo_fused(const pmce_dims_t& d) { return ca_fused_ok(VERTX_HEADS, d.num_vert_ds, d.num_joint) && d.num_joint <= JKV_ROWS; }
 
+// E tables of the embed-mode cross-attention kernel for blocks [k0, k0 + n): weights only, so pmce_forward makes them on the
+// image-feature stream
+int ca_embed_tables(const Layout& L, const Weights& W, int k0, int n, const Workspace& ws, cudaStream_t st) {
+    CaEmbedTableArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < n; ++i) {
+        const CoevoW& w = L.blk[k0 + i];
+        a.bias[i] = W.f + w.vprojb; a.pos[i] = W.f + w.vpos; a.q[i] = W.f + w.vQ; a.out[i] = ws.etab[k0 + i];
+    }
+    a.n = L.d.num_vert_ds;
+    ca_embed_table_kernel<<<dim3(cdiv(a.n * 64, 256), n), 256, 0, st>>>(a);
+    CKL();
+    return 0;
+}
+
+// PMCE_CA_EMBED=1: the vertex cross-attention kernel builds its query stream from the coordinates (embed mode, ca_fused.cuh) instead
+// of reading what a separate coevo_embed_kernel launch wrote. Parity-green, one launch and 110 KB/clip of HBM reads less - and
+// SLOWER (same box: kernel 22.9 -> 24.1 us at 256 clips, 70.4 -> 78.5 us at 1024; forward 24.7k -> 24.5k clips/s): the kernel is
+// bound by the instructions and latencies of its per-item chain, not by DRAM bytes, and the embedding adds ~350 of them per row.
+// Off by default; the measurement is the point.
+bool ca_embed_enabled() {
+    static int on = -1;
+    if (on < 0) on = pmce_env_int("PMCE_CA_EMBED", 0) ? 1 : 0;
+    return on == 1;
+}
+
 // prefolded: the folded operands of this block (ws.fold[k]) and, for block 3, the joint query stream ws.xqj were already made
 // by decoder_fold_all (the joint side of all three blocks depends only on the lifter's joints and on gb).
 int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, const float* verts_in, const float* gb, int B,
@@ -881,10 +909,15 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
         CKL();
         RET(proj64(ws.Jf_s, nj, W, w.j2vw, w.j2vb, ws.xkj, st, W.f + w.j2vK, J));
     }
-    coevo_embed_kernel<<<cdiv((long long)nv * 16, 256), 256, 0, st>>>(verts_in, nv, Vd, W.f + w.vprojw, W.f + w.vprojb, W.f + w.vpos, W.f + w.vQ,
-                                                                      ja ? ws.Vf : nullptr, ja ? ws.Vf_s : NO_SPLIT, ws.xqv);
-    CKL();
-    if (ja) RET(proj64(ws.Vf_s, nv, W, w.v2jw, w.v2jb, ws.xkv, st, W.f + w.v2jK, Vd));
+    // vertex query stream: in embed mode the cross-attention kernel builds it from the coordinates itself (ca_fused.cuh)
+    const bool emb = fused && ca_embed_enabled();
+    if (emb && !prefolded) RET(ca_embed_tables(L, W, k, 1, ws, st));
+    if (!emb) {
+        coevo_embed_kernel<<<cdiv((long long)nv * 16, 256), 256, 0, st>>>(verts_in, nv, Vd, W.f + w.vprojw, W.f + w.vprojb, W.f + w.vpos, W.f + w.vQ,
+                                                                          ja ? ws.Vf : nullptr, ja ? ws.Vf_s : NO_SPLIT, ws.xqv);
+        CKL();
+        if (ja) RET(proj64(ws.Vf_s, nv, W, w.v2jw, w.v2jb, ws.xkv, st, W.f + w.v2jK, Vd));
+    }
 
     if (ja) {
         // the joint branch only reads pre-update features: it runs on the side stream next to the vertex branch
@@ -893,6 +926,12 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
             CK(cudaEventRecord(aux->fork2, sj));
             CK(cudaStreamWaitEvent(aux->side, aux->fork2, 0));
             sj = aux->side;
+        }
+        if (emb) {      // the vertex FEATURES (keys / values of the joint cross-attention) are only needed here
+            coevo_embed_kernel<<<cdiv((long long)nv * 16, 256), 256, 0, sj>>>(verts_in, nv, Vd, W.f + w.vprojw, W.f + w.vprojb, W.f + w.vpos, nullptr,
+                                                                              ws.Vf, ws.Vf_s, nullptr);
+            CKL();
+            RET(proj64(ws.Vf_s, nv, W, w.v2jw, w.v2jb, ws.xkv, sj, W.f + w.v2jK, Vd));
         }
         const AttnScratch s = joint_scratch(ws);
         // joint cross-attention block: q = joints (J), k/v = vertices (431); 8 heads x 8; then joint self-attention
@@ -909,7 +948,8 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
     MlpTail tv_ca, tv_sa;
     tv_ca.epi = MLP_EPI_T; tv_ca.slot_next = w.vsa.s1; tv_ca.t = sv.tq;
     tv_sa.epi = MLP_EPI_F2C; tv_sa.f2cw = w.vf2cw; tv_sa.f2cb = w.vf2cb; tv_sa.coords_in = verts_in; tv_sa.coords_out = verts_out;
-    RET(cross_attn_query(W, w.vca, VERTX_HEADS, ws.xqv, Vd, J, gb, B, sv, fused, st, tv_ca));
+    CaEmbed ce{verts_in, ws.etab[k], W.f + w.vprojw};
+    RET(cross_attn_query(W, w.vca, VERTX_HEADS, ws.xqv, Vd, J, gb, B, sv, fused, st, tv_ca, emb ? &ce : nullptr));
     RET(self_attn_block(W, w.vsa, VERTX_HEADS, ws.xqv, Vd, gb, B, sv, st, true, tv_sa));
     if (ja && aux) CK(cudaStreamWaitEvent(st, aux->join2, 0));
     return 0;
@@ -957,6 +997,7 @@ int decoder_front(const Layout& L, const Weights& W, int B, int nfr, int fstride
     NvtxRange nvtx("pmce/image-feature stream (GRU + AdaLN gamma/beta + linear_cur)");
     RET(gru_mid(L, W, B, nfr, fstride, ws.g, ws, st, few));
     RET(adaln_gammabeta(L, W, ws.g, B, ws.gb, ws.g_s, st));
+    if (coevo_fused(L.d) && ca_embed_enabled()) RET(ca_embed_tables(L, W, 0, 3, ws, st));
     return mesh_residual(L, W, ws.g, B, ws, st);
 }
 
@@ -1105,6 +1146,32 @@ extern "C" int pmce_ca_vertex_fused(const pmce_dims_t* dims, const void* weights
         RET(adaln(xq, B, Vd, gb, w.s2, t, st));
     }
     return 0;
+}
+
+extern "C" int pmce_ca_vertex_fused_embed(const pmce_dims_t* dims, const void* weights, int block, const float* coords, float* xq_out,
+                                          const float* K, const float* V, const float* gb, int B, void* fold_ws, int fold, float* table_ws,
+                                          void* stream) {
+    GET_LAYOUT();
+    if (block < 1 || block > 3) { pmce_set_error("pmce_ca_vertex_fused_embed: block must be 1..3 (got %d)", block); return 2; }
+    if (!coords || !xq_out || !K || !V || !gb || !fold_ws || !table_ws || B < 1) { pmce_set_error("pmce_ca_vertex_fused_embed: bad argument"); return 2; }
+    if (((uintptr_t)fold_ws & 255) || ((uintptr_t)table_ws & 255)) { pmce_set_error("pmce_ca_vertex_fused_embed: fold_ws / table_ws must be 256-byte aligned"); return 2; }
+    const int J = dims->num_joint, Vd = dims->num_vert_ds;
+    if (!ca_vertex_fused_supported(VERTX_HEADS, J) || Vd < 128) { pmce_set_error("pmce_ca_vertex_fused_embed: unsupported shape (J=%d, Vd=%d)", J, Vd); return 3; }
+    const CoevoW& cw = L.blk[block - 1];
+    const CaW& w = cw.vca;
+    CaFolded f;
+    f.kq_hi = (bf16*)fold_ws; f.kq_lo = f.kq_hi + (size_t)B * CAF_NS * 64; f.vp_hi = f.kq_lo + (size_t)B * CAF_NS * 64;
+    f.vp_lo = f.vp_hi + (size_t)B * CAF_NS * 64; f.sb = (float*)(f.vp_lo + (size_t)B * CAF_NS * 64);
+    if (fold) {
+        RET(ca_fold(W, nullptr, w, nullptr, K, V, nullptr, gb, B, J, VERTX_HEADS, f, st));
+        CaEmbedTableArgs ta;
+        memset(&ta, 0, sizeof(ta));
+        ta.bias[0] = W.f + cw.vprojb; ta.pos[0] = W.f + cw.vpos; ta.q[0] = W.f + cw.vQ; ta.out[0] = table_ws; ta.n = Vd;
+        ca_embed_table_kernel<<<dim3(cdiv(Vd * 64, 256), 1), 256, 0, st>>>(ta);
+        CKL();
+    }
+    CaEmbed ce{coords, table_ws, W.f + cw.vprojw};
+    return ca_fused_launch(xq_out, Vd, J, B, f, st, &ce);
 }
 
 extern "C" int pmce_self_attn_block(const pmce_dims_t* dims, const void* weights, int block, int which, const float* x, const float* gb,

@@ -43,7 +43,8 @@ constexpr int CA_WT = CAF_NS * 128;                     // one operand tile [48]
 constexpr int CA_W = 4 * CA_WT;                         // KQ' hi | KQ' lo | VP' hi | VP' lo
 constexpr int CA_GBUF = CA_X + CA_W;                    // 56 KB per group (1024-byte aligned pieces)
 constexpr int CA_OFF_BAR = CA_G * CA_GBUF;
-constexpr int CA_SMEM = CA_OFF_BAR + 256 + 1024;        // barriers + alignment slack
+constexpr int CA_OFF_WE = CA_OFF_BAR + 256;             // W_e [64,3] of the embed mode (768 B)
+constexpr int CA_SMEM = CA_OFF_WE + 768 + 1024;         // barriers + W_e + alignment slack
 static_assert(CA_SMEM <= 227 * 1024, "shared memory");
 static_assert(CA_WT % 1024 == 0, "operand tiles must stay 1024-byte aligned");
 
@@ -91,13 +92,20 @@ struct CaFusedArgs {
     const float* sb;         // [B, 48] folded score bias sb' (log2 domain)
     int B, N1, N2, qtiles;
     float eps;
+    // embed mode (coords != nullptr): the query stream does not exist in memory yet - row i of clip b is
+    //   xq[b,i,:] = W_e coords[b,i,:] + E[i,:],  E = b_e + pos + Q_embed  (CoevoDecoder.py:178,182; E is one [N1,64] table per block)
+    // the kernel loads E tiles (shared by every clip: L2 hits) where it would load xq, adds the 3-term product per element and
+    // writes the updated stream to xq: the block's first pass over the vertex stream costs a write instead of write + read + write
+    const float* coords;     // [B, N1, 3] or nullptr (then xq is read and updated in place)
+    const float* we;         // W_e [64,3] (device): staged once per CTA in shared memory, read as 16-byte broadcasts
 };
 
 template <int NK>
 __global__ void __launch_bounds__(CA_THREADS, 1)
 ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_kq_hi,
                        const __grid_constant__ CUtensorMap tm_kq_lo, const __grid_constant__ CUtensorMap tm_vp_hi,
-                       const __grid_constant__ CUtensorMap tm_vp_lo, CaFusedArgs a) {
+                       const __grid_constant__ CUtensorMap tm_vp_lo, const __grid_constant__ CUtensorMap tm_e,
+                       CaFusedArgs a) {
     static_assert(NK <= CAF_MAXJ, "too many keys");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -115,6 +123,9 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     const int ntiles = a.B * a.qtiles;
     uint8_t* gptr = smem + g * CA_GBUF;
     const int tile0 = blockIdx.x + g * gridDim.x, tstep = CA_G * gridDim.x;       // this group's items
+    const bool embed = a.coords != nullptr;
+    float* s_we = reinterpret_cast<float*>(smem + CA_OFF_WE);
+    if (embed && tid < 192) s_we[tid] = a.we[tid];                                 // visible after the __syncthreads below
     if (leader) {
         tc::mbar_init(&in_full[g], 1); tc::mbar_init(&kq_full[g], 1); tc::mbar_init(&vp_full[g], 1); tc::mbar_init(&mma_bar[g], 1);
         tc::fence_barrier_init();
@@ -122,8 +133,8 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         if (tile0 < ntiles) {       // the group's first item is requested before TMEM is allocated and the CTA assembles
             const int b = tile0 / a.qtiles, row0 = (tile0 % a.qtiles) * 128;
             tc::mbar_arrive_expect_tx(&in_full[g], CA_X);
-            tc::tma_load_3d(gptr, &tm_x, &in_full[g], 0, row0, b);
-            tc::tma_load_3d(gptr + 16384, &tm_x, &in_full[g], 32, row0, b);
+            tc::tma_load_3d(gptr, embed ? &tm_e : &tm_x, &in_full[g], 0, row0, embed ? 0 : b);
+            tc::tma_load_3d(gptr + 16384, embed ? &tm_e : &tm_x, &in_full[g], 32, row0, embed ? 0 : b);
             tc::mbar_arrive_expect_tx(&kq_full[g], 2 * CA_WT);
             tc::tma_load_2d(gptr + CA_X, &tm_kq_hi, &kq_full[g], 0, b * CAF_NS);
             tc::tma_load_2d(gptr + CA_X + CA_WT, &tm_kq_lo, &kq_full[g], 0, b * CAF_NS);
@@ -151,6 +162,11 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         const int nb = has_next ? next / a.qtiles : 0, nrow0 = has_next ? (next % a.qtiles) * 128 : 0;
 
         // ---- the row: shared memory -> registers -> (a) the output accumulator (residual), (b) statistics, (c) A tiles in place ----
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+        if (embed && row0 + r < a.N1) {           // this row's coordinates: in flight while the tile arrives
+            const float* cp = a.coords + ((size_t)b * a.N1 + row0 + r) * 3;
+            p0 = __ldg(cp); p1 = __ldg(cp + 1); p2 = __ldg(cp + 2);
+        }
         tc::mbar_wait(&in_full[g], j & 1);
         float inv, nmi;
         {
@@ -159,6 +175,17 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             for (int c = 0; c < 16; ++c) {
                 const float4 v = tc::lds16(row_addr + (c >> 3) * 16384 + (((c & 7) ^ sw) << 4));
                 x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+            }
+            if (embed) {
+#pragma unroll
+                for (int c4 = 0; c4 < 16; ++c4) {          // 4 channels = 12 weights = three 16-byte broadcasts
+                    const float4 wa = *reinterpret_cast<const float4*>(s_we + 12 * c4), wb = *reinterpret_cast<const float4*>(s_we + 12 * c4 + 4),
+                                 wc = *reinterpret_cast<const float4*>(s_we + 12 * c4 + 8);
+                    x[4 * c4] += (wa.x * p0 + wa.y * p1) + wa.z * p2;
+                    x[4 * c4 + 1] += (wa.w * p0 + wb.x * p1) + wb.y * p2;
+                    x[4 * c4 + 2] += (wb.z * p0 + wb.w * p1) + wc.x * p2;
+                    x[4 * c4 + 3] += (wc.y * p0 + wc.z * p1) + wc.w * p2;
+                }
             }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -308,8 +335,8 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             tc::tma_store_wait_read<0>();         // the buffer has been read: the next item's rows may land in it
             if (has_next) {
                 tc::mbar_arrive_expect_tx(&in_full[g], CA_X);
-                tc::tma_load_3d(gptr, &tm_x, &in_full[g], 0, nrow0, nb);
-                tc::tma_load_3d(gptr + 16384, &tm_x, &in_full[g], 32, nrow0, nb);
+                tc::tma_load_3d(gptr, embed ? &tm_e : &tm_x, &in_full[g], 0, nrow0, embed ? 0 : nb);
+                tc::tma_load_3d(gptr + 16384, embed ? &tm_e : &tm_x, &in_full[g], 32, nrow0, embed ? 0 : nb);
             }
         }
     }
@@ -338,7 +365,7 @@ static inline int launch_ca_vertex_fused_t(const CUtensorMap* maps, const CaFuse
     const int ntiles = a.B * a.qtiles;
     const int cap = tc_num_sms();                      // one CTA per SM (225 KB of shared memory), CA_G items in flight each
     const int grid = ntiles < cap ? ntiles : cap;
-    ca_vertex_fused_kernel<NK><<<grid, CA_THREADS, CA_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], a);
+    ca_vertex_fused_kernel<NK><<<grid, CA_THREADS, CA_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
@@ -352,15 +379,42 @@ struct CaFolded {
     float* sb;
 };
 
-// xq [B, N1, 64] fp32, updated in place
-static inline int launch_ca_vertex_fused(float* xq, const CaFolded& f, CaFusedArgs a, cudaStream_t st) {
-    CUtensorMap maps[5];
+// Embed mode of the kernel: coords [B, N1, 3], table E [N1, 64] (made by ca_embed_table_kernel), we = W_e [64, 3]; all device memory
+struct CaEmbed {
+    const float* coords;
+    const float* table;
+    const float* we;         // [64, 3] device
+};
+
+// E[i][c] = (b_e[c] + pos[i][c]) + Q[i][c] for up to three blocks in one launch (grid.y = block)
+struct CaEmbedTableArgs {
+    const float *bias[3], *pos[3], *q[3];
+    float* out[3];
+    int n;                   // rows (N1)
+};
+__global__ void ca_embed_table_kernel(CaEmbedTableArgs a) {
+    const int k = blockIdx.y;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.n * 64) return;
+    a.out[k][idx] = (a.bias[k][idx & 63] + a.pos[k][idx]) + a.q[k][idx];
+}
+
+// xq [B, N1, 64] fp32: updated in place, or (embed != nullptr) written from the coordinates
+static inline int launch_ca_vertex_fused(float* xq, const CaFolded& f, CaFusedArgs a, cudaStream_t st, const CaEmbed* embed = nullptr) {
+    CUtensorMap maps[6];
     a.qtiles = (a.N1 + 127) / 128;
     a.sb = f.sb;
+    a.coords = nullptr;
+    if (embed) {
+        a.coords = embed->coords;
+        a.we = embed->we;
+        if (make_tmap_3d(&maps[5], embed->table, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 64, a.N1, 1, 64, 64LL * a.N1, 32, 128, 1)) return 1;
+    }
     if (make_tmap_3d(&maps[0], xq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 64, a.N1, a.B, 64, 64LL * a.N1, 32, 128, 1) ||
         make_tmap_bf16(&maps[1], f.kq_hi, a.B * CAF_NS, 64, 64, CAF_NS) || make_tmap_bf16(&maps[2], f.kq_lo, a.B * CAF_NS, 64, 64, CAF_NS) ||
         make_tmap_bf16(&maps[3], f.vp_hi, a.B * CAF_NS, 64, 64, CAF_NS) || make_tmap_bf16(&maps[4], f.vp_lo, a.B * CAF_NS, 64, 64, CAF_NS))
         return 1;
+    if (!embed) maps[5] = maps[0];
     if (a.N2 == 17) return launch_ca_vertex_fused_t<17>(maps, a, st);
     if (a.N2 == 19) return launch_ca_vertex_fused_t<19>(maps, a, st);
     return 4;

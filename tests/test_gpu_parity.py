@@ -138,6 +138,41 @@ def test_attention_blocks_vs_oracle(base, B):
         eng.cross_attn_block(1, 0, xs[0].cuda(), xs[1].cuda(), xs[1].cuda(), gb)
 
 
+@pytest.mark.parametrize("B", [2, 64])
+def test_ca_vertex_fused_embed_mode(base, lib, B):
+    """The cross-attention kernel in embed mode (coordinates in, query stream out: PMCE_CA_EMBED=1 in the forward) equals embedding with
+    torch (CoevoDecoder.py:178,182) and then running the same kernel in place on that stream (whose parity with the oracle is
+    test_attention_blocks_vs_oracle / test_coevo_blocks_vs_oracle)."""
+    import ctypes as C
+    from oracle import pmce_oracle as po
+    eng, sd = base["eng"], base["sd"]
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(23 + B)
+    J, Vd, D = 17, 431, 64
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = base["inter"]["g"][torch.arange(B) % 2].contiguous()
+    gb = eng.adaln_gammabeta(g.cuda())
+    for k in (1, 3):
+        p = f"pose_mesh_coevo.coevoblock{k}."
+        coords = (torch.randn(B, Vd, 3, generator=gen) * 0.4)
+        K = torch.randn(B, J, D, generator=gen)
+        V = torch.randn(B, J, D, generator=gen)
+        x_ref = po._lin(sd, p + "vertx_proj", coords) + sd[p + "vertx_pos_embed"] + sd[p + "v_Q_embed"]        # pmce_oracle.coevo_block
+        fold_ws = torch.empty(lib.pmce_ca_fold_bytes(B), dtype=torch.uint8, device=dev)
+        table_ws = torch.empty(Vd * D, device=dev)
+        x_in = x_ref.contiguous().cuda()
+        assert lib.pmce_ca_vertex_fused(eng._dp, P(eng.weights), k, P(x_in), P(K.cuda()), P(V.cuda()), P(gb), B, C.c_void_p(0), C.c_void_p(0),
+                                        P(fold_ws), 1, st) == 0, lib.pmce_last_error()
+        out = torch.empty(B, Vd, D, device=dev)
+        cc, Kc, Vc = coords.cuda(), K.cuda(), V.cuda()
+        assert lib.pmce_ca_vertex_fused_embed(eng._dp, P(eng.weights), k, P(cc), P(out), P(Kc), P(Vc), P(gb), B, P(fold_ws), 1, P(table_ws),
+                                              st) == 0, lib.pmce_last_error()
+        torch.cuda.synchronize()
+        scale = max(1.0, float(x_in.abs().max()))
+        assert _maxabs(out, x_in.cpu()) < 2e-5 * scale, k
+
+
 def test_mesh_epilogue_vs_oracle(base):
     import torch.nn.functional as F
     sd, inter = base["sd"], base["inter"]
@@ -439,6 +474,7 @@ def test_headline_configs_vs_oracle(assets_root, lib, J, C, T, B):
                                  {"PMCE_GRU_FEW_STEPS": "100"},
                                  {"PMCE_GRU_FEW": "6", "PMCE_GRU_FEW_STEPS": "7", "PMCE_GRU_FEW_U": "64"},
                                  {"PMCE_MLP_FUSED": "0", "PMCE_ATTN_ROWS": "0", "PMCE_CA_FUSED": "0"},
+                                 {"PMCE_CA_EMBED": "1"},
                                  {"PMCE_TC_DIRECT": "1", "PMCE_TC_NBUF": "2", "PMCE_TC_PAIR_RELAXED": "1"}])
 def test_alternative_paths_in_subprocess(env):
     """The opt-in / A-B variants stay parity-green: the persistent GRU layer kernel, the few-CTA GRU step kernel (all steps / the

@@ -17,4 +17,5 @@ lib = _lib.load()
 peaks = bench.load_peaks()
 for B in [int(v) for v in sys.argv[1:]] or [64, 256, 1024]:
     r = bench.cross_attn_roofline(lib, eng, dev, peaks, B, nsets=max(4, min(24, 16 * 64 // B)))
-    print(B, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items() if k in ("us_per_launch", "frac", "frac_kernel_io", "achieved")}, flush=True)
+    print(B, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items() if k in ("us_per_launch", "frac", "frac_kernel_io", "achieved")},
+          "embed mode:", {k: round(v, 3) for k, v in r["embed_mode"].items() if k in ("us_per_launch", "frac")}, flush=True)
