@@ -37,6 +37,8 @@
     } while (0)
 #define CKL() do { count_launch(); CK(cudaGetLastError()); } while (0)
 #define CKG(expr) do { count_launch(); CK(expr); } while (0)
+// kernel launch with programmatic stream serialisation (host_once.h pmce_launch): the kernel calls pdl_wait() / pdl_enter()
+#define PLAUNCH(kernel, grid, block, smem, st, ...) CKG(pmce_launch(kernel, dim3(grid), dim3(block), smem, st, 0, __VA_ARGS__))
 #define RET(x) do { int _r = (x); if (_r) return _r; } while (0)
 
 // NVTX ranges (header-only NVTX3; a no-op unless a profiler is attached) around the stages of the forward, so nsys / ncu
@@ -187,8 +189,7 @@ int linear_tc(const SplitOut& A, int lda, int M, int K, const Weights& W, size_t
 }
 
 int split_rows(const float* x, int rows, int cols, int ld, bool relu, const SplitOut& o, int ld_out, cudaStream_t st) {
-    split_rows_kernel<<<cdiv((long long)rows * (cols / 4), 256), 256, 0, st>>>(x, rows, cols, ld, relu ? 1 : 0, o.hi, o.lo, ld_out);
-    CKL();
+    PLAUNCH(split_rows_kernel, cdiv((long long)rows * (cols / 4), 256), 256, 0, st, x, rows, cols, ld, relu ? 1 : 0, o.hi, o.lo, ld_out);
     return 0;
 }
 
@@ -201,8 +202,7 @@ int launch_attn_d(const float* Q, AttnAddr aq, const float* K, const float* V, A
     const int threads = N1 >= 128 ? 128 : (N1 > 64 ? 96 : (N1 > 32 ? 64 : 32));
     if (nseq > 65535) { pmce_set_error("too many attention sequences (%d) for one launch", nseq); return 3; }
     dim3 grid(cdiv(N1, threads), H, nseq);
-    attn_kernel<D><<<grid, threads, smem, st>>>(Q, aq, K, V, akv, O, Os, ao, N1, N2, 1.0f / sqrtf((float)D));
-    CKL();
+    PLAUNCH(attn_kernel<D>, grid, threads, smem, st, Q, aq, K, V, akv, O, Os, ao, N1, N2, 1.0f / sqrtf((float)D));
     return 0;
 }
 
@@ -240,18 +240,16 @@ int ln_rows(const float* x, int nrows, int C, const LnParams* a, const float* po
     LnParams za{nullptr, nullptr, 0.f};
     const int nv = C / 128;
     const dim3 grid(cdiv(nrows, 8));
-#define LN_LAUNCH(MV) ln_rows_kernel<MV><<<grid, 256, 0, st>>>(x, nrows, C, a ? *a : za, a ? 1 : 0, pos, pos_div, pos_mod, out1, b ? *b : za, nullptr, \
-                                                          b ? out2s : NO_SPLIT, map_rows, map_stride)
+#define LN_LAUNCH(MV) PLAUNCH(ln_rows_kernel<MV>, grid, 256, 0, st, x, nrows, C, a ? *a : za, a ? 1 : 0, pos, pos_div, pos_mod, out1, b ? *b : za, nullptr, \
+                              b ? out2s : NO_SPLIT, map_rows, map_stride)
     if (nv <= 1) LN_LAUNCH(1); else if (nv <= 2) LN_LAUNCH(2); else if (nv <= 4) LN_LAUNCH(4); else LN_LAUNCH(8);
 #undef LN_LAUNCH
-    CKL();
     return 0;
 }
 
 int adaln(const float* x, int B, int ntok, const float* gb, int slot, const SplitOut& ys, cudaStream_t st) {
     const int nrows = B * ntok;
-    adaln_apply_kernel<<<cdiv(nrows, 8), 256, 0, st>>>(x, nrows, ntok, gb, PMCE_ADALN_SLOTS * 128, slot, 1e-6f, nullptr, ys);
-    CKL();
+    PLAUNCH(adaln_apply_kernel, cdiv(nrows, 8), 256, 0, st, x, nrows, ntok, gb, PMCE_ADALN_SLOTS * 128, slot, 1e-6f, nullptr, ys);
     return 0;
 }
 
@@ -329,13 +327,12 @@ int lifter(const Layout& L, const Weights& W, const float* pose2d, int B, int nf
     const int nvc = C / 128;
 #define ROWK_LAUNCH(KERNEL, GRID, ...)                                            \
     do {                                                                           \
-        if (nvc <= 1) KERNEL<1><<<GRID, 256, 0, st>>>(__VA_ARGS__);                \
-        else if (nvc <= 2) KERNEL<2><<<GRID, 256, 0, st>>>(__VA_ARGS__);           \
-        else if (nvc <= 4) KERNEL<4><<<GRID, 256, 0, st>>>(__VA_ARGS__);           \
-        else KERNEL<8><<<GRID, 256, 0, st>>>(__VA_ARGS__);                         \
+        if (nvc <= 1) PLAUNCH(KERNEL<1>, GRID, 256, 0, st, __VA_ARGS__);           \
+        else if (nvc <= 2) PLAUNCH(KERNEL<2>, GRID, 256, 0, st, __VA_ARGS__);      \
+        else if (nvc <= 4) PLAUNCH(KERNEL<4>, GRID, 256, 0, st, __VA_ARGS__);      \
+        else PLAUNCH(KERNEL<8>, GRID, 256, 0, st, __VA_ARGS__);                    \
     } while (0)
     ROWK_LAUNCH(lifter_embed_kernel, cdiv(nfr * J, 8), pose2d, ws.imgemb, W.f + L.jew, W.f + L.jeb, W.f + L.spos, nfr * J, J, C, s0n1, ws.x, nullptr, ws.xn_s);
-    CKL();
     LnParams ns{W.f + L.nsw, W.f + L.nsb, 1e-6f}, nt{W.f + L.ntw, W.f + L.ntb, 1e-6f};
     for (int i = 0; i < d.depth; ++i) {
         RET(vit_block(d, W, L.sp[i], ws, i == 0 ? nfr : B * T, false, st));
@@ -357,9 +354,7 @@ int lifter(const Layout& L, const Weights& W, const float* pose2d, int B, int nf
     LnParams nh{W.f + L.r0w, W.f + L.r0b, 1e-5f};
     ROWK_LAUNCH(lifter_head_kernel, cdiv(N, 8), ws.x, N, C, nt, nh, W.f + L.r1w, W.f + L.r1b, ws.r3);
 #undef ROWK_LAUNCH
-    CKL();
-    lifter_fuse_kernel<<<cdiv(B * J * 3, 256), 256, 0, st>>>(ws.r3, W.f + L.fusw, W.f + L.fusb, B, T, J, pose3d, ws.joints_m);
-    CKL();
+    PLAUNCH(lifter_fuse_kernel, cdiv(B * J * 3, 256), 256, 0, st, ws.r3, W.f + L.fusw, W.f + L.fusb, B, T, J, pose3d, ws.joints_m);
     return 0;
 }
 
@@ -458,8 +453,7 @@ int gru_step(const GruStep* s, int ndir, const Weights& W, int B, int H, int few
     }
     if (!s[0].d.hprev) {   // first step of both directions (they always start together)
         dim3 grid(H / 16, cdiv(B, 64), ndir);
-        gru_step_kernel<<<grid, 256, 0, st>>>(s[0].d, s[ndir > 1 ? 1 : 0].d, B, H);
-        CKL();
+        PLAUNCH(gru_step_kernel, grid, 256, 0, st, s[0].d, s[ndir > 1 ? 1 : 0].d, B, H);
         return 0;
     }
     GruTcMaps maps[2];
@@ -476,8 +470,7 @@ int gru_step(const GruStep* s, int ndir, const Weights& W, int B, int H, int few
     }
     if (!pmce_configure_smem<gru_step_tc_kernel>(GRU_SMEM)) { pmce_set_error("gru_step: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); return 10; }
     dim3 grid(H / GRU_U, ndir, cdiv(B, 128));
-    gru_step_tc_kernel<<<grid, 192, GRU_SMEM, st>>>(maps[0], maps[1], dirs[0], dirs[1], B, H);
-    CKL();
+    PLAUNCH(gru_step_tc_kernel, grid, 192, GRU_SMEM, st, maps[0], maps[1], dirs[0], dirs[1], B, H);
     return 0;
 }
 
@@ -694,8 +687,7 @@ int adaln_mlp(const Weights& W, int s2, size_t fc1w, size_t fc1b, size_t fc2w, s
     { EpiOpt o; o.bias = W.f + fc1b; o.act = 1; o.outs = hid; o.ld_split = 256; RET(linear_tc(tmp, 64, M, 64, W, fc1w, 64, 256, o, st)); }
     { EpiOpt o; o.bias = W.f + fc2b; o.resid = x; o.ld_resid = 64; o.out = x; o.ld_out = 64; RET(linear_tc(hid, 256, M, 256, W, fc2w, 256, 64, o, st)); }
     if (tail.epi == MLP_EPI_F2C) {
-        feat2coor_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, M, W.f + tail.f2cw, W.f + tail.f2cb, tail.coords_in, tail.coords_out);
-        CKL();
+        PLAUNCH(feat2coor_kernel, cdiv(M, 8), 256, 0, st, x, M, W.f + tail.f2cw, W.f + tail.f2cb, tail.coords_in, tail.coords_out);
     } else if (tail.epi == MLP_EPI_T) {
         RET(adaln(x, B, ntok, gb, tail.slot_next, tail.t, st));
     }
@@ -769,8 +761,7 @@ JointFoldArgs ca_fold_args(const Weights& W, const CoevoW* cw, const CaW& w, con
 
 int ca_fold_launch(const JointFoldArgs3& args, int nblk, int B, cudaStream_t st) {
     if (!pmce_configure_smem<ca_joint_fold_kernel>(JKV_SMEM)) { pmce_set_error("ca_fold: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); return 10; }
-    ca_joint_fold_kernel<<<dim3(B, nblk), JKV_THREADS, JKV_SMEM, st>>>(args);
-    CKL();
+    PLAUNCH(ca_joint_fold_kernel, dim3(B, nblk), JKV_THREADS, JKV_SMEM, st, args);
     return 0;
 }
 
@@ -904,19 +895,16 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
         // the whole joint side of the vertex cross-attention (embed, key projection, AdaLN_k/v, Wk/Wv, fold) per clip in one kernel
         if (!prefolded) RET(ca_fold(W, &w, w.vca, joints, nullptr, nullptr, ja ? ws.xqj : nullptr, gb, B, J, VERTX_HEADS, sv.fold, st));
     } else {
-        coevo_embed_kernel<<<cdiv((long long)nj * 16, 256), 256, 0, st>>>(joints, nj, J, W.f + w.jprojw, W.f + w.jprojb, W.f + w.jpos,
-                                                                          ja ? W.f + w.jQ : nullptr, ws.Jf, ws.Jf_s, ja ? ws.xqj : nullptr);
-        CKL();
+        PLAUNCH(coevo_embed_kernel, cdiv((long long)nj * 16, 256), 256, 0, st, joints, nj, J, W.f + w.jprojw, W.f + w.jprojb, W.f + w.jpos,
+                ja ? W.f + w.jQ : nullptr, ws.Jf, ws.Jf_s, ja ? ws.xqj : nullptr);
         RET(proj64(ws.Jf_s, nj, W, w.j2vw, w.j2vb, ws.xkj, st, W.f + w.j2vK, J));
     }
     // vertex query stream: in embed mode the cross-attention kernel builds it from the coordinates itself (ca_fused.cuh)
     const bool emb = fused && ca_embed_enabled();
     if (emb && !prefolded) RET(ca_embed_tables(L, W, k, 1, ws, st));
     if (!emb) {
-        coevo_embed_kernel<<<cdiv((long long)nv * 16, 256), 256, 0, st>>>(verts_in, nv, Vd, W.f + w.vprojw, W.f + w.vprojb, W.f + w.vpos, W.f + w.vQ,
-                                                                          ja ? ws.Vf : nullptr, ja ? ws.Vf_s : NO_SPLIT, ws.xqv);
-        CKL();
-        if (ja) RET(proj64(ws.Vf_s, nv, W, w.v2jw, w.v2jb, ws.xkv, st, W.f + w.v2jK, Vd));
+        PLAUNCH(coevo_embed_kernel, cdiv((long long)nv * 16, 256), 256, 0, st, verts_in, nv, Vd, W.f + w.vprojw, W.f + w.vprojb, W.f + w.vpos, W.f + w.vQ,
+                ja ? ws.Vf : nullptr, ja ? ws.Vf_s : NO_SPLIT, ws.xqv);
     }
 
     if (ja) {
@@ -928,11 +916,12 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
             sj = aux->side;
         }
         if (emb) {      // the vertex FEATURES (keys / values of the joint cross-attention) are only needed here
-            coevo_embed_kernel<<<cdiv((long long)nv * 16, 256), 256, 0, sj>>>(verts_in, nv, Vd, W.f + w.vprojw, W.f + w.vprojb, W.f + w.vpos, nullptr,
-                                                                              ws.Vf, ws.Vf_s, nullptr);
-            CKL();
-            RET(proj64(ws.Vf_s, nv, W, w.v2jw, w.v2jb, ws.xkv, sj, W.f + w.v2jK, Vd));
+            PLAUNCH(coevo_embed_kernel, cdiv((long long)nv * 16, 256), 256, 0, sj, verts_in, nv, Vd, W.f + w.vprojw, W.f + w.vprojb, W.f + w.vpos, nullptr,
+                    ws.Vf, ws.Vf_s, nullptr);
         }
+        // keys of the joint cross-attention: proj_v2j(Vf) + v2j_K. Only the joint branch reads them, so the projection (a
+        // row-embedding epilogue: the direct-store path, 38 us at 64 clips) stays off the vertex branch's stream
+        RET(proj64(ws.Vf_s, nv, W, w.v2jw, w.v2jb, ws.xkv, sj, W.f + w.v2jK, Vd));
         const AttnScratch s = joint_scratch(ws);
         // joint cross-attention block: q = joints (J), k/v = vertices (431); 8 heads x 8; then joint self-attention
         MlpTail tj_ca, tj_sa;                                  // the Mlp kernels also produce the next AdaLN / the coordinates
@@ -951,7 +940,7 @@ int coevo_block(const Layout& L, const Weights& W, int k, const float* joints, c
     CaEmbed ce{verts_in, ws.etab[k], W.f + w.vprojw};
     RET(cross_attn_query(W, w.vca, VERTX_HEADS, ws.xqv, Vd, J, gb, B, sv, fused, st, tv_ca, emb ? &ce : nullptr));
     RET(self_attn_block(W, w.vsa, VERTX_HEADS, ws.xqv, Vd, gb, B, sv, st, true, tv_sa));
-    if (ja && aux) CK(cudaStreamWaitEvent(st, aux->join2, 0));
+    // with a side stream the CALLER joins (aux->join2): decoder_back puts the up-sampling before the join
     return 0;
 }
 
@@ -974,8 +963,7 @@ int mesh_residual(const Layout& L, const Weights& W, const float* g, int B, cons
 int mesh_upsample(const Layout& L, const Weights& W, const float* verts3, int B, float* mesh, const Workspace& ws, cudaStream_t st) {
     const pmce_dims_t& d = L.d;
     const int Vd = d.num_vert_ds, V = d.num_vert, ldk = L.ups_ld;
-    upsample_im2col_kernel<<<cdiv((long long)B * 3 * ldk, 256), 256, 0, st>>>(verts3, B, Vd, ldk, nullptr, ws.im2col_s);
-    CKL();
+    PLAUNCH(upsample_im2col_kernel, cdiv((long long)B * 3 * ldk, 256), 256, 0, st, verts3, B, Vd, ldk, nullptr, ws.im2col_s);
     EpiOpt o; o.bias = W.f + L.ups_b; o.out = mesh; o.resid = ws.lc_mesh; o.mapped = true;
     o.rmap.div = 3; o.rmap.s0 = (long long)V * 3; o.rmap.s1 = 1;
     o.cmap.div = 1; o.cmap.s0 = 3; o.cmap.s1 = 0;
@@ -1007,8 +995,7 @@ int decoder_back(const Layout& L, const Weights& W, const float* joints, const i
     const pmce_dims_t& d = L.d;
     const int J = d.num_joint, Vd = d.num_vert_ds;
     float* v0 = verts0_out ? verts0_out : ws.verts[2];
-    gather_verts_kernel<<<cdiv((long long)B * Vd * 3, 256), 256, 0, st>>>(joints, vj, B, J, Vd, v0);
-    CKL();
+    PLAUNCH(gather_verts_kernel, cdiv((long long)B * Vd * 3, 256), 256, 0, st, joints, vj, B, J, Vd, v0);
     const bool pre = coevo_fused(d);
     if (pre) {   // every block reads the SAME joints (CoevoDecoder.py:235-237 pass P, not P^k): one launch makes all three joint sides
         JointFoldArgs3 args;
@@ -1021,6 +1008,7 @@ int decoder_back(const Layout& L, const Weights& W, const float* joints, const i
     RET(coevo_block(L, W, 1, joints, ws.verts[0], ws.gb, B, nullptr, ws.verts[1], ws, st, nullptr, pre));
     RET(coevo_block(L, W, 2, joints, ws.verts[1], ws.gb, B, cam_pose, ws.verts[0], ws, st, aux, pre));
     RET(mesh_upsample(L, W, ws.verts[0], B, cam_mesh, ws, st));
+    if (aux) CK(cudaStreamWaitEvent(st, aux->join2, 0));     // block 3's joint branch (cam_pose) ran beside the vertex branch and the up-sampling
     return 0;
 }
 

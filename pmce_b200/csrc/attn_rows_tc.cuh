@@ -81,6 +81,8 @@ attn_rows_tc_kernel(const __grid_constant__ CUtensorMap tm_att, SplitOut Os, Att
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t tS = tmem_base, tD = tmem_base + AR_MAXK;
+    pdl_trigger();
+    pdl_wait();          // the prologue above overlapped the previous kernel; its outputs are visible from here
 
     const int qtiles = (N1 + 127) / 128;
     const int nchunks = (N2 + 127) / 128;                                   // <= 4 (N2 <= 448)
@@ -247,6 +249,6 @@ static inline int launch_attn_rows_tc(const __nv_bfloat16* att, SplitOut Os, Att
     const long long work = (long long)nseq * H * ((N + 127) / 128);
     const int sms = tc_num_sms();
     const int grid = (int)(work < sms ? (work < 1 ? 1 : work) : sms);
-    attn_rows_tc_kernel<<<grid, AR_THREADS, AR_SMEM, st>>>(tm, Os, ao, N, N, nseq, H);
+    if (pmce_launch(attn_rows_tc_kernel, dim3(grid), dim3(AR_THREADS), AR_SMEM, st, 0, tm, Os, ao, N, N, nseq, H) != cudaSuccess) return 3;
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }

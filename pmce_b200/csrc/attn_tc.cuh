@@ -90,6 +90,8 @@ attn_tile_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     const int ntiles = (nseq + G - 1) / G;
+    pdl_trigger();
+    pdl_wait();          // the prologue above overlapped the previous kernel; its outputs are visible from here
     const int nwork = ntiles * H;
     // this CTA's items: work = blockIdx.x + n * gridDim.x, n = 0, 1, ...; item n belongs to group n & 1
 
@@ -329,6 +331,7 @@ static inline int launch_attn_tile_tc(const __nv_bfloat16* qkv_hi, const __nv_bf
     const int grid = (int)(want < sms ? (want < 1 ? 1 : want) : sms);
     static int dbg = -1;   // PMCE_ATTN_DEBUG: profiling knobs (wrong results): 1 no loads, 2 no math, 4 no softmax, 8 no stores
     if (dbg < 0) dbg = pmce_profiling_knob("PMCE_ATTN_DEBUG");
-    attn_tile_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(th, tl, toh, tol, temporal ? 1 : 0, C, J, T, L, G, nseq, H, 1.0f / sqrtf(64.0f), dbg);
+    if (pmce_launch(attn_tile_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, 0, th, tl, toh, tol, temporal ? 1 : 0, C, J, T, L, G, nseq, H,
+                    1.0f / sqrtf(64.0f), dbg) != cudaSuccess) return 3;
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }

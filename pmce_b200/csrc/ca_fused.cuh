@@ -130,7 +130,11 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         tc::mbar_init(&in_full[g], 1); tc::mbar_init(&kq_full[g], 1); tc::mbar_init(&vp_full[g], 1); tc::mbar_init(&mma_bar[g], 1);
         tc::fence_barrier_init();
         tc::fence_proxy_async();
-        if (tile0 < ntiles) {       // the group's first item is requested before TMEM is allocated and the CTA assembles
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_ptr_smem, CA_G * 128);
+    if (leader) {
+        pdl_wait();                 // x and the folded operands are the previous kernels' outputs
+        if (tile0 < ntiles) {       // the group's first item is requested before the CTA assembles
             const int b = tile0 / a.qtiles, row0 = (tile0 % a.qtiles) * 128;
             tc::mbar_arrive_expect_tx(&in_full[g], CA_X);
             tc::tma_load_3d(gptr, embed ? &tm_e : &tm_x, &in_full[g], 0, row0, embed ? 0 : b);
@@ -143,11 +147,12 @@ ca_vertex_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             tc::tma_load_2d(gptr + CA_X + 3 * CA_WT, &tm_vp_lo, &vp_full[g], 0, b * CAF_NS);
         }
     }
-    if (warp == 0) tc::tmem_alloc(tmem_ptr_smem, CA_G * 128);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_trigger();
+    pdl_wait();
 
     const uint32_t s_x = sbase + g * CA_GBUF, s_ahi = s_x, s_alo = s_x + AT_TILE, s_w = s_x + CA_X;
     const uint32_t tS = tmem_base + g * 128, tO = tS + 64;
@@ -365,8 +370,8 @@ static inline int launch_ca_vertex_fused_t(const CUtensorMap* maps, const CaFuse
     const int ntiles = a.B * a.qtiles;
     const int cap = tc_num_sms();                      // one CTA per SM (225 KB of shared memory), CA_G items in flight each
     const int grid = ntiles < cap ? ntiles : cap;
-    ca_vertex_fused_kernel<NK><<<grid, CA_THREADS, CA_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a);
-    return cudaGetLastError() == cudaSuccess ? 0 : 3;
+    return pmce_launch(ca_vertex_fused_kernel<NK>, dim3(grid), dim3(CA_THREADS), CA_SMEM, st, 0, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a)
+                   == cudaSuccess ? 0 : 3;
 }
 
 // true when the fused kernel covers (heads, keys): the reference's vertex stream has 2 heads; 17 (h36m) / 19 (coco) joints
@@ -513,6 +518,7 @@ ca_joint_fold_kernel(const __grid_constant__ JointFoldArgs3 args) {
     } else {
         jkv_stage_weight(a.wq, Wq, tid); jkv_stage_weight(a.wp, Wp, tid); cp_async_commit();
     }
+    pdl_enter();          // the weights (constants) are already in flight; joints / K / V / gamma-beta are other kernels' outputs
     if (a.joints) {
         const float* P = a.joints + (size_t)b * J * 3;
         {

@@ -6,6 +6,17 @@
 
 #define PMCE_WARP 32
 
+// Programmatic dependent launch (PDL): every kernel of the forward is launched with programmatic stream serialisation
+// (host_once.h pmce_launch), so its CTAs may be scheduled - and run their prologue: barrier init, TMEM allocation, descriptor
+// prefetch - while the previous kernel of the stream is still draining. pdl_wait() blocks until that kernel has COMPLETED and
+// its writes are visible; nothing before it may touch global memory another kernel writes or reads-then-overwrites.
+// EVERY kernel launched through pmce_launch must execute pdl_wait() (completion is transitive only through it), and kernels
+// that allocate TMEM call pdl_trigger() only after the allocation (a dependent CTA that lands on the same SM and takes the
+// columns first would otherwise block this CTA's allocation for ever). Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }     // kernels without a prologue worth overlapping
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

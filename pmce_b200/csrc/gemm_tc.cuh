@@ -164,6 +164,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (NCTA == 2 || CL > 1) tc::cluster_sync_all();     // the peers' barriers are initialised before anything signals them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_trigger();      // TMEM is ours: the next kernel's CTAs may be scheduled behind this one
+    pdl_wait();         // everything above overlapped the previous kernel's tail; its outputs (A, residual) are visible from here
 
     if (warp == 0) {
         if (lane == 0) {
@@ -414,6 +416,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // fp32 [rows, cols] (ld) -> bf16 hi / lo [rows, ld_out]; optional relu on the way (linear_cur input).
 __global__ void split_rows_kernel(const float* __restrict__ x, int rows, int cols, int ld, int relu, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, int ld_out) {
+    pdl_enter();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per 4 elements
     const int c4 = cols / 4;
     if (idx >= (size_t)rows * c4) return;
@@ -519,14 +522,8 @@ static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap
         if (!pmce_configure_smem<linear_tc_kernel<BNP, MODE, 1, 1, TC_CL>>(K4::SMEM_BYTES)) return 2;
         const long long tiles = (long long)((N + 255) / 256) * (((M + TC_BM - 1) / TC_BM + TC_CL - 1) / TC_CL);
         const int clusters = (int)(tiles < tc_num_sms() / TC_CL ? tiles : tc_num_sms() / TC_CL);
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(TC_CL * clusters); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = K4::SMEM_BYTES; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = TC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 1, 1, TC_CL>, ta[0], ta[1], tw[4], tw[5], om, M, N, K, e) == cudaSuccess ? 0 : 3;
+        return pmce_launch(linear_tc_kernel<BNP, MODE, 1, 1, TC_CL>, dim3(TC_CL * clusters), dim3(TC_THREADS), K4::SMEM_BYTES, st, TC_CL,
+                           ta[0], ta[1], tw[4], tw[5], om, M, N, K, e) == cudaSuccess ? 0 : 3;
     }
     if (BN == 256 && tc_pair_enabled(M, N, K)) {
         constexpr int BNP = BN == 256 ? 256 : 256;
@@ -534,27 +531,20 @@ static inline int launch_linear_tc_mode(const CUtensorMap* ta, const CUtensorMap
         if (nbuf < 0) nbuf = pmce_env_int("PMCE_TC_NBUF", 1);
         const long long tiles = (long long)((N + 255) / 256) * ((M + 2 * TC_BM - 1) / (2 * TC_BM));
         const int pairs = tc_balanced_grid(tiles, (tc_num_sms() - tc_sm_reserve) / 2);
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
         if (nbuf == 2 && MODE != TC_GENERIC && MODE != TC_NULL) {
             if (!pmce_configure_smem<linear_tc_kernel<BNP, MODE, 2, 2>>(TcCfg<BNP, 2, 2>::SMEM_BYTES)) return 2;
-            cfg.dynamicSmemBytes = TcCfg<BNP, 2, 2>::SMEM_BYTES;
-            return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 2, 2>, ta[0], ta[1], tw[2], tw[3], om, M, N, K, e) == cudaSuccess ? 0 : 3;
+            return pmce_launch(linear_tc_kernel<BNP, MODE, 2, 2>, dim3(2 * pairs), dim3(TC_THREADS), TcCfg<BNP, 2, 2>::SMEM_BYTES, st, 2,
+                               ta[0], ta[1], tw[2], tw[3], om, M, N, K, e) == cudaSuccess ? 0 : 3;
         }
         if (!pmce_configure_smem<linear_tc_kernel<BNP, MODE, 2>>(TcCfg<BNP, 2>::SMEM_BYTES)) return 2;
-        cfg.dynamicSmemBytes = TcCfg<BNP, 2>::SMEM_BYTES;
-        return cudaLaunchKernelEx(&cfg, linear_tc_kernel<BNP, MODE, 2>, ta[0], ta[1], tw[2], tw[3], om, M, N, K, e) == cudaSuccess ? 0 : 3;
+        return pmce_launch(linear_tc_kernel<BNP, MODE, 2>, dim3(2 * pairs), dim3(TC_THREADS), TcCfg<BNP, 2>::SMEM_BYTES, st, 2,
+                           ta[0], ta[1], tw[2], tw[3], om, M, N, K, e) == cudaSuccess ? 0 : 3;
     }
     if (!pmce_configure_smem<linear_tc_kernel<BN, MODE, 1>>(TcCfg<BN>::SMEM_BYTES)) return 2;
     const long long tiles = (long long)((N + BN - 1) / BN) * ((M + TC_BM - 1) / TC_BM);
     const int grid = tc_balanced_grid(tiles, tc_num_sms() - tc_sm_reserve);
-    linear_tc_kernel<BN, MODE, 1><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta[0], ta[1], tw[0], tw[1], om, M, N, K, e);
-    return cudaGetLastError() == cudaSuccess ? 0 : 3;
+    return pmce_launch(linear_tc_kernel<BN, MODE, 1>, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES, st, 0,
+                       ta[0], ta[1], tw[0], tw[1], om, M, N, K, e) == cudaSuccess ? 0 : 3;
 }
 
 template <int BN>

@@ -60,24 +60,38 @@ gru_step_tc_kernel(const __grid_constant__ GruTcMaps m0_, const __grid_constant_
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_trigger();
+    if (threadIdx.x != 0) pdl_wait();   // the producer first requests the W_hh tiles of the ring's first pass (constants)
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % GRU_STAGES;
-                const uint32_t ph = (kb / GRU_STAGES) & 1;
-                tc::mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* st = smem + s * GRU_STAGE;
-                tc::mbar_arrive_expect_tx(&full_bar[s], GRU_STAGE);
-                tc::tma_load_2d(st, &mp.h_hi, &full_bar[s], kb * 64, b0);
-                tc::tma_load_2d(st + GRU_A_TILE, &mp.h_lo, &full_bar[s], kb * 64, b0);
-                uint8_t* wh = st + 2 * GRU_A_TILE;
+            auto load_w = [&](int kb, int s) {
+                uint8_t* wh = smem + s * GRU_STAGE + 2 * GRU_A_TILE;
                 uint8_t* wl = wh + GRU_W_TILE;
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
                     tc::tma_load_2d(wh + g * GRU_U * 128, &mp.w_hi, &full_bar[s], kb * 64, g * H + j0);
                     tc::tma_load_2d(wl + g * GRU_U * 128, &mp.w_lo, &full_bar[s], kb * 64, g * H + j0);
                 }
+            };
+            auto load_h = [&](int kb, int s) {
+                uint8_t* st = smem + s * GRU_STAGE;
+                tc::tma_load_2d(st, &mp.h_hi, &full_bar[s], kb * 64, b0);
+                tc::tma_load_2d(st + GRU_A_TILE, &mp.h_lo, &full_bar[s], kb * 64, b0);
+            };
+            // first pass over the ring (every stage is free): the weight tiles go out before the previous step has finished,
+            // h_prev (its output) after
+            const int pre = nkb < GRU_STAGES ? nkb : GRU_STAGES;
+            for (int kb = 0; kb < pre; ++kb) { tc::mbar_arrive_expect_tx(&full_bar[kb], GRU_STAGE); load_w(kb, kb); }
+            pdl_wait();
+            for (int kb = 0; kb < pre; ++kb) load_h(kb, kb);
+            for (int kb = pre; kb < nkb; ++kb) {
+                const int s = kb % GRU_STAGES;
+                const uint32_t ph = (kb / GRU_STAGES) & 1;
+                tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                tc::mbar_arrive_expect_tx(&full_bar[s], GRU_STAGE);
+                load_h(kb, s);
+                load_w(kb, s);
             }
         }
     } else if (warp == 1) {

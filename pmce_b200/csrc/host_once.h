@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <atomic>
 
 constexpr int PMCE_MAX_DEVICES = 64;
@@ -42,6 +43,37 @@ static inline int tc_num_sms() {
 static inline int pmce_env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return s ? atoi(s) : dflt;
+}
+
+// PMCE_PDL=0: plain stream-ordered launches (A/B of programmatic dependent launch; results are identical either way)
+static inline bool pmce_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) on = pmce_env_int("PMCE_PDL", 1) ? 1 : 0;
+    return on == 1;
+}
+
+// Launch with programmatic stream serialisation (common.cuh pdl_wait / pdl_trigger): the kernel MUST call pdl_wait() before its
+// first access to memory other kernels produce or reuse. cluster > 0 adds a cluster dimension along x. Captured into CUDA graphs
+// the dependency becomes a programmatic edge.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pmce_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster > 0) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pmce_pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // Profiling knob that makes the kernels produce WRONG results on purpose (skip loads / math / stores to time the rest).

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, int nrows, int C, LnParams a, int has_a, const float* __restrict__ pos,
                int pos_div, int pos_mod, float* __restrict__ out1, LnParams bparm, float* __restrict__ out2, SplitOut out2s,
                int map_rows, int map_stride) {
+    pdl_enter();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= nrows) return;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256)
 lifter_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ imgemb, const float* __restrict__ wje,
                     const float* __restrict__ bje, const float* __restrict__ spos, int ntok, int J, int C, LnParams n1,
                     float* __restrict__ x0, float* __restrict__ xn, SplitOut xns) {
+    pdl_enter();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= ntok) return;
@@ -162,6 +164,7 @@ template <int MAXV>
 __global__ void __launch_bounds__(256)
 lifter_head_kernel(const float* __restrict__ y, int ntok, int C, LnParams nt, LnParams nh, const float* __restrict__ wr,
                    const float* __restrict__ br, float* __restrict__ r3) {
+    pdl_enter();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= ntok) return;
@@ -193,6 +196,7 @@ lifter_head_kernel(const float* __restrict__ y, int ntok, int C, LnParams nt, Ln
 // pose3d[b,j,c] = sum_t w[t] r[b,t,j,c] + bias ; joints = pose3d / 1000
 __global__ void lifter_fuse_kernel(const float* __restrict__ r3, const float* __restrict__ wf, const float* __restrict__ bf,
                                    int B, int T, int J, float* __restrict__ pose3d, float* __restrict__ joints_m) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = B * J * 3;
     if (idx >= n) return;
@@ -221,6 +225,7 @@ template <int D>
 __global__ void __launch_bounds__(128)
 attn_kernel(const float* __restrict__ Q, AttnAddr aq, const float* __restrict__ K, const float* __restrict__ V, AttnAddr akv,
             float* __restrict__ O, SplitOut Os, AttnAddr ao, int N1, int N2, float scale) {
+    pdl_enter();
     extern __shared__ __align__(16) float smem[];
     float* Ks = smem;                       // [N2][D]
     float* Vs = smem + (size_t)N2 * D;      // [N2][D]
@@ -324,6 +329,7 @@ attn_kernel(const float* __restrict__ Q, AttnAddr aq, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 adaln_apply_kernel(const float* __restrict__ x, int nrows, int rows_per_batch, const float* __restrict__ gb, int gb_ld,
                    int slot, float eps, float* __restrict__ y, SplitOut ys) {
+    pdl_enter();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= nrows) return;
@@ -350,6 +356,7 @@ adaln_apply_kernel(const float* __restrict__ x, int nrows, int rows_per_batch, c
 __global__ void coevo_embed_kernel(const float* __restrict__ coords, int nrows, int ntok, const float* __restrict__ w,
                                    const float* __restrict__ bias, const float* __restrict__ pos,
                                    const float* __restrict__ qemb, float* __restrict__ out_f, SplitOut out_fs, float* __restrict__ out_q) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nrows * 16) return;
     const int row = idx >> 4, c = (idx & 15) * 4;
@@ -373,6 +380,7 @@ __global__ void coevo_embed_kernel(const float* __restrict__ coords, int nrows, 
 __global__ void __launch_bounds__(256)
 feat2coor_kernel(const float* __restrict__ x, int nrows, const float* __restrict__ w, const float* __restrict__ bias,
                  const float* __restrict__ coords, float* __restrict__ out) {
+    pdl_enter();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= nrows) return;
@@ -389,6 +397,7 @@ feat2coor_kernel(const float* __restrict__ x, int nrows, const float* __restrict
 // verts0[b,i,:] = joints[b, vj[i], :]  (CoevoDecoder.py:232) — pure copy, bit exact.
 __global__ void gather_verts_kernel(const float* __restrict__ joints, const int32_t* __restrict__ vj, int B, int J, int Vd,
                                     float* __restrict__ verts) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * Vd * 3) return;
     const int c = idx % 3, i = (idx / 3) % Vd, b = idx / (3 * Vd);
@@ -398,6 +407,7 @@ __global__ void gather_verts_kernel(const float* __restrict__ joints, const int3
 // im2col for upsample_conv (Conv1d(431->6890,k=3,pad=1) over the xyz axis, CoevoDecoder.py:214,238):
 //   A[(b,l), c*3+k] = verts[b,c,l+k-1] (0 outside [0,3)), padded to ldk columns with zeros.
 __global__ void upsample_im2col_kernel(const float* __restrict__ verts, int B, int Vd, int ldk, float* __restrict__ A, SplitOut As) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = B * 3 * ldk;
     if (idx >= total) return;
@@ -429,6 +439,7 @@ struct GruDir {
 
 __global__ void __launch_bounds__(256)
 gru_step_kernel(GruDir d0, GruDir d1, int B, int H) {
+    pdl_enter();
     const GruDir d = blockIdx.z == 0 ? d0 : d1;
     constexpr int BM = 64, BJ = 16, BK = 16;
     __shared__ __align__(16) float Hs[BK][BM + 4];

@@ -125,6 +125,8 @@ mlp64_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t tH = tmem_base, tO = tmem_base + 256;
+    pdl_trigger();
+    if (warp != 8) pdl_wait();     // the producer first requests the weights (constants), which then land under the previous kernel's tail
 
     if (warp == 8) {
         // ================= producer =================
@@ -137,6 +139,7 @@ mlp64_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 tc::tma_load_2d(smem + MLP_OFF_W2 + kb * 8192, &tm_w2_hi, w_full, kb * 64, 0);
                 tc::tma_load_2d(smem + MLP_OFF_W2 + MLP_W2 / 2 + kb * 8192, &tm_w2_lo, w_full, kb * 64, 0);
             }
+            pdl_wait();            // x is the previous kernel's output
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 tc::mbar_wait(x_empty, (it & 1) ^ 1);
@@ -328,8 +331,8 @@ static inline int launch_mlp64_fused_t(const CUtensorMap* m, const MlpFusedArgs&
     if (!pmce_configure_smem<mlp64_fused_kernel<EPI>>(MLP_SMEM)) return 2;
     const int ntiles = (a.rows + 127) / 128;
     const int cap = tc_num_sms();
-    mlp64_fused_kernel<EPI><<<ntiles < cap ? ntiles : cap, MLP_THREADS, MLP_SMEM, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], a);
-    return cudaGetLastError() == cudaSuccess ? 0 : 3;
+    return pmce_launch(mlp64_fused_kernel<EPI>, dim3(ntiles < cap ? ntiles : cap), dim3(MLP_THREADS), MLP_SMEM, st, 0,
+                       m[0], m[1], m[2], m[3], m[4], m[5], m[6], a) == cudaSuccess ? 0 : 3;
 }
 
 // x [rows, 64] fp32 in place; t (MLP_EPI_T only): split-bf16 [rows, 64]
