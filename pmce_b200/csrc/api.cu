@@ -196,6 +196,17 @@ int split_rows(const float* x, int rows, int cols, int ld, bool relu, const Spli
 template <int D>
 int launch_attn_d(const float* Q, AttnAddr aq, const float* K, const float* V, AttnAddr akv, float* O, SplitOut Os, AttnAddr ao, int nseq,
                   int H, int N1, int N2, cudaStream_t st) {
+    static int fewq = -1;     // PMCE_ATTN_FEWQ=0: the lane-per-query kernel for every shape (A/B, tests)
+    if (fewq < 0) fewq = pmce_env_int("PMCE_ATTN_FEWQ", 1) ? 1 : 0;
+    if (fewq && N1 <= 32 && N2 >= 64 && N2 <= 32 * ATTN_FEWQ_KPL && nseq <= 65535) {
+        // few queries over many keys (joint <- vertex cross-attention): keys across the lanes, a warp per query
+        const size_t sm = (size_t)N2 * (D + 4) * 2 * sizeof(float);
+        if (sm <= 227 * 1024) {
+            if (sm > 48 * 1024 && !pmce_configure_smem<attn_fewq_kernel<D>>(227 * 1024)) { pmce_set_error("attn_fewq: cudaFuncSetAttribute failed"); return 10; }
+            PLAUNCH(attn_fewq_kernel<D>, dim3(H, nseq), 256, sm, st, Q, aq, K, V, akv, O, Os, ao, N1, N2, 1.0f / sqrtf((float)D));
+            return 0;
+        }
+    }
     const size_t smem = (size_t)N2 * D * 2 * sizeof(float);
     if (smem > 227 * 1024) { pmce_set_error("attention K/V tile (%zu B) exceeds shared memory", smem); return 3; }
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1209,10 +1220,11 @@ static int forward_windows(const pmce_dims_t* dims, const void* weights, const f
     CK(cudaEventRecord(aux->fork, st));
     CK(cudaStreamWaitEvent(aux->side, aux->fork, 0));
     const GruFew few = gru_few_plan(L.d, B);
-    if (!(skip_mask() & 2)) RET(decoder_front(L, W, B, nfr, fstride, ws, aux->side, few));
+    if (!(skip_mask() & 2)) { PdlScope sc(PMCE_PDL_SIDE); RET(decoder_front(L, W, B, nfr, fstride, ws, aux->side, few)); }
     CK(cudaEventRecord(aux->join, aux->side));
     tc_sm_reserve = few.steps > 0 ? few.ctas : 0;
-    const int lrc = (skip_mask() & 4) ? 0 : lifter(L, W, pose2d, B, nfr, fstride, pose3d, ws, st);
+    int lrc = 0;
+    if (!(skip_mask() & 4)) { PdlScope sc(PMCE_PDL_LIFTER); lrc = lifter(L, W, pose2d, B, nfr, fstride, pose3d, ws, st); }
     tc_sm_reserve = 0;
     if (lrc) return lrc;
     CK(cudaStreamWaitEvent(st, aux->join, 0));

@@ -50,6 +50,7 @@ struct TcEpi {
     int direct;             // epilogue stores straight from registers with 256-bit st.global (one full 32-byte sector per thread and
                             // instruction) instead of shared-memory staging + TMA store (PMCE_TC_DIRECT=1, A/B knob)
     int pair_relaxed;       // CTA pairs: release the accumulator with a relaxed cluster-scope arrive (PMCE_TC_PAIR_RELAXED=1)
+    int wpre;               // request the W tiles of the ring's first pass before griddepcontrol.wait (PMCE_PDL_WPRE, default 1)
 };
 
 struct TcOutMaps {          // TMA descriptors of the epilogue tensors (box = 32 rows x 16 columns)
@@ -165,10 +166,33 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     pdl_trigger();      // TMEM is ours: the next kernel's CTAs may be scheduled behind this one
-    pdl_wait();         // everything above overlapped the previous kernel's tail; its outputs (A, residual) are visible from here
+    // everything above overlapped the previous kernel's tail; its outputs (A, residual) are visible after the wait. The producer
+    // thread waits later: it first requests the W tiles (constants) of the ring's first pass
+    if (threadIdx.x != 0) pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
+            // first pass over the ring (every stage is free): W tiles before the grid dependency resolves, A tiles after
+            uint32_t pre = 0;
+            if (CL == 1 && e.wpre) {
+                for (int tile = tile0; tile < num_tiles && pre < (uint32_t)STAGES; tile += tile_step) {
+                    const int n0 = (tile % tiles_n) * BN + (int)rank * (BN / NCTA);
+                    for (int kb = 0; kb < nkb && pre < (uint32_t)STAGES; ++kb, ++pre) {
+                        uint8_t* st = smem + pre * Cfg::STAGE_BYTES;
+                        if (NCTA == 1) {
+                            tc::mbar_arrive_expect_tx(&full_bar[pre], Cfg::STAGE_BYTES);
+                            tc::tma_load_2d(st + 2 * Cfg::A_TILE, &tmW_hi, &full_bar[pre], kb * TC_BK, n0);
+                            tc::tma_load_2d(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tmW_lo, &full_bar[pre], kb * TC_BK, n0);
+                        } else {
+                            const uint32_t fb = tc::mapa_rank(tc::smem_u32(&full_bar[pre]), 0);
+                            if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[pre], 2 * Cfg::STAGE_BYTES);
+                            tc::tma_load_2d_pair(st + 2 * Cfg::A_TILE, &tmW_hi, fb, kb * TC_BK, n0);
+                            tc::tma_load_2d_pair(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tmW_lo, fb, kb * TC_BK, n0);
+                        }
+                    }
+                }
+            }
+            pdl_wait();
             uint32_t it = 0;                                    // global k-block counter across tiles
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int m0 = ((tile / tiles_n) * CL + (CL > 1 ? (int)crank : 0)) * (NCTA * TC_BM) + (int)rank * TC_BM,
@@ -176,8 +200,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    tc::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                    if (it < pre) {                             // stage armed and its W tiles requested above
+                        if (NCTA == 1) {
+                            tc::tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
+                            tc::tma_load_2d(st + Cfg::A_TILE, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
+                        } else {
+                            const uint32_t fb = tc::mapa_rank(tc::smem_u32(&full_bar[s]), 0);
+                            tc::tma_load_2d_pair(st, &tmA_hi, fb, kb * TC_BK, m0);
+                            tc::tma_load_2d_pair(st + Cfg::A_TILE, &tmA_lo, fb, kb * TC_BK, m0);
+                        }
+                        continue;
+                    }
+                    tc::mbar_wait(&empty_bar[s], ph ^ 1);
                     if (CL > 1) {
                         // own A rows; this CTA's CL-th of the W tile goes to every CTA of the cluster (all CTAs' MMAs have released the stage)
                         constexpr int WQ = Cfg::W_TILE / CL;
@@ -568,6 +603,9 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
     static int relaxed = -1;   // ncu shows the release.cluster arrive (a cluster-scope fence per accumulator release) at 15 % of the pair kernel's stall samples
     if (relaxed < 0) relaxed = pmce_env_int("PMCE_TC_PAIR_RELAXED", 0) ? 1 : 0;
     const_cast<TcEpi&>(e).pair_relaxed = relaxed;
+    static int wpre = -1;
+    if (wpre < 0) wpre = pmce_env_int("PMCE_PDL_WPRE", 1) ? 1 : 0;
+    const_cast<TcEpi&>(e).wpre = wpre;
     static int direct = -1;
     if (direct < 0) direct = pmce_env_int("PMCE_TC_DIRECT", 0);
     // 256-bit stores need 32-byte aligned rows: leading dimensions in multiples of 16 bf16 / 8 fp32 and 32-byte aligned bases

@@ -45,11 +45,25 @@ static inline int pmce_env_int(const char* name, int dflt) {
     return s ? atoi(s) : dflt;
 }
 
-// PMCE_PDL=0: plain stream-ordered launches (A/B of programmatic dependent launch; results are identical either way)
+// Which launches carry the programmatic-serialisation attribute: PMCE_PDL is a mask over the launch SCOPE the orchestration sets
+// (bit 0: the pose lifter while the image-feature stream runs beside it, bit 1: the image-feature stream, bit 2: everything else -
+// the decoder and stand-alone C-ABI calls). Results are identical for every mask; what changes is how the two concurrent streams
+// share the SMs: a PDL chain never leaves a gap, so a chain on the high-priority side stream keeps its SMs until it ends and
+// starves the lifter (measured: the forward gets SLOWER with the GRU steps chained, although each stage alone gets faster).
+constexpr int PMCE_PDL_LIFTER = 0, PMCE_PDL_SIDE = 1, PMCE_PDL_REST = 2;
+static inline int& pmce_pdl_scope() {
+    static thread_local int scope = PMCE_PDL_REST;
+    return scope;
+}
+struct PdlScope {          // RAII: launches issued by this thread inside the scope belong to `s`
+    int prev;
+    explicit PdlScope(int s) : prev(pmce_pdl_scope()) { pmce_pdl_scope() = s; }
+    ~PdlScope() { pmce_pdl_scope() = prev; }
+};
 static inline bool pmce_pdl_enabled() {
-    static int on = -1;
-    if (on < 0) on = pmce_env_int("PMCE_PDL", 1) ? 1 : 0;
-    return on == 1;
+    static int mask = -1;
+    if (mask < 0) mask = pmce_env_int("PMCE_PDL", 5) & 7;
+    return (mask >> pmce_pdl_scope()) & 1;
 }
 
 // Launch with programmatic stream serialisation (common.cuh pdl_wait / pdl_trigger): the kernel MUST call pdl_wait() before its

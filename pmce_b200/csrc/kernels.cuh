@@ -323,6 +323,98 @@ attn_kernel(const float* __restrict__ Q, AttnAddr aq, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Few queries, many keys: the joint stream's cross-attention (CoevoDecoder.py:167 joint_CA_FFN -> :47-62: 17 queries x 431 keys,
+// 8 heads of 8). attn_kernel gives every query ONE lane that walks all keys (17 lanes x 431 dependent softmax updates = 37 us at
+// 64 clips); here a CTA owns (head, sequence), a warp owns a query and the KEYS are spread over its lanes: each lane keeps the
+// scores of its <= KPL keys in registers (exact two-pass softmax), the row max / sum / output are warp reductions.
+// Shared rows are padded to D + 4 floats so a quarter-warp's 16-byte reads fall into distinct banks.
+// ------------------------------------------------------------------------------------------------------
+constexpr int ATTN_FEWQ_KPL = 16;        // keys per lane: N2 <= 512
+template <int D>
+__global__ void __launch_bounds__(256)
+attn_fewq_kernel(const float* __restrict__ Q, AttnAddr aq, const float* __restrict__ K, const float* __restrict__ V, AttnAddr akv,
+                 float* __restrict__ O, SplitOut Os, AttnAddr ao, int N1, int N2, float scale) {
+    pdl_enter();
+    constexpr int LD = D + 4, D4 = D / 4;
+    extern __shared__ __align__(16) float smem[];
+    float* Ks = smem;                        // [N2][LD]
+    float* Vs = smem + (size_t)N2 * LD;      // [N2][LD]
+    const int h = blockIdx.x, s = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    const long long kv0 = akv.seq(s);
+    for (int idx = tid; idx < N2 * D4; idx += blockDim.x) {
+        const int r = idx / D4, c = (idx % D4) * 4;
+        const size_t g = (size_t)(kv0 + (long long)r * akv.tok) * akv.ld + h * D + c;
+        st4(Ks + r * LD + c, ld4(K + g));
+        st4(Vs + r * LD + c, ld4(V + g));
+    }
+    __syncthreads();
+    for (int qi = warp; qi < N1; qi += nw) {
+        const float* qp = Q + (size_t)(aq.seq(s) + (long long)qi * aq.tok) * aq.ld + h * D;
+        float q[D];
+#pragma unroll
+        for (int c = 0; c < D; c += 4) {
+            const float4 v = ld4(qp + c);
+            q[c] = v.x * scale; q[c + 1] = v.y * scale; q[c + 2] = v.z * scale; q[c + 3] = v.w * scale;
+        }
+        float sc[ATTN_FEWQ_KPL];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < ATTN_FEWQ_KPL; ++j) {
+            const int k = lane + 32 * j;
+            sc[j] = -INFINITY;
+            if (k < N2) {
+                const float* kr = Ks + k * LD;
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < D; c += 4) {
+                    const float4 kk = ld4(kr + c);
+                    s0 = fmaf(q[c], kk.x, s0); s1 = fmaf(q[c + 1], kk.y, s1);
+                    s0 = fmaf(q[c + 2], kk.z, s0); s1 = fmaf(q[c + 3], kk.w, s1);
+                }
+                sc[j] = s0 + s1;
+            }
+            m = fmaxf(m, sc[j]);
+        }
+        m = warp_max(m);
+        float l = 0.f, o[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) o[c] = 0.f;
+#pragma unroll
+        for (int j = 0; j < ATTN_FEWQ_KPL; ++j) {
+            const int k = lane + 32 * j;
+            if (k < N2) {
+                const float pj = expf(sc[j] - m);
+                l += pj;
+                const float* vr = Vs + k * LD;
+#pragma unroll
+                for (int c = 0; c < D; c += 4) {
+                    const float4 vv = ld4(vr + c);
+                    o[c] = fmaf(pj, vv.x, o[c]); o[c + 1] = fmaf(pj, vv.y, o[c + 1]);
+                    o[c + 2] = fmaf(pj, vv.z, o[c + 2]); o[c + 3] = fmaf(pj, vv.w, o[c + 3]);
+                }
+            }
+        }
+        l = warp_sum(l);
+        float mine = 0.f;                    // lane c keeps output element c (c, c + 32, ... for D > 32)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const float t = warp_sum(o[c]);
+            if ((c & 31) == lane) {
+                const size_t oi = (size_t)(ao.seq(s) + (long long)qi * ao.tok) * ao.ld + h * D + c;
+                mine = t / l;
+                if (O) O[oi] = mine;
+                if (Os.hi) {
+                    __nv_bfloat16 hi, lo;
+                    tc::split_bf16(mine, hi, lo);
+                    Os.hi[oi] = hi; Os.lo[oi] = lo;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // AdaLayerNorm apply (CoevoDecoder.py:23-29), 64 features per row, one warp per row:
 //   y = gamma_b * (x - mean) / (std_unbiased + eps) + beta_b,  gamma/beta = gb[b, slot, 0:64 | 64:128]
 // ------------------------------------------------------------------------------------------------------
