@@ -196,8 +196,7 @@ int split_rows(const float* x, int rows, int cols, int ld, bool relu, const Spli
 template <int D>
 int launch_attn_d(const float* Q, AttnAddr aq, const float* K, const float* V, AttnAddr akv, float* O, SplitOut Os, AttnAddr ao, int nseq,
                   int H, int N1, int N2, cudaStream_t st) {
-    static int fewq = -1;     // PMCE_ATTN_FEWQ=0: the lane-per-query kernel for every shape (A/B, tests)
-    if (fewq < 0) fewq = pmce_env_int("PMCE_ATTN_FEWQ", 1) ? 1 : 0;
+    const int fewq = pmce_env_int("PMCE_ATTN_FEWQ", 1);     // 0: the lane-per-query kernel for every shape (A/B, tests; read live)
     if (fewq && N1 <= 32 && N2 >= 64 && N2 <= 32 * ATTN_FEWQ_KPL && nseq <= 65535) {
         // few queries over many keys (joint <- vertex cross-attention): keys across the lanes, a warp per query
         const size_t sm = (size_t)N2 * (D + 4) * 2 * sizeof(float);
@@ -644,7 +643,8 @@ Aux* get_aux(cudaStream_t caller) {
         if (!a.side) {       // highest priority: its few-CTA kernels take the first SMs any lifter kernel frees
             int lo = 0, hi = 0;
             if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
-            if (cudaStreamCreateWithPriority(&a.side, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+            // PMCE_SIDE_PRIO=0: default priority (A/B knob, read when the side stream of a caller stream is first made)
+            if (cudaStreamCreateWithPriority(&a.side, cudaStreamNonBlocking, pmce_env_int("PMCE_SIDE_PRIO", 1) ? hi : lo) != cudaSuccess) return nullptr;
         }
         if (!a.fork && cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (!a.join && cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;

@@ -603,9 +603,7 @@ static inline int launch_linear_tc_bn(const TcOperand& A, const TcOperand& W, co
     static int relaxed = -1;   // ncu shows the release.cluster arrive (a cluster-scope fence per accumulator release) at 15 % of the pair kernel's stall samples
     if (relaxed < 0) relaxed = pmce_env_int("PMCE_TC_PAIR_RELAXED", 0) ? 1 : 0;
     const_cast<TcEpi&>(e).pair_relaxed = relaxed;
-    static int wpre = -1;
-    if (wpre < 0) wpre = pmce_env_int("PMCE_PDL_WPRE", 1) ? 1 : 0;
-    const_cast<TcEpi&>(e).wpre = wpre;
+    const_cast<TcEpi&>(e).wpre = pmce_env_int("PMCE_PDL_WPRE", 1) ? 1 : 0;      // live, like PMCE_PDL
     static int direct = -1;
     if (direct < 0) direct = pmce_env_int("PMCE_TC_DIRECT", 0);
     // 256-bit stores need 32-byte aligned rows: leading dimensions in multiples of 16 bf16 / 8 fp32 and 32-byte aligned bases

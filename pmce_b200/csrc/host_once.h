@@ -61,8 +61,9 @@ struct PdlScope {          // RAII: launches issued by this thread inside the sc
     ~PdlScope() { pmce_pdl_scope() = prev; }
 };
 static inline bool pmce_pdl_enabled() {
-    static int mask = -1;
-    if (mask < 0) mask = pmce_env_int("PMCE_PDL", 5) & 7;
+    // read at every launch (not cached): tools/ab_graphs.py captures one CUDA graph per mask in ONE process and replays them
+    // interleaved, the only A/B that survives the box-to-box and thermal drift of +-1.5 %
+    const int mask = pmce_env_int("PMCE_PDL", 5) & 7;
     return (mask >> pmce_pdl_scope()) & 1;
 }
 

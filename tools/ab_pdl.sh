@@ -1,17 +1,7 @@
 #!/bin/bash
-# A/B on one box: whole-forward time for PMCE_PDL scope masks (bit 0 lifter, bit 1 image-feature stream, bit 2 the rest), the
-# W-before-wait producer, the few-query attention kernel; then the parity tests the changed kernels touch.
+# Same-process interleaved A/B (tools/ab_graphs.py) of the PDL scope masks and friends at B=64 and B=256
 OUT=gpurun_out; mkdir -p $OUT
-: > $OUT/ab_pdl2.txt
-run() { echo "$*" >> $OUT/ab_pdl2.txt; env "$@" timeout 240 python tools/forward_time.py >> $OUT/ab_pdl2.txt 2>$OUT/ab_err.txt || { echo "FAILED rc=$?" >> $OUT/ab_pdl2.txt; tail -5 $OUT/ab_err.txt >> $OUT/ab_pdl2.txt; }; }
-run PMCE_PDL=5
-run PMCE_PDL=0
-run PMCE_PDL=4
-run PMCE_PDL=7
-run PMCE_PDL=1
-run PMCE_PDL=5 PMCE_PDL_WPRE=0
-run PMCE_PDL=5 PMCE_ATTN_FEWQ=0
-run PMCE_PDL=5
-run PMCE_PDL=0
-cat $OUT/ab_pdl2.txt
-timeout 600 python -m pytest tests/test_gpu_tc.py tests/test_gpu_parity.py -m gpu -x -q -k "tc or attention or coevo or golden or headline or decoder" 2>&1 | tail -6 | tee $OUT/ab_pdl2_tests.txt
+C="PMCE_PDL=0 PMCE_PDL=5 PMCE_PDL=4 PMCE_PDL=7 PMCE_PDL=1 PMCE_PDL=2 PMCE_PDL=5,PMCE_PDL_WPRE=0 PMCE_PDL=0,PMCE_ATTN_FEWQ=0 PMCE_PDL=0,PMCE_SIDE_PRIO=0 PMCE_PDL=7,PMCE_SIDE_PRIO=0 PMCE_PDL=0"
+timeout 300 python tools/ab_graphs.py 64 $C 2>$OUT/ab3_err.txt | tee $OUT/ab_pdl3.txt
+timeout 300 python tools/ab_graphs.py 256 PMCE_PDL=0 PMCE_PDL=5 PMCE_PDL=4 PMCE_PDL=7 2>>$OUT/ab3_err.txt | tee -a $OUT/ab_pdl3.txt
+tail -3 $OUT/ab3_err.txt
