@@ -630,7 +630,7 @@ int gru_mid(const Layout& L, const Weights& W, int B, int nfr, int fstride, floa
 // never freed (a destroyed-and-recreated stream handle simply reuses its entry).
 struct Aux {
     cudaStream_t side = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr, join3 = nullptr;
 };
 Aux* get_aux(cudaStream_t caller) {
     static std::mutex mu;
@@ -649,6 +649,7 @@ Aux* get_aux(cudaStream_t caller) {
         if (!a.fork && cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (!a.join && cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (!a.fork2 && cudaEventCreateWithFlags(&a.fork2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (!a.join3 && cudaEventCreateWithFlags(&a.join3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&a.join2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
     return &a;
@@ -992,10 +993,14 @@ int prepare_feat(const Layout& L, const float* img_feat, int nfr, const Workspac
 }
 
 // image-feature stream of the two-stream encoder: GRU -> y[T//2] -> all AdaLN gamma/beta (independent of the pose stream)
-int decoder_front(const Layout& L, const Weights& W, int B, int nfr, int fstride, const Workspace& ws, cudaStream_t st, GruFew few = GruFew{0, 0}) {
+// gb_ready: recorded once gamma/beta exist - all the co-evolution blocks wait for; the linear_cur mesh residual behind it (169 MB of
+// weights streamed once, needed only by the final up-sampling) then runs beside the decoder's latency-bound kernels
+int decoder_front(const Layout& L, const Weights& W, int B, int nfr, int fstride, const Workspace& ws, cudaStream_t st, GruFew few = GruFew{0, 0},
+                  cudaEvent_t gb_ready = nullptr) {
     NvtxRange nvtx("pmce/image-feature stream (GRU + AdaLN gamma/beta + linear_cur)");
     RET(gru_mid(L, W, B, nfr, fstride, ws.g, ws, st, few));
     RET(adaln_gammabeta(L, W, ws.g, B, ws.gb, ws.g_s, st));
+    if (gb_ready) CK(cudaEventRecord(gb_ready, st));
     if (coevo_fused(L.d) && ca_embed_enabled()) RET(ca_embed_tables(L, W, 0, 3, ws, st));
     return mesh_residual(L, W, ws.g, B, ws, st);
 }
@@ -1018,6 +1023,7 @@ int decoder_back(const Layout& L, const Weights& W, const float* joints, const i
     RET(coevo_block(L, W, 0, joints, v0, ws.gb, B, nullptr, ws.verts[0], ws, st, nullptr, pre));
     RET(coevo_block(L, W, 1, joints, ws.verts[0], ws.gb, B, nullptr, ws.verts[1], ws, st, nullptr, pre));
     RET(coevo_block(L, W, 2, joints, ws.verts[1], ws.gb, B, cam_pose, ws.verts[0], ws, st, aux, pre));
+    if (aux) CK(cudaStreamWaitEvent(st, aux->join3, 0));     // the linear_cur residual (image-feature stream) feeds the up-sampling's epilogue
     RET(mesh_upsample(L, W, ws.verts[0], B, cam_mesh, ws, st));
     if (aux) CK(cudaStreamWaitEvent(st, aux->join2, 0));     // block 3's joint branch (cam_pose) ran beside the vertex branch and the up-sampling
     return 0;
@@ -1220,8 +1226,11 @@ static int forward_windows(const pmce_dims_t* dims, const void* weights, const f
     CK(cudaEventRecord(aux->fork, st));
     CK(cudaStreamWaitEvent(aux->side, aux->fork, 0));
     const GruFew few = gru_few_plan(L.d, B);
-    if (!(skip_mask() & 2)) { PdlScope sc(PMCE_PDL_SIDE); RET(decoder_front(L, W, B, nfr, fstride, ws, aux->side, few)); }
-    CK(cudaEventRecord(aux->join, aux->side));
+    // PMCE_LC_LATE=0: join only after the linear_cur residual (A/B; read live)
+    const bool lc_late = pmce_env_int("PMCE_LC_LATE", 1) != 0 && !(skip_mask() & 2);
+    if (!(skip_mask() & 2)) { PdlScope sc(PMCE_PDL_SIDE); RET(decoder_front(L, W, B, nfr, fstride, ws, aux->side, few, lc_late ? aux->join : nullptr)); }
+    if (!lc_late) CK(cudaEventRecord(aux->join, aux->side));
+    CK(cudaEventRecord(aux->join3, aux->side));
     tc_sm_reserve = few.steps > 0 ? few.ctas : 0;
     int lrc = 0;
     if (!(skip_mask() & 4)) { PdlScope sc(PMCE_PDL_LIFTER); lrc = lifter(L, W, pose2d, B, nfr, fstride, pose3d, ws, st); }

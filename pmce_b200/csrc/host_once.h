@@ -47,9 +47,12 @@ static inline int pmce_env_int(const char* name, int dflt) {
 
 // Which launches carry the programmatic-serialisation attribute: PMCE_PDL is a mask over the launch SCOPE the orchestration sets
 // (bit 0: the pose lifter while the image-feature stream runs beside it, bit 1: the image-feature stream, bit 2: everything else -
-// the decoder and stand-alone C-ABI calls). Results are identical for every mask; what changes is how the two concurrent streams
-// share the SMs: a PDL chain never leaves a gap, so a chain on the high-priority side stream keeps its SMs until it ends and
-// starves the lifter (measured: the forward gets SLOWER with the GRU steps chained, although each stage alone gets faster).
+// the decoder and stand-alone C-ABI calls). Results are bit-identical for every mask (tools/ab_graphs.py checks it).
+// DEFAULT 0 (off) - measured on B200, B=64 (profiles/r2y_pdl_ab.txt): each stage ALONE gets faster with PDL (lifter 1606 -> 1577 us,
+// GRU -> y[T//2] 555 -> 514, decoder 1230 -> 1165), but the whole two-stream forward does not (2704 vs 2704 us for mask 5, +1 % for
+// mask 4, +3 % for mask 7; at B=256 +1..4 %): a PDL chain never leaves a gap, so the chained GRU steps on the high-priority side
+// stream keep their 128 SMs until the chain ends and the lifter starves (mask 7 = the two streams run one after the other),
+// while on the lifter's stream the gaps PDL closes were already being filled by the other stream's CTAs.
 constexpr int PMCE_PDL_LIFTER = 0, PMCE_PDL_SIDE = 1, PMCE_PDL_REST = 2;
 static inline int& pmce_pdl_scope() {
     static thread_local int scope = PMCE_PDL_REST;
@@ -63,7 +66,7 @@ struct PdlScope {          // RAII: launches issued by this thread inside the sc
 static inline bool pmce_pdl_enabled() {
     // read at every launch (not cached): tools/ab_graphs.py captures one CUDA graph per mask in ONE process and replays them
     // interleaved, the only A/B that survives the box-to-box and thermal drift of +-1.5 %
-    const int mask = pmce_env_int("PMCE_PDL", 5) & 7;
+    const int mask = pmce_env_int("PMCE_PDL", 0) & 7;
     return (mask >> pmce_pdl_scope()) & 1;
 }
 

@@ -470,16 +470,42 @@ def test_headline_configs_vs_oracle(assets_root, lib, J, C, T, B):
         assert e[0] < TOL and e[1] < TOL and e[2] < 1e-4 and mpve < TOL
 
 
+def test_scheduling_knobs_are_bit_identical(base):
+    """Programmatic dependent launch (PMCE_PDL scope masks) and the placement of the linear_cur residual (PMCE_LC_LATE) only change
+    WHEN kernels run, never what they compute: the forward is bit-identical under every setting (both knobs are read live)."""
+    m, p2d, feat = base["m"], base["p2d"].cuda(), base["feat"].cuda()
+    keep = {k: os.environ.get(k) for k in ("PMCE_PDL", "PMCE_LC_LATE")}
+    try:
+        os.environ["PMCE_PDL"], os.environ["PMCE_LC_LATE"] = "0", "1"
+        ref = [t.clone() for t in m(p2d, feat)]
+        for pdl, late in (("7", "1"), ("5", "0"), ("2", "1"), ("0", "0")):
+            os.environ["PMCE_PDL"], os.environ["PMCE_LC_LATE"] = pdl, late
+            for _ in range(2):
+                out = m(p2d, feat)
+                torch.cuda.synchronize()
+                assert all(torch.equal(a, b) for a, b in zip(out, ref)), (pdl, late)
+    finally:
+        for k, v in keep.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 @pytest.mark.parametrize("env", [{"PMCE_GRU_PERSISTENT": "1"},
                                  {"PMCE_GRU_FEW_STEPS": "100"},
                                  {"PMCE_GRU_FEW": "6", "PMCE_GRU_FEW_STEPS": "7", "PMCE_GRU_FEW_U": "64"},
                                  {"PMCE_MLP_FUSED": "0", "PMCE_ATTN_ROWS": "0", "PMCE_CA_FUSED": "0"},
                                  {"PMCE_CA_EMBED": "1"},
-                                 {"PMCE_TC_DIRECT": "1", "PMCE_TC_NBUF": "2", "PMCE_TC_PAIR_RELAXED": "1"}])
+                                 {"PMCE_TC_DIRECT": "1", "PMCE_TC_NBUF": "2", "PMCE_TC_PAIR_RELAXED": "1"},
+                                 {"PMCE_PDL": "7"},
+                                 {"PMCE_PDL": "5", "PMCE_PDL_WPRE": "0", "PMCE_ATTN_FEWQ": "0", "PMCE_LC_LATE": "0"}])
 def test_alternative_paths_in_subprocess(env):
     """The opt-in / A-B variants stay parity-green: the persistent GRU layer kernel, the few-CTA GRU step kernel (all steps / the
     first 7 on 6 CTAs with 64-unit tiles), the unfused launch sequences the fused
-    kernels replaced, and the GEMM epilogue variants (the library reads its knobs once per process, hence the subprocess)."""
+    kernels replaced, the GEMM epilogue variants, programmatic dependent launch on every scope / on the lifter and decoder without
+    the W-before-wait producer, the lane-per-query joint cross-attention and the early linear_cur residual (the library reads
+    most knobs once per process, hence the subprocess)."""
     import subprocess
     import sys
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k",
