@@ -16,12 +16,13 @@ from pmce_b200 import synth  # noqa: E402
 args = sys.argv[1:]
 B = int(args.pop(0)) if args and args[0].isdigit() else bench.B_PER_GPU
 confs = args or ["PMCE_PDL=0", "PMCE_PDL=5"]
+labels = [f"{i}:{c}" for i, c in enumerate(confs)]          # the same configuration may be listed twice (graph-placement noise)
 dev = torch.device("cuda")
 model, sd = bench.build_model(dev)
 model.engine().use_graph = False
 p2d, feat = [t.to(dev) for t in synth.make_inputs(B, bench.T, bench.J, seed=3)]
 graphs = []
-for c in confs:
+for lab, c in zip(labels, confs):
     kv = dict(x.split("=") for x in c.split(","))
     old = {k: os.environ.get(k) for k in kv}
     os.environ.update(kv)
@@ -36,7 +37,7 @@ for c in confs:
     torch.cuda.current_stream().wait_stream(side)
     g.replay()
     torch.cuda.synchronize()
-    graphs.append((c, g, [o.clone() for o in out]))
+    graphs.append((lab, g, [o.clone() for o in out]))
     for k, v in old.items():
         if v is None:
             os.environ.pop(k, None)
@@ -44,7 +45,7 @@ for c in confs:
             os.environ[k] = v
 ref = graphs[0][2]
 same = {c: all(torch.equal(a, b) for a, b in zip(o, ref)) for c, _, o in graphs}
-times = {c: [] for c in confs}
+times = {c: [] for c in labels}
 n = 20
 for r in range(30):
     for c, g, _ in graphs:

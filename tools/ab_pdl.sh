@@ -1,7 +1,7 @@
 #!/bin/bash
-# Same-process interleaved A/B (tools/ab_graphs.py) of the PDL scope masks and friends at B=64 and B=256
+# Call 4: (1) interleaved A/B of the linear_cur placement, (2) the new GPU tests, (3) a full bench line, (4) the launch list
 OUT=gpurun_out; mkdir -p $OUT
-C="PMCE_PDL=0 PMCE_PDL=5 PMCE_PDL=4 PMCE_PDL=7 PMCE_PDL=1 PMCE_PDL=2 PMCE_PDL=5,PMCE_PDL_WPRE=0 PMCE_PDL=0,PMCE_ATTN_FEWQ=0 PMCE_PDL=0,PMCE_SIDE_PRIO=0 PMCE_PDL=7,PMCE_SIDE_PRIO=0 PMCE_PDL=0"
-timeout 300 python tools/ab_graphs.py 64 $C 2>$OUT/ab3_err.txt | tee $OUT/ab_pdl3.txt
-timeout 300 python tools/ab_graphs.py 256 PMCE_PDL=0 PMCE_PDL=5 PMCE_PDL=4 PMCE_PDL=7 2>>$OUT/ab3_err.txt | tee -a $OUT/ab_pdl3.txt
-tail -3 $OUT/ab3_err.txt
+timeout 200 python tools/ab_graphs.py 64 PMCE_LC_LATE=0 PMCE_LC_LATE=1 PMCE_LC_LATE=0 PMCE_LC_LATE=1 PMCE_LC_LATE=0 PMCE_LC_LATE=1 2>$OUT/ab4_err.txt | tee $OUT/ab_lc_late.txt
+timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "scheduling_knobs or env6 or env7" 2>&1 | tail -4 | tee $OUT/ab4_tests.txt
+timeout 400 python bench.py > $OUT/r2y_bench.json 2> $OUT/r2y_bench_err.txt; tail -c 1500 $OUT/r2y_bench.json
+FULL=0 timeout 300 bash profiles/collect.sh r2y > /dev/null 2>&1; head -12 $OUT/r2y_launches_summary.txt
