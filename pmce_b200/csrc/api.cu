@@ -170,6 +170,7 @@ struct EpiOpt {
     SplitOut outs{nullptr, nullptr}; int ld_split = 0;
     bf16* att = nullptr; float qscale = 1.0f;       // TC_ATTN32: operand records of attn_rows_tc_kernel (gemm_tc.cuh)
     bool mapped = false; RowMap rmap{1, 0, 0}, cmap{1, 0, 0};
+    int force_bn = 0;                                // tile width of this launch (0: cost model)
 };
 
 // out = epi(A[M,K] * W[N,K]^T) on the tcgen05 path; A split [M,K] (ld lda), W at float offset w_off in the blob (ld ldw).
@@ -181,7 +182,7 @@ int linear_tc(const SplitOut& A, int lda, int M, int K, const Weights& W, size_t
     e.bias = o.bias; e.act = o.act; e.resid = o.resid; e.ld_resid = o.ld_resid; e.rowadd = o.rowadd; e.rowadd_period = o.period;
     e.out_f32 = o.out; e.ld_out = o.ld_out; e.out_hi = o.outs.hi; e.out_lo = o.outs.lo; e.ld_split = o.ld_split;
     e.mapped = o.mapped ? 1 : 0; e.rmap = o.rmap; e.cmap = o.cmap;
-    e.out_att = o.att; e.qscale = o.qscale;
+    e.out_att = o.att; e.qscale = o.qscale; e.force_bn = o.force_bn;
     count_launch();
     const int rc = launch_linear_tc(a, w, e, st);
     if (rc) { pmce_set_error("tensor-core GEMM launch failed (%d; M=%d N=%d K=%d): %s", rc, M, N, K, cudaGetErrorString(cudaGetLastError())); return 10; }
@@ -977,6 +978,7 @@ int mesh_upsample(const Layout& L, const Weights& W, const float* verts3, int B,
     const int Vd = d.num_vert_ds, V = d.num_vert, ldk = L.ups_ld;
     PLAUNCH(upsample_im2col_kernel, cdiv((long long)B * 3 * ldk, 256), 256, 0, st, verts3, B, Vd, ldk, nullptr, ws.im2col_s);
     EpiOpt o; o.bias = W.f + L.ups_b; o.out = mesh; o.resid = ws.lc_mesh; o.mapped = true;
+    o.force_bn = pmce_env_int("PMCE_UPS_BN", 0);     // A/B of the tile width of this skinny GEMM (M = 3 B rows, N = 6890; read live)
     o.rmap.div = 3; o.rmap.s0 = (long long)V * 3; o.rmap.s1 = 1;
     o.cmap.div = 1; o.cmap.s0 = 3; o.cmap.s1 = 0;
     return linear_tc(ws.im2col_s, ldk, B * 3, ldk, W, L.ups_w, ldk, V, o, st);

@@ -51,6 +51,7 @@ struct TcEpi {
                             // instruction) instead of shared-memory staging + TMA store (PMCE_TC_DIRECT=1, A/B knob)
     int pair_relaxed;       // CTA pairs: release the accumulator with a relaxed cluster-scope arrive (PMCE_TC_PAIR_RELAXED=1)
     int wpre;               // request the W tiles of the ring's first pass before griddepcontrol.wait (PMCE_PDL_WPRE, default 1)
+    int force_bn;           // 0 = tile width from the cost model; 32 / 64 / 128 / 256 = this launch's tile width (per-call A/B knobs)
 };
 
 struct TcOutMaps {          // TMA descriptors of the epilogue tensors (box = 32 rows x 16 columns)
@@ -646,6 +647,10 @@ static inline int launch_linear_tc(const TcOperand& A, const TcOperand& W, const
     const int sms = tc_num_sms();
     static int forced = -1;   // PMCE_TC_BN=<32|64|128|256>: tile-sweep knob for profiling (tools/gemm_sweep.py)
     if (forced < 0) forced = pmce_env_int("PMCE_TC_BN", 0);
+    if (e.force_bn == 256) return launch_linear_tc_bn<256>(A, W, e, st);
+    if (e.force_bn == 128) return launch_linear_tc_bn<128>(A, W, e, st);
+    if (e.force_bn == 64) return launch_linear_tc_bn<64>(A, W, e, st);
+    if (e.force_bn == 32) return launch_linear_tc_bn<32>(A, W, e, st);
     if (forced == 256) return launch_linear_tc_bn<256>(A, W, e, st);
     if (forced == 128) return launch_linear_tc_bn<128>(A, W, e, st);
     if (forced == 64) return launch_linear_tc_bn<64>(A, W, e, st);

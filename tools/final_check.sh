@@ -10,3 +10,5 @@ print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches")}, d["e2e"]["val
       "fc1 frac", round(d["roofline"]["frac"], 4), "CA frac", round(d["roofline_cross_attn"]["frac"], 4), round(d["roofline_cross_attn"]["at_B256"]["frac"], 4))
 PY
 timeout 200 python __graft_entry__.py smoke 2>&1 | tail -2
+# spare time: interleaved A/B of the up-sampling GEMM's tile width (bit-identical by construction: N-tiling does not change a dot product)
+timeout 200 python tools/ab_graphs.py 64 PMCE_UPS_BN=0 PMCE_UPS_BN=64 PMCE_UPS_BN=256 PMCE_UPS_BN=32 PMCE_UPS_BN=0 PMCE_UPS_BN=64 PMCE_UPS_BN=256 PMCE_UPS_BN=32 2>/dev/null | tee $OUT/${TAG}_ups_bn_ab.txt
