@@ -246,7 +246,8 @@ def bench_config(world, note=None):
            "parallelism": f"batch-shard x{world}" + (" + 1 all-gather" if world > 1 else ""),
            "weights": "seeded random init (no checkpoints are published)",
            "l2": "per-step working set (weights 0.46 GB + activations) exceeds the 126 MB L2; inputs rotate over 4 resident sets",
-           "cuda_graph": True}
+           "cuda_graph": True,
+           "in_flight": "2 forwards (models.PMCE.forward_iter: two buffer slots, each with its own workspace, graph and stream)"}
     if note:
         cfg["note"] = note
     return cfg
@@ -332,18 +333,48 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                  # sampling runs from the warm-up to the end of the last timed region
-    for i in range(W):
-        step(i)
+    # multi-GPU hooks of the pipelined loops: the forwards write into the rank's rows of the two all-gather buffers, every step's
+    # all-gather is issued from the slot's forward stream onto the communication stream
+    hooks = {}
+    if sf is not None:
+        hooks = dict(out_slots=[sf.views(sf.bufs[k], rank) for k in range(2)], before_forward=sf.wait_slot_free, after_forward=sf.gather_async)
+
+    def run_value(k):
+        """k steps through the device-resident public loop (models.PMCE.forward_iter): inputs already in HBM, two forwards in flight"""
+        n = 0
+        for _ in model.forward_iter((sets[i % NSETS] for i in range(k)), **hooks):
+            n += 1
+        if sf is not None:
+            for k2 in range(2):
+                sf.result(k2)                                           # the last gathers are part of the timed region
+        assert n == k
+        return n
+
+    def timed_block(run, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(k)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    run_value(W)
     t_a = time.perf_counter()
-    ms = timed(step, K)
+    ms = timed_block(run_value, K)
     sampler.window(t_a, time.perf_counter())
     value = world * B * K / (ms * 1e-3)
+    # the same K steps as K separate module calls on one stream (one forward at a time), for comparison
+    for i in range(W):
+        step(i)
+    ms_single = timed(step, K)
 
     # e2e: the public host-buffer API, pipelined over the K batches (H2D of batch i+1 / D2H of batch i-1 overlap forward i);
     # every step copies its own inputs from pinned host memory and its three outputs back, and the consumer reads them
-    hooks = {}
-    if sf is not None:        # e2e at N > 1 includes the all-gather of every step (issued from the pipeline's forward stream)
-        hooks = dict(out_slots=[sf.views(sf.bufs[k], rank) for k in range(2)], before_forward=sf.wait_slot_free, after_forward=sf.gather_async)
+    # e2e at N > 1 includes the all-gather of every step (same hooks as the device-resident loop)
 
     def run_e2e(k):
         acc = 0.0
@@ -354,21 +385,9 @@ def main():
                 sf.result(k2)                                           # the last gathers are part of the timed region
         return acc
 
-    def timed_host(k):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run_e2e(k)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     run_e2e(W)
     t_a = time.perf_counter()
-    ms_e2e = timed_host(K)
+    ms_e2e = timed_block(run_e2e, K)
     sampler.window(t_a, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     for i in range(W):
@@ -411,6 +430,8 @@ def main():
                         "neighbouring steps overlapped with the forward (the reference loop lib/core/base.py:218-238, pipelined)",
                 "unpipelined": {"value": world * B * K / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync / K,
                                 "path": "models.PMCE.forward_host: H2D -> forward -> D2H -> sync per step"}},
+        "one_forward_at_a_time": {"value": world * B * K / (ms_single * 1e-3), "ms_per_step": ms_single / K,
+                                  "path": "K separate models.PMCE.forward calls on one stream (CUDA-graph replay each)"},
         "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
         "config3_B1024_x8": b1024, "clocks": clocks, "roofline": roof, "roofline_cross_attn": roof_ca, "roofline_lbs": roof_lbs, "spin_feature_extractor": spin,
         "peaks": peaks,

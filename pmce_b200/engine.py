@@ -99,6 +99,17 @@ class Engine:
             self._pipe.clear()
         return self._ws
 
+    def _workspace2(self, B, device):
+        """The second workspace: the pipelined iterators keep TWO forwards in flight (one per slot, each on its own stream)."""
+        need = self.lib.pmce_workspace_bytes(self._dp, B)
+        if need == 0:
+            check(1, "pmce_workspace_bytes")
+        ws2 = getattr(self, "_ws2", None)
+        if ws2 is None or ws2.numel() < need or ws2.device != device:
+            self._ws2 = torch.empty(need, dtype=torch.uint8, device=device)
+            self._pipe.clear()
+        return self._ws2
+
     def _ready(self, need_vj=False):
         if self.weights is None:
             raise PmceError("weights have not been packed (call Engine.pack / load_state_dict first)")
@@ -106,9 +117,10 @@ class Engine:
             raise PmceError("vj_relation has not been set")
 
     # ---- whole forward (a1) --------------------------------------------------------------------------
-    def _forward_eager(self, pose2d, img_feat, mesh, cam_pose, pose3d):
+    def _forward_eager(self, pose2d, img_feat, mesh, cam_pose, pose3d, ws=None):
         B = pose2d.shape[0]
-        ws = self._workspace(B, pose2d.device)
+        if ws is None:
+            ws = self._workspace(B, pose2d.device)
         check(self.lib.pmce_forward(self._dp, _ptr(self.weights), _ptr(pose2d), _ptr(img_feat), _ptr(self.vj), B,
                                     _ptr(mesh), _ptr(cam_pose), _ptr(pose3d), _ptr(ws), ws.numel(), _stream()),
               "pmce_forward")
@@ -240,11 +252,14 @@ class Engine:
 
     # ---- pipelined host loop ---------------------------------------------------------------------------
     def _pipeline(self, B, dev, out_slots=None):
-        """Two slots of static device buffers + captured graphs + pinned host outputs, three streams (H2D / forward / D2H).
-        Both graphs replay on the one forward stream, so they share the workspace. `out_slots`: two caller-owned
-        (cam_mesh, cam_pose, pose3d) triples the two graphs write into (e.g. the rank's rows of two all-gather buffers)."""
-        ws = self._workspace(B, dev)
-        baked = (ws.data_ptr(), self.weights.data_ptr(), self.vj.data_ptr()) + (        # pointers the captured graphs hold
+        """Two slots of static device buffers + captured graphs + pinned host outputs; streams: H2D, one forward stream PER SLOT,
+        D2H. Each slot has its own workspace, so the forwards of two consecutive batches are IN FLIGHT TOGETHER: the decoder
+        third of a forward is a chain of latency-bound kernels, and the other batch's lifter GEMMs fill what it leaves idle
+        (B=64: 2,486 vs 2,748 us per forward, tools/two_in_flight.py). `out_slots`: two caller-owned (cam_mesh, cam_pose, pose3d)
+        triples the two graphs write into (e.g. the rank's rows of two all-gather buffers)."""
+        wss = (self._workspace(B, dev), self._workspace2(B, dev))
+        ws = wss[0]
+        baked = (ws.data_ptr(), wss[1].data_ptr(), self.weights.data_ptr(), self.vj.data_ptr()) + (        # pointers the captured graphs hold
             tuple(t.data_ptr() for sl in out_slots for t in sl) if out_slots is not None else ())
         pipe = self._pipe.get(B)
         if pipe is not None and pipe["baked"] == baked:
@@ -260,20 +275,20 @@ class Engine:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):      # warm-up outside capture
-                self._forward_eager(sl["p2d"], sl["feat"], sl["mesh"], sl["cam_pose"], sl["pose3d"])
+                self._forward_eager(sl["p2d"], sl["feat"], sl["mesh"], sl["cam_pose"], sl["pose3d"], ws=wss[k])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self._forward_eager(sl["p2d"], sl["feat"], sl["mesh"], sl["cam_pose"], sl["pose3d"])
+                self._forward_eager(sl["p2d"], sl["feat"], sl["mesh"], sl["cam_pose"], sl["pose3d"], ws=wss[k])
             sl["graph"] = graph
             slots.append(sl)
         # THREE pinned host output sets for two device slots: result i (host set i % 3) is not written again before batch i+3
         # is submitted, i.e. before the consumer asks for result i+2
         hosts = [(torch.empty(B, d.num_vert, 3).pin_memory(), torch.empty(B, d.num_joint, 3).pin_memory(),
                   torch.empty(B, d.num_joint, 3).pin_memory()) for _ in range(3)]
-        pipe = dict(ws=ws, baked=baked, slots=slots, hosts=hosts, s_in=torch.cuda.Stream(device=dev), s_fwd=torch.cuda.Stream(device=dev),
-                    s_out=torch.cuda.Stream(device=dev))
+        pipe = dict(ws=ws, baked=baked, slots=slots, hosts=hosts, s_in=torch.cuda.Stream(device=dev),
+                    s_fwd=[torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)], s_out=torch.cuda.Stream(device=dev))
         self._pipe[B] = pipe
         return pipe
 
@@ -282,14 +297,15 @@ class Engine:
 
         `batches` yields (pose2d [B,T,J,2], img_feat [B,T,2048]) contiguous float32 CPU tensors (pinned for asynchronous
         copies) of one batch size; the generator yields (cam_mesh, cam_pose, pose3d) pinned CPU tensors in the same order.
-        The H2D copy of batch i+1 and the D2H copy of batch i-1 run on the copy engines while batch i is in the forward
-        (three streams, two device buffer slots with one captured graph each, three pinned host output sets). A yielded
+        The H2D copy of batch i+1 and the D2H copy of batch i-1 run on the copy engines while batch i is in the forward, and the
+        forwards of batches i and i+1 are in flight together on the two slots' own streams and workspaces (two device buffer
+        slots with one captured graph each, three pinned host output sets). A yielded
         triple stays valid while the NEXT result is requested and consumed; it is overwritten once the result after next is
         requested, so consume (or copy) it before asking for the batch after next. `list(forward_host_iter(...))` therefore
         aliases buffers: copy each triple as it arrives.
 
         Multi-GPU hooks (pmce_b200.dist.ShardedForward): `out_slots` = the two device output triples the forwards write into;
-        `before_forward(k)` / `after_forward(k)` run on the forward stream around the replay of slot k (wait until the slot's
+        `before_forward(k)` / `after_forward(k)` run on slot k's forward stream around the replay of slot k (wait until the slot's
         previous all-gather has finished / issue this step's all-gather on the communication stream)."""
         self._ready(need_vj=True)
         dev = self.weights.device
@@ -302,7 +318,7 @@ class Engine:
                     if pipe is None:
                         B = hp.shape[0]
                         pipe = self._pipeline(B, dev, out_slots)
-                        for s in (pipe["s_in"], pipe["s_fwd"], pipe["s_out"]):
+                        for s in (pipe["s_in"], *pipe["s_fwd"], pipe["s_out"]):
                             s.wait_stream(cur)
                     elif hp.shape[0] != B:
                         raise PmceError("forward_host_iter: every batch must have the same size (pad or run the tail through forward_host)")
@@ -314,14 +330,15 @@ class Engine:
                         sl["p2d"].copy_(hp, non_blocking=True)
                         sl["feat"].copy_(hf, non_blocking=True)
                         sl["h2d"].record(pipe["s_in"])
-                    with torch.cuda.stream(pipe["s_fwd"]):
-                        pipe["s_fwd"].wait_event(sl["h2d"])
+                    s_fwd = pipe["s_fwd"][i & 1]
+                    with torch.cuda.stream(s_fwd):
+                        s_fwd.wait_event(sl["h2d"])
                         if sl["used"]:
-                            pipe["s_fwd"].wait_event(sl["d2h"])      # this slot's previous outputs have left the device
+                            s_fwd.wait_event(sl["d2h"])              # this slot's previous outputs have left the device
                         if before_forward is not None:
                             before_forward(i & 1)
                         sl["graph"].replay()
-                        sl["fwd"].record(pipe["s_fwd"])
+                        sl["fwd"].record(s_fwd)
                         if after_forward is not None:
                             after_forward(i & 1)
                     with torch.cuda.stream(pipe["s_out"]):
@@ -344,10 +361,62 @@ class Engine:
             finally:
                 # also on early exit (the consumer stopped iterating, or a batch was rejected): drain and rejoin the caller's stream
                 if pipe is not None:
-                    for s in (pipe["s_in"], pipe["s_fwd"], pipe["s_out"]):
+                    for s in (pipe["s_in"], *pipe["s_fwd"], pipe["s_out"]):
                         cur.wait_stream(s)
                     for sl in pipe["slots"]:
                         sl["used"] = False
+
+    def forward_iter(self, batches, out_slots=None, before_forward=None, after_forward=None):
+        """Device-resident form of the pipelined loop: `batches` yields (pose2d [B,T,J,2], img_feat [B,T,2048]) CUDA tensors of one
+        batch size, the generator yields (cam_mesh, cam_pose, pose3d) CUDA tensors in the same order, with TWO forwards in flight
+        (the slots of `_pipeline`: own static buffers, workspace, captured graph and stream each). Results are bit-identical to
+        `forward()`. A yielded triple is the slot's output buffers: the caller's current stream has been made to wait for them,
+        and they stay valid until the NEXT result is requested - the batch submitted then reuses the slot, after everything the
+        consumer queued on its stream (copy what must live longer). Inputs are read on the slot's stream after everything
+        already queued on the caller's stream. `out_slots` / hooks: as `forward_host_iter`."""
+        self._ready(need_vj=True)
+        d = self.dims
+        dev = self.weights.device
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream()
+            pipe, pending, i = None, [], 0
+            try:
+                for p2d, feat in batches:
+                    B = p2d.shape[0] if isinstance(p2d, torch.Tensor) and p2d.dim() == 4 else -1
+                    p2d = _require_cuda_f32(p2d, "pose2d", (B, d.seqlen, d.num_joint, 2))
+                    feat = _require_cuda_f32(feat, "img_feat", (B, d.seqlen, d.feat_dim))
+                    if pipe is None:
+                        B0 = B
+                        pipe = self._pipeline(B, dev, out_slots)
+                    elif B != B0:
+                        raise PmceError("forward_iter: every batch must have the same size (run the tail through forward)")
+                    sl = pipe["slots"][i & 1]
+                    s_fwd = pipe["s_fwd"][i & 1]
+                    # the inputs were produced, and the slot's previous outputs consumed, by work queued on the caller's stream
+                    s_fwd.wait_stream(cur)
+                    with torch.cuda.stream(s_fwd):
+                        sl["p2d"].copy_(p2d, non_blocking=True)
+                        sl["feat"].copy_(feat, non_blocking=True)
+                        if before_forward is not None:
+                            before_forward(i & 1)
+                        sl["graph"].replay()
+                        sl["fwd"].record(s_fwd)
+                        if after_forward is not None:
+                            after_forward(i & 1)
+                    pending.append(sl)
+                    i += 1
+                    if len(pending) == 2:
+                        done = pending.pop(0)
+                        cur.wait_event(done["fwd"])
+                        yield done["mesh"], done["cam_pose"], done["pose3d"]
+                while pending:
+                    done = pending.pop(0)
+                    cur.wait_event(done["fwd"])
+                    yield done["mesh"], done["cam_pose"], done["pose3d"]
+            finally:
+                if pipe is not None:        # also on early exit: nothing of the pipeline outlives the call un-joined
+                    for s in pipe["s_fwd"]:
+                        cur.wait_stream(s)
 
     # ---- sub-paths (each is a C-ABI entry point; used by the module API and by the parity tests) --------
     def lifter(self, pose2d, img_feat):

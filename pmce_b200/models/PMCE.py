@@ -53,6 +53,12 @@ class PMCE(EngineModule):
         overlap the forward (Engine.forward_host_iter). Yields (cam_mesh, cam_pose, pose3d) pinned CPU tensors in order."""
         return self.engine().forward_host_iter(batches, **hooks)
 
+    @torch.no_grad()
+    def forward_iter(self, batches, **hooks):
+        """Device-resident pipelined loop: `for mesh, cam_pose, pose3d in model.forward_iter(cuda_batches)` - the forwards of two
+        consecutive batches are in flight together (Engine.forward_iter); results are bit-identical to calling the module."""
+        return self.engine().forward_iter(batches, **hooks)
+
 
 def get_model(num_joint, embed_dim, depth):
     return PMCE(num_joint, embed_dim, depth)

@@ -260,6 +260,40 @@ def test_pipelined_host_iter_matches_forward(base):
         list(m.forward_host_iter(iter([batches[0], (p2d.pin_memory(), feat.pin_memory())])))
 
 
+@pytest.mark.parametrize("B", [2, 64])
+def test_forward_iter_two_in_flight_matches_forward(base, B):
+    """Engine.forward_iter keeps the forwards of two consecutive batches in flight (two slots: own workspace, graph and stream):
+    every result is bit-identical to the module call on the same batch, in order (a triple is the slot's output buffers, valid
+    until the next result is requested), for odd / single / empty sequences, and with work still queued on the caller's stream
+    that produces the inputs."""
+    m = base["m"]
+    cases = [synth.make_inputs(B, 16, 17, seed=300 + i) for i in range(5)]
+    dev_cases = [(p.cuda(), f.cuda()) for p, f in cases]
+    refs = [[t.clone() for t in m(p, f)] for p, f in dev_cases]
+    torch.cuda.synchronize()
+    for n in (5, 1, 2, 0):
+        got = [[t.clone() for t in res] for res in m.forward_iter(iter(dev_cases[:n]))]      # clones queue on the caller's stream
+        torch.cuda.synchronize()
+        assert len(got) == n
+        for r, g in zip(refs, got):
+            assert all(torch.equal(a, b) for a, b in zip(r, g)), n
+
+    def produced():                              # inputs made by kernels still queued on the caller's stream
+        for p, f in dev_cases[:3]:
+            yield (p * 2.0) * 0.5, (f + 1.0) - 1.0
+    want = [[t.clone() for t in m((p * 2.0) * 0.5, (f + 1.0) - 1.0)] for p, f in dev_cases[:3]]
+    got = [[t.clone() for t in res] for res in m.forward_iter(produced())]
+    torch.cuda.synchronize()
+    for r, g in zip(want, got):
+        assert all(torch.equal(a, b) for a, b in zip(r, g))
+    from pmce_b200._lib import PmceError
+    with pytest.raises(PmceError, match="same size"):
+        list(m.forward_iter(iter([dev_cases[0], (dev_cases[0][0][:1].contiguous(), dev_cases[0][1][:1].contiguous())])))
+    out = m(*dev_cases[0])                       # the ordinary call still works after an aborted pipeline
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(out, refs[0]))
+
+
 def test_clips_are_independent_at_full_batch(base):
     """Size-independent property at BASELINE batch sizes: every clip's output depends on that clip only, so a B=64
     batch made of the golden clips (repeated, permuted) reproduces the B=2 rows exactly-ish, and ragged B works."""
