@@ -271,7 +271,13 @@ class Engine:
                                                             torch.empty(B, d.num_joint, 3, device=dev))
             sl = dict(p2d=torch.zeros(B, d.seqlen, d.num_joint, 2, device=dev), feat=torch.zeros(B, d.seqlen, d.feat_dim, device=dev),
                       mesh=o[0], cam_pose=o[1], pose3d=o[2],
-                      h2d=torch.cuda.Event(), fwd=torch.cuda.Event(), d2h=torch.cuda.Event(), used=False)
+                      # staging copies for the host loop: the H2D of the slot's NEXT batch and the D2H of its PREVIOUS result must
+                      # not wait for / hold up the forward that owns the graph's static buffers (a 14 MB device copy per step buys
+                      # ~170 us of H2D + ~100 us of D2H off the slot's critical path)
+                      p2d_in=torch.zeros(B, d.seqlen, d.num_joint, 2, device=dev), feat_in=torch.zeros(B, d.seqlen, d.feat_dim, device=dev),
+                      mesh_out=torch.empty(B, d.num_vert, 3, device=dev), cam_pose_out=torch.empty(B, d.num_joint, 3, device=dev),
+                      pose3d_out=torch.empty(B, d.num_joint, 3, device=dev),
+                      h2d=torch.cuda.Event(), in_free=torch.cuda.Event(), fwd=torch.cuda.Event(), d2h=torch.cuda.Event(), used=False)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):      # warm-up outside capture
@@ -326,26 +332,32 @@ class Engine:
                     host = pipe["hosts"][i % 3]
                     with torch.cuda.stream(pipe["s_in"]):
                         if sl["used"]:
-                            pipe["s_in"].wait_event(sl["fwd"])       # the forward that read this slot's inputs has finished
-                        sl["p2d"].copy_(hp, non_blocking=True)
-                        sl["feat"].copy_(hf, non_blocking=True)
+                            pipe["s_in"].wait_event(sl["in_free"])   # the slot's previous batch has left the staging inputs
+                        sl["p2d_in"].copy_(hp, non_blocking=True)
+                        sl["feat_in"].copy_(hf, non_blocking=True)
                         sl["h2d"].record(pipe["s_in"])
                     s_fwd = pipe["s_fwd"][i & 1]
                     with torch.cuda.stream(s_fwd):
                         s_fwd.wait_event(sl["h2d"])
-                        if sl["used"]:
-                            s_fwd.wait_event(sl["d2h"])              # this slot's previous outputs have left the device
+                        sl["p2d"].copy_(sl["p2d_in"], non_blocking=True)     # staging -> the graph's static inputs (device copy)
+                        sl["feat"].copy_(sl["feat_in"], non_blocking=True)
+                        sl["in_free"].record(s_fwd)
                         if before_forward is not None:
                             before_forward(i & 1)
                         sl["graph"].replay()
-                        sl["fwd"].record(s_fwd)
                         if after_forward is not None:
                             after_forward(i & 1)
+                        if sl["used"]:
+                            s_fwd.wait_event(sl["d2h"])              # the slot's previous result has left the staging outputs
+                        sl["mesh_out"].copy_(sl["mesh"], non_blocking=True)
+                        sl["cam_pose_out"].copy_(sl["cam_pose"], non_blocking=True)
+                        sl["pose3d_out"].copy_(sl["pose3d"], non_blocking=True)
+                        sl["fwd"].record(s_fwd)
                     with torch.cuda.stream(pipe["s_out"]):
                         pipe["s_out"].wait_event(sl["fwd"])
-                        host[0].copy_(sl["mesh"], non_blocking=True)
-                        host[1].copy_(sl["cam_pose"], non_blocking=True)
-                        host[2].copy_(sl["pose3d"], non_blocking=True)
+                        host[0].copy_(sl["mesh_out"], non_blocking=True)
+                        host[1].copy_(sl["cam_pose_out"], non_blocking=True)
+                        host[2].copy_(sl["pose3d_out"], non_blocking=True)
                         sl["d2h"].record(pipe["s_out"])
                     sl["used"] = True
                     pending.append((sl["d2h"], host))     # the slot's event is re-recorded only after this entry was popped
