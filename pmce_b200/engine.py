@@ -397,6 +397,8 @@ class Engine:
                     B = p2d.shape[0] if isinstance(p2d, torch.Tensor) and p2d.dim() == 4 else -1
                     p2d = _require_cuda_f32(p2d, "pose2d", (B, d.seqlen, d.num_joint, 2))
                     feat = _require_cuda_f32(feat, "img_feat", (B, d.seqlen, d.feat_dim))
+                    if p2d.device != dev or feat.device != dev:
+                        raise PmceError(f"forward_iter: inputs on {p2d.device} / {feat.device} but weights on {dev}")
                     if pipe is None:
                         B0 = B
                         pipe = self._pipeline(B, dev, out_slots)
